@@ -1,0 +1,328 @@
+"""audio_network_b200 -- Python (ctypes) mirror of include/anmodem.h.
+
+The product is libanmodem.so (sm_100a CUDA kernels behind a C ABI).  This module only
+loads it and mirrors its functions with the same names and argument meaning, so tests and
+bench.py read like calls to the C interface.  There is no Python or CPU implementation of
+the receive path here: every compute call fails loudly (AnmError) when the shared object
+or a CUDA device is missing.
+
+Reference seam being mirrored: SURVEY.md section 8(b) -- the pb_istream_t byte source of
+hardware/src/network.cpp:262-305 and the `<module>_initialize()` idiom of
+hardware/README.md:10-14.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libanmodem.so")
+
+ANM_MAX_TONES = 64
+ANM_MAX_PREAMBLE = 32
+ANM_SILENCE = 0xFF
+ANM_SNR_CLEAN = 2**31 - 1
+ANM_FLAG_SYMBOLS = 1
+
+ANM_OK, ANM_ERR_ARG, ANM_ERR_CUDA, ANM_ERR_NOMEM, ANM_ERR_ALIGN, ANM_ERR_OVERFLOW, ANM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+
+
+class AnmError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("anmodem error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_uint32),
+        ("sym_len", C.c_uint32),
+        ("hops_per_sym", C.c_uint32),
+        ("n_tones", C.c_uint32),
+        ("tone_bin", C.c_uint32 * ANM_MAX_TONES),
+        ("preamble_len", C.c_uint32),
+        ("preamble", C.c_uint8 * ANM_MAX_PREAMBLE),
+        ("sync_tol", C.c_uint32),
+        ("max_payload", C.c_uint32),
+        ("trk_epoch", C.c_uint32),
+        ("trk_thresh", C.c_uint32),
+    ]
+
+    @property
+    def hop(self):
+        return self.sym_len // self.hops_per_sym
+
+    @property
+    def bits_per_sym(self):
+        return int(self.n_tones).bit_length() - 1
+
+
+class Frame(C.Structure):
+    _fields_ = [
+        ("channel", C.c_uint32),
+        ("len", C.c_uint32),
+        ("start_sample", C.c_uint64),
+        ("crc_ok", C.c_uint32),
+        ("offset", C.c_uint32),
+    ]
+
+
+class ChanStats(C.Structure):
+    _fields_ = [
+        ("locks", C.c_uint32),
+        ("header_fail", C.c_uint32),
+        ("frames_ok", C.c_uint32),
+        ("frames_bad", C.c_uint32),
+        ("symbols", C.c_uint64),
+        ("trk_moves", C.c_int32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class TxParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("start_offset", C.c_int64),
+        ("amplitude_q15", C.c_uint32),
+        ("snr_mdb", C.c_int32),
+        ("ppm_x1000", C.c_int32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+FRAME_DTYPE = np.dtype(
+    [("channel", "<u4"), ("len", "<u4"), ("start_sample", "<u8"), ("crc_ok", "<u4"), ("offset", "<u4")]
+)
+TXPARAMS_DTYPE = np.dtype(
+    [("seed", "<u8"), ("start_offset", "<i8"), ("amplitude_q15", "<u4"), ("snr_mdb", "<i4"), ("ppm_x1000", "<i4"), ("reserved", "<u4")]
+)
+STATS_DTYPE = np.dtype(
+    [("locks", "<u4"), ("header_fail", "<u4"), ("frames_ok", "<u4"), ("frames_bad", "<u4"), ("symbols", "<u8"), ("trk_moves", "<i4"), ("reserved", "<u4")]
+)
+
+# every symbol include/anmodem.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "anm_config_preset", "anm_config_validate", "anm_twiddles", "anm_crc16", "anm_crc8",
+    "anm_frame_num_symbols", "anm_frame_symbols", "anm_tx_render", "anm_tx_render_device",
+    "anm_tone_energies_device", "anm_demod_create", "anm_demod_destroy", "anm_demod_reset",
+    "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_collect", "anm_demod_read_frames",
+    "anm_demod_read_symbols", "anm_demod_stats", "anm_demod_launch_count", "anm_demod_last_kernel_ms",
+    "anm_last_error", "anm_version", "demod_initialize", "demod_create", "demod_feed",
+    "demod_read_symbols", "demod_read_frames", "demod_destroy",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libanmodem.so (building is __graft_entry__.build()'s job); fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AnmError(ANM_ERR_UNSUPPORTED, "%s is missing: run `python audio-network_b200/build.py` (no fallback exists)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, i16p, f32p, u32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_int16), C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    cfgp = C.POINTER(Config)
+    sig = {
+        "anm_config_preset": (C.c_int, [C.c_char_p, cfgp]),
+        "anm_config_validate": (C.c_int, [cfgp]),
+        "anm_twiddles": (C.c_int, [cfgp, vp]),
+        "anm_crc16": (C.c_uint16, [vp, C.c_size_t, C.c_uint16]),
+        "anm_crc8": (C.c_uint8, [vp, C.c_size_t, C.c_uint8]),
+        "anm_frame_num_symbols": (C.c_size_t, [cfgp, C.c_size_t]),
+        "anm_frame_symbols": (C.c_size_t, [cfgp, vp, C.c_size_t, vp, C.c_size_t]),
+        "anm_tx_render": (C.c_int, [cfgp, vp, C.c_size_t, C.POINTER(TxParams), C.c_uint64, vp, C.c_size_t]),
+        "anm_tx_render_device": (C.c_int, [cfgp, vp, C.c_size_t, vp, vp, C.c_uint32, C.c_uint64, vp, C.c_size_t, C.c_size_t, vp]),
+        "anm_tx_params_prepare": (None, [vp, C.c_size_t]),
+        "anm_tone_energies_device": (C.c_int, [cfgp, vp, C.c_uint32, C.c_size_t, C.c_size_t, vp, vp, vp, vp]),
+        "anm_demod_create": (C.c_int, [cfgp, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(vp)]),
+        "anm_demod_destroy": (None, [vp]),
+        "anm_demod_reset": (C.c_int, [vp]),
+        "anm_demod_feed_device": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp]),
+        "anm_demod_feed_host": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
+        "anm_demod_collect": (C.c_long, [vp]),
+        "anm_demod_read_frames": (C.c_size_t, [vp, vp, C.c_size_t, vp, C.c_size_t]),
+        "anm_demod_read_symbols": (C.c_size_t, [vp, C.c_uint32, vp, C.c_size_t]),
+        "anm_demod_stats": (C.c_int, [vp, vp]),
+        "anm_demod_launch_count": (C.c_uint64, [vp]),
+        "anm_demod_last_kernel_ms": (C.c_float, [vp]),
+        "anm_demod_kernel_time": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "anm_demod_launch_geometry": (C.c_int, [vp, u32p, u32p, u32p]),
+        "anm_last_error": (C.c_char_p, []),
+        "anm_version": (C.c_char_p, []),
+        "demod_initialize": (C.c_int, [cfgp]),
+        "demod_create": (vp, []),
+        "demod_feed": (C.c_int, [vp, vp, C.c_size_t]),
+        "demod_read_symbols": (C.c_size_t, [vp, vp, C.c_size_t]),
+        "demod_read_frames": (C.c_size_t, [vp, vp, C.c_size_t]),
+        "demod_destroy": (None, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise AnmError(rc, (lib().anm_last_error() or b"").decode())
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------- host helpers
+def config_preset(name):
+    cfg = Config()
+    _check(lib().anm_config_preset(name.encode(), C.byref(cfg)))
+    return cfg
+
+
+def twiddles(cfg):
+    out = np.empty((cfg.sym_len, cfg.n_tones, 2), dtype=np.float32)
+    _check(lib().anm_twiddles(C.byref(cfg), _ptr(out)))
+    return out
+
+
+def crc16(data, crc=0xFFFF):
+    b = np.frombuffer(bytes(data), dtype=np.uint8)
+    return lib().anm_crc16(_ptr(b) if len(b) else None, len(b), crc)
+
+
+def crc8(data, crc=0):
+    b = np.frombuffer(bytes(data), dtype=np.uint8)
+    return lib().anm_crc8(_ptr(b) if len(b) else None, len(b), crc)
+
+
+def frame_symbols(cfg, payload):
+    """Tone indices (preamble + header + body) of a frame carrying `payload`."""
+    pl = np.frombuffer(bytes(payload), dtype=np.uint8)
+    n = lib().anm_frame_num_symbols(C.byref(cfg), len(pl))
+    if n == 0:
+        raise AnmError(ANM_ERR_ARG, "invalid payload length %d" % len(pl))
+    out = np.empty(n, dtype=np.uint8)
+    got = lib().anm_frame_symbols(C.byref(cfg), _ptr(pl), len(pl), _ptr(out), n)
+    if got != n:
+        raise AnmError(ANM_ERR_ARG, "frame_symbols failed")
+    return out
+
+
+def tx_params(seed=0, start_offset=0, amplitude=0.5, snr_db=None, ppm=0.0):
+    p = TxParams()
+    p.seed = seed
+    p.start_offset = start_offset
+    p.amplitude_q15 = int(round(amplitude * 32768))
+    p.snr_mdb = ANM_SNR_CLEAN if snr_db is None else int(round(snr_db * 1000))
+    p.ppm_x1000 = int(round(ppm * 1000))
+    return p
+
+
+def tx_render(cfg, program, params, first_sample, n):
+    """CPU transmitter stand-in: int16 PCM of rx samples [first_sample, first_sample + n)."""
+    prog = np.ascontiguousarray(program, dtype=np.uint8)
+    out = np.empty(n, dtype=np.int16)
+    _check(lib().anm_tx_render(C.byref(cfg), _ptr(prog), len(prog), C.byref(params), first_sample, _ptr(out), n))
+    return out
+
+
+def tx_params_array(plist):
+    arr = np.zeros(len(plist), dtype=TXPARAMS_DTYPE)
+    for i, p in enumerate(plist):
+        arr[i] = (p.seed, p.start_offset, p.amplitude_q15, p.snr_mdb, p.ppm_x1000, 0)
+    lib().anm_tx_params_prepare(_ptr(arr), len(arr))
+    return arr
+
+
+def tx_render_device(cfg, d_programs, prog_stride, d_prog_len, d_params, n_ch, first_sample, d_pcm, ch_stride, n, stream=0):
+    """GPU renderer; all d_* are raw device pointers (ints)."""
+    _check(lib().anm_tx_render_device(C.byref(cfg), d_programs, prog_stride, d_prog_len, d_params, n_ch, first_sample, d_pcm, ch_stride, n, stream))
+
+
+def tone_energies_device(cfg, d_pcm, n_ch, ch_stride, n_samples, d_energy=None, d_sym=None, d_emax=None, stream=0):
+    _check(lib().anm_tone_energies_device(C.byref(cfg), d_pcm, n_ch, ch_stride, n_samples, d_energy, d_sym, d_emax, stream))
+
+
+class Demod:
+    """Batched streaming demodulator handle (anm_demod_*)."""
+
+    def __init__(self, cfg, n_channels, device=0, flags=0):
+        self.cfg = cfg
+        self.n_channels = n_channels
+        self._h = C.c_void_p()
+        _check(lib().anm_demod_create(C.byref(cfg), n_channels, device, flags, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().anm_demod_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().anm_demod_reset(self._h))
+
+    def feed_device(self, d_pcm, ch_stride, n_samples, stream=0):
+        _check(lib().anm_demod_feed_device(self._h, d_pcm, ch_stride, n_samples, stream))
+
+    def feed_host(self, pcm):
+        """pcm: int16 array [n_channels, n_samples] (C-contiguous rows)."""
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n_channels
+        assert pcm.strides[1] == 2
+        _check(lib().anm_demod_feed_host(self._h, _ptr(pcm), pcm.strides[0] // 2, pcm.shape[1]))
+
+    def feed_host_ptr(self, ptr, ch_stride, n_samples):
+        _check(lib().anm_demod_feed_host(self._h, ptr, ch_stride, n_samples))
+
+    def collect(self):
+        return _check(lib().anm_demod_collect(self._h))
+
+    def read_frames(self, cap=1 << 16, bytes_cap=1 << 24):
+        """Returns (records ndarray FRAME_DTYPE, bytes ndarray) in (channel, start_sample) order."""
+        recs = np.zeros(cap, dtype=FRAME_DTYPE)
+        by = np.zeros(bytes_cap, dtype=np.uint8)
+        n = lib().anm_demod_read_frames(self._h, _ptr(recs), cap, _ptr(by), bytes_cap)
+        recs = recs[:n]
+        used = int(recs["len"].sum()) if n else 0
+        return recs, by[:used]
+
+    def read_symbols(self, channel, cap=1 << 20):
+        out = np.zeros(cap, dtype=np.uint8)
+        n = lib().anm_demod_read_symbols(self._h, channel, _ptr(out), cap)
+        return out[:n]
+
+    def stats(self):
+        out = np.zeros(self.n_channels, dtype=STATS_DTYPE)
+        _check(lib().anm_demod_stats(self._h, _ptr(out)))
+        return out
+
+    def launch_count(self):
+        return int(lib().anm_demod_launch_count(self._h))
+
+    def kernel_time(self):
+        """(sum of kernel device time in ms, launches) since the previous call."""
+        ms = C.c_float()
+        n = _check(lib().anm_demod_kernel_time(self._h, C.byref(ms)))
+        return float(ms.value), n
+
+    def launch_geometry(self):
+        g, w, s = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().anm_demod_launch_geometry(self._h, C.byref(g), C.byref(w), C.byref(s)))
+        return g.value, w.value, s.value
+
+
+def frames_to_list(recs, by):
+    """[(channel, start_sample, crc_ok, payload bytes)] from read_frames output."""
+    out = []
+    for r in recs:
+        o = int(r["offset"])
+        out.append((int(r["channel"]), int(r["start_sample"]), int(r["crc_ok"]), bytes(by[o:o + int(r["len"])])))
+    return out

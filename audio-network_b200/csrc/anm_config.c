@@ -1,0 +1,146 @@
+/*
+ * anm_config.c -- presets, validation, twiddle table, CRCs and transmit-side
+ * framing of the SPEC.md modem.  Host C, no device code.
+ *
+ * Reference context: the payload carried by a frame is one varint-delimited
+ * ip.proto message (protocol/ip.proto:9-64; consumer pb_decode_delimited at
+ * hardware/src/network.cpp:411).  Everything else here is defined by SPEC.md.
+ */
+#include "anm_internal.h"
+
+#include <math.h>
+#include <string.h>
+
+static const uint8_t PRE4[16] = {3, 0, 1, 2, 3, 2, 0, 2, 1, 0, 3, 1, 2, 0, 2, 3};
+static const uint8_t PRE8[16] = {5, 0, 2, 1, 4, 2, 3, 7, 0, 6, 3, 6, 5, 7, 1, 3};
+static const uint8_t PRE16[16] = {12, 13, 5, 11, 2, 14, 3, 5, 12, 11, 15, 0, 15, 1, 9, 12};
+static const uint8_t PRE64[16] = {58, 3, 29, 22, 23, 11, 32, 4, 9, 10, 2, 57, 1, 35, 31, 34};
+static const uint8_t PRE2[32] = {1, 0, 1, 1, 0, 1, 0, 0, 1, 1, 0, 0, 0, 1, 0, 1,
+                                 1, 1, 0, 0, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1, 1};
+
+static void base(anm_config_t *c, uint32_t N, uint32_t S, uint32_t T, uint32_t bin0, uint32_t step,
+                 const uint8_t *pre, uint32_t P, uint32_t tol) {
+    memset(c, 0, sizeof *c);
+    c->sample_rate = 44100;
+    c->sym_len = N;
+    c->hops_per_sym = S;
+    c->n_tones = T;
+    for (uint32_t k = 0; k < T; ++k) c->tone_bin[k] = bin0 + k * step;
+    c->preamble_len = P;
+    memcpy(c->preamble, pre, P);
+    c->sync_tol = tol;
+    c->max_payload = 1024;
+    c->trk_epoch = 16;
+    c->trk_thresh = 3;
+}
+
+int anm_config_preset(const char *name, anm_config_t *out) {
+    if (!name || !out) return ANM_ERR_ARG;
+    if (!strcmp(name, "ref4")) base(out, 128, 4, 4, 10, 2, PRE4, 16, 2);
+    else if (!strcmp(name, "bfsk2")) base(out, 128, 4, 2, 12, 4, PRE2, 32, 3);
+    else if (!strcmp(name, "mfsk8")) base(out, 128, 4, 8, 8, 2, PRE8, 16, 2);
+    else if (!strcmp(name, "mfsk16")) base(out, 128, 4, 16, 8, 2, PRE16, 16, 2);
+    else if (!strcmp(name, "wide64")) base(out, 256, 4, 64, 16, 1, PRE64, 16, 2);
+    else return ANM_ERR_ARG;
+    return ANM_OK;
+}
+
+static int is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+int anm_config_validate(const anm_config_t *c) {
+    if (!c) return ANM_ERR_ARG;
+    if (!is_pow2(c->sym_len) || c->sym_len < 32 || c->sym_len > 512) return ANM_ERR_ARG;
+    if (c->hops_per_sym != 2 && c->hops_per_sym != 4 && c->hops_per_sym != 8) return ANM_ERR_ARG;
+    if ((c->sym_len / c->hops_per_sym) % 8) return ANM_ERR_ARG;
+    if (!is_pow2(c->n_tones) || c->n_tones < 2 || c->n_tones > ANM_MAX_TONES) return ANM_ERR_ARG;
+    for (uint32_t k = 0; k < c->n_tones; ++k) {
+        if (c->tone_bin[k] == 0 || c->tone_bin[k] >= c->sym_len / 2) return ANM_ERR_ARG;
+        for (uint32_t j = 0; j < k; ++j)
+            if (c->tone_bin[j] == c->tone_bin[k]) return ANM_ERR_ARG;
+    }
+    if (c->preamble_len != 8 && c->preamble_len != 16 && c->preamble_len != 32) return ANM_ERR_ARG;
+    for (uint32_t p = 0; p < c->preamble_len; ++p)
+        if (c->preamble[p] >= c->n_tones) return ANM_ERR_ARG;
+    if (c->sync_tol >= c->preamble_len) return ANM_ERR_ARG;
+    if (c->max_payload == 0 || c->max_payload > 4104) return ANM_ERR_ARG;
+    if (c->trk_epoch == 0 || c->trk_thresh == 0) return ANM_ERR_ARG;
+    return ANM_OK;
+}
+
+int anm_twiddles(const anm_config_t *c, float *out) {
+    if (anm_config_validate(c) != ANM_OK || !out) return ANM_ERR_ARG;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (uint32_t m = 0; m < c->sym_len; ++m)
+        for (uint32_t k = 0; k < c->n_tones; ++k) {
+            /* reduce the angle exactly before calling libm: (bin*m) mod N */
+            uint32_t r = (c->tone_bin[k] * m) % c->sym_len;
+            double a = two_pi * (double)r / (double)c->sym_len;
+            out[(m * c->n_tones + k) * 2 + 0] = (float)cos(a);
+            out[(m * c->n_tones + k) * 2 + 1] = (float)sin(a);
+        }
+    return ANM_OK;
+}
+
+uint16_t anm_crc16(const uint8_t *data, size_t len, uint16_t crc) {
+    for (size_t i = 0; i < len; ++i) {
+        crc ^= (uint16_t)data[i] << 8;
+        for (int b = 0; b < 8; ++b) crc = (crc & 0x8000) ? (uint16_t)((crc << 1) ^ 0x1021) : (uint16_t)(crc << 1);
+    }
+    return crc;
+}
+
+uint8_t anm_crc8(const uint8_t *data, size_t len, uint8_t crc) {
+    for (size_t i = 0; i < len; ++i) {
+        crc ^= data[i];
+        for (int b = 0; b < 8; ++b) crc = (crc & 0x80) ? (uint8_t)((crc << 1) ^ 0x07) : (uint8_t)(crc << 1);
+    }
+    return crc;
+}
+
+uint32_t anm_bits_per_sym(const anm_config_t *c) {
+    uint32_t b = 0;
+    while ((1u << b) < c->n_tones) ++b;
+    return b;
+}
+
+size_t anm_frame_num_symbols(const anm_config_t *c, size_t len) {
+    if (anm_config_validate(c) != ANM_OK || len == 0 || len > c->max_payload) return 0;
+    uint32_t b = anm_bits_per_sym(c);
+    return c->preamble_len + (24 + b - 1) / b + ((len + 2) * 8 + b - 1) / b;
+}
+
+/* bits MSB first -> b-bit values -> Gray-mapped tone indices, zero padded */
+static size_t pack_section(const uint8_t *bytes, size_t nbytes, uint32_t b, uint8_t *syms) {
+    size_t nbits = nbytes * 8, ns = (nbits + b - 1) / b;
+    for (size_t s = 0; s < ns; ++s) {
+        uint32_t v = 0;
+        for (uint32_t i = 0; i < b; ++i) {
+            size_t bit = s * b + i;
+            uint32_t x = bit < nbits ? (bytes[bit >> 3] >> (7 - (bit & 7))) & 1u : 0u;
+            v = (v << 1) | x;
+        }
+        syms[s] = (uint8_t)(v ^ (v >> 1));
+    }
+    return ns;
+}
+
+size_t anm_frame_symbols(const anm_config_t *c, const uint8_t *payload, size_t len, uint8_t *syms,
+                         size_t cap) {
+    size_t total = anm_frame_num_symbols(c, len);
+    if (!total || !payload || !syms || cap < total) return 0;
+    uint32_t b = anm_bits_per_sym(c);
+    size_t n = 0;
+    memcpy(syms, c->preamble, c->preamble_len);
+    n += c->preamble_len;
+    uint8_t hdr[3] = {(uint8_t)(len >> 8), (uint8_t)len, 0};
+    hdr[2] = anm_crc8(hdr, 2, 0);
+    n += pack_section(hdr, 3, b, syms + n);
+    /* body = payload | crc16(LEN bytes + payload); build in a bounded buffer */
+    uint8_t body[4104 + 2];
+    memcpy(body, payload, len);
+    uint16_t crc = anm_crc16(payload, len, anm_crc16(hdr, 2, 0xFFFF));
+    body[len] = (uint8_t)(crc >> 8);
+    body[len + 1] = (uint8_t)crc;
+    n += pack_section(body, len + 2, b, syms + n);
+    return n;
+}

@@ -1,0 +1,612 @@
+/*
+ * anm_cuda.cu -- C-ABI host side of the batched demodulator (include/anmodem.h):
+ * handle management, kernel dispatch, result collection.  Host code is C-style C++
+ * calling the sm_100a kernels of anm_kernels.cuh; there is no CPU compute fallback.
+ *
+ * Reference seam: this is the byte source that would stand where the socket-backed
+ * pb_istream_t stands today (hardware/src/network.cpp:262-305, consumed at :406-411);
+ * the single-channel demod_* functions follow the reference's module idiom
+ * (hardware/README.md:10-14, hardware/include/playback.hpp:15).
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "anm_kernels.cuh"
+
+using namespace anm;
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            anm_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return ANM_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+namespace {
+
+typedef void (*kern_fn)(const KParams);
+
+struct Variant {
+    uint32_t T, N, S;
+    bool twc;
+    kern_fn fn;
+    uint32_t warp_smem, state_bytes;
+};
+
+#define VARIANT(T_, N_, S_)                                                                             \
+    {T_, N_, S_, (T_ * N_ <= kMaxConstTw), (kern_fn)k_demod<T_, N_, S_, (T_ * N_ <= kMaxConstTw)>, \
+     warp_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
+
+const Variant kVariants[] = {
+    VARIANT(4, 128, 4),  VARIANT(2, 128, 4),  VARIANT(8, 128, 4), VARIANT(16, 128, 4),
+    VARIANT(64, 256, 4), VARIANT(4, 128, 8),  VARIANT(4, 128, 2), VARIANT(4, 64, 4),
+};
+
+const Variant *find_variant(const anm_config_t *c) {
+    for (const Variant &v : kVariants)
+        if (v.T == c->n_tones && v.N == c->sym_len && v.S == c->hops_per_sym) return &v;
+    return nullptr;
+}
+
+/* which configuration currently sits in constant bank 3, per device */
+std::mutex g_tw_mu;
+const void *g_tw_owner[64] = {nullptr};
+
+struct EvPair {
+    cudaEvent_t a, b;
+};
+
+} /* namespace */
+
+struct anm_demod {
+    anm_config_t cfg;
+    const Variant *var;
+    int device;
+    uint32_t n_ch, flags;
+    int num_sms;
+    uint32_t warps_per_cta, grid;
+    size_t smem_bytes;
+    unsigned char *d_state;
+    uint8_t *d_fsyms;
+    uint32_t fsym_stride, max_frame_syms;
+    anm_frame_t *d_frames;
+    uint8_t *d_bytes;
+    uint32_t *d_counters;
+    uint32_t frames_cap, bytes_cap;
+    uint8_t *d_osyms;
+    uint32_t osym_cap;
+    float2 *d_tw;
+    std::vector<float> h_tw;
+    int16_t *d_stage;
+    size_t stage_cap;
+    cudaStream_t own_stream, last_stream;
+    uint64_t samples_fed, syms_since_collect, launches;
+    std::vector<EvPair> evs;
+    size_t ev_used;
+    /* host-side result queues */
+    std::vector<anm_frame_t> q_frames;
+    std::vector<uint8_t> q_bytes;
+    std::vector<std::deque<uint8_t>> q_syms;
+    int overflow;
+    KParams kp;
+};
+
+static int set_device(const anm_demod *h) {
+    CK(cudaSetDevice(h->device));
+    return ANM_OK;
+}
+
+static void choose_launch(anm_demod *h) {
+    const uint32_t per_warp = h->var->warp_smem;
+    const uint32_t smem_max = 227u * 1024u - 1024u;
+    uint32_t wmax = std::min<uint32_t>(16u, smem_max / per_warp);
+    if (wmax < 1) wmax = 1;
+    const uint32_t sms = (uint32_t)h->num_sms;
+    uint32_t W = wmax;
+    if (h->n_ch <= sms * wmax) {
+        W = std::max<uint32_t>(1u, (h->n_ch + sms - 1) / sms);
+        h->grid = (h->n_ch + W - 1) / W;
+    } else {
+        double best = -1.0;
+        for (uint32_t w = wmax; w >= std::max<uint32_t>(1u, wmax / 2); --w) {
+            const uint64_t slots = (uint64_t)sms * w;
+            const uint64_t passes = (h->n_ch + slots - 1) / slots;
+            const double eff = (double)h->n_ch / (double)(passes * slots);
+            if (eff > best + 1e-9) { best = eff; W = w; }
+        }
+        h->grid = sms;
+    }
+    h->warps_per_cta = W;
+    h->smem_bytes = (size_t)W * per_warp;
+}
+
+extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, int device, uint32_t flags,
+                                anm_demod_t **out) {
+    if (!cfg || !out || n_channels == 0) return ANM_ERR_ARG;
+    if (anm_config_validate(cfg) != ANM_OK) { anm_set_error("invalid configuration"); return ANM_ERR_ARG; }
+    const Variant *var = find_variant(cfg);
+    if (!var) {
+        anm_set_error("no kernel instance for T=%u N=%u S=%u", cfg->n_tones, cfg->sym_len, cfg->hops_per_sym);
+        return ANM_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        anm_set_error("no CUDA device: the demodulator has no CPU fallback");
+        return ANM_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) return ANM_ERR_ARG;
+    anm_demod *h = new (std::nothrow) anm_demod();
+    if (!h) return ANM_ERR_NOMEM;
+    h->cfg = *cfg;
+    h->var = var;
+    h->device = device;
+    h->n_ch = n_channels;
+    h->flags = flags;
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    choose_launch(h);
+    CK(cudaFuncSetAttribute((const void *)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 1024)));
+    const uint32_t b = anm_bits_per_sym(cfg);
+    const uint32_t hdr_syms = (24 + b - 1) / b;
+    h->max_frame_syms = hdr_syms + ((cfg->max_payload + 2) * 8 + b - 1) / b;
+    h->fsym_stride = (h->max_frame_syms + 63u) & ~63u;
+    h->frames_cap = std::max<uint32_t>(4096u, n_channels * 32u);
+    h->bytes_cap = std::max<uint32_t>(1u << 20, n_channels * 2048u);
+    h->osym_cap = (flags & ANM_FLAG_SYMBOLS) ? 4096u : 0u;
+    CK(cudaMalloc(&h->d_state, (size_t)n_channels * var->state_bytes));
+    CK(cudaMalloc(&h->d_fsyms, (size_t)n_channels * h->fsym_stride));
+    CK(cudaMalloc(&h->d_frames, (size_t)h->frames_cap * sizeof(anm_frame_t)));
+    CK(cudaMalloc(&h->d_bytes, h->bytes_cap));
+    CK(cudaMalloc(&h->d_counters, 16));
+    if (h->osym_cap) CK(cudaMalloc(&h->d_osyms, (size_t)n_channels * h->osym_cap));
+    h->h_tw.resize((size_t)cfg->sym_len * cfg->n_tones * 2);
+    anm_twiddles(cfg, h->h_tw.data());
+    CK(cudaMalloc(&h->d_tw, h->h_tw.size() * sizeof(float)));
+    CK(cudaMemcpy(h->d_tw, h->h_tw.data(), h->h_tw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->last_stream = h->own_stream;
+    h->evs.resize(64);
+    for (EvPair &e : h->evs) {
+        CK(cudaEventCreate(&e.a));
+        CK(cudaEventCreate(&e.b));
+    }
+    h->q_syms.resize((flags & ANM_FLAG_SYMBOLS) ? n_channels : 0);
+    /* constant part of the kernel parameters */
+    KParams &k = h->kp;
+    memset(&k, 0, sizeof k);
+    k.n_ch = n_channels;
+    k.state = h->d_state;
+    k.state_stride = var->state_bytes;
+    k.do_sm = 1;
+    k.fsyms = h->d_fsyms;
+    k.fsym_stride = h->fsym_stride;
+    k.max_frame_syms = h->max_frame_syms;
+    k.frames = h->d_frames;
+    k.bytes = h->d_bytes;
+    k.counters = h->d_counters;
+    k.frames_cap = h->frames_cap;
+    k.bytes_cap = h->bytes_cap;
+    k.osyms = h->d_osyms;
+    k.osym_cap = h->osym_cap;
+    k.P = cfg->preamble_len;
+    k.tol = cfg->sync_tol;
+    k.max_payload = cfg->max_payload;
+    k.trk_epoch = cfg->trk_epoch;
+    k.trk_thresh = cfg->trk_thresh;
+    k.hdr_syms = hdr_syms;
+    for (uint32_t j = 0; j < 7; ++j) {
+        uint32_t m = 0;
+        for (uint32_t pp = 0; pp < cfg->preamble_len; ++pp) m |= ((cfg->preamble[pp] >> j) & 1u) << pp;
+        k.pre_plane[j] = m;
+    }
+    memcpy(k.preamble, cfg->preamble, ANM_MAX_PREAMBLE);
+    k.tw_global = h->d_tw;
+    int rc = anm_demod_reset(h);
+    if (rc != ANM_OK) { anm_demod_destroy(h); return rc; }
+    *out = h;
+    return ANM_OK;
+}
+
+static int init_state(const Variant *var, unsigned char *d_state, uint32_t n_ch, cudaStream_t s) {
+    /* zero everything, then set the hop-decision history to 0xFF ("before the stream") */
+    CK(cudaMemsetAsync(d_state, 0, (size_t)n_ch * var->state_bytes, s));
+    CK(cudaMemset2DAsync(d_state + sizeof(ChanScalars), var->state_bytes, 0xFF, 32u * var->S * 4u, n_ch, s));
+    return ANM_OK;
+}
+
+extern "C" int anm_demod_reset(anm_demod_t *h) {
+    if (!h) return ANM_ERR_ARG;
+    if (set_device(h)) return ANM_ERR_CUDA;
+    CK(cudaStreamSynchronize(h->last_stream));
+    int rc = init_state(h->var, h->d_state, h->n_ch, h->own_stream);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->d_counters, 0, 16, h->own_stream));
+    CK(cudaStreamSynchronize(h->own_stream));
+    h->samples_fed = 0;
+    h->syms_since_collect = 0;
+    h->ev_used = 0;
+    h->q_frames.clear();
+    h->q_bytes.clear();
+    for (auto &q : h->q_syms) q.clear();
+    h->overflow = 0;
+    return ANM_OK;
+}
+
+extern "C" void anm_demod_destroy(anm_demod_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    {
+        std::lock_guard<std::mutex> lk(g_tw_mu);
+        if (h->device < 64 && g_tw_owner[h->device] == h) g_tw_owner[h->device] = nullptr;
+    }
+    cudaFree(h->d_state);
+    cudaFree(h->d_fsyms);
+    cudaFree(h->d_frames);
+    cudaFree(h->d_bytes);
+    cudaFree(h->d_counters);
+    cudaFree(h->d_osyms);
+    cudaFree(h->d_tw);
+    cudaFree(h->d_stage);
+    for (EvPair &e : h->evs) {
+        if (e.a) cudaEventDestroy(e.a);
+        if (e.b) cudaEventDestroy(e.b);
+    }
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+/* make sure constant bank 3 holds this handle's twiddles before its kernel runs */
+static int bind_twiddles(const void *owner, int device, const std::vector<float> &tw, bool twc, cudaStream_t s) {
+    if (!twc) return ANM_OK;
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    if (device < 64 && g_tw_owner[device] == owner) return ANM_OK;
+    CK(cudaDeviceSynchronize()); /* kernels of another configuration may still read the bank */
+    CK(cudaMemcpyToSymbolAsync(c_tw, tw.data(), tw.size() * sizeof(float), 0, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    if (device < 64) g_tw_owner[device] = owner;
+    return ANM_OK;
+}
+
+static int launch(anm_demod *h, const KParams &k, cudaStream_t s, bool timed) {
+    int rc = bind_twiddles(h, h->device, h->h_tw, h->var->twc, s);
+    if (rc) return rc;
+    EvPair *ev = nullptr;
+    if (timed && h->ev_used < h->evs.size()) ev = &h->evs[h->ev_used++];
+    if (ev) CK(cudaEventRecord(ev->a, s));
+    void *args[] = {(void *)&k};
+    CK(cudaLaunchKernel((const void *)h->var->fn, dim3(h->grid), dim3(h->warps_per_cta * 32), args, h->smem_bytes, s));
+    if (ev) CK(cudaEventRecord(ev->b, s));
+    h->launches++;
+    return ANM_OK;
+}
+
+extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride, size_t n_samples,
+                                     void *stream) {
+    if (!h || (!d_pcm && n_samples)) return ANM_ERR_ARG;
+    if (n_samples == 0) return ANM_OK;
+    const uint32_t N = h->cfg.sym_len;
+    if (n_samples % N) { anm_set_error("n_samples must be a multiple of sym_len=%u", N); return ANM_ERR_ALIGN; }
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15u) || ((ch_stride * 2) & 15u) || ch_stride < n_samples) {
+        anm_set_error("pcm base and channel stride must be 16-byte aligned, stride >= n_samples");
+        return ANM_ERR_ALIGN;
+    }
+    if (set_device(h)) return ANM_ERR_CUDA;
+    const uint64_t nsyms = n_samples / N;
+    if (h->osym_cap && h->syms_since_collect + nsyms + 8 > h->osym_cap) {
+        long rc = anm_demod_collect(h);
+        if (rc < 0) return (int)rc;
+        if (nsyms + 8 > h->osym_cap) { anm_set_error("chunk longer than the symbol buffer"); return ANM_ERR_ARG; }
+    }
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
+    KParams k = h->kp;
+    k.pcm = d_pcm;
+    k.ch_stride = ch_stride;
+    k.n_syms = (uint32_t)nsyms;
+    k.hop_base = h->samples_fed / (N / h->cfg.hops_per_sym);
+    int rc = launch(h, k, s, true);
+    if (rc) return rc;
+    h->last_stream = s;
+    h->samples_fed += n_samples;
+    h->syms_since_collect += nsyms;
+    return ANM_OK;
+}
+
+extern "C" int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples) {
+    if (!h || (!h_pcm && n_samples)) return ANM_ERR_ARG;
+    if (n_samples == 0) return ANM_OK;
+    if (n_samples % h->cfg.sym_len) return ANM_ERR_ALIGN;
+    if (set_device(h)) return ANM_ERR_CUDA;
+    const size_t need = (size_t)h->n_ch * n_samples;
+    if (need > h->stage_cap) {
+        CK(cudaStreamSynchronize(h->last_stream));
+        cudaFree(h->d_stage);
+        h->d_stage = nullptr;
+        h->stage_cap = 0;
+        CK(cudaMalloc(&h->d_stage, need * sizeof(int16_t)));
+        h->stage_cap = need;
+    }
+    cudaStream_t s = h->own_stream;
+    if (h->last_stream != s) CK(cudaStreamSynchronize(h->last_stream));
+    CK(cudaMemcpy2DAsync(h->d_stage, n_samples * 2, h_pcm, ch_stride * 2, n_samples * 2, h->n_ch,
+                         cudaMemcpyHostToDevice, s));
+    int rc = anm_demod_feed_device(h, h->d_stage, n_samples, n_samples, s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    return ANM_OK;
+}
+
+extern "C" long anm_demod_collect(anm_demod_t *h) {
+    if (!h) return ANM_ERR_ARG;
+    if (set_device(h)) return ANM_ERR_CUDA;
+    cudaStream_t s = h->last_stream;
+    CK(cudaStreamSynchronize(s));
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    CK(cudaMemcpy(cnt, h->d_counters, 16, cudaMemcpyDeviceToHost));
+    const uint32_t nf = std::min(cnt[0], h->frames_cap);
+    const uint32_t nb = std::min(cnt[1], h->bytes_cap);
+    if (cnt[2] || cnt[0] > h->frames_cap || cnt[1] > h->bytes_cap) h->overflow = 1;
+    if (nf) {
+        const size_t f0 = h->q_frames.size(), b0 = h->q_bytes.size();
+        h->q_frames.resize(f0 + nf);
+        h->q_bytes.resize(b0 + nb);
+        CK(cudaMemcpy(h->q_frames.data() + f0, h->d_frames, (size_t)nf * sizeof(anm_frame_t), cudaMemcpyDeviceToHost));
+        if (nb) CK(cudaMemcpy(h->q_bytes.data() + b0, h->d_bytes, nb, cudaMemcpyDeviceToHost));
+        for (size_t i = f0; i < f0 + nf; ++i) h->q_frames[i].offset += (uint32_t)b0;
+    }
+    CK(cudaMemset(h->d_counters, 0, 16));
+    if (h->osym_cap && h->syms_since_collect) {
+        std::vector<uint32_t> oc(h->n_ch);
+        const size_t off = offsetof(ChanScalars, osym_cnt);
+        CK(cudaMemcpy2D(oc.data(), 4, h->d_state + off, h->var->state_bytes, 4, h->n_ch, cudaMemcpyDeviceToHost));
+        uint32_t mx = 0;
+        for (uint32_t c : oc) mx = std::max(mx, std::min(c, h->osym_cap));
+        if (mx) {
+            std::vector<uint8_t> tmp((size_t)h->n_ch * mx);
+            CK(cudaMemcpy2D(tmp.data(), mx, h->d_osyms, h->osym_cap, mx, h->n_ch, cudaMemcpyDeviceToHost));
+            for (uint32_t c = 0; c < h->n_ch; ++c) {
+                const uint32_t n = std::min(oc[c], h->osym_cap);
+                if (oc[c] > h->osym_cap) h->overflow = 1;
+                h->q_syms[c].insert(h->q_syms[c].end(), tmp.begin() + (size_t)c * mx, tmp.begin() + (size_t)c * mx + n);
+            }
+        }
+        CK(cudaMemset2D(h->d_state + off, h->var->state_bytes, 0, 4, h->n_ch));
+    }
+    h->syms_since_collect = 0;
+    if (h->overflow) { anm_set_error("an output queue overflowed; some frames or symbols were dropped"); }
+    return (long)h->q_frames.size();
+}
+
+extern "C" size_t anm_demod_read_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8_t *bytes, size_t bytes_cap) {
+    if (!h || !out || !cap) return 0;
+    /* deterministic order: (channel, start_sample) */
+    std::vector<size_t> idx(h->q_frames.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
+        const anm_frame_t &x = h->q_frames[a], &y = h->q_frames[b];
+        if (x.channel != y.channel) return x.channel < y.channel;
+        return x.start_sample < y.start_sample;
+    });
+    size_t n = 0, bo = 0;
+    std::vector<char> taken(idx.size(), 0);
+    for (size_t ii = 0; ii < idx.size() && n < cap; ++ii) {
+        const anm_frame_t &f = h->q_frames[idx[ii]];
+        if (bo + f.len > bytes_cap) break;
+        out[n] = f;
+        out[n].offset = (uint32_t)bo;
+        if (bytes && f.len) memcpy(bytes + bo, h->q_bytes.data() + f.offset, f.len);
+        bo += f.len;
+        taken[idx[ii]] = 1;
+        ++n;
+    }
+    /* keep what was not taken (compact) */
+    std::vector<anm_frame_t> rest;
+    std::vector<uint8_t> rest_b;
+    for (size_t i = 0; i < h->q_frames.size(); ++i)
+        if (!taken[i]) {
+            anm_frame_t f = h->q_frames[i];
+            const uint32_t o = (uint32_t)rest_b.size();
+            rest_b.insert(rest_b.end(), h->q_bytes.begin() + f.offset, h->q_bytes.begin() + f.offset + f.len);
+            f.offset = o;
+            rest.push_back(f);
+        }
+    h->q_frames.swap(rest);
+    h->q_bytes.swap(rest_b);
+    return n;
+}
+
+extern "C" size_t anm_demod_read_symbols(anm_demod_t *h, uint32_t channel, uint8_t *out, size_t cap) {
+    if (!h || !out || channel >= h->q_syms.size()) return 0;
+    std::deque<uint8_t> &q = h->q_syms[channel];
+    const size_t n = std::min(cap, q.size());
+    std::copy(q.begin(), q.begin() + n, out);
+    q.erase(q.begin(), q.begin() + n);
+    return n;
+}
+
+extern "C" int anm_demod_stats(anm_demod_t *h, anm_chan_stats_t *out) {
+    if (!h || !out) return ANM_ERR_ARG;
+    if (set_device(h)) return ANM_ERR_CUDA;
+    CK(cudaStreamSynchronize(h->last_stream));
+    CK(cudaMemcpy2D(out, sizeof(anm_chan_stats_t), h->d_state + offsetof(ChanScalars, stats), h->var->state_bytes,
+                    sizeof(anm_chan_stats_t), h->n_ch, cudaMemcpyDeviceToHost));
+    return ANM_OK;
+}
+
+extern "C" uint64_t anm_demod_launch_count(const anm_demod_t *h) { return h ? h->launches : 0; }
+
+/* sums the device time of the kernels launched since the last call (at most 64 are
+ * tracked between calls); returns the number of launches summed */
+extern "C" int anm_demod_kernel_time(anm_demod_t *h, float *sum_ms) {
+    if (!h || !sum_ms) return ANM_ERR_ARG;
+    if (set_device(h)) return ANM_ERR_CUDA;
+    float tot = 0.f;
+    const size_t n = h->ev_used;
+    for (size_t i = 0; i < n; ++i) {
+        float ms = 0.f;
+        CK(cudaEventSynchronize(h->evs[i].b));
+        CK(cudaEventElapsedTime(&ms, h->evs[i].a, h->evs[i].b));
+        tot += ms;
+    }
+    h->ev_used = 0;
+    *sum_ms = tot;
+    return (int)n;
+}
+
+extern "C" float anm_demod_last_kernel_ms(anm_demod_t *h) {
+    if (!h || h->ev_used == 0) return -1.f;
+    float ms = -1.f;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1.f;
+    const EvPair &e = h->evs[h->ev_used - 1];
+    if (cudaEventSynchronize(e.b) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+extern "C" int anm_demod_launch_geometry(const anm_demod_t *h, uint32_t *grid, uint32_t *warps_per_cta, uint32_t *smem) {
+    if (!h) return ANM_ERR_ARG;
+    if (grid) *grid = h->grid;
+    if (warps_per_cta) *warps_per_cta = h->warps_per_cta;
+    if (smem) *smem = (uint32_t)h->smem_bytes;
+    return ANM_OK;
+}
+
+/* ---- stateless tone-energy pass ----------------------------------------------- */
+extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *d_pcm, uint32_t n_ch, size_t ch_stride,
+                                        size_t n_samples, float *d_energy, uint8_t *d_sym, float *d_emax, void *stream) {
+    if (!cfg || !d_pcm || n_ch == 0) return ANM_ERR_ARG;
+    if (anm_config_validate(cfg) != ANM_OK) return ANM_ERR_ARG;
+    const Variant *var = find_variant(cfg);
+    if (!var) return ANM_ERR_UNSUPPORTED;
+    if (n_samples % cfg->sym_len) return ANM_ERR_ALIGN;
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15u) || ((ch_stride * 2) & 15u)) return ANM_ERR_ALIGN;
+    if (n_samples == 0) return ANM_OK;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *d_state = nullptr;
+    float2 *d_tw = nullptr;
+    std::vector<float> tw((size_t)cfg->sym_len * cfg->n_tones * 2);
+    anm_twiddles(cfg, tw.data());
+    CK(cudaMalloc(&d_state, (size_t)n_ch * var->state_bytes));
+    CK(cudaMalloc(&d_tw, tw.size() * sizeof(float)));
+    int rc = init_state(var, d_state, n_ch, s);
+    if (rc == ANM_OK && cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = ANM_ERR_CUDA;
+    static int dummy_owner;
+    if (rc == ANM_OK) {
+        /* a one-shot pass owns the constant bank only for its own launch */
+        std::lock_guard<std::mutex> lk(g_tw_mu);
+        if (dev < 64) g_tw_owner[dev] = nullptr;
+    }
+    if (rc == ANM_OK) rc = bind_twiddles(&dummy_owner, dev, tw, var->twc, s);
+    if (rc == ANM_OK) {
+        KParams k;
+        memset(&k, 0, sizeof k);
+        k.pcm = d_pcm;
+        k.ch_stride = ch_stride;
+        k.n_ch = n_ch;
+        k.n_syms = (uint32_t)(n_samples / cfg->sym_len);
+        k.hop_base = 0;
+        k.state = d_state;
+        k.state_stride = var->state_bytes;
+        k.do_sm = 0;
+        k.trE = d_energy;
+        k.trD = d_sym;
+        k.trEmax = d_emax;
+        k.tr_hops = n_samples / (cfg->sym_len / cfg->hops_per_sym);
+        k.P = cfg->preamble_len;
+        k.tw_global = d_tw;
+        const uint32_t W = std::min<uint32_t>(8u, (227u * 1024u - 1024u) / var->warp_smem);
+        const uint32_t grid = (n_ch + W - 1) / W;
+        cudaFuncSetAttribute((const void *)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 1024));
+        void *args[] = {(void *)&k};
+        cudaError_t e = cudaLaunchKernel((const void *)var->fn, dim3(std::min<uint32_t>(grid, (uint32_t)sms * 4u)), dim3(W * 32), args,
+                                         (size_t)W * var->warp_smem, s);
+        if (e != cudaSuccess) { anm_set_error("launch: %s", cudaGetErrorString(e)); rc = ANM_ERR_CUDA; }
+    }
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (rc == ANM_OK && e2 != cudaSuccess) { anm_set_error("tone pass: %s", cudaGetErrorString(e2)); rc = ANM_ERR_CUDA; }
+    {
+        std::lock_guard<std::mutex> lk(g_tw_mu);
+        if (dev < 64 && g_tw_owner[dev] == &dummy_owner) g_tw_owner[dev] = nullptr;
+    }
+    cudaFree(d_state);
+    cudaFree(d_tw);
+    return rc;
+}
+
+/* ---- tx params helper: fills the host-computed noise scale the GPU renderer reads ---- */
+extern "C" void anm_tx_params_prepare(anm_tx_params_t *p, size_t n) {
+    for (size_t i = 0; i < n; ++i) p[i].reserved = anm_tx_noise_scale(p[i].amplitude_q15, p[i].snr_mdb);
+}
+
+/* ---- firmware-idiom single-channel interface ---------------------------------------- */
+struct demod {
+    anm_demod_t *h;
+    std::vector<int16_t> pend; /* samples not yet forming a whole symbol period */
+};
+static anm_config_t g_cfg;
+static bool g_cfg_set = false;
+
+extern "C" int demod_initialize(const anm_config_t *cfg) {
+    if (!cfg || anm_config_validate(cfg) != ANM_OK) return ANM_ERR_ARG;
+    g_cfg = *cfg;
+    g_cfg_set = true;
+    return ANM_OK;
+}
+extern "C" demod_t *demod_create(void) {
+    if (!g_cfg_set) { anm_set_error("demod_initialize() was not called"); return nullptr; }
+    demod *d = new (std::nothrow) demod();
+    if (!d) return nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (anm_demod_create(&g_cfg, 1, dev, ANM_FLAG_SYMBOLS, &d->h) != ANM_OK) { delete d; return nullptr; }
+    return d;
+}
+extern "C" int demod_feed(demod_t *d, const int16_t *pcm, size_t n) {
+    if (!d || (!pcm && n)) return ANM_ERR_ARG;
+    d->pend.insert(d->pend.end(), pcm, pcm + n);
+    const size_t N = d->h->cfg.sym_len;
+    const size_t whole = d->pend.size() / N * N;
+    if (!whole) return ANM_OK;
+    int rc = anm_demod_feed_host(d->h, d->pend.data(), whole, whole);
+    if (rc) return rc;
+    d->pend.erase(d->pend.begin(), d->pend.begin() + whole);
+    long c = anm_demod_collect(d->h);
+    return c < 0 ? (int)c : ANM_OK;
+}
+extern "C" size_t demod_read_symbols(demod_t *d, uint8_t *out, size_t cap) {
+    return d ? anm_demod_read_symbols(d->h, 0, out, cap) : 0;
+}
+extern "C" size_t demod_read_frames(demod_t *d, demod_frame_t *out, size_t cap) {
+    if (!d || !out) return 0;
+    size_t n = 0;
+    std::vector<uint8_t> buf(4104);
+    while (n < cap) {
+        anm_frame_t f;
+        if (anm_demod_read_frames(d->h, &f, 1, buf.data(), buf.size()) != 1) break;
+        out[n].sample_offset = f.start_sample;
+        out[n].len = f.len;
+        out[n].crc_ok = f.crc_ok;
+        memcpy(out[n].bytes, buf.data(), f.len);
+        ++n;
+    }
+    return n;
+}
+extern "C" void demod_destroy(demod_t *d) {
+    if (!d) return;
+    anm_demod_destroy(d->h);
+    delete d;
+}

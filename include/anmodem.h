@@ -1,0 +1,185 @@
+/*
+ * anmodem.h -- C ABI of the B200-native batched audio-modem receive path.
+ *
+ * What this boundary replaces.  BASELINE.json's north_star names "the firmware
+ * demodulator's C interface (sample buffer in, decoded symbols and frames out)"
+ * feeding the nanopb ip.proto decoder.  SURVEY.md section 0 establishes that the
+ * reference (tmarsteel/audio-network) contains no such demodulator; the nearest
+ * real seams are
+ *   - the nanopb input stream the firmware decodes ToReceiver messages from:
+ *     hardware/lib/nanopb/src/pb_decode.h:28-46 (struct pb_istream_s) and its
+ *     socket-backed instance hardware/src/network.cpp:262-305, consumed by
+ *     pb_decode_delimited at hardware/src/network.cpp:406-411;
+ *   - the module convention `<module>_initialize()` + handle functions,
+ *     hardware/README.md:10-14, hardware/include/playback.hpp:15.
+ * The functions below are therefore the interface SURVEY.md section 8(b)
+ * proposes for that seam: firmware-idiom single-channel calls (demod_*), and the
+ * batched form (anm_demod_*) that the hot path actually runs.  The modem itself
+ * (tone set, timing, preamble, framing, CRC and the exact fp32 operation order)
+ * is defined by SPEC.md in this repository, not by the reference.
+ *
+ * All entry points are plain C: pointers and sizes only.  Return values are 0 on
+ * success or a negative ANM_ERR_* code (the esp_err_t idiom of the reference,
+ * hardware/src/playback.cpp:174-191); nothing throws, nothing falls back to a
+ * CPU implementation -- without a CUDA device every compute entry point returns
+ * ANM_ERR_CUDA.
+ */
+#ifndef ANMODEM_H_INCLUDED
+#define ANMODEM_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANM_MAX_TONES 64
+#define ANM_MAX_PREAMBLE 32
+#define ANM_SILENCE 0xFF /* tx program entry: no tone during this symbol */
+
+enum {
+    ANM_OK = 0,
+    ANM_ERR_ARG = -1,      /* invalid argument / configuration */
+    ANM_ERR_CUDA = -2,     /* CUDA runtime error or no device */
+    ANM_ERR_NOMEM = -3,    /* host or device allocation failed */
+    ANM_ERR_ALIGN = -4,    /* buffer not 16-byte aligned / length not a multiple of sym_len */
+    ANM_ERR_OVERFLOW = -5, /* an output queue overflowed; results were dropped */
+    ANM_ERR_UNSUPPORTED = -6
+};
+
+/* Modem configuration (SPEC.md section 2). */
+typedef struct anm_config {
+    uint32_t sample_rate;  /* Hz; informational (44100) */
+    uint32_t sym_len;      /* N: samples per symbol; power of two, 32..512 */
+    uint32_t hops_per_sym; /* S: timing hypotheses per symbol; 2, 4 or 8 */
+    uint32_t n_tones;      /* T: power of two, 2..64; bits/symbol = log2 T */
+    uint32_t tone_bin[ANM_MAX_TONES]; /* DFT bin of tone k over a sym_len window */
+    uint32_t preamble_len; /* P: 8, 16 or 32 symbols */
+    uint8_t preamble[ANM_MAX_PREAMBLE]; /* tone index per preamble symbol */
+    uint32_t sync_tol;     /* max preamble symbol mismatches accepted */
+    uint32_t max_payload;  /* largest payload length accepted, bytes (<= 4104) */
+    uint32_t trk_epoch;    /* symbols between timing-tracker decisions */
+    uint32_t trk_thresh;   /* |vote sum| needed to move timing by one hop */
+} anm_config_t;
+
+/* One decoded frame.  `offset` indexes the byte arena returned alongside. */
+typedef struct anm_frame {
+    uint32_t channel;
+    uint32_t len;          /* payload bytes */
+    uint64_t start_sample; /* stream index of the first preamble sample */
+    uint32_t crc_ok;       /* 1 if CRC-16 matched */
+    uint32_t offset;       /* payload position in the byte arena */
+} anm_frame_t;
+
+/* Per-channel counters since create. */
+typedef struct anm_chan_stats {
+    uint32_t locks;        /* preambles detected */
+    uint32_t header_fail;  /* header check failures */
+    uint32_t frames_ok;
+    uint32_t frames_bad;   /* CRC-16 failures */
+    uint64_t symbols;      /* symbols decided while locked */
+    int32_t trk_moves;     /* net timing moves, hops */
+    uint32_t reserved;
+} anm_chan_stats_t;
+
+/* Transmit-side synthetic channel description (SPEC.md section 6). */
+typedef struct anm_tx_params {
+    uint64_t seed;          /* noise PRNG seed */
+    int64_t start_offset;   /* tx sample position at rx sample 0 (may be negative: leading silence) */
+    uint32_t amplitude_q15; /* tone peak amplitude, Q15 of full scale */
+    int32_t snr_mdb;        /* full-band SNR in milli-dB; ANM_SNR_CLEAN = no noise */
+    int32_t ppm_x1000;      /* transmitter clock error, 1/1000 ppm */
+    uint32_t reserved;
+} anm_tx_params_t;
+#define ANM_SNR_CLEAN INT32_MAX
+
+/* ---- configuration / framing helpers (host C, no device) ---------------- */
+int anm_config_preset(const char *name, anm_config_t *out); /* "ref4", "bfsk2", "mfsk8", "mfsk16", "wide64" */
+int anm_config_validate(const anm_config_t *cfg);
+/* twiddle table [sym_len][n_tones][2] = (cos, sin)(2*pi*bin*m/N) rounded to fp32 */
+int anm_twiddles(const anm_config_t *cfg, float *out);
+uint16_t anm_crc16(const uint8_t *data, size_t len, uint16_t crc);
+uint8_t anm_crc8(const uint8_t *data, size_t len, uint8_t crc);
+/* number of symbols (preamble + header + body) of a frame carrying len bytes */
+size_t anm_frame_num_symbols(const anm_config_t *cfg, size_t len);
+/* writes tone indices; returns count or 0 if cap too small / len invalid */
+size_t anm_frame_symbols(const anm_config_t *cfg, const uint8_t *payload, size_t len,
+                         uint8_t *syms, size_t cap);
+
+/* ---- transmitter stand-in (integer DDS; bit-identical on CPU and GPU) ---- */
+/* CPU render of rx samples [first_sample, first_sample+n) of one channel that
+ * cyclically plays `program` (tone indices or ANM_SILENCE). */
+int anm_tx_render(const anm_config_t *cfg, const uint8_t *program, size_t prog_len,
+                  const anm_tx_params_t *p, uint64_t first_sample, int16_t *out, size_t n);
+/* GPU render of n_ch channels into d_pcm[ch * ch_stride + i]; programs are
+ * device-resident: d_programs[ch * prog_stride + j], prog_len[ch] entries used. */
+int anm_tx_render_device(const anm_config_t *cfg, const uint8_t *d_programs, size_t prog_stride,
+                         const uint32_t *d_prog_len, const anm_tx_params_t *d_params,
+                         uint32_t n_ch, uint64_t first_sample, int16_t *d_pcm, size_t ch_stride,
+                         size_t n, void *stream);
+
+/* ---- stateless tone-energy pass (parity / debug mode) ------------------- */
+/* For each channel and each hop h in [0, n_samples/hop): energies of the window
+ * of sym_len samples ending with hop h (zero history before sample 0).
+ * d_energy [n_ch][n_hops][n_tones] fp32 (may be NULL), d_sym [n_ch][n_hops]
+ * argmax tone (may be NULL), d_emax [n_ch][n_hops] (may be NULL). */
+int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *d_pcm, uint32_t n_ch,
+                             size_t ch_stride, size_t n_samples, float *d_energy,
+                             uint8_t *d_sym, float *d_emax, void *stream);
+
+/* ---- batched streaming demodulator --------------------------------------- */
+typedef struct anm_demod anm_demod_t;
+
+#define ANM_FLAG_SYMBOLS 1u /* also record decided symbols per channel */
+
+int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, int device, uint32_t flags,
+                     anm_demod_t **out);
+void anm_demod_destroy(anm_demod_t *h);
+int anm_demod_reset(anm_demod_t *h);
+/* PCM already in HBM: d_pcm[ch * ch_stride + i], i < n_samples; n_samples must be
+ * a multiple of sym_len, d_pcm and ch_stride*2 multiples of 16 bytes.  Launches
+ * on `stream` (a cudaStream_t, NULL = default) and returns without waiting. */
+int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride,
+                          size_t n_samples, void *stream);
+/* PCM in host memory (pinned for full speed): copies to an internal HBM staging
+ * buffer, demodulates, and waits for completion. */
+int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples);
+/* Waits for outstanding work and moves newly produced frames/symbols to the
+ * host queues.  Returns number of frames now queued, or a negative error. */
+long anm_demod_collect(anm_demod_t *h);
+/* Pops up to cap frames in (channel, start_sample) order; payload bytes are
+ * appended to `bytes` (frame.offset indexes it).  Returns frames written. */
+size_t anm_demod_read_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8_t *bytes,
+                             size_t bytes_cap);
+/* Pops up to cap decided symbols (tone indices) of one channel. */
+size_t anm_demod_read_symbols(anm_demod_t *h, uint32_t channel, uint8_t *out, size_t cap);
+int anm_demod_stats(anm_demod_t *h, anm_chan_stats_t *out /*[n_channels]*/);
+/* number of kernels this handle has launched (bench.py's gpu_launches) */
+uint64_t anm_demod_launch_count(const anm_demod_t *h);
+/* duration in ms of the most recent feed's kernel, measured with CUDA events on
+ * the launching stream (waits for it). */
+float anm_demod_last_kernel_ms(anm_demod_t *h);
+const char *anm_last_error(void);
+const char *anm_version(void);
+
+/* ---- firmware-idiom single-channel interface ------------ */
+typedef struct demod demod_t;
+typedef struct demod_frame {
+    uint64_t sample_offset;
+    uint32_t len;
+    uint32_t crc_ok;
+    uint8_t bytes[4104];
+} demod_frame_t;
+
+int demod_initialize(const anm_config_t *cfg); /* sets the process-wide configuration */
+demod_t *demod_create(void);
+int demod_feed(demod_t *d, const int16_t *pcm, size_t n_samples); /* borrowed input, any length */
+size_t demod_read_symbols(demod_t *d, uint8_t *out, size_t cap);
+size_t demod_read_frames(demod_t *d, demod_frame_t *out, size_t cap);
+void demod_destroy(demod_t *d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANMODEM_H_INCLUDED */
