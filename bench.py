@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the receive-side demodulation hot path (BASELINE.json metric).
+
+Workload (config 3 of BASELINE.json, weak-scaled): 65,536 channels x 44.1 kHz at 10 dB SNR
+sharded over 8 GPUs = 8,192 channels per GPU, streamed in chunks of 344 symbol periods
+(44,032 samples, ~1 s).  One "step" = one chunk of every channel of this rank through the
+demodulator (PCM -> tone energies -> sync -> symbols -> frames + CRC).  PCM is synthetic
+(transmitter stand-in rendered on the GPU, per-channel payloads seeded by channel id).
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [...]                    CPU arm: the in-repo C oracle on
+                                                            all host cores (there is no
+                                                            reference demodulator)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+CHUNK_SYMS = 344          # symbol periods per chunk (~1 s at N=128)
+CH_PER_GPU = 8192         # 65,536 channels / 8 GPUs
+SNR_DB = 10.0
+PAYLOAD = 32              # payload bytes per frame
+METRIC = "demodulated Msamples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=CH_PER_GPU, help="channels per GPU")
+    ap.add_argument("--preset", default="ref4")
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-channels", type=int, default=0, help="channels in the CPU sample (0 = 4 per core)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_programs(cfg, anm, n_ch, ch0, max_len=512):
+    """Per-channel cyclic symbol programs: frames of PAYLOAD random bytes (seed = global
+    channel id) separated by 4..16 symbols of silence."""
+    progs = np.full((n_ch, max_len), anm.ANM_SILENCE, dtype=np.uint8)
+    lens = np.zeros(n_ch, dtype=np.int32)
+    params = []
+    for c in range(n_ch):
+        rng = np.random.default_rng(ch0 + c)
+        parts, total = [], 0
+        while True:
+            pl = rng.integers(0, 256, size=PAYLOAD, dtype=np.uint8).tobytes()
+            syms = anm.frame_symbols(cfg, pl)
+            gap = int(rng.integers(4, 17))
+            if total + len(syms) + gap > max_len:
+                break
+            parts += [syms, np.full(gap, anm.ANM_SILENCE, dtype=np.uint8)]
+            total += len(syms) + gap
+        p = np.concatenate(parts)
+        progs[c, : len(p)] = p
+        lens[c] = len(p)
+        params.append(anm.tx_params(seed=ch0 + c, start_offset=-int(rng.integers(0, 4 * cfg.sym_len)),
+                                    amplitude=0.5, snr_db=SNR_DB, ppm=0.0))
+    return progs, lens, anm.tx_params_array(params)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(cfg, pcm, n_threads, chunk_samples):
+    """The in-repo C oracle, one channel at a time per core, on a bounded sample."""
+    from oracle_binding import run_batch
+
+    sec, ok, bad, by, _ = run_batch(cfg, pcm, n_threads)
+    msps = pcm.shape[0] * pcm.shape[1] / sec / 1e6
+    return {
+        "value": round(msps, 3), "unit": "Msamples/s", "cores": n_threads, "kind": "port",
+        "sample": "%d channels x %d samples of the same workload (in-repo C oracle, gcc -O2 -mfma, one channel per core; "
+                  "no reference demodulator exists, SURVEY.md 0)" % (pcm.shape[0], chunk_samples),
+        "seconds": round(sec, 3), "frames_ok": int(ok), "decoded_bits_per_s": round(by * 8 / sec, 1),
+    }
+
+
+def reference_arm(args):
+    """--impl reference: the CPU oracle with all host threads on bounded samples of the workload."""
+    import audio_network_b200 as anm
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = anm.config_preset(args.preset)
+    cores = os.cpu_count() or 1
+    n_ch = args.cpu_channels or min(cores * 64, CH_PER_GPU)
+    n = CHUNK_SYMS * cfg.sym_len
+    progs, lens, params = build_programs(cfg, anm, n_ch, 0)
+    steps_total = args.warmup + args.steps
+    pcm = np.zeros((n_ch, n), dtype=np.int16)
+    plist = params.view(anm.TXPARAMS_DTYPE)
+    from oracle_binding import run_batch
+
+    # the sample is rendered once (CPU transmitter stand-in); every step demodulates it from a reset state
+    for c in range(n_ch):
+        p = anm.TxParams()
+        p.seed, p.start_offset = int(plist[c]["seed"]), int(plist[c]["start_offset"])
+        p.amplitude_q15, p.snr_mdb, p.ppm_x1000 = int(plist[c]["amplitude_q15"]), int(plist[c]["snr_mdb"]), int(plist[c]["ppm_x1000"])
+        pcm[c] = anm.tx_render(cfg, progs[c, : lens[c]], p, 0, n)
+    times, ok_total, by_total = [], 0, 0
+    for s in range(steps_total):
+        sec, ok, bad, by, _ = run_batch(cfg, pcm, cores)
+        if s >= args.warmup:
+            times.append(sec)
+            ok_total += ok
+            by_total += by
+    tot = sum(times)
+    msps = n_ch * n * len(times) / tot / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(msps, 3), "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * tot / len(times), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3 sample: %d channels x %d samples per step, 10 dB SNR, preset %s (each step a bounded "
+                               "sample of the 8192-channel/GPU chunk)" % (n_ch, n, args.preset)},
+        "decoded_bits_per_s": round(by_total * 8 / tot, 1),
+        "cpu_baseline": {"value": round(msps, 3), "unit": "Msamples/s", "cores": cores, "kind": "port",
+                         "sample": "%d channels x %d samples per step; in-repo C oracle (no reference demodulator exists)" % (n_ch, n)},
+        "e2e": {"value": round(msps, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import audio_network_b200 as anm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = anm.config_preset(args.preset)
+    N = cfg.sym_len
+    n_ch = args.channels
+    chunk = CHUNK_SYMS * N
+    steps_total = args.warmup + args.steps
+    resident = min(steps_total, 48)          # distinct chunks kept in HBM (inputs >> L2: 721 MB per step)
+    total = resident * chunk
+
+    # ---- synthesize this rank's channels in HBM (not timed) ----
+    progs, lens, params = build_programs(cfg, anm, n_ch, rank * n_ch)
+    d_prog = torch.from_numpy(progs).to(dev)
+    d_len = torch.from_numpy(lens).to(dev)
+    d_par = torch.from_numpy(params.view(np.uint8).copy()).to(dev)
+    d_pcm = torch.empty((n_ch, total), dtype=torch.int16, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    anm.tx_render_device(cfg, d_prog.data_ptr(), progs.shape[1], d_len.data_ptr(), d_par.data_ptr(), n_ch, 0,
+                         d_pcm.data_ptr(), total, total, stream)
+    torch.cuda.synchronize()
+
+    dm = anm.Demod(cfg, n_ch, device=local)
+
+    def step(i):
+        off = (i % resident) * chunk
+        dm.feed_device(d_pcm.data_ptr() + off * 2, total, chunk, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    dm.collect()
+    dm.read_frames()
+    dm.kernel_time()
+    l0 = dm.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = dm.launch_count() - l0
+    k_ms, k_n = dm.kernel_time()
+    dm.collect()
+    recs, by = dm.read_frames(cap=1 << 22, bytes_cap=1 << 28)
+    bits_ok = int(recs["len"][recs["crc_ok"] == 1].sum()) * 8
+    frames_ok = int((recs["crc_ok"] == 1).sum())
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(bits_ok), float(frames_ok), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)   # host-side gather of decoded totals; no data-path collective
+    ms_max = float(t.item())
+    samples_all = float(world) * n_ch * chunk * args.steps
+    value = samples_all / (ms_max * 1e-3) / 1e6
+
+    # ---- e2e: host PCM -> feed_host (H2D inside) -> collect + read frames (D2H) ----
+    e2e = None
+    if args.e2e_steps > 0:
+        nh = min(2, resident)
+        host = [torch.empty((n_ch, chunk), dtype=torch.int16).pin_memory() for _ in range(nh)]
+        for j in range(nh):
+            host[j].copy_(d_pcm[:, j * chunk: (j + 1) * chunk])
+        torch.cuda.synchronize()
+        dm2 = anm.Demod(cfg, n_ch, device=local)
+        dm2.feed_host_ptr(host[0].data_ptr(), chunk, chunk)   # warm-up (allocates the staging buffer)
+        dm2.collect()
+        dm2.read_frames()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for j in range(args.e2e_steps):
+            dm2.feed_host_ptr(host[(j + 1) % nh].data_ptr(), chunk, chunk)
+            dm2.collect()
+            r2, b2 = dm2.read_frames(cap=1 << 20, bytes_cap=1 << 26)
+            d2h += 16 + r2.nbytes + b2.nbytes
+        torch.cuda.synchronize()
+        te = time.perf_counter() - t0
+        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(float(world) * n_ch * chunk * args.e2e_steps / float(tt.item()) / 1e6, 2), "unit": "Msamples/s",
+               "h2d_bytes_per_step": n_ch * chunk * 2, "d2h_bytes_per_step": int(d2h // args.e2e_steps), "steps": args.e2e_steps,
+               "note": "pinned host PCM -> cudaMemcpy2DAsync -> kernel -> frames D2H, per step, through anm_demod_feed_host/collect"}
+        dm2.close()
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle on a bounded sample of the same PCM ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cch = args.cpu_channels or min(64 * cores, n_ch)
+        nchunks = min(2, resident)
+        sample = d_pcm[:cch, : nchunks * chunk].cpu().numpy()
+        cpu = cpu_baseline(cfg, np.ascontiguousarray(sample), cores, nchunks * chunk)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_launch_bytes = n_ch * chunk * 2
+        avg_ms = (k_ms / k_n) if k_n else ms / max(1, args.steps)
+        achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
+        grid, wpc, smem = dm.launch_geometry()
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg3 weak-scaled: %d channels/GPU x %d-sample chunks (344 symbol periods), 10 dB SNR, "
+                                   "preset %s, %d-byte payload frames" % (n_ch, chunk, args.preset, PAYLOAD),
+                       "channels_total": world * n_ch, "chunk_samples": chunk, "l2_policy": "inputs larger than L2 (%.0f MB per step, %d distinct chunks resident)" % (per_launch_bytes / 1e6, resident),
+                       "launch": {"grid": grid, "warps_per_cta": wpc, "smem_bytes": smem}},
+            "decoded_bits_per_s": round(float(agg[0].item()) / (ms_max * 1e-3), 1),
+            "frames_ok": int(agg[1].item()),
+            "gpu_launches": int(agg[2].item()),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_demod<%d,%d,%d>" % (cfg.n_tones, cfg.sym_len, cfg.hops_per_sym),
+                         "avg_kernel_ms": round(avg_ms, 4), "launches_timed": k_n,
+                         "algorithmic_bytes_per_launch": per_launch_bytes},
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    dm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

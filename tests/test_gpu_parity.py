@@ -1,0 +1,248 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded PCM.  Bit-exact for symbols, frames, CRC verdicts; tone energies are checked
+bit-exact AND against north_star's stated tolerance (1e-4 relative, fp32)."""
+import numpy as np
+import pytest
+
+import audio_network_b200 as anm
+from oracle_binding import Oracle, oracle_frames_batch
+from sigutil import make_channels
+
+pytestmark = pytest.mark.gpu
+
+PRESETS = ["ref4", "bfsk2", "mfsk8", "mfsk16", "wide64"]
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _variant(name, S=None, N=None):
+    cfg = anm.config_preset(name)
+    if S is not None:
+        cfg.hops_per_sym = S
+    if N is not None:
+        cfg.sym_len = N
+    return cfg
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_tone_energies_match_oracle(preset):
+    torch = _torch()
+    cfg = anm.config_preset(preset)
+    n_ch, n_sym = 6, 75  # ragged last step (75 = 2*32 + 11)
+    n = n_sym * cfg.sym_len
+    pcm, _ = make_channels(cfg, n_ch, n, seed=3, snr_db=6.0, offset_max=300)
+    hops = n // cfg.hop
+    d_pcm = torch.from_numpy(pcm).cuda()
+    dE = torch.zeros((n_ch, hops, cfg.n_tones), dtype=torch.float32, device="cuda")
+    dD = torch.zeros((n_ch, hops), dtype=torch.uint8, device="cuda")
+    dM = torch.zeros((n_ch, hops), dtype=torch.float32, device="cuda")
+    anm.tone_energies_device(cfg, d_pcm.data_ptr(), n_ch, n, n, dE.data_ptr(), dD.data_ptr(), dM.data_ptr())
+    torch.cuda.synchronize()
+    E, D, M = dE.cpu().numpy(), dD.cpu().numpy(), dM.cpu().numpy()
+    for c in range(n_ch):
+        o = Oracle(cfg, trace_hops=hops)
+        o.feed(pcm[c])
+        # stated contract: 1e-4 relative in fp32
+        denom = np.maximum(np.abs(o.E), 1e-30)
+        assert np.max(np.abs(E[c] - o.E) / denom) <= 1e-4
+        # achieved: identical bits (SPEC 3 pins the operation order)
+        assert np.array_equal(E[c].view(np.uint32), o.E.view(np.uint32))
+        assert np.array_equal(D[c], o.D)
+        assert np.array_equal(M[c].view(np.uint32), o.Emax.view(np.uint32))
+
+
+def _run_gpu(cfg, pcm, chunks=None, flags=anm.ANM_FLAG_SYMBOLS):
+    torch = _torch()
+    n_ch, n = pcm.shape
+    d_pcm = torch.from_numpy(pcm).cuda()
+    dm = anm.Demod(cfg, n_ch, device=0, flags=flags)
+    pos = 0
+    chunks = chunks or [n]
+    i = 0
+    while pos < n:
+        ln = min(chunks[i % len(chunks)] * cfg.sym_len, n - pos)
+        dm.feed_device(d_pcm.data_ptr() + pos * 2, n, ln, torch.cuda.current_stream().cuda_stream)
+        pos += ln
+        i += 1
+    dm.collect()
+    frames = anm.frames_to_list(*dm.read_frames())
+    syms = [dm.read_symbols(c) for c in range(n_ch)] if flags & anm.ANM_FLAG_SYMBOLS else None
+    stats = dm.stats()
+    dm.close()
+    return frames, syms, stats
+
+
+def _check_against_oracle(cfg, pcm, chunks=None):
+    frames, syms, stats = _run_gpu(cfg, pcm, chunks)
+    want = []
+    for c in range(pcm.shape[0]):
+        o = Oracle(cfg)
+        o.feed(pcm[c])
+        want.extend(o.frames(c))
+        assert np.array_equal(syms[c], o.symbols()), "decided symbols differ on channel %d" % c
+        st = o.stats()
+        for k in ("locks", "header_fail", "frames_ok", "frames_bad", "symbols", "trk_moves"):
+            assert int(stats[c][k]) == int(st[k]), (c, k, int(stats[c][k]), int(st[k]))
+    want.sort(key=lambda f: (f[0], f[1]))
+    assert frames == want
+    return frames
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_frames_bit_exact_clean(preset):
+    cfg = anm.config_preset(preset)
+    pcm, meta = make_channels(cfg, 24, 700 * cfg.sym_len, seed=5, offset_max=2000)
+    frames = _check_against_oracle(cfg, pcm)
+    assert len(frames) >= 24
+    assert all(f[2] == 1 for f in frames)
+    # every frame fully inside the capture decodes to the payload that was sent
+    sent = {c: meta[c][1] for c in range(24)}
+    for ch, _start, _ok, payload in frames:
+        assert payload in sent[ch]
+
+
+def test_frames_bit_exact_noisy_drift():
+    cfg = anm.config_preset("ref4")
+    pcm, _ = make_channels(cfg, 48, 900 * cfg.sym_len, seed=9, snr_db=2.0, ppm_max=200.0, offset_max=4000)
+    frames = _check_against_oracle(cfg, pcm)
+    assert sum(f[2] for f in frames) > 40
+
+
+def test_noise_only_and_silence():
+    cfg = anm.config_preset("ref4")
+    rng = np.random.default_rng(1)
+    pcm = np.zeros((4, 200 * cfg.sym_len), dtype=np.int16)
+    pcm[1] = rng.integers(-3000, 3000, size=pcm.shape[1])
+    pcm[2] = 32767
+    pcm[3] = -32768
+    _check_against_oracle(cfg, pcm)
+
+
+@pytest.mark.parametrize("chunks", [[1], [3, 1, 40, 7], [32], [33, 31], [250]])
+def test_chunking_invariance(chunks):
+    cfg = anm.config_preset("ref4")
+    pcm, _ = make_channels(cfg, 16, 500 * cfg.sym_len, seed=13, snr_db=8.0, ppm_max=150.0, offset_max=1000)
+    _check_against_oracle(cfg, pcm, chunks)
+
+
+@pytest.mark.parametrize("S", [2, 8])
+def test_other_hop_counts(S):
+    cfg = _variant("ref4", S=S)
+    pcm, _ = make_channels(cfg, 12, 400 * cfg.sym_len, seed=17, snr_db=10.0, ppm_max=100.0, offset_max=700)
+    frames = _check_against_oracle(cfg, pcm, [37])
+    assert len(frames) > 0
+
+
+def test_short_symbols():
+    cfg = _variant("ref4", N=64)
+    cfg.tone_bin[0], cfg.tone_bin[1], cfg.tone_bin[2], cfg.tone_bin[3] = 5, 7, 9, 11
+    pcm, _ = make_channels(cfg, 12, 600 * cfg.sym_len, seed=19, snr_db=12.0, offset_max=300)
+    frames = _check_against_oracle(cfg, pcm, [50, 9])
+    assert len(frames) > 0
+
+
+def test_long_frames_and_max_payload():
+    cfg = anm.config_preset("ref4")
+    pcm, meta = make_channels(cfg, 4, 9000 * cfg.sym_len, seed=23, payload_len=(900, 1024), gap=(1, 5))
+    frames = _check_against_oracle(cfg, pcm, [1000])
+    assert any(len(f[3]) >= 900 and f[2] for f in frames)
+
+
+def test_feed_host_equals_feed_device():
+    cfg = anm.config_preset("ref4")
+    pcm, _ = make_channels(cfg, 32, 300 * cfg.sym_len, seed=29, snr_db=10.0)
+    dm = anm.Demod(cfg, 32, device=0)
+    dm.feed_host(pcm[:, : 100 * cfg.sym_len])
+    dm.feed_host(np.ascontiguousarray(pcm[:, 100 * cfg.sym_len:]))
+    dm.collect()
+    got = anm.frames_to_list(*dm.read_frames())
+    dm.close()
+    assert got == oracle_frames_batch(cfg, pcm)
+
+
+def test_alignment_and_argument_errors():
+    torch = _torch()
+    cfg = anm.config_preset("ref4")
+    dm = anm.Demod(cfg, 2, device=0)
+    buf = torch.zeros(4096, dtype=torch.int16, device="cuda")
+    with pytest.raises(anm.AnmError) as e:
+        dm.feed_device(buf.data_ptr(), 2048, 100, 0)  # not a multiple of sym_len
+    assert e.value.code == anm.ANM_ERR_ALIGN
+    with pytest.raises(anm.AnmError) as e:
+        dm.feed_device(buf.data_ptr() + 2, 2048, 128, 0)  # misaligned base
+    assert e.value.code == anm.ANM_ERR_ALIGN
+    dm.close()
+    bad = anm.config_preset("ref4")
+    bad.sym_len = 96
+    with pytest.raises(anm.AnmError):
+        anm.Demod(bad, 2, device=0)
+
+
+def test_tx_render_gpu_equals_cpu():
+    torch = _torch()
+    cfg = anm.config_preset("ref4")
+    rng = np.random.default_rng(31)
+    n_ch, n = 5, 40 * cfg.sym_len + 13
+    plist, progs = [], []
+    for c in range(n_ch):
+        progs.append(rng.integers(0, 5, size=37 + c).astype(np.uint8))
+        progs[-1][progs[-1] == 4] = anm.ANM_SILENCE
+        plist.append(anm.tx_params(seed=100 + c, start_offset=-int(rng.integers(0, 900)) + 300 * (c == 0),
+                                   amplitude=0.3 + 0.1 * c, snr_db=[None, 10.0, 0.0, 3.0, 20.0][c],
+                                   ppm=[0.0, 200.0, -200.0, 37.5, -0.001][c]))
+    stride = 64
+    P = np.zeros((n_ch, stride), dtype=np.uint8)
+    for c in range(n_ch):
+        P[c, : len(progs[c])] = progs[c]
+    d_prog = torch.from_numpy(P).cuda()
+    d_len = torch.tensor([len(p) for p in progs], dtype=torch.int32, device="cuda")
+    d_par = torch.from_numpy(anm.tx_params_array(plist).view(np.uint8)).cuda()
+    first = 12345
+    ch_stride = ((n + 7) // 8) * 8
+    d_pcm = torch.zeros((n_ch, ch_stride), dtype=torch.int16, device="cuda")
+    anm.tx_render_device(cfg, d_prog.data_ptr(), stride, d_len.data_ptr(), d_par.data_ptr(), n_ch, first, d_pcm.data_ptr(), ch_stride, n)
+    torch.cuda.synchronize()
+    got = d_pcm.cpu().numpy()[:, :n]
+    for c in range(n_ch):
+        want = anm.tx_render(cfg, progs[c], plist[c], first, n)
+        assert np.array_equal(got[c], want), "channel %d differs" % c
+
+
+def test_single_channel_firmware_interface():
+    import ctypes as C
+
+    cfg = anm.config_preset("ref4")
+    pcm, meta = make_channels(cfg, 1, 400 * cfg.sym_len, seed=37, snr_db=10.0, offset_max=100)
+    L = anm.lib()
+    assert L.demod_initialize(C.byref(cfg)) == 0
+    d = L.demod_create()
+    assert d
+    # arbitrary feed sizes, as firmware would hand over DMA buffers
+    pos, sizes, i = 0, [441, 1000, 77, 4096, 5], 0
+    x = pcm[0]
+    while pos < len(x):
+        ln = min(sizes[i % len(sizes)], len(x) - pos)
+        seg = np.ascontiguousarray(x[pos: pos + ln])
+        assert L.demod_feed(d, seg.ctypes.data, ln) == 0
+        pos += ln
+        i += 1
+
+    class DF(C.Structure):
+        _fields_ = [("sample_offset", C.c_uint64), ("len", C.c_uint32), ("crc_ok", C.c_uint32), ("bytes", C.c_uint8 * 4104)]
+
+    out = (DF * 64)()
+    n = L.demod_read_frames(d, out, 64)
+    got = [(0, int(out[i].sample_offset), int(out[i].crc_ok), bytes(out[i].bytes[: out[i].len])) for i in range(n)]
+    want = oracle_frames_batch(cfg, pcm[:, : (len(x) // cfg.sym_len) * cfg.sym_len])
+    assert got == want and len(got) > 0
+    syms = np.zeros(1 << 16, dtype=np.uint8)
+    ns = L.demod_read_symbols(d, syms.ctypes.data, len(syms))
+    o = Oracle(cfg)
+    o.feed(pcm[0, : (len(x) // cfg.sym_len) * cfg.sym_len])
+    assert np.array_equal(syms[:ns], o.symbols())
+    L.demod_destroy(d)
