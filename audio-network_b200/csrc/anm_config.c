@@ -70,13 +70,20 @@ int anm_config_validate(const anm_config_t *c) {
 int anm_twiddles(const anm_config_t *c, float *out) {
     if (anm_config_validate(c) != ANM_OK || !out) return ANM_ERR_ARG;
     const double two_pi = 6.283185307179586476925286766559;
-    for (uint32_t m = 0; m < c->sym_len; ++m)
-        for (uint32_t k = 0; k < c->n_tones; ++k) {
-            /* reduce the angle exactly before calling libm: (bin*m) mod N */
-            uint32_t r = (c->tone_bin[k] * m) % c->sym_len;
-            double a = two_pi * (double)r / (double)c->sym_len;
-            out[(m * c->n_tones + k) * 2 + 0] = (float)cos(a);
-            out[(m * c->n_tones + k) * 2 + 1] = (float)sin(a);
+    const uint32_t N = c->sym_len, T = c->n_tones;
+    /* first half from libm (angle reduced exactly in integers first); second half by the exact
+     * symmetry e^{-j2pi b (m+N/2)/N} = (-1)^b e^{-j2pi b m/N}, which the CUDA path relies on
+     * (SPEC 3) */
+    for (uint32_t m = 0; m < N / 2; ++m)
+        for (uint32_t k = 0; k < T; ++k) {
+            uint32_t r = (c->tone_bin[k] * m) % N;
+            double a = two_pi * (double)r / (double)N;
+            float co = (float)cos(a), si = (float)sin(a);
+            float sg = (c->tone_bin[k] & 1u) ? -1.0f : 1.0f;
+            out[(m * T + k) * 2 + 0] = co;
+            out[(m * T + k) * 2 + 1] = si;
+            out[((m + N / 2) * T + k) * 2 + 0] = sg * co;
+            out[((m + N / 2) * T + k) * 2 + 1] = sg * si;
         }
     return ANM_OK;
 }

@@ -39,13 +39,14 @@ typedef void (*kern_fn)(const KParams);
 struct Variant {
     uint32_t T, N, S;
     bool twc;
-    kern_fn fn;
+    kern_fn fn;       /* streaming demodulator */
+    kern_fn fn_trace; /* stateless tone-energy pass */
     uint32_t warp_smem, state_bytes;
 };
 
-#define VARIANT(T_, N_, S_)                                                                             \
-    {T_, N_, S_, (T_ * N_ <= kMaxConstTw), (kern_fn)k_demod<T_, N_, S_, (T_ * N_ <= kMaxConstTw)>, \
-     warp_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
+#define VARIANT(T_, N_, S_)                                                                                \
+    {T_, N_, S_, (T_ * N_ <= kMaxConstTw), (kern_fn)k_demod<T_, N_, S_, (T_ * N_ <= kMaxConstTw), 0>, \
+     (kern_fn)k_demod<T_, N_, S_, (T_ * N_ <= kMaxConstTw), 1>, warp_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
 
 const Variant kVariants[] = {
     VARIANT(4, 128, 4),  VARIANT(2, 128, 4),  VARIANT(8, 128, 4), VARIANT(16, 128, 4),
@@ -100,6 +101,16 @@ struct anm_demod {
     int overflow;
     KParams kp;
 };
+
+/* bit k set: tone_bin[k] is odd, so twiddle[m + N/2][k] = -twiddle[m][k] (anm_twiddles builds the
+ * table with exactly this symmetry) */
+static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
+    unsigned long long m = 0;
+    for (uint32_t t = 0; t < cfg->n_tones; ++t)
+        if (cfg->tone_bin[t] & 1u) m |= 1ull << t;
+    k->tw_sign = (uint32_t)m;
+    k->tw_sign_hi = m >> 32;
+}
 
 static int set_device(const anm_demod *h) {
     CK(cudaSetDevice(h->device));
@@ -188,7 +199,6 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     k.n_ch = n_channels;
     k.state = h->d_state;
     k.state_stride = var->state_bytes;
-    k.do_sm = 1;
     k.fsyms = h->d_fsyms;
     k.fsym_stride = h->fsym_stride;
     k.max_frame_syms = h->max_frame_syms;
@@ -212,6 +222,7 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     }
     memcpy(k.preamble, cfg->preamble, ANM_MAX_PREAMBLE);
     k.tw_global = h->d_tw;
+    set_tw_sign(cfg, &k);
     int rc = anm_demod_reset(h);
     if (rc != ANM_OK) { anm_demod_destroy(h); return rc; }
     *out = h;
@@ -309,7 +320,7 @@ extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_
         if (rc < 0) return (int)rc;
         if (nsyms + 8 > h->osym_cap) { anm_set_error("chunk longer than the symbol buffer"); return ANM_ERR_ARG; }
     }
-    cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
+    cudaStream_t s = (cudaStream_t)stream; /* NULL is the legacy default stream, as in the CUDA runtime */
     KParams k = h->kp;
     k.pcm = d_pcm;
     k.ch_stride = ch_stride;
@@ -521,7 +532,7 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
         k.hop_base = 0;
         k.state = d_state;
         k.state_stride = var->state_bytes;
-        k.do_sm = 0;
+        set_tw_sign(cfg, &k);
         k.trE = d_energy;
         k.trD = d_sym;
         k.trEmax = d_emax;
@@ -530,9 +541,9 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
         k.tw_global = d_tw;
         const uint32_t W = std::min<uint32_t>(8u, (227u * 1024u - 1024u) / var->warp_smem);
         const uint32_t grid = (n_ch + W - 1) / W;
-        cudaFuncSetAttribute((const void *)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 1024));
+        cudaFuncSetAttribute((const void *)var->fn_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 1024));
         void *args[] = {(void *)&k};
-        cudaError_t e = cudaLaunchKernel((const void *)var->fn, dim3(std::min<uint32_t>(grid, (uint32_t)sms * 4u)), dim3(W * 32), args,
+        cudaError_t e = cudaLaunchKernel((const void *)var->fn_trace, dim3(std::min<uint32_t>(grid, (uint32_t)sms * 4u)), dim3(W * 32), args,
                                          (size_t)W * var->warp_smem, s);
         if (e != cudaSuccess) { anm_set_error("launch: %s", cudaGetErrorString(e)); rc = ANM_ERR_CUDA; }
     }
