@@ -71,19 +71,21 @@ int anm_twiddles(const anm_config_t *c, float *out) {
     if (anm_config_validate(c) != ANM_OK || !out) return ANM_ERR_ARG;
     const double two_pi = 6.283185307179586476925286766559;
     const uint32_t N = c->sym_len, T = c->n_tones;
-    /* first half from libm (angle reduced exactly in integers first); second half by the exact
-     * symmetry e^{-j2pi b (m+N/2)/N} = (-1)^b e^{-j2pi b m/N}, which the CUDA path relies on
-     * (SPEC 3) */
-    for (uint32_t m = 0; m < N / 2; ++m)
+    /* First quarter from libm (angle reduced exactly in integers first).  The other quarters
+     * follow from e^{-j2pi b (m + q N/4)/N} = (-j)^{b q} e^{-j2pi b m/N}: an exact swap / negation
+     * of (cos, sin), which the CUDA path relies on (SPEC 3). */
+    for (uint32_t m = 0; m < N / 4; ++m)
         for (uint32_t k = 0; k < T; ++k) {
-            uint32_t r = (c->tone_bin[k] * m) % N;
-            double a = two_pi * (double)r / (double)N;
+            uint32_t r0 = (c->tone_bin[k] * m) % N;
+            double a = two_pi * (double)r0 / (double)N;
             float co = (float)cos(a), si = (float)sin(a);
-            float sg = (c->tone_bin[k] & 1u) ? -1.0f : 1.0f;
-            out[(m * T + k) * 2 + 0] = co;
-            out[(m * T + k) * 2 + 1] = si;
-            out[((m + N / 2) * T + k) * 2 + 0] = sg * co;
-            out[((m + N / 2) * T + k) * 2 + 1] = sg * si;
+            for (uint32_t q = 0; q < 4; ++q) {
+                uint32_t r = (c->tone_bin[k] * q) & 3u;
+                float cq = r == 0 ? co : r == 1 ? -si : r == 2 ? -co : si;
+                float sq = r == 0 ? si : r == 1 ? co : r == 2 ? -si : -co;
+                out[((m + q * (N / 4)) * T + k) * 2 + 0] = cq;
+                out[((m + q * (N / 4)) * T + k) * 2 + 1] = sq;
+            }
         }
     return ANM_OK;
 }

@@ -38,15 +38,14 @@ typedef void (*kern_fn)(const KParams);
 
 struct Variant {
     uint32_t T, N, S;
-    bool twc;
     kern_fn fn;       /* streaming demodulator */
     kern_fn fn_trace; /* stateless tone-energy pass */
-    uint32_t warp_smem, state_bytes;
+    uint32_t warp_smem, cta_smem, state_bytes;
 };
 
-#define VARIANT(T_, N_, S_)                                                                                \
-    {T_, N_, S_, (T_ * N_ <= kMaxConstTw), (kern_fn)k_demod<T_, N_, S_, (T_ * N_ <= kMaxConstTw), 0>, \
-     (kern_fn)k_demod<T_, N_, S_, (T_ * N_ <= kMaxConstTw), 1>, warp_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
+#define VARIANT(T_, N_, S_)                                                                       \
+    {T_, N_, S_, (kern_fn)k_demod<T_, N_, S_, 0>, (kern_fn)k_demod<T_, N_, S_, 1>, warp_smem_bytes<T_, N_, S_>(), \
+     cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
 
 const Variant kVariants[] = {
     VARIANT(4, 128, 4),  VARIANT(2, 128, 4),  VARIANT(8, 128, 4), VARIANT(16, 128, 4),
@@ -58,10 +57,6 @@ const Variant *find_variant(const anm_config_t *c) {
         if (v.T == c->n_tones && v.N == c->sym_len && v.S == c->hops_per_sym) return &v;
     return nullptr;
 }
-
-/* which configuration currently sits in constant bank 3, per device */
-std::mutex g_tw_mu;
-const void *g_tw_owner[64] = {nullptr};
 
 struct EvPair {
     cudaEvent_t a, b;
@@ -102,14 +97,12 @@ struct anm_demod {
     KParams kp;
 };
 
-/* bit k set: tone_bin[k] is odd, so twiddle[m + N/2][k] = -twiddle[m][k] (anm_twiddles builds the
- * table with exactly this symmetry) */
+/* two bits per tone: tone_bin mod 4, the rotation (in quarter turns) a twiddle picks up when the
+ * sample position advances by N/4 (anm_twiddles builds the table with exactly this symmetry) */
 static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
-    unsigned long long m = 0;
+    k->tw_rot[0] = k->tw_rot[1] = 0;
     for (uint32_t t = 0; t < cfg->n_tones; ++t)
-        if (cfg->tone_bin[t] & 1u) m |= 1ull << t;
-    k->tw_sign = (uint32_t)m;
-    k->tw_sign_hi = m >> 32;
+        k->tw_rot[t >> 5] |= (unsigned long long)(cfg->tone_bin[t] & 3u) << (2 * (t & 31));
 }
 
 static int set_device(const anm_demod *h) {
@@ -119,7 +112,7 @@ static int set_device(const anm_demod *h) {
 
 static void choose_launch(anm_demod *h) {
     const uint32_t per_warp = h->var->warp_smem;
-    const uint32_t smem_max = 227u * 1024u - 1024u;
+    const uint32_t smem_max = 227u * 1024u - h->var->cta_smem;
     uint32_t wmax = std::min<uint32_t>(16u, smem_max / per_warp);
     if (wmax < 1) wmax = 1;
     const uint32_t sms = (uint32_t)h->num_sms;
@@ -138,7 +131,7 @@ static void choose_launch(anm_demod *h) {
         h->grid = sms;
     }
     h->warps_per_cta = W;
-    h->smem_bytes = (size_t)W * per_warp;
+    h->smem_bytes = (size_t)W * per_warp + h->var->cta_smem;
 }
 
 extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, int device, uint32_t flags,
@@ -167,7 +160,7 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     choose_launch(h);
-    CK(cudaFuncSetAttribute((const void *)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 1024)));
+    CK(cudaFuncSetAttribute((const void *)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     const uint32_t b = anm_bits_per_sym(cfg);
     const uint32_t hdr_syms = (24 + b - 1) / b;
     h->max_frame_syms = hdr_syms + ((cfg->max_payload + 2) * 8 + b - 1) / b;
@@ -258,10 +251,6 @@ extern "C" void anm_demod_destroy(anm_demod_t *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    {
-        std::lock_guard<std::mutex> lk(g_tw_mu);
-        if (h->device < 64 && g_tw_owner[h->device] == h) g_tw_owner[h->device] = nullptr;
-    }
     cudaFree(h->d_state);
     cudaFree(h->d_fsyms);
     cudaFree(h->d_frames);
@@ -278,21 +267,7 @@ extern "C" void anm_demod_destroy(anm_demod_t *h) {
     delete h;
 }
 
-/* make sure constant bank 3 holds this handle's twiddles before its kernel runs */
-static int bind_twiddles(const void *owner, int device, const std::vector<float> &tw, bool twc, cudaStream_t s) {
-    if (!twc) return ANM_OK;
-    std::lock_guard<std::mutex> lk(g_tw_mu);
-    if (device < 64 && g_tw_owner[device] == owner) return ANM_OK;
-    CK(cudaDeviceSynchronize()); /* kernels of another configuration may still read the bank */
-    CK(cudaMemcpyToSymbolAsync(c_tw, tw.data(), tw.size() * sizeof(float), 0, cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
-    if (device < 64) g_tw_owner[device] = owner;
-    return ANM_OK;
-}
-
 static int launch(anm_demod *h, const KParams &k, cudaStream_t s, bool timed) {
-    int rc = bind_twiddles(h, h->device, h->h_tw, h->var->twc, s);
-    if (rc) return rc;
     EvPair *ev = nullptr;
     if (timed && h->ev_used < h->evs.size()) ev = &h->evs[h->ev_used++];
     if (ev) CK(cudaEventRecord(ev->a, s));
@@ -515,13 +490,6 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
     CK(cudaMalloc(&d_tw, tw.size() * sizeof(float)));
     int rc = init_state(var, d_state, n_ch, s);
     if (rc == ANM_OK && cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = ANM_ERR_CUDA;
-    static int dummy_owner;
-    if (rc == ANM_OK) {
-        /* a one-shot pass owns the constant bank only for its own launch */
-        std::lock_guard<std::mutex> lk(g_tw_mu);
-        if (dev < 64) g_tw_owner[dev] = nullptr;
-    }
-    if (rc == ANM_OK) rc = bind_twiddles(&dummy_owner, dev, tw, var->twc, s);
     if (rc == ANM_OK) {
         KParams k;
         memset(&k, 0, sizeof k);
@@ -539,20 +507,16 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
         k.tr_hops = n_samples / (cfg->sym_len / cfg->hops_per_sym);
         k.P = cfg->preamble_len;
         k.tw_global = d_tw;
-        const uint32_t W = std::min<uint32_t>(8u, (227u * 1024u - 1024u) / var->warp_smem);
+        const uint32_t W = std::min<uint32_t>(8u, (227u * 1024u - var->cta_smem) / var->warp_smem);
         const uint32_t grid = (n_ch + W - 1) / W;
-        cudaFuncSetAttribute((const void *)var->fn_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - 1024));
+        cudaFuncSetAttribute((const void *)var->fn_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         void *args[] = {(void *)&k};
         cudaError_t e = cudaLaunchKernel((const void *)var->fn_trace, dim3(std::min<uint32_t>(grid, (uint32_t)sms * 4u)), dim3(W * 32), args,
-                                         (size_t)W * var->warp_smem, s);
+                                         (size_t)W * var->warp_smem + var->cta_smem, s);
         if (e != cudaSuccess) { anm_set_error("launch: %s", cudaGetErrorString(e)); rc = ANM_ERR_CUDA; }
     }
     cudaError_t e2 = cudaStreamSynchronize(s);
     if (rc == ANM_OK && e2 != cudaSuccess) { anm_set_error("tone pass: %s", cudaGetErrorString(e2)); rc = ANM_ERR_CUDA; }
-    {
-        std::lock_guard<std::mutex> lk(g_tw_mu);
-        if (dev < 64 && g_tw_owner[dev] == &dummy_owner) g_tw_owner[dev] = nullptr;
-    }
     cudaFree(d_state);
     cudaFree(d_tw);
     return rc;

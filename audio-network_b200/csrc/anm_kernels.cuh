@@ -21,9 +21,6 @@
 
 namespace anm {
 
-constexpr int kMaxConstTw = 6144; /* float2 entries = 48 KB of constant bank 3 */
-__constant__ float2 c_tw[kMaxConstTw]; /* single translation unit: anm_cuda.cu */
-
 enum : uint32_t { ST_SEARCH = 0, ST_PEAK = 1, ST_HEADER = 2, ST_BODY = 3 };
 
 /* Uniform (per-channel) part of the carried state; lane-distributed parts follow it. */
@@ -48,7 +45,7 @@ struct KParams {
     unsigned long long hop_base;  /* absolute index of the chunk's first hop */
     unsigned char *state;         /* per channel: ChanScalars | lane records | tree carry */
     uint32_t state_stride;        /* bytes */
-    uint32_t tw_sign;             /* bit k: tone_bin[k] is odd, i.e. twiddle[m+N/2][k] = -twiddle[m][k] (first 32 tones) */
+    uint32_t pad0;
     uint8_t *fsyms;               /* per channel frame symbol store */
     uint32_t fsym_stride;
     uint32_t max_frame_syms;
@@ -65,8 +62,8 @@ struct KParams {
     uint32_t P, tol, max_payload, trk_epoch, trk_thresh, hdr_syms;
     uint32_t pre_plane[7];        /* bit-planes of the preamble tone indices */
     uint8_t preamble[ANM_MAX_PREAMBLE];
-    const float2 *tw_global;      /* [N][T] (cos, sin); used when the table exceeds c_tw */
-    unsigned long long tw_sign_hi; /* same for tones 32..63 */
+    const float2 *tw_global;      /* [N][T] (cos, sin) twiddle table in HBM; its first N/NQ rows are staged per CTA */
+    unsigned long long tw_rot[2];  /* 2 bits per tone: tone_bin mod 4 (quarter-period rotation code) */
 };
 
 __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
@@ -131,52 +128,61 @@ template <int N>
 __host__ __device__ constexpr uint32_t stage_bytes() { return 32u * N * 2u; }
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t warp_smem_bytes() { return 2u * stage_bytes<N>() + (uint32_t)(S - 1) * T * 8u; }
+/* Hops that share one pass over the twiddle table: the table holds the first 1/NQ of a symbol
+ * period; hop offsets that differ by N/NQ rotate every twiddle by an exact multiple of 90 degrees. */
+template <int S>
+__host__ __device__ constexpr int quad_hops() { return S >= 4 ? 4 : 2; }
+/* CTA-shared twiddle table: (N / NQ) positions x T tones x (cos, sin) */
+template <int T, int N, int S>
+__host__ __device__ constexpr uint32_t cta_smem_bytes() { return (uint32_t)(N / quad_hops<S>()) * T * 8u; }
 
 /* MODE 0: streaming demodulator (sync, slicing, framing; no trace output).
  * MODE 1: stateless tone-energy pass (trace outputs only; parity / debug). */
-template <int T, int N, int S, bool TWC, int MODE>
+template <int T, int N, int S, int MODE>
 __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p) {
     constexpr int H = N / S;
     constexpr int B = Log2<T>::v;
-    constexpr int TG = T < 8 ? T : 8; /* tones per register group */
+    constexpr int NQ = quad_hops<S>(); /* hops per table pass */
+    constexpr int TL = N / NQ;         /* table positions */
+    constexpr int GR = S / NQ;         /* passes per symbol period (hop = pass + q*GR) */
+    constexpr int TG = (T * NQ <= 16) ? T : (16 / NQ); /* tones per register group: NQ*TG accumulators */
     constexpr int NG = T / TG;
     constexpr int LV = Log2<S>::v;
-    constexpr int HS = S / 2;  /* hop-pair iterations: hops i and i+S/2 share twiddles up to sign */
     constexpr int CPH = H / 8; /* 16-byte chunks per hop */
     constexpr int CPS = N / 8; /* 16-byte chunks per symbol period */
     constexpr uint32_t FULL = 0xffffffffu;
     static_assert(N >= 64 && (H % 8) == 0 && S >= 2, "unsupported geometry");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint16_t s_crc[256];
-    if (MODE == 0) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-            uint32_t c = (uint32_t)i << 8;
-            for (int k = 0; k < 8; ++k) c = (c & 0x8000u) ? ((c << 1) ^ 0x1021u) : (c << 1);
-            s_crc[i] = (uint16_t)c;
-        }
-        __syncthreads();
-    }
-
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    unsigned char *wsm = smem_raw + (size_t)wib * warp_smem_bytes<T, N, S>();
+    /* CTA-shared twiddle table (first 1/NQ of a symbol period), read back as broadcast LDS.128 */
+    {
+        const float4 *gsrc = reinterpret_cast<const float4 *>(p.tw_global);
+        float4 *dst = reinterpret_cast<float4 *>(smem_raw);
+        for (int i = threadIdx.x; i < TL * T / 2; i += blockDim.x) dst[i] = __ldg(&gsrc[i]);
+        __syncthreads();
+    }
+    const uint32_t stw = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    unsigned char *wsm = smem_raw + cta_smem_bytes<T, N, S>() + (size_t)wib * warp_smem_bytes<T, N, S>();
     const uint32_t sbuf0 = (uint32_t)__cvta_generic_to_shared(wsm);
     float2 *carry = reinterpret_cast<float2 *>(wsm + 2 * stage_bytes<N>()); /* [(S-1)*T] */
 
     /* lane-constant pieces of the swizzled addresses */
     const uint32_t sw = lane & 7u;
-    constexpr uint32_t LOWM = (uint32_t)(CPH - 1) & 7u, HIM = 7u & ~LOWM;
-    uint32_t swc[CPH];
-#pragma unroll
-    for (int c = 0; c < CPH; ++c) swc[c] = (((uint32_t)c ^ (sw & LOWM))) << 4;
-    const uint32_t swhi = sw & HIM;
     /* cp.async: lane copies 16-byte chunk (q*32 + lane) of the step; destination slot and
      * chunk-in-slot are lane constants up to a per-q constant */
     constexpr int LPS = (CPS >= 32) ? 1 : 32 / CPS; /* symbol slots covered by one cp.async instruction */
     const uint32_t cp_slot = (CPS >= 32) ? 0u : (uint32_t)lane / (uint32_t)CPS;
     const uint32_t cp_chunk = (uint32_t)lane % (uint32_t)CPS;
+
+    /* CRC-16 lane constant: x^(8(31-lane)+16) mod p (see frame assembly) */
+    uint32_t crc_k = 1;
+    if (MODE == 0) {
+        const int nsh = 8 * (31 - lane) + 16;
+        for (int i = 0; i < nsh; ++i) crc_k = ((crc_k << 1) ^ ((crc_k & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
+    }
 
     const uint32_t n_steps = (p.n_syms + 31u) / 32u;
     const uint32_t total_warps = gridDim.x * wpb;
@@ -254,63 +260,65 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
 
 #pragma unroll 1
             for (int g = 0; g < NG; ++g) {
-                float2 PA[HS][TG], PB[HS][TG]; /* PA[i] = P[hop i], PB[i] = P[hop i + S/2] */
+                float2 Pp[S][TG]; /* hop partials of this tone group */
+                /* All 32 lanes run the arithmetic (lanes beyond a ragged chunk end read stale shared
+                 * memory; their results are discarded below).  One pass accumulates the NQ hops whose
+                 * offsets differ by N/NQ: they see the same twiddle sequence up to an exact rotation by
+                 * multiples of 90 degrees, applied once after the chain. */
 #pragma unroll
-                for (int i = 0; i < HS; ++i)
+                for (int pass = 0; pass < GR; ++pass) {
+                    float2 acc[NQ][TG];
 #pragma unroll
-                    for (int t = 0; t < TG; ++t) { PA[i][t] = make_float2(0.f, 0.f); PB[i][t] = make_float2(0.f, 0.f); }
-                /* all 32 lanes run the arithmetic (warp-uniform control flow keeps the twiddle loads on
-                 * the uniform datapath); lanes beyond a ragged chunk end read stale shared memory and
-                 * their results are discarded below */
-                {
-                    /* fully unrolled: static twiddle offsets become LDCU.128 with immediate addresses */
+                    for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                    for (int it = 0; it < HS; ++it) {
-                        float2 aA[TG], aB[TG];
+                        for (int t = 0; t < TG; ++t) acc[q][t] = make_float2(0.f, 0.f);
+                    /* table position of this pass's first sample: pass*H; chunk index of hop q: (pass + q*GR)*CPH */
+                    uint32_t twa = stw + (uint32_t)((pass * H) * T + g * TG) * 8u;
+#pragma unroll 1
+                    for (int c = 0; c < TL / 8 / GR; ++c, twa += 8 * T * 8) {
+                        uint4 v[NQ];
 #pragma unroll
-                        for (int t = 0; t < TG; ++t) { aA[t] = make_float2(0.f, 0.f); aB[t] = make_float2(0.f, 0.f); }
-                        const uint32_t baseA = (uint32_t)it * CPH, baseB = baseA + (uint32_t)HS * CPH;
-                        const uint32_t hiA = row + ((baseA ^ swhi) << 4), hiB = row + ((baseB ^ swhi) << 4);
-                        const int twb = it * (H * T) + g * TG; /* uniform twiddle base of this hop */
+                        for (int q = 0; q < NQ; ++q) {
+                            const uint32_t cc = (uint32_t)((pass + q * GR) * CPH + c);
+                            v[q] = lds128(row + ((cc ^ sw) << 4));
+                        }
 #pragma unroll
-                        for (int c = 0; c < CPH; ++c) {
-                            const uint4 vA = lds128(hiA + swc[c]);
-                            const uint4 vB = lds128(hiB + swc[c]);
-                            const uint32_t wA[4] = {vA.x, vA.y, vA.z, vA.w};
-                            const uint32_t wB[4] = {vB.x, vB.y, vB.z, vB.w};
+                        for (int j = 0; j < 8; ++j) {
+                            float x[NQ];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float xA0 = (float)(short)(wA[q] & 0xffffu), xA1 = (float)((int)wA[q] >> 16);
-                                const float xB0 = (float)(short)(wB[q] & 0xffffu), xB1 = (float)((int)wB[q] >> 16);
-                                const int m = (c * 8 + q * 2) * T;
+                            for (int q = 0; q < NQ; ++q) {
+                                const uint32_t w = (j < 2) ? v[q].x : (j < 4) ? v[q].y : (j < 6) ? v[q].z : v[q].w;
+                                x[q] = (j & 1) ? (float)((int)w >> 16) : (float)(short)(w & 0xffffu);
+                            }
 #pragma unroll
-                                for (int t = 0; t < TG; ++t) {
-                                    const float2 w0 = TWC ? c_tw[twb + m + t] : __ldg(&p.tw_global[twb + m + t]);
-                                    aA[t] = ffma2(xA0, w0, aA[t]);
-                                    aB[t] = ffma2(xB0, w0, aB[t]);
-                                }
+                            for (int t = 0; t < TG; t += 2) {
+                                float4 w2;
+                                asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                             : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w)
+                                             : "r"(twa + (uint32_t)(j * T + t) * 8u));
 #pragma unroll
-                                for (int t = 0; t < TG; ++t) {
-                                    const float2 w1 = TWC ? c_tw[twb + m + T + t] : __ldg(&p.tw_global[twb + m + T + t]);
-                                    aA[t] = ffma2(xA1, w1, aA[t]);
-                                    aB[t] = ffma2(xB1, w1, aB[t]);
+                                for (int q = 0; q < NQ; ++q) {
+                                    acc[q][t] = ffma2(x[q], make_float2(w2.x, w2.y), acc[q][t]);
+                                    acc[q][t + 1] = ffma2(x[q], make_float2(w2.z, w2.w), acc[q][t + 1]);
                                 }
                             }
                         }
-                        /* twiddle[m + N/2][k] = -twiddle[m][k] for odd bins: negate exactly */
-                        const unsigned long long sgn = ((unsigned long long)p.tw_sign | (p.tw_sign_hi << 32)) >> (g * TG);
+                    }
+                    /* rotate hop q by (-j)^(bin*q*4/NQ): exact swap / negate (SPEC 3, table symmetry) */
+                    const unsigned long long rots = (g * TG < 32) ? (p.tw_rot[0] >> (2 * g * TG)) : (p.tw_rot[1] >> (2 * (g * TG - 32)));
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
 #pragma unroll
                         for (int t = 0; t < TG; ++t) {
-                            const uint32_t mk = ((uint32_t)(sgn >> t) & 1u) << 31;
-                            aB[t].x = __uint_as_float(__float_as_uint(aB[t].x) ^ mk);
-                            aB[t].y = __uint_as_float(__float_as_uint(aB[t].y) ^ mk);
+                            const uint32_t r = (((uint32_t)(rots >> (2 * t)) & 3u) * (uint32_t)(q * (4 / NQ))) & 3u;
+                            const float a = acc[q][t].x, b2 = acc[q][t].y;
+                            const float ni = (r & 1u) ? b2 : a;  /* r=1: I=-Q', r=3: I=Q' */
+                            const float nq = (r & 1u) ? a : b2;  /* r=1: Q=I',  r=3: Q=-I' */
+                            const uint32_t sI = (r == 1u || r == 2u) ? 0x80000000u : 0u;
+                            const uint32_t sQ = (r == 2u || r == 3u) ? 0x80000000u : 0u;
+                            Pp[pass + q * GR][t] = make_float2(__uint_as_float(__float_as_uint(ni) ^ sI),
+                                                               __uint_as_float(__float_as_uint(nq) ^ sQ));
                         }
-#pragma unroll
-                        for (int j = 0; j + 1 < HS; ++j)
-#pragma unroll
-                            for (int t = 0; t < TG; ++t) { PA[j][t] = PA[j + 1][t]; PB[j][t] = PB[j + 1][t]; }
-#pragma unroll
-                        for (int t = 0; t < TG; ++t) { PA[HS - 1][t] = aA[t]; PB[HS - 1][t] = aB[t]; }
                     }
                 }
                 /* window tree: lane 0 takes the previous step's tail from the carry buffer */
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                     __syncwarp();
                     float2 L[S];
 #pragma unroll
-                    for (int i = 0; i < S; ++i) L[i] = (i < HS) ? PA[i % HS][t] : PB[i % HS][t];
+                    for (int i = 0; i < S; ++i) L[i] = Pp[i][t];
 #pragma unroll
                     for (int lv = 1; lv <= LV; ++lv) {
                         const int d = 1 << (lv - 1);
@@ -485,45 +493,53 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                          * symbol sits one slot back at the same phase; for e == 0 at the carried hop. */
                         uint32_t bl, be;
                         {
-                            const int r0 = (int)((long long)(sc.prev_hop - hbs));
-                            uint32_t d0[3];
-                            float e0[3];
-#pragma unroll
-                            for (int z = 0; z < 3; ++z) rec_at(r0 - 1 + z, d0[z], e0[z]);
-                            /* same-phase neighbours, fetched with one rotate-by-one each */
+                            /* Common case: the previous symbol sits exactly one slot back at the same phase
+                             * (no timing move in between), so every lane -- including the first of the run,
+                             * whose predecessor may be lane 31 of the previous step -- fetches its records
+                             * with one rotate of a merged current/previous register. */
                             const int phe = (phi >= 1) ? phi - 1 : S - 1, phl = (phi + 1 < S) ? phi + 1 : 0;
-                            const uint32_t von_d = pick<S>(dc, phi);
-                            const float von_e = pick<S>(ec, phi);
-                            (void)von_d;
-                            const uint32_t ea_d = pick<S>(dc, phe), la_d = pick<S>(dc, phl);
-                            const float ea_e = pick<S>(ec, phe), la_e = pick<S>(ec, phl);
-                            /* e >= 1 implies lane >= 1 (and >= 2 when two slots back are needed only if e >= 1 and
-                             * phi == 0, where slot-2 >= s0-1 >= -1 can be the previous step: use the carried copy) */
-                            float e_on = __shfl_up_sync(FULL, von_e, 1);
-                            uint32_t d_ea;
-                            float e_ea;
+                            const bool l31 = lane == 31, l30 = lane >= 30;
+                            const float on_src = l31 ? pick<S>(pe, phi) : pick<S>(ec, phi);
+                            float e_on = __shfl_sync(FULL, on_src, (lane - 1) & 31);
+                            uint32_t d_ea, d_la;
+                            float e_ea, e_la;
                             if (phi >= 1) {
-                                d_ea = __shfl_up_sync(FULL, ea_d, 1);
-                                e_ea = __shfl_up_sync(FULL, ea_e, 1);
+                                const uint32_t dsrc = l31 ? pick<S>(pd, phe) : pick<S>(dc, phe);
+                                const float esrc = l31 ? pick<S>(pe, phe) : pick<S>(ec, phe);
+                                d_ea = __shfl_sync(FULL, dsrc, (lane - 1) & 31);
+                                e_ea = __shfl_sync(FULL, esrc, (lane - 1) & 31);
                             } else {
-                                const uint32_t pd_l = pick<S>(pd, S - 1);
-                                const float pe_l = pick<S>(pe, S - 1);
-                                const uint32_t dsrc = (lane >= 30) ? pd_l : ea_d;
-                                const float esrc = (lane >= 30) ? pe_l : ea_e;
+                                const uint32_t dsrc = l30 ? pick<S>(pd, S - 1) : pick<S>(dc, S - 1);
+                                const float esrc = l30 ? pick<S>(pe, S - 1) : pick<S>(ec, S - 1);
                                 d_ea = __shfl_sync(FULL, dsrc, (lane - 2) & 31);
                                 e_ea = __shfl_sync(FULL, esrc, (lane - 2) & 31);
                             }
-                            uint32_t d_la = (phi + 1 < S) ? __shfl_up_sync(FULL, la_d, 1) : la_d;
-                            float e_la = (phi + 1 < S) ? __shfl_up_sync(FULL, la_e, 1) : la_e;
+                            if (phi + 1 < S) {
+                                const uint32_t dsrc = l31 ? pick<S>(pd, phl) : pick<S>(dc, phl);
+                                const float esrc = l31 ? pick<S>(pe, phl) : pick<S>(ec, phl);
+                                d_la = __shfl_sync(FULL, dsrc, (lane - 1) & 31);
+                                e_la = __shfl_sync(FULL, esrc, (lane - 1) & 31);
+                            } else {
+                                d_la = dc[0];
+                                e_la = ec[0];
+                            }
                             uint32_t sj = __shfl_up_sync(FULL, sym, 1);
                             uint32_t sjm = __shfl_up_sync(FULL, sym, 2);
                             if (e == 1) sjm = sc.s_prev;
-                            if (e == 0) {
-                                d_ea = d0[0]; e_ea = e0[0];
-                                e_on = e0[1];
-                                d_la = d0[2]; e_la = e0[2];
-                                sj = sc.s_prev;
-                                sjm = sc.s_prev2;
+                            if (e == 0) { sj = sc.s_prev; sjm = sc.s_prev2; }
+                            if (sc.prev_hop + S != sc.next) {
+                                /* rare: a timing move separates the first symbol of the run from its
+                                 * predecessor; fetch that predecessor's records by absolute hop */
+                                const int r0 = (int)((long long)(sc.prev_hop - hbs));
+                                uint32_t d0[3];
+                                float e0[3];
+#pragma unroll
+                                for (int z = 0; z < 3; ++z) rec_at(r0 - 1 + z, d0[z], e0[z]);
+                                if (e == 0) {
+                                    d_ea = d0[0]; e_ea = e0[0];
+                                    e_on = e0[1];
+                                    d_la = d0[2]; e_la = e0[2];
+                                }
                             }
                             const bool voter = e >= 0 && e < (int)cnt && (sc.nsym + e >= 1);
                             const float ve = (d_ea == sj) ? e_ea : 0.0f;
@@ -599,11 +615,61 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                             fidx = __shfl_sync(FULL, fidx, 0);
                             boff = __shfl_sync(FULL, boff, 0);
                             const bool fits = fidx < p.frames_cap && boff + len <= p.bytes_cap;
-                            /* bits -> bytes, lane-parallel over body bytes (payload + CRC16) */
+                            /* bits -> bytes and CRC-16, both lane-parallel.  The message (LEN bytes +
+                             * payload) is consumed 32 bytes per round, right-aligned: lane l holds the byte
+                             * that is 31-l positions from the end of the round, multiplies it by
+                             * x^(8(31-l)+16) mod p (crc_k, a lane constant) in GF(2)[x], and the round is the
+                             * XOR of all lanes; the running CRC enters the next round through its first two
+                             * bytes (a CRC register R equals XORing R into the next two message bytes). */
                             const uint8_t *bs = fs + p.hdr_syms;
-                            uint32_t crc_rx = 0;
+                            const uint32_t mlen = len + 2; /* CRC'd bytes: LEN hi, LEN lo, payload */
+                            uint32_t crc = 0xFFFFu, crc_rx = 0;
+                            uint32_t done = 0;
+                            uint32_t take = mlen & 31u; /* first (short) round */
+                            if (take == 0) take = 32;
 #pragma unroll 1
-                            for (uint32_t byi = lane; byi < len + 2; byi += 32) {
+                            while (done < mlen) {
+                                const int li = lane - (32 - (int)take);  /* index within the round */
+                                uint32_t v8 = 0;
+                                if (li >= 0) {
+                                    const uint32_t mi = done + li;       /* index in the CRC'd message */
+                                    if (mi < 2) {
+                                        v8 = (mi == 0) ? (len >> 8) : (len & 0xffu);
+                                    } else {
+                                        const uint32_t byi = mi - 2;     /* payload byte */
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) {
+                                            const uint32_t bit = byi * 8 + k;
+                                            const uint32_t v = gray_inv(bs[bit / B]);
+                                            v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
+                                        }
+                                        if (fits) p.bytes[boff + byi] = (uint8_t)v8;
+                                    }
+                                    if (li == 0) v8 ^= crc >> 8;
+                                    if (li == 1) v8 ^= crc & 0xffu;
+                                }
+                                /* v8 * crc_k mod p, Horner over the 8 bits */
+                                uint32_t acc = 0;
+#pragma unroll
+                                for (int k = 7; k >= 0; --k) {
+                                    acc = ((acc << 1) ^ ((acc & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
+                                    if ((v8 >> k) & 1u) acc ^= crc_k;
+                                }
+                                acc ^= __shfl_xor_sync(FULL, acc, 16);
+                                acc ^= __shfl_xor_sync(FULL, acc, 8);
+                                acc ^= __shfl_xor_sync(FULL, acc, 4);
+                                acc ^= __shfl_xor_sync(FULL, acc, 2);
+                                acc ^= __shfl_xor_sync(FULL, acc, 1);
+                                /* a 1-byte round has no second byte to carry the register's low byte:
+                                 * R_lo * x^(8n) with n = 1 is R_lo << 8 */
+                                if (take == 1) acc ^= (crc & 0xffu) << 8;
+                                crc = acc;
+                                done += take;
+                                take = 32;
+                            }
+                            /* received CRC-16: the two bytes after the payload */
+                            if (lane < 2) {
+                                const uint32_t byi = len + lane;
                                 uint32_t v8 = 0;
 #pragma unroll
                                 for (int k = 0; k < 8; ++k) {
@@ -611,25 +677,13 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                                     const uint32_t v = gray_inv(bs[bit / B]);
                                     v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
                                 }
-                                if (byi < len) { if (fits) p.bytes[boff + byi] = (uint8_t)v8; }
-                                else crc_rx |= v8 << (8 * (len + 1 - byi));
+                                crc_rx = v8 << (8 * (1 - lane));
                             }
-                            crc_rx |= __shfl_xor_sync(FULL, crc_rx, 16);
-                            crc_rx |= __shfl_xor_sync(FULL, crc_rx, 8);
-                            crc_rx |= __shfl_xor_sync(FULL, crc_rx, 4);
-                            crc_rx |= __shfl_xor_sync(FULL, crc_rx, 2);
                             crc_rx |= __shfl_xor_sync(FULL, crc_rx, 1);
-                            __syncwarp();
-                            uint32_t ok = 0;
+                            crc_rx = __shfl_sync(FULL, crc_rx, 0);
+                            const uint32_t ok = crc == crc_rx;
                             if (fits) {
-                                uint32_t crc = 0xFFFFu;
                                 if (lane == 0) {
-                                    crc = ((crc << 8) ^ s_crc[((crc >> 8) ^ (len >> 8)) & 0xffu]) & 0xffffu;
-                                    crc = ((crc << 8) ^ s_crc[((crc >> 8) ^ (len & 0xffu)) & 0xffu]) & 0xffffu;
-#pragma unroll 1
-                                    for (uint32_t z = 0; z < len; ++z)
-                                        crc = ((crc << 8) ^ s_crc[((crc >> 8) ^ p.bytes[boff + z]) & 0xffu]) & 0xffffu;
-                                    ok = crc == crc_rx;
                                     anm_frame_t f;
                                     f.channel = ch;
                                     f.len = len;
@@ -638,7 +692,6 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                                     f.offset = boff;
                                     p.frames[fidx] = f;
                                 }
-                                ok = __shfl_sync(FULL, ok, 0);
                                 if (ok) sc.stats.frames_ok++; else sc.stats.frames_bad++;
                             } else if (lane == 0) {
                                 atomicOr(&p.counters[2], 1u);
