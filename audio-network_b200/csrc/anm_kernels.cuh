@@ -321,14 +321,75 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                         }
                     }
                 }
-                /* window tree: lane 0 takes the previous step's tail from the carry buffer */
+                /* ---- window tree (SPEC 3).  Each lane needs the S-1 tail values of the lane before it
+                 * (lane 0: of the previous step, kept in `carry`).  With one tone group the PCM stage is
+                 * dead by now and serves as the exchange buffer; otherwise the tails travel by shuffle. */
+                float2 pin[TG][S - 1];
+                {
+                    float2 tails[TG][S - 1];
+#pragma unroll
+                    for (int t = 0; t < TG; ++t) {
+                        float2 Lc[S];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) Lc[i] = Pp[i][t];
+#pragma unroll
+                        for (int lv = 1; lv <= LV; ++lv) {
+                            const int d = 1 << (lv - 1);
+#pragma unroll
+                            for (int j = 0; j < d; ++j) tails[t][d - 1 + j] = Lc[S - d + j];
+                            if (lv < LV) {
+#pragma unroll
+                                for (int i = S - 1; i >= 2 * d - 1; --i) Lc[i] = fadd2(Lc[i - d], Lc[i]);
+                            }
+                        }
+                    }
+                    float2 *cg = carry + g * TG * (S - 1);
+                    if (NG == 1) {
+                        constexpr uint32_t TB = (uint32_t)TG * (S - 1) * 8u;             /* tail bytes per lane */
+                        constexpr uint32_t XS = ((TB / 16u) & 1u) ? TB : TB + 16u;      /* odd multiple of 16: conflict-free */
+                        static_assert(33u * XS <= stage_bytes<N>(), "exchange buffer exceeds the stage");
+                        const uint32_t xb = sbuf0 + (step & 1u) * stage_bytes<N>();
+                        __syncwarp(); /* every lane is done reading PCM */
+                        float4 *mine = reinterpret_cast<float4 *>(&tails[0][0]);
+#pragma unroll
+                        for (uint32_t k = 0; k < TB / 16u; ++k)
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xb + (uint32_t)(lane + 1) * XS + k * 16u),
+                                         "f"(mine[k].x), "f"(mine[k].y), "f"(mine[k].z), "f"(mine[k].w) : "memory");
+                        __syncwarp();
+                        const uint32_t rsrc = (lane == 0) ? (uint32_t)__cvta_generic_to_shared(cg) : xb + (uint32_t)lane * XS;
+                        float4 *pv = reinterpret_cast<float4 *>(&pin[0][0]);
+#pragma unroll
+                        for (uint32_t k = 0; k < TB / 16u; ++k)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv[k].x), "=f"(pv[k].y), "=f"(pv[k].z), "=f"(pv[k].w)
+                                         : "r"(rsrc + k * 16u) : "memory");
+                        __syncwarp(); /* lane 0 has read the old carry before it is replaced */
+                        if (lane == nvalid - 1) {
+#pragma unroll
+                            for (int t = 0; t < TG; ++t)
+#pragma unroll
+                                for (int k = 0; k < S - 1; ++k) cg[t * (S - 1) + k] = tails[t][k];
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < TG; ++t)
+#pragma unroll
+                            for (int k = 0; k < S - 1; ++k) {
+                                const float2 c0 = (lane == 0) ? cg[t * (S - 1) + k] : make_float2(0.f, 0.f);
+                                const float2 sh = shfl2(tails[t][k], (lane + 31) & 31);
+                                pin[t][k] = (lane == 0) ? c0 : sh;
+                            }
+                        __syncwarp();
+                        if (lane == nvalid - 1) {
+#pragma unroll
+                            for (int t = 0; t < TG; ++t)
+#pragma unroll
+                                for (int k = 0; k < S - 1; ++k) cg[t * (S - 1) + k] = tails[t][k];
+                        }
+                    }
+                }
 #pragma unroll
                 for (int t = 0; t < TG; ++t) {
                     const int tg = g * TG + t;
-                    float2 cin[S - 1];
-#pragma unroll
-                    for (int i = 0; i < S - 1; ++i) cin[i] = (lane == 0) ? carry[tg * (S - 1) + i] : make_float2(0.f, 0.f);
-                    __syncwarp();
                     float2 L[S];
 #pragma unroll
                     for (int i = 0; i < S; ++i) L[i] = Pp[i][t];
@@ -337,18 +398,7 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                         const int d = 1 << (lv - 1);
                         float2 Nw[S];
 #pragma unroll
-                        for (int i = 0; i < S; ++i) {
-                            float2 a;
-                            if (i >= d) {
-                                a = L[i - d];
-                            } else {
-                                const float2 tail = L[S - d + i];
-                                a = shfl2(tail, (lane + 31) & 31);
-                                if (lane == 0) a = cin[d - 1 + i];
-                                if (lane == nvalid - 1) carry[tg * (S - 1) + d - 1 + i] = tail;
-                            }
-                            Nw[i] = fadd2(a, L[i]);
-                        }
+                        for (int i = 0; i < S; ++i) Nw[i] = fadd2((i >= d) ? L[(i >= d) ? i - d : 0] : pin[t][d - 1 + i], L[i]);
 #pragma unroll
                         for (int i = 0; i < S; ++i) L[i] = Nw[i];
                     }
@@ -382,6 +432,31 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
 
             /* ================= sync / slicing / framing (SPEC 5) ================= */
             if (MODE == 0) {
+                /* The PCM stage of this step is dead: publish the hop records of the previous and the
+                 * current step there, indexed by hop relative to the step start (r in [-32S, 32S)), so
+                 * that every later look-up is one LDS. */
+                const uint32_t se = sbuf0 + (step & 1u) * stage_bytes<N>(); /* float emax[64*S] */
+                const uint32_t sd = se + 64u * S * 4u;                        /* u8    d[64*S]   */
+                static_assert(64u * S * 5u <= stage_bytes<N>(), "record scratch exceeds the stage");
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (uint32_t)(lane * S + i) * 4u), "f"(pe[i]) : "memory");
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (uint32_t)((32 + lane) * S + i) * 4u), "f"(ec[i]) : "memory");
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + (uint32_t)(lane * S + i)), "r"(pd[i] & 0xffu) : "memory");
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + (uint32_t)((32 + lane) * S + i)), "r"(dc[i] & 0xffu) : "memory");
+                }
+                __syncwarp();
+                auto RD = [&](int r) -> uint32_t {
+                    uint32_t v;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sd + (uint32_t)(r + 32 * S)) : "memory");
+                    return v;
+                };
+                auto RE = [&](int r) -> float {
+                    float v;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(se + (uint32_t)(r + 32 * S) * 4u) : "memory");
+                    return v;
+                };
                 const int endh = nvalid * S;
                 int cur = 0;
                 bool have_cand = false;
@@ -389,24 +464,13 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
 #pragma unroll
                 for (int i = 0; i < S; ++i) cand[i] = 0;
 
-                /* record (d, emax) of relative hop rr (warp-uniform, may lie in the previous step) */
-                auto rec_at = [&](int rr, uint32_t &dv, float &ev) {
-                    const int sl = rr >> LV, ph = rr & (S - 1);
-                    const uint32_t dsel = sl < 0 ? pick<S>(pd, ph) : pick<S>(dc, ph);
-                    const float esel = sl < 0 ? pick<S>(pe, ph) : pick<S>(ec, ph);
-                    dv = __shfl_sync(FULL, dsel, sl & 31);
-                    ev = __shfl_sync(FULL, esel, sl & 31);
-                };
-                /* quality of the alignment ending at (slot sh, phase ph): SPEC 5 q(h) */
-                auto quality = [&](int sh, int ph) -> float {
-                    const int ss = sh - (int)(p.P - 1) + lane; /* slot of preamble symbol `lane` */
-                    const uint32_t dcur_ = pick<S>(dc, ph), dprev_ = pick<S>(pd, ph);
-                    const float ecur_ = pick<S>(ec, ph), eprev_ = pick<S>(pe, ph);
-                    const uint32_t d1 = __shfl_sync(FULL, dcur_, ss & 31), d0 = __shfl_sync(FULL, dprev_, ss & 31);
-                    const float e1 = __shfl_sync(FULL, ecur_, ss & 31), e0 = __shfl_sync(FULL, eprev_, ss & 31);
-                    const uint32_t dv = ss >= 0 ? d1 : d0;
-                    const float ev = ss >= 0 ? e1 : e0;
-                    float leaf = (lane < (int)p.P && dv == (uint32_t)p.preamble[lane & 31]) ? ev : 0.0f;
+                /* quality of the alignment whose last preamble symbol ends at relative hop h: SPEC 5 q(h) */
+                auto quality = [&](int h) -> float {
+                    const int pl = min(lane, (int)p.P - 1);
+                    const int r = h - ((int)p.P - 1 - pl) * S;
+                    const uint32_t dv = RD(r);
+                    const float ev = RE(r);
+                    float leaf = (lane < (int)p.P && dv == (uint32_t)p.preamble[pl]) ? ev : 0.0f;
                     for (uint32_t w = 1; w < p.P; w <<= 1) leaf = __fadd_rn(leaf, __shfl_xor_sync(FULL, leaf, w));
                     return __shfl_sync(FULL, leaf, 0);
                 };
@@ -443,7 +507,7 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                                 if (mk) h0 = min(h0, ((__ffs(mk) - 1) << LV) + i);
                             }
                             if (h0 == 0x7fffffff) { cur = endh; break; }
-                            sc.best_q = quality(h0 >> LV, h0 & (S - 1));
+                            sc.best_q = quality(h0);
                             sc.best_h = hbs + h0;
                             sc.peak_end = hbs + h0 + S - 1;
                             sc.state = ST_PEAK;
@@ -451,9 +515,8 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                         } else {
                             const long long pend = (long long)(sc.peak_end - hbs);
                             while (cur < endh && cur <= pend) {
-                                const int sl = cur >> LV, ph = cur & (S - 1);
-                                if ((pick<S>(cand, ph) >> sl) & 1u) {
-                                    const float q = quality(sl, ph);
+                                if ((pick<S>(cand, cur & (S - 1)) >> (cur >> LV)) & 1u) {
+                                    const float q = quality(cur);
                                     if (q > sc.best_q) { sc.best_q = q; sc.best_h = hbs + cur; }
                                 }
                                 ++cur;
@@ -478,83 +541,40 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                         const int first = (int)firstl;
                         const uint32_t until_evt = (sc.state == ST_HEADER ? p.hdr_syms : sc.total) - sc.nsym;
                         uint32_t cnt = min(until_evt, (uint32_t)(((endh - 1 - first) >> LV) + 1));
-                        const int phi = first & (S - 1), s0 = first >> LV;
-                        const int e = lane - s0;
-                        const uint32_t sym = pick<S>(dc, phi);
+                        const int e = lane - (first >> LV);          /* index of this lane's symbol in the run */
+                        const bool part = e >= 0 && e < (int)cnt;
+                        const int hr = part ? first + (e << LV) : first; /* relative hop of this lane's symbol */
+                        const uint32_t sym = RD(hr);
                         uint8_t *fs = p.fsyms + (size_t)ch * p.fsym_stride;
-                        if (e >= 0 && e < (int)cnt) {
+                        if (part) {
                             fs[sc.nsym + e] = (uint8_t)sym;
                             if (p.osyms) {
                                 const uint32_t oi = sc.osym_cnt + e;
                                 if (oi < p.osym_cap) p.osyms[(size_t)ch * p.osym_cap + oi] = (uint8_t)sym;
                             }
                         }
-                        /* tracker votes (SPEC 5): lane e votes for symbol nsym+e-1.  For e >= 1 that
-                         * symbol sits one slot back at the same phase; for e == 0 at the carried hop. */
-                        uint32_t bl, be;
-                        {
-                            /* Common case: the previous symbol sits exactly one slot back at the same phase
-                             * (no timing move in between), so every lane -- including the first of the run,
-                             * whose predecessor may be lane 31 of the previous step -- fetches its records
-                             * with one rotate of a merged current/previous register. */
-                            const int phe = (phi >= 1) ? phi - 1 : S - 1, phl = (phi + 1 < S) ? phi + 1 : 0;
-                            const bool l31 = lane == 31, l30 = lane >= 30;
-                            const float on_src = l31 ? pick<S>(pe, phi) : pick<S>(ec, phi);
-                            float e_on = __shfl_sync(FULL, on_src, (lane - 1) & 31);
-                            uint32_t d_ea, d_la;
-                            float e_ea, e_la;
-                            if (phi >= 1) {
-                                const uint32_t dsrc = l31 ? pick<S>(pd, phe) : pick<S>(dc, phe);
-                                const float esrc = l31 ? pick<S>(pe, phe) : pick<S>(ec, phe);
-                                d_ea = __shfl_sync(FULL, dsrc, (lane - 1) & 31);
-                                e_ea = __shfl_sync(FULL, esrc, (lane - 1) & 31);
-                            } else {
-                                const uint32_t dsrc = l30 ? pick<S>(pd, S - 1) : pick<S>(dc, S - 1);
-                                const float esrc = l30 ? pick<S>(pe, S - 1) : pick<S>(ec, S - 1);
-                                d_ea = __shfl_sync(FULL, dsrc, (lane - 2) & 31);
-                                e_ea = __shfl_sync(FULL, esrc, (lane - 2) & 31);
-                            }
-                            if (phi + 1 < S) {
-                                const uint32_t dsrc = l31 ? pick<S>(pd, phl) : pick<S>(dc, phl);
-                                const float esrc = l31 ? pick<S>(pe, phl) : pick<S>(ec, phl);
-                                d_la = __shfl_sync(FULL, dsrc, (lane - 1) & 31);
-                                e_la = __shfl_sync(FULL, esrc, (lane - 1) & 31);
-                            } else {
-                                d_la = dc[0];
-                                e_la = ec[0];
-                            }
-                            uint32_t sj = __shfl_up_sync(FULL, sym, 1);
-                            uint32_t sjm = __shfl_up_sync(FULL, sym, 2);
-                            if (e == 1) sjm = sc.s_prev;
-                            if (e == 0) { sj = sc.s_prev; sjm = sc.s_prev2; }
-                            if (sc.prev_hop + S != sc.next) {
-                                /* rare: a timing move separates the first symbol of the run from its
-                                 * predecessor; fetch that predecessor's records by absolute hop */
-                                const int r0 = (int)((long long)(sc.prev_hop - hbs));
-                                uint32_t d0[3];
-                                float e0[3];
-#pragma unroll
-                                for (int z = 0; z < 3; ++z) rec_at(r0 - 1 + z, d0[z], e0[z]);
-                                if (e == 0) {
-                                    d_ea = d0[0]; e_ea = e0[0];
-                                    e_on = e0[1];
-                                    d_la = d0[2]; e_la = e0[2];
-                                }
-                            }
-                            const bool voter = e >= 0 && e < (int)cnt && (sc.nsym + e >= 1);
-                            const float ve = (d_ea == sj) ? e_ea : 0.0f;
-                            const float vl = (d_la == sj) ? e_la : 0.0f;
-                            bl = __ballot_sync(FULL, voter && (sym != sj) && vl > e_on);
-                            be = __ballot_sync(FULL, voter && (sjm != sj) && ve > e_on);
-                        }
+                        /* tracker votes (SPEC 5): the lane of symbol n votes for symbol n-1, whose hop is one
+                         * symbol back -- or, for the first symbol of the run, the carried prev_hop */
+                        const int r0 = (int)((long long)(sc.prev_hop - hbs));
+                        const int hj = (e <= 0) ? r0 : hr - S;
+                        /* tones of symbols n-1 and n-2; for the first symbols of a frame these are the carried
+                         * values (s_{-1} is the nominal last preamble tone, not a decision) */
+                        const uint32_t sj = (e <= 0) ? sc.s_prev : RD(hr - S);
+                        const uint32_t sjm = (e >= 2) ? RD(hr - 2 * S) : ((e == 1) ? sc.s_prev : sc.s_prev2);
+                        const float e_on = RE(hj);
+                        const float ve = (RD(hj - 1) == sj) ? RE(hj - 1) : 0.0f;
+                        const float vl = (RD(hj + 1) == sj) ? RE(hj + 1) : 0.0f;
+                        const bool voter = part && (sc.nsym + e >= 1);
+                        const uint32_t bl = __ballot_sync(FULL, voter && (sym != sj) && vl > e_on);
+                        const uint32_t be = __ballot_sync(FULL, voter && (sjm != sj) && ve > e_on);
                         /* tracker epochs inside the run: only an actual timing move ends the run early */
                         int adj = 0;
                         {
+                            const uint32_t s0 = (uint32_t)(first >> LV);
                             uint32_t pos = 0;
                             while (true) {
                                 const uint32_t eb = pos + sc.ep_left; /* symbols of the run up to the next boundary */
                                 const uint32_t hi = min(eb, cnt);
-                                /* lanes [s0+pos, s0+hi) */
                                 const uint32_t lo_m = 0xffffffffu << (s0 + pos);
                                 const uint32_t hi_m = (s0 + hi >= 32u) ? 0xffffffffu : ((1u << (s0 + hi)) - 1u);
                                 sc.acc += __popc(bl & lo_m & hi_m) - __popc(be & lo_m & hi_m);
@@ -568,26 +588,26 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                                 if (pos == cnt) break;
                             }
                         }
-                        const int last = s0 + (int)cnt - 1;
-                        const uint32_t ns1 = __shfl_sync(FULL, sym, last);
-                        const uint32_t ns2 = __shfl_sync(FULL, sym, (last - 1) & 31);
-                        sc.s_prev2 = (cnt >= 2) ? ns2 : sc.s_prev;
-                        sc.s_prev = ns1;
-                        sc.prev_hop = hbs + first + ((cnt - 1) << LV);
+                        const int lasth = first + (int)((cnt - 1) << LV);
+                        sc.s_prev2 = (cnt >= 2) ? RD(lasth - S) : sc.s_prev;
+                        sc.s_prev = RD(lasth);
+                        sc.prev_hop = hbs + lasth;
                         sc.nsym += cnt;
                         sc.osym_cnt += cnt;
                         sc.next += ((unsigned long long)cnt << LV) + adj;
                         sc.stats.symbols += cnt;
                         sc.stats.trk_moves += adj;
-                        cur = first + (int)((cnt - 1) << LV) + 1;
+                        cur = lasth + 1;
                         if (sc.state == ST_HEADER && sc.nsym == p.hdr_syms) {
                             __syncwarp();
-                            uint32_t hdr = 0;
-#pragma unroll
-                            for (int bit = 0; bit < 24; ++bit) {
-                                const uint32_t v = gray_inv(fs[bit / B]);
-                                hdr = (hdr << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
+                            /* 24 header bits from hdr_syms symbols, one symbol per lane, OR-reduced */
+                            uint32_t contrib = 0;
+                            if (lane < (int)p.hdr_syms) {
+                                const uint32_t v = gray_inv(fs[lane]);
+                                const int pos = 24 - B * (lane + 1);
+                                contrib = (pos >= 0) ? (v << pos) : (v >> (-pos));
                             }
+                            const uint32_t hdr = __reduce_or_sync(FULL, contrib);
                             const uint32_t len = hdr >> 8;
                             uint32_t c8 = 0;
 #pragma unroll
@@ -615,35 +635,46 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                             fidx = __shfl_sync(FULL, fidx, 0);
                             boff = __shfl_sync(FULL, boff, 0);
                             const bool fits = fidx < p.frames_cap && boff + len <= p.bytes_cap;
+                            const uint8_t *bs = fs + p.hdr_syms;
+                            /* body byte byi (payload, then the two CRC bytes) from its symbols */
+                            auto body_byte = [&](uint32_t byi) -> uint32_t {
+                                uint32_t v8 = 0;
+                                if (8 % B == 0) {
+                                    constexpr int SPB = (8 % B == 0) ? 8 / B : 1;
+#pragma unroll
+                                    for (int j = 0; j < SPB; ++j) v8 |= gray_inv(bs[byi * SPB + j]) << (B * (SPB - 1 - j));
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) {
+                                        const uint32_t bit = byi * 8 + k;
+                                        const uint32_t v = gray_inv(bs[bit / B]);
+                                        v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
+                                    }
+                                }
+                                return v8;
+                            };
                             /* bits -> bytes and CRC-16, both lane-parallel.  The message (LEN bytes +
                              * payload) is consumed 32 bytes per round, right-aligned: lane l holds the byte
                              * that is 31-l positions from the end of the round, multiplies it by
                              * x^(8(31-l)+16) mod p (crc_k, a lane constant) in GF(2)[x], and the round is the
                              * XOR of all lanes; the running CRC enters the next round through its first two
                              * bytes (a CRC register R equals XORing R into the next two message bytes). */
-                            const uint8_t *bs = fs + p.hdr_syms;
                             const uint32_t mlen = len + 2; /* CRC'd bytes: LEN hi, LEN lo, payload */
-                            uint32_t crc = 0xFFFFu, crc_rx = 0;
+                            uint32_t crc = 0xFFFFu;
                             uint32_t done = 0;
                             uint32_t take = mlen & 31u; /* first (short) round */
                             if (take == 0) take = 32;
 #pragma unroll 1
                             while (done < mlen) {
-                                const int li = lane - (32 - (int)take);  /* index within the round */
+                                const int li = lane - (32 - (int)take); /* index within the round */
                                 uint32_t v8 = 0;
                                 if (li >= 0) {
-                                    const uint32_t mi = done + li;       /* index in the CRC'd message */
+                                    const uint32_t mi = done + li; /* index in the CRC'd message */
                                     if (mi < 2) {
                                         v8 = (mi == 0) ? (len >> 8) : (len & 0xffu);
                                     } else {
-                                        const uint32_t byi = mi - 2;     /* payload byte */
-#pragma unroll
-                                        for (int k = 0; k < 8; ++k) {
-                                            const uint32_t bit = byi * 8 + k;
-                                            const uint32_t v = gray_inv(bs[bit / B]);
-                                            v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
-                                        }
-                                        if (fits) p.bytes[boff + byi] = (uint8_t)v8;
+                                        v8 = body_byte(mi - 2);
+                                        if (fits) p.bytes[boff + mi - 2] = (uint8_t)v8;
                                     }
                                     if (li == 0) v8 ^= crc >> 8;
                                     if (li == 1) v8 ^= crc & 0xffu;
@@ -655,11 +686,7 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                                     acc = ((acc << 1) ^ ((acc & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
                                     if ((v8 >> k) & 1u) acc ^= crc_k;
                                 }
-                                acc ^= __shfl_xor_sync(FULL, acc, 16);
-                                acc ^= __shfl_xor_sync(FULL, acc, 8);
-                                acc ^= __shfl_xor_sync(FULL, acc, 4);
-                                acc ^= __shfl_xor_sync(FULL, acc, 2);
-                                acc ^= __shfl_xor_sync(FULL, acc, 1);
+                                acc = __reduce_xor_sync(FULL, acc);
                                 /* a 1-byte round has no second byte to carry the register's low byte:
                                  * R_lo * x^(8n) with n = 1 is R_lo << 8 */
                                 if (take == 1) acc ^= (crc & 0xffu) << 8;
@@ -668,19 +695,8 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                                 take = 32;
                             }
                             /* received CRC-16: the two bytes after the payload */
-                            if (lane < 2) {
-                                const uint32_t byi = len + lane;
-                                uint32_t v8 = 0;
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    const uint32_t bit = byi * 8 + k;
-                                    const uint32_t v = gray_inv(bs[bit / B]);
-                                    v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
-                                }
-                                crc_rx = v8 << (8 * (1 - lane));
-                            }
-                            crc_rx |= __shfl_xor_sync(FULL, crc_rx, 1);
-                            crc_rx = __shfl_sync(FULL, crc_rx, 0);
+                            const uint32_t rx = (lane < 2) ? (body_byte(len + lane) << (8 * (1 - lane))) : 0u;
+                            const uint32_t crc_rx = __reduce_or_sync(FULL, rx);
                             const uint32_t ok = crc == crc_rx;
                             if (fits) {
                                 if (lane == 0) {
