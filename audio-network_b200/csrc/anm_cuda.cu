@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "anm_kernels.cuh"
+#include "../../include/anmodem_pb.h"
 
 using namespace anm;
 
@@ -129,6 +130,10 @@ static void choose_launch(anm_demod *h) {
             if (eff > best + 1e-9) { best = eff; W = w; }
         }
         h->grid = sms;
+    }
+    if (const char *env = getenv("ANM_WARPS")) { /* experiment knob: force warps per CTA */
+        const uint32_t w = (uint32_t)atoi(env);
+        if (w >= 1 && w <= wmax) { W = w; h->grid = std::min<uint32_t>(sms, (h->n_ch + W - 1) / W); }
     }
     h->warps_per_cta = W;
     h->smem_bytes = (size_t)W * per_warp + h->var->cta_smem;
@@ -531,6 +536,7 @@ extern "C" void anm_tx_params_prepare(anm_tx_params_t *p, size_t n) {
 struct demod {
     anm_demod_t *h;
     std::vector<int16_t> pend; /* samples not yet forming a whole symbol period */
+    anm_pb_queue_t *pbq;       /* CRC-valid payloads handed to the protobuf decoder */
 };
 static anm_config_t g_cfg;
 static bool g_cfg_set = false;
@@ -583,5 +589,19 @@ extern "C" size_t demod_read_frames(demod_t *d, demod_frame_t *out, size_t cap) 
 extern "C" void demod_destroy(demod_t *d) {
     if (!d) return;
     anm_demod_destroy(d->h);
+    anm_pb_queue_destroy(d->pbq);
     delete d;
+}
+
+/* SURVEY.md 8(b) seam #1: the byte source pb_decode_delimited() reads, standing where
+ * network_pb_istream_from_socket() (hardware/src/network.cpp:299-305) stands today. */
+extern "C" anm_pb_istream_t demod_as_pb_istream(demod_t *d) {
+    anm_pb_istream_t none = {nullptr, nullptr, 0, "no demodulator"};
+    if (!d) return none;
+    if (!d->pbq) d->pbq = anm_pb_queue_create();
+    std::vector<uint8_t> buf(4104);
+    anm_frame_t f;
+    while (anm_demod_read_frames(d->h, &f, 1, buf.data(), buf.size()) == 1)
+        if (f.crc_ok) anm_pb_queue_push(d->pbq, buf.data(), f.len);
+    return anm_pb_istream_from_queue(d->pbq);
 }

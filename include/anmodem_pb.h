@@ -1,0 +1,70 @@
+/*
+ * anmodem_pb.h -- the hand-off from the demodulator to the reference's protobuf decoder.
+ *
+ * Reference interfaces this file stands in for / plugs into:
+ *   - struct pb_istream_s, hardware/lib/nanopb/src/pb_decode.h:28-46: the byte source
+ *     pb_decode_delimited() pulls from (callback contract at pb_decode.h:20-27: return
+ *     false on I/O error, buf == NULL means skip, state is the callee's).
+ *   - its socket-backed instance, hardware/src/network.cpp:262-305, consumed in the
+ *     receive loop at hardware/src/network.cpp:406-411.
+ * anm_pb_istream_t is layout-compatible with pb_istream_t of nanopb 0.4.5 built WITHOUT
+ * PB_BUFFER_ONLY (the reference's configuration), so a maintainer can write
+ *     pb_istream_t is; memcpy(&is, &s, sizeof is);      // or cast the pointer
+ *     pb_decode_delimited(&is, ToReceiver_fields, &msg);
+ * exactly where network_pb_istream_from_socket() is used today.
+ *
+ * The small encode/scan helpers below build and walk varint-delimited ip.proto messages
+ * (protocol/ip.proto:9-64) without nanopb; they exist so that tests and tools can make
+ * frame payloads on a machine that does not have the reference tree.  They are checked
+ * against the reference's nanopb in tests/test_pb.py.
+ */
+#ifndef ANMODEM_PB_H_INCLUDED
+#define ANMODEM_PB_H_INCLUDED
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "anmodem.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct anm_pb_istream anm_pb_istream_t;
+struct anm_pb_istream {
+    bool (*callback)(anm_pb_istream_t *stream, uint8_t *buf, size_t count);
+    void *state;
+    size_t bytes_left;
+    const char *errmsg;
+};
+
+/* A byte queue fed with CRC-valid frame payloads, drained through the stream callback. */
+typedef struct anm_pb_queue anm_pb_queue_t;
+anm_pb_queue_t *anm_pb_queue_create(void);
+void anm_pb_queue_destroy(anm_pb_queue_t *q);
+int anm_pb_queue_push(anm_pb_queue_t *q, const uint8_t *bytes, size_t len);
+size_t anm_pb_queue_size(const anm_pb_queue_t *q);
+/* stream over the queue: reading past the queued bytes fails (callback returns false),
+ * which nanopb reports as "io error"/"end-of-stream" just like a closed socket */
+anm_pb_istream_t anm_pb_istream_from_queue(anm_pb_queue_t *q);
+
+/* Firmware-idiom: moves every CRC-valid frame decoded so far by `d` into an internal queue
+ * and returns a stream over it (SURVEY.md 8(b) seam #1). */
+anm_pb_istream_t demod_as_pb_istream(demod_t *d);
+
+/* ---- minimal ip.proto wire helpers (proto2, protocol/ip.proto) ---------------------- */
+size_t anm_pb_varint(uint64_t v, uint8_t *out); /* returns bytes written (<= 10) */
+/* delimited ToReceiver{audio_data{opus_encoded_frame = data}}; returns length or 0 */
+size_t anm_pb_encode_to_receiver_audio(const uint8_t *data, size_t len, uint8_t *out, size_t cap);
+/* delimited BroadcastMessage{magic_word, discovery_request = true} */
+size_t anm_pb_encode_broadcast_request(uint32_t magic, uint8_t *out, size_t cap);
+/* Walks one delimited ToReceiver message: on success returns the total encoded length
+ * consumed and sets *payload / *payload_len to the AudioData bytes inside buf; returns 0 on
+ * malformed input (bad varint, truncated field, unknown wire type). */
+size_t anm_pb_scan_to_receiver_audio(const uint8_t *buf, size_t len, const uint8_t **payload, size_t *payload_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
