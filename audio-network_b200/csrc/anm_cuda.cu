@@ -41,12 +41,12 @@ struct Variant {
     uint32_t T, N, S;
     kern_fn fn;       /* streaming demodulator */
     kern_fn fn_trace; /* stateless tone-energy pass */
-    uint32_t warp_smem, cta_smem, state_bytes;
+    uint32_t warp_smem, cta_smem, state_bytes, rec_d_off;
 };
 
 #define VARIANT(T_, N_, S_)                                                                       \
     {T_, N_, S_, (kern_fn)k_demod<T_, N_, S_, 0>, (kern_fn)k_demod<T_, N_, S_, 1>, warp_smem_bytes<T_, N_, S_>(), \
-     cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
+     cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>(), state_rec_d_offset<T_, S_>()}
 
 const Variant kVariants[] = {
     VARIANT(4, 128, 4),  VARIANT(2, 128, 4),  VARIANT(8, 128, 4), VARIANT(16, 128, 4),
@@ -114,7 +114,7 @@ static int set_device(const anm_demod *h) {
 static void choose_launch(anm_demod *h) {
     const uint32_t per_warp = h->var->warp_smem;
     const uint32_t smem_max = 227u * 1024u - h->var->cta_smem;
-    uint32_t wmax = std::min<uint32_t>(16u, smem_max / per_warp);
+    uint32_t wmax = std::min<uint32_t>((uint32_t)kMaxWarps, smem_max / per_warp);
     if (wmax < 1) wmax = 1;
     const uint32_t sms = (uint32_t)h->num_sms;
     uint32_t W = wmax;
@@ -122,12 +122,13 @@ static void choose_launch(anm_demod *h) {
         W = std::max<uint32_t>(1u, (h->n_ch + sms - 1) / sms);
         h->grid = (h->n_ch + W - 1) / W;
     } else {
-        double best = -1.0;
+        /* passes x (latency floor + per-warp issue time): measured per-pass time grows as ~(7 + W) */
+        double best = 1e30;
         for (uint32_t w = wmax; w >= std::max<uint32_t>(1u, wmax / 2); --w) {
             const uint64_t slots = (uint64_t)sms * w;
             const uint64_t passes = (h->n_ch + slots - 1) / slots;
-            const double eff = (double)h->n_ch / (double)(passes * slots);
-            if (eff > best + 1e-9) { best = eff; W = w; }
+            const double cost = (double)passes * (7.0 + (double)w);
+            if (cost < best - 1e-9) { best = cost; W = w; }
         }
         h->grid = sms;
     }
@@ -230,7 +231,7 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
 static int init_state(const Variant *var, unsigned char *d_state, uint32_t n_ch, cudaStream_t s) {
     /* zero everything, then set the hop-decision history to 0xFF ("before the stream") */
     CK(cudaMemsetAsync(d_state, 0, (size_t)n_ch * var->state_bytes, s));
-    CK(cudaMemset2DAsync(d_state + sizeof(ChanScalars), var->state_bytes, 0xFF, 32u * var->S * 4u, n_ch, s));
+    CK(cudaMemset2DAsync(d_state + var->rec_d_off, var->state_bytes, 0xFF, 32u * var->S, n_ch, s));
     return ANM_OK;
 }
 

@@ -7,8 +7,9 @@
  * S-1 shuffles per tone per step, the preamble correlation is ballots + popc over
  * bit-planes of the hop decisions, and symbol slicing / tracking / framing are
  * lane-parallel over up to 32 symbols at a time.  PCM moves HBM -> shared memory with
- * coalesced 16-byte cp.async into an XOR-swizzled double buffer, and is read back with
- * conflict-free LDS.128.
+ * coalesced 16-byte cp.async into an XOR-swizzled stage (refilled for the next step as soon
+ * as the arithmetic of this step has consumed it), and is read back with conflict-free
+ * LDS.128.
  *
  * There is no reference kernel for any of this; the behaviour is
  * SPEC.md's, the structure is B200-first.
@@ -119,15 +120,20 @@ struct Log2 { static constexpr int v = 1 + Log2<T / 2>::v; };
 template <>
 struct Log2<1> { static constexpr int v = 0; };
 
-/* bytes of lane-distributed + carry state after ChanScalars */
+/* Per-channel state in HBM: ChanScalars | emax[32 slots][S] | d[32 slots][S] (bytes) | tree carry */
 template <int T, int S>
-__host__ __device__ constexpr uint32_t state_bytes() {
-    return (uint32_t)sizeof(ChanScalars) + 32u * S * 8u /* d (u32) + emax per lane per phase */ + (uint32_t)(S - 1) * T * 8u;
-}
+__host__ __device__ constexpr uint32_t state_rec_d_offset() { return (uint32_t)sizeof(ChanScalars) + 32u * S * 4u; }
+template <int T, int S>
+__host__ __device__ constexpr uint32_t state_carry_offset() { return state_rec_d_offset<T, S>() + ((32u * S + 15u) & ~15u); }
+template <int T, int S>
+__host__ __device__ constexpr uint32_t state_bytes() { return state_carry_offset<T, S>() + (uint32_t)(S - 1) * T * 8u; }
 template <int N>
 __host__ __device__ constexpr uint32_t stage_bytes() { return 32u * N * 2u; }
+/* Per-warp shared memory: PCM stage | emax ring[64 slots][S] | d ring[64 slots][S] | scalars | tree carry */
 template <int T, int N, int S>
-__host__ __device__ constexpr uint32_t warp_smem_bytes() { return 2u * stage_bytes<N>() + (uint32_t)(S - 1) * T * 8u; }
+__host__ __device__ constexpr uint32_t warp_smem_bytes() {
+    return stage_bytes<N>() + 64u * S * 4u + 64u * S + 128u + (uint32_t)(S - 1) * T * 8u;
+}
 /* Hops that share one pass over the twiddle table: the table holds the first 1/NQ of a symbol
  * period; hop offsets that differ by N/NQ rotate every twiddle by an exact multiple of 90 degrees. */
 template <int S>
@@ -136,10 +142,12 @@ __host__ __device__ constexpr int quad_hops() { return S >= 4 ? 4 : 2; }
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t cta_smem_bytes() { return (uint32_t)(N / quad_hops<S>()) * T * 8u; }
 
+constexpr int kMaxWarps = 19; /* 19 warps x 104 registers fill the register file; 3 passes cover 8,192 channels on 148 SMs */
+
 /* MODE 0: streaming demodulator (sync, slicing, framing; no trace output).
  * MODE 1: stateless tone-energy pass (trace outputs only; parity / debug). */
 template <int T, int N, int S, int MODE>
-__global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant__ KParams p) {
     constexpr int H = N / S;
     constexpr int B = Log2<T>::v;
     constexpr int NQ = quad_hops<S>(); /* hops per table pass */
@@ -150,6 +158,7 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
     constexpr int LV = Log2<S>::v;
     constexpr int CPH = H / 8; /* 16-byte chunks per hop */
     constexpr int CPS = N / 8; /* 16-byte chunks per symbol period */
+    constexpr uint32_t RM = 64u * S - 1u; /* record ring mask (hops) */
     constexpr uint32_t FULL = 0xffffffffu;
     static_assert(N >= 64 && (H % 8) == 0 && S >= 2, "unsupported geometry");
 
@@ -166,13 +175,14 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
     }
     const uint32_t stw = (uint32_t)__cvta_generic_to_shared(smem_raw);
     unsigned char *wsm = smem_raw + cta_smem_bytes<T, N, S>() + (size_t)wib * warp_smem_bytes<T, N, S>();
-    const uint32_t sbuf0 = (uint32_t)__cvta_generic_to_shared(wsm);
-    float2 *carry = reinterpret_cast<float2 *>(wsm + 2 * stage_bytes<N>()); /* [(S-1)*T] */
+    const uint32_t stage = (uint32_t)__cvta_generic_to_shared(wsm);
+    const uint32_t se = stage + stage_bytes<N>();   /* float emax ring [64*S] */
+    const uint32_t sd = se + 64u * S * 4u;           /* u8 d ring [64*S] */
+    ChanScalars *ssc = reinterpret_cast<ChanScalars *>(wsm + stage_bytes<N>() + 64u * S * 5u);
+    float2 *carry = reinterpret_cast<float2 *>(wsm + stage_bytes<N>() + 64u * S * 5u + 128u); /* [(S-1)*T] */
 
-    /* lane-constant pieces of the swizzled addresses */
     const uint32_t sw = lane & 7u;
-    /* cp.async: lane copies 16-byte chunk (q*32 + lane) of the step; destination slot and
-     * chunk-in-slot are lane constants up to a per-q constant */
+    /* cp.async: lane copies 16-byte chunk (q*32 + lane) of the step */
     constexpr int LPS = (CPS >= 32) ? 1 : 32 / CPS; /* symbol slots covered by one cp.async instruction */
     const uint32_t cp_slot = (CPS >= 32) ? 0u : (uint32_t)lane / (uint32_t)CPS;
     const uint32_t cp_chunk = (uint32_t)lane % (uint32_t)CPS;
@@ -189,49 +199,45 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
 
     for (uint32_t ch = blockIdx.x * wpb + wib; ch < p.n_ch; ch += total_warps) {
         unsigned char *stp = p.state + (size_t)ch * p.state_stride;
-        ChanScalars *gsc = reinterpret_cast<ChanScalars *>(stp);
-        uint32_t *grec_d = reinterpret_cast<uint32_t *>(stp + sizeof(ChanScalars));
-        float *grec_e = reinterpret_cast<float *>(stp + sizeof(ChanScalars) + 32 * S * 4);
-        float2 *gcarry = reinterpret_cast<float2 *>(stp + sizeof(ChanScalars) + 32 * S * 8);
+        float *grec_e = reinterpret_cast<float *>(stp + sizeof(ChanScalars));
+        uint8_t *grec_d = stp + state_rec_d_offset<T, S>();
+        float2 *gcarry = reinterpret_cast<float2 *>(stp + state_carry_offset<T, S>());
 
-        /* ---- restore carried state ---- */
-        uint32_t pd[S];
-        float pe[S];
+        /* ---- restore carried state: the last 32 symbol slots go to ring slots 32..63 ---- */
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            pd[i] = grec_d[i * 32 + lane];
-            pe[i] = grec_e[i * 32 + lane];
+            const float ev = grec_e[lane * S + i];
+            const uint32_t dv = grec_d[lane * S + i];
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (uint32_t)((32 + lane) * S + i) * 4u), "f"(ev) : "memory");
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + (uint32_t)((32 + lane) * S + i)), "r"(dv) : "memory");
         }
         for (int i = lane; i < (S - 1) * T; i += 32) carry[i] = gcarry[i];
-        ChanScalars sc;
-        if (MODE == 0) sc = *gsc; /* uniform loads */
+        if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = reinterpret_cast<const uint32_t *>(stp)[lane];
         __syncwarp();
 
         const char *src = reinterpret_cast<const char *>(p.pcm + (size_t)ch * p.ch_stride);
         auto issue = [&](uint32_t step) {
-            const uint32_t buf = sbuf0 + (step & 1u) * stage_bytes<N>();
             const uint32_t nv = min(32u, p.n_syms - step * 32u);
             const char *g = src + (size_t)step * (32u * N * 2u) + (size_t)lane * 16u;
             if (CPS >= 32) {
-                /* one instruction covers 512 bytes of one slot (N >= 256) */
                 constexpr uint32_t IPS = (CPS >= 32) ? CPS / 32 : 1; /* instructions per slot */
 #pragma unroll 4
                 for (uint32_t q = 0; q < (uint32_t)CPS; ++q) {
                     const uint32_t sl = q / IPS, c = (q % IPS) * 32u + lane;
-                    if (sl < nv) cp_async16(buf + sl * (2 * N) + ((c ^ (sl & 7u)) << 4), g + (size_t)q * 512u);
+                    if (sl < nv) cp_async16(stage + sl * (2 * N) + ((c ^ (sl & 7u)) << 4), g + (size_t)q * 512u);
                 }
             } else if (nv == 32u) {
 #pragma unroll
                 for (int q = 0; q < CPS; ++q) {
-                    /* slot = q*LPS + cp_slot; (slot & 7) = ((q*LPS) & 7) ^ cp_slot since LPS is a power of two > cp_slot */
                     const uint32_t sl7 = ((uint32_t)(q * LPS) & 7u) | (cp_slot & 7u);
-                    cp_async16(buf + (uint32_t)(q * LPS) * (2 * N) + cp_slot * (2 * N) + ((cp_chunk ^ sl7) << 4), g + (size_t)q * 512u);
+                    cp_async16(stage + (uint32_t)(q * LPS) * (2 * N) + cp_slot * (2 * N) + ((cp_chunk ^ sl7) << 4), g + (size_t)q * 512u);
                 }
             } else {
 #pragma unroll 4
                 for (int q = 0; q < CPS; ++q) {
                     const uint32_t sl = (uint32_t)(q * LPS) + cp_slot;
-                    if (sl < nv) cp_async16(buf + sl * (2 * N) + ((cp_chunk ^ (sl & 7u)) << 4), g + (size_t)q * 512u);
+                    if (sl < nv) cp_async16(stage + sl * (2 * N) + ((cp_chunk ^ (sl & 7u)) << 4), g + (size_t)q * 512u);
                 }
             }
             cp_async_commit();
@@ -240,17 +246,13 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
 
 #pragma unroll 1
         for (uint32_t step = 0; step < n_steps; ++step) {
-            if (step + 1 < n_steps) {
-                issue(step + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
+            cp_async_wait<0>();
             __syncwarp();
-            const uint32_t row = sbuf0 + (step & 1u) * stage_bytes<N>() + (uint32_t)lane * (2 * N);
+            const uint32_t row = stage + (uint32_t)lane * (2 * N);
             const int nvalid = (int)min(32u, p.n_syms - step * 32u);
             const bool active = lane < nvalid;
             const unsigned long long hbs = p.hop_base + (unsigned long long)step * 32u * S;
+            const uint32_t hic = step * 32u * S; /* hop index of the step start within the chunk (ring position) */
 
             /* ================= tone energies (SPEC 3) ================= */
             uint32_t dc[S];
@@ -272,7 +274,6 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                     for (int q = 0; q < NQ; ++q)
 #pragma unroll
                         for (int t = 0; t < TG; ++t) acc[q][t] = make_float2(0.f, 0.f);
-                    /* table position of this pass's first sample: pass*H; chunk index of hop q: (pass + q*GR)*CPH */
                     uint32_t twa = stw + (uint32_t)((pass * H) * T + g * TG) * 8u;
 #pragma unroll 1
                     for (int c = 0; c < TL / 8 / GR; ++c, twa += 8 * T * 8) {
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                             for (int t = 0; t < TG; t += 2) {
                                 float4 w2;
                                 asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                             : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w)
-                                             : "r"(twa + (uint32_t)(j * T + t) * 8u));
+                                    : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w)
+                                    : "r"(twa + (uint32_t)(j * T + t) * 8u));
 #pragma unroll
                                 for (int q = 0; q < NQ; ++q) {
                                     acc[q][t] = ffma2(x[q], make_float2(w2.x, w2.y), acc[q][t]);
@@ -323,7 +324,8 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                 }
                 /* ---- window tree (SPEC 3).  Each lane needs the S-1 tail values of the lane before it
                  * (lane 0: of the previous step, kept in `carry`).  With one tone group the PCM stage is
-                 * dead by now and serves as the exchange buffer; otherwise the tails travel by shuffle. */
+                 * dead by now and serves as the exchange buffer; otherwise the tails travel by shuffle.
+                 * Once the last group has consumed the stage, the next step's PCM starts streaming in. */
                 float2 pin[TG][S - 1];
                 {
                     float2 tails[TG][S - 1];
@@ -345,30 +347,23 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                     }
                     float2 *cg = carry + g * TG * (S - 1);
                     if (NG == 1) {
-                        constexpr uint32_t TB = (uint32_t)TG * (S - 1) * 8u;             /* tail bytes per lane */
-                        constexpr uint32_t XS = ((TB / 16u) & 1u) ? TB : TB + 16u;      /* odd multiple of 16: conflict-free */
+                        constexpr uint32_t TB = (uint32_t)TG * (S - 1) * 8u;         /* tail bytes per lane */
+                        constexpr uint32_t XS = ((TB / 16u) & 1u) ? TB : TB + 16u;  /* odd multiple of 16: conflict-free */
                         static_assert(33u * XS <= stage_bytes<N>(), "exchange buffer exceeds the stage");
-                        const uint32_t xb = sbuf0 + (step & 1u) * stage_bytes<N>();
                         __syncwarp(); /* every lane is done reading PCM */
                         float4 *mine = reinterpret_cast<float4 *>(&tails[0][0]);
 #pragma unroll
                         for (uint32_t k = 0; k < TB / 16u; ++k)
-                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(xb + (uint32_t)(lane + 1) * XS + k * 16u),
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage + (uint32_t)(lane + 1) * XS + k * 16u),
                                          "f"(mine[k].x), "f"(mine[k].y), "f"(mine[k].z), "f"(mine[k].w) : "memory");
                         __syncwarp();
-                        const uint32_t rsrc = (lane == 0) ? (uint32_t)__cvta_generic_to_shared(cg) : xb + (uint32_t)lane * XS;
+                        const uint32_t rsrc = (lane == 0) ? (uint32_t)__cvta_generic_to_shared(cg) : stage + (uint32_t)lane * XS;
                         float4 *pv = reinterpret_cast<float4 *>(&pin[0][0]);
 #pragma unroll
                         for (uint32_t k = 0; k < TB / 16u; ++k)
                             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv[k].x), "=f"(pv[k].y), "=f"(pv[k].z), "=f"(pv[k].w)
                                          : "r"(rsrc + k * 16u) : "memory");
-                        __syncwarp(); /* lane 0 has read the old carry before it is replaced */
-                        if (lane == nvalid - 1) {
-#pragma unroll
-                            for (int t = 0; t < TG; ++t)
-#pragma unroll
-                                for (int k = 0; k < S - 1; ++k) cg[t * (S - 1) + k] = tails[t][k];
-                        }
+                        __syncwarp(); /* exchange buffer and old carry consumed */
                     } else {
 #pragma unroll
                         for (int t = 0; t < TG; ++t)
@@ -379,13 +374,14 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                                 pin[t][k] = (lane == 0) ? c0 : sh;
                             }
                         __syncwarp();
-                        if (lane == nvalid - 1) {
-#pragma unroll
-                            for (int t = 0; t < TG; ++t)
-#pragma unroll
-                                for (int k = 0; k < S - 1; ++k) cg[t * (S - 1) + k] = tails[t][k];
-                        }
                     }
+                    if (lane == nvalid - 1) {
+#pragma unroll
+                        for (int t = 0; t < TG; ++t)
+#pragma unroll
+                            for (int k = 0; k < S - 1; ++k) cg[t * (S - 1) + k] = tails[t][k];
+                    }
+                    if (g == NG - 1 && step + 1 < n_steps) issue(step + 1);
                 }
 #pragma unroll
                 for (int t = 0; t < TG; ++t) {
@@ -419,6 +415,17 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
 #pragma unroll
                 for (int i = 0; i < S; ++i) { dc[i] = 0xFFu; ec[i] = 0.0f; }
             }
+            /* publish this step's hop records in the ring (slots of lanes past a ragged end keep their
+             * older content: they are never addressed) */
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const uint32_t idx = (hic + (uint32_t)(lane * S + i)) & RM;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + idx * 4u), "f"(ec[i]) : "memory");
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + idx), "r"(dc[i]) : "memory");
+                }
+            }
+            __syncwarp();
             if (MODE == 1) {
                 if (p.trD && active) {
 #pragma unroll
@@ -432,31 +439,18 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
 
             /* ================= sync / slicing / framing (SPEC 5) ================= */
             if (MODE == 0) {
-                /* The PCM stage of this step is dead: publish the hop records of the previous and the
-                 * current step there, indexed by hop relative to the step start (r in [-32S, 32S)), so
-                 * that every later look-up is one LDS. */
-                const uint32_t se = sbuf0 + (step & 1u) * stage_bytes<N>(); /* float emax[64*S] */
-                const uint32_t sd = se + 64u * S * 4u;                        /* u8    d[64*S]   */
-                static_assert(64u * S * 5u <= stage_bytes<N>(), "record scratch exceeds the stage");
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < S; ++i) {
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (uint32_t)(lane * S + i) * 4u), "f"(pe[i]) : "memory");
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (uint32_t)((32 + lane) * S + i) * 4u), "f"(ec[i]) : "memory");
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + (uint32_t)(lane * S + i)), "r"(pd[i] & 0xffu) : "memory");
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + (uint32_t)((32 + lane) * S + i)), "r"(dc[i] & 0xffu) : "memory");
-                }
-                __syncwarp();
+                /* hop records by hop index r relative to the step start, r in [-32S, 32S) */
                 auto RD = [&](int r) -> uint32_t {
                     uint32_t v;
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sd + (uint32_t)(r + 32 * S)) : "memory");
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sd + ((hic + (uint32_t)r) & RM)) : "memory");
                     return v;
                 };
                 auto RE = [&](int r) -> float {
                     float v;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(se + (uint32_t)(r + 32 * S) * 4u) : "memory");
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(se + ((hic + (uint32_t)r) & RM) * 4u) : "memory");
                     return v;
                 };
+                ChanScalars sc = *ssc; /* warp-uniform broadcast loads */
                 const int endh = nvalid * S;
                 int cur = 0;
                 bool have_cand = false;
@@ -484,11 +478,12 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                             const uint32_t pmask = (p.P >= 32) ? 0xffffffffu : ((1u << p.P) - 1u);
 #pragma unroll
                             for (int i = 0; i < S; ++i) {
+                                const uint32_t dprev = RD((lane - 32) * S + i); /* same lane, previous step */
                                 uint32_t mism = 0;
 #pragma unroll
                                 for (int j = 0; j <= B; ++j) {
                                     const uint32_t bc = (j < B) ? ((dc[i] >> j) & 1u) : (dc[i] > (uint32_t)(T - 1));
-                                    const uint32_t bp = (j < B) ? ((pd[i] >> j) & 1u) : (pd[i] > (uint32_t)(T - 1));
+                                    const uint32_t bp = (j < B) ? ((dprev >> j) & 1u) : (dprev > (uint32_t)(T - 1));
                                     const unsigned long long hist = ((unsigned long long)__ballot_sync(FULL, bc) << 32) | __ballot_sync(FULL, bp);
                                     const uint32_t w = (uint32_t)(hist >> sh);
                                     mism |= (j < B) ? (w ^ p.pre_plane[j]) : w;
@@ -716,32 +711,26 @@ __global__ void __launch_bounds__(512) k_demod(const __grid_constant__ KParams p
                         }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) *ssc = sc;
+                __syncwarp();
             }
-
-            /* ---- this step's records become the history of the next ---- */
-            if (nvalid == 32) {
-#pragma unroll
-                for (int i = 0; i < S; ++i) { pd[i] = dc[i]; pe[i] = ec[i]; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < S; ++i) {
-                    const uint32_t a = __shfl_sync(FULL, pd[i], (lane + nvalid) & 31), b = __shfl_sync(FULL, dc[i], (lane + nvalid) & 31);
-                    const float fa = __shfl_sync(FULL, pe[i], (lane + nvalid) & 31), fb = __shfl_sync(FULL, ec[i], (lane + nvalid) & 31);
-                    pd[i] = (lane < 32 - nvalid) ? a : b;
-                    pe[i] = (lane < 32 - nvalid) ? fa : fb;
-                }
-            }
-            __syncwarp();
         }
 
-        /* ---- save carried state ---- */
+        /* ---- save carried state: the last 32 symbol slots of the chunk ---- */
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            grec_d[i * 32 + lane] = pd[i];
-            grec_e[i * 32 + lane] = pe[i];
+            const uint32_t idx = ((p.n_syms - 32u + (uint32_t)lane) * S + (uint32_t)i) & RM;
+            float ev;
+            uint32_t dv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ev) : "r"(se + idx * 4u) : "memory");
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(dv) : "r"(sd + idx) : "memory");
+            grec_e[lane * S + i] = ev;
+            grec_d[lane * S + i] = (uint8_t)dv;
         }
         for (int i = lane; i < (S - 1) * T; i += 32) gcarry[i] = carry[i];
-        if (MODE == 0 && lane == 0) *gsc = sc;
+        if (MODE == 0) reinterpret_cast<uint32_t *>(stp)[lane] = reinterpret_cast<const uint32_t *>(ssc)[lane];
         __syncwarp();
     }
 }
