@@ -102,8 +102,12 @@ struct anm_demod {
  * sample position advances by N/4 (anm_twiddles builds the table with exactly this symmetry) */
 static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
     k->tw_rot[0] = k->tw_rot[1] = 0;
-    for (uint32_t t = 0; t < cfg->n_tones; ++t)
+    uint32_t any = 0;
+    for (uint32_t t = 0; t < cfg->n_tones; ++t) {
         k->tw_rot[t >> 5] |= (unsigned long long)(cfg->tone_bin[t] & 3u) << (2 * (t & 31));
+        any |= cfg->tone_bin[t] & 3u;
+    }
+    k->rot_mode = (any == 0) ? 0u : ((any & 1u) ? 2u : 1u);
 }
 
 static int set_device(const anm_demod *h) {

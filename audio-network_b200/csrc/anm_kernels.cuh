@@ -46,7 +46,7 @@ struct KParams {
     unsigned long long hop_base;  /* absolute index of the chunk's first hop */
     unsigned char *state;         /* per channel: ChanScalars | lane records | tree carry */
     uint32_t state_stride;        /* bytes */
-    uint32_t pad0;
+    uint32_t rot_mode;            /* 0: all tone bins = 0 mod 4; 1: all bins even; 2: general */
     uint8_t *fsyms;               /* per channel frame symbol store */
     uint32_t fsym_stride;
     uint32_t max_frame_syms;
@@ -305,20 +305,43 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                             }
                         }
                     }
-                    /* rotate hop q by (-j)^(bin*q*4/NQ): exact swap / negate (SPEC 3, table symmetry) */
+                    /* rotate hop q by (-j)^(bin*q*4/NQ): exact swap / negate (SPEC 3, table symmetry).
+                     * rot_mode 0: every rotation is the identity; 1: all bins even, sign flips only. */
                     const unsigned long long rots = (g * TG < 32) ? (p.tw_rot[0] >> (2 * g * TG)) : (p.tw_rot[1] >> (2 * (g * TG - 32)));
+                    if (p.rot_mode == 0u) {
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
+                        for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                        for (int t = 0; t < TG; ++t) {
-                            const uint32_t r = (((uint32_t)(rots >> (2 * t)) & 3u) * (uint32_t)(q * (4 / NQ))) & 3u;
-                            const float a = acc[q][t].x, b2 = acc[q][t].y;
-                            const float ni = (r & 1u) ? b2 : a;  /* r=1: I=-Q', r=3: I=Q' */
-                            const float nq = (r & 1u) ? a : b2;  /* r=1: Q=I',  r=3: Q=-I' */
-                            const uint32_t sI = (r == 1u || r == 2u) ? 0x80000000u : 0u;
-                            const uint32_t sQ = (r == 2u || r == 3u) ? 0x80000000u : 0u;
-                            Pp[pass + q * GR][t] = make_float2(__uint_as_float(__float_as_uint(ni) ^ sI),
-                                                               __uint_as_float(__float_as_uint(nq) ^ sQ));
+                            for (int t = 0; t < TG; ++t) Pp[pass + q * GR][t] = acc[q][t];
+                    } else if (p.rot_mode == 1u) {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+                            for (int t = 0; t < TG; ++t) {
+                                /* bins even: r = (bin mod 4) * m mod 4 with m = q*4/NQ is 2 iff m is odd and bin = 2 mod 4 */
+                                if (((q * (4 / NQ)) & 1) == 0) {
+                                    Pp[pass + q * GR][t] = acc[q][t];
+                                } else {
+                                    const uint32_t mk = (((uint32_t)(rots >> (2 * t)) & 2u) != 0u) ? 0x80000000u : 0u;
+                                    Pp[pass + q * GR][t] = make_float2(__uint_as_float(__float_as_uint(acc[q][t].x) ^ mk),
+                                                                       __uint_as_float(__float_as_uint(acc[q][t].y) ^ mk));
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+                            for (int t = 0; t < TG; ++t) {
+                                const uint32_t r = (((uint32_t)(rots >> (2 * t)) & 3u) * (uint32_t)(q * (4 / NQ))) & 3u;
+                                const float a = acc[q][t].x, b2 = acc[q][t].y;
+                                const float ni = (r & 1u) ? b2 : a;  /* r=1: I=-Q', r=3: I=Q' */
+                                const float nq = (r & 1u) ? a : b2;  /* r=1: Q=I',  r=3: Q=-I' */
+                                const uint32_t sI = (r == 1u || r == 2u) ? 0x80000000u : 0u;
+                                const uint32_t sQ = (r == 2u || r == 3u) ? 0x80000000u : 0u;
+                                Pp[pass + q * GR][t] = make_float2(__uint_as_float(__float_as_uint(ni) ^ sI),
+                                                                   __uint_as_float(__float_as_uint(nq) ^ sQ));
+                            }
                         }
                     }
                 }
