@@ -99,6 +99,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
     return v;
 }
 
+/* int16 half HI of a packed word -> fp32 in one instruction (I2F.S16 Rd, Rs.H0/.H1) */
+template <int HI>
+__device__ __forceinline__ float cvt_s16(uint32_t w) {
+    float f;
+    if (HI) asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, hi; }" : "=f"(f) : "r"(w));
+    else asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, lo; }" : "=f"(f) : "r"(w));
+    return f;
+}
+
 /* select element ph (warp-uniform, runtime) of a register array without local memory */
 template <int S, typename V>
 __device__ __forceinline__ V pick(const V (&r)[S], int ph) {
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 #pragma unroll
                             for (int q = 0; q < NQ; ++q) {
                                 const uint32_t w = (j < 2) ? v[q].x : (j < 4) ? v[q].y : (j < 6) ? v[q].z : v[q].w;
-                                x[q] = (j & 1) ? (float)((int)w >> 16) : (float)(short)(w & 0xffffu);
+                                x[q] = (j & 1) ? cvt_s16<1>(w) : cvt_s16<0>(w);
                             }
 #pragma unroll
                             for (int t = 0; t < TG; t += 2) {
