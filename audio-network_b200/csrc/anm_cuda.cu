@@ -335,8 +335,11 @@ extern "C" int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t 
     }
     cudaStream_t s = h->own_stream;
     if (h->last_stream != s) CK(cudaStreamSynchronize(h->last_stream));
-    CK(cudaMemcpy2DAsync(h->d_stage, n_samples * 2, h_pcm, ch_stride * 2, n_samples * 2, h->n_ch,
-                         cudaMemcpyHostToDevice, s));
+    if (ch_stride == n_samples)
+        CK(cudaMemcpyAsync(h->d_stage, h_pcm, need * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    else
+        CK(cudaMemcpy2DAsync(h->d_stage, n_samples * 2, h_pcm, ch_stride * 2, n_samples * 2, h->n_ch,
+                             cudaMemcpyHostToDevice, s));
     int rc = anm_demod_feed_device(h, h->d_stage, n_samples, n_samples, s);
     if (rc) return rc;
     CK(cudaStreamSynchronize(s));

@@ -39,7 +39,7 @@ METRIC = "demodulated Msamples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=CH_PER_GPU, help="channels per GPU")
@@ -48,6 +48,16 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-channels", type=int, default=0, help="channels in the CPU sample (0 = 4 per core)")
     return ap.parse_args()
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "r1_k_demod_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+    return None
 
 
 def peaks():
@@ -113,26 +123,35 @@ class NvmlSampler:
             self.err = repr(e)
 
     def start(self):
+        """Starts polling (call well before the timed region: the first NVML calls are slow)."""
         if not self.ok:
             return
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
 
+    def mark(self):
+        return time.perf_counter()
+
     def _run(self):
         nv = self.nv
         while not self.stop_flag:
             try:
-                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+                c = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((time.perf_counter(), c, r))
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(0.0005)
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
         self.stop_flag = True
         self.t.join(timeout=1)
+        rows = [(c, r) for (t, c, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)]
+        if not rows:   # region shorter than one poll: take the samples closest to it
+            rows = [(c, r) for (t, c, r) in self.rows[-3:]]
+        self.rows = rows
         nv = self.nv
         names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                  "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
@@ -220,7 +239,7 @@ def reference_arm(args):
         return
     cfg = anm.config_preset(args.preset)
     cores = os.cpu_count() or 1
-    n_ch = args.cpu_channels or min(cores * 64, CH_PER_GPU)
+    n_ch = args.cpu_channels or min(cores * 128, CH_PER_GPU)
     n = CHUNK_SYMS * cfg.sym_len
     progs, lens, params = build_programs(cfg, anm, n_ch, 0)
     steps_total = args.warmup + args.steps
@@ -307,24 +326,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = NvmlSampler(local)
+    if not sampler.ok:
+        sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
     dm.collect()
     dm.read_frames()
     dm.kernel_time()
     l0 = dm.launch_count()
-    sampler = NvmlSampler(local)
-    if not sampler.ok:
-        sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    t_mark0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    t_mark1 = time.perf_counter()
+    clocks = sampler.stop(t_mark0, t_mark1) if isinstance(sampler, NvmlSampler) else sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = dm.launch_count() - l0
     k_ms, k_n = dm.kernel_time()
@@ -399,7 +420,7 @@ def main():
             "frames_ok": int(agg[1].item()),
             "gpu_launches": int(agg[2].item()),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic() if (n_ch == CH_PER_GPU and args.preset == "ref4") else None, "peak_source": peak_src,
                          "kernel": "k_demod<%d,%d,%d>" % (cfg.n_tones, cfg.sym_len, cfg.hops_per_sym),
                          "avg_kernel_ms": round(avg_ms, 4), "launches_timed": k_n,
                          "algorithmic_bytes_per_launch": per_launch_bytes},
