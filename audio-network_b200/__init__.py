@@ -106,7 +106,7 @@ EXPORTS = [
     "anm_frame_num_symbols", "anm_frame_symbols", "anm_tx_render", "anm_tx_render_device",
     "anm_tone_energies_device", "anm_demod_create", "anm_demod_destroy", "anm_demod_reset",
     "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_collect", "anm_demod_read_frames",
-    "anm_demod_read_symbols", "anm_demod_stats", "anm_demod_launch_count", "anm_demod_last_kernel_ms",
+    "anm_demod_read_symbols", "anm_demod_stats", "anm_demod_launch_count", "anm_demod_overflowed", "anm_demod_last_kernel_ms",
     "anm_last_error", "anm_version", "demod_initialize", "demod_create", "demod_feed",
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
 ]
@@ -146,6 +146,7 @@ def lib():
         "anm_demod_read_symbols": (C.c_size_t, [vp, C.c_uint32, vp, C.c_size_t]),
         "anm_demod_stats": (C.c_int, [vp, vp]),
         "anm_demod_launch_count": (C.c_uint64, [vp]),
+        "anm_demod_overflowed": (C.c_int, [vp]),
         "anm_demod_last_kernel_ms": (C.c_float, [vp]),
         "anm_demod_kernel_time": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "anm_demod_launch_geometry": (C.c_int, [vp, u32p, u32p, u32p]),
@@ -303,6 +304,9 @@ class Demod:
         out = np.zeros(self.n_channels, dtype=STATS_DTYPE)
         _check(lib().anm_demod_stats(self._h, _ptr(out)))
         return out
+
+    def overflowed(self):
+        return bool(lib().anm_demod_overflowed(self._h))
 
     def launch_count(self):
         return int(lib().anm_demod_launch_count(self._h))

@@ -175,8 +175,10 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     const uint32_t hdr_syms = (24 + b - 1) / b;
     h->max_frame_syms = hdr_syms + ((cfg->max_payload + 2) * 8 + b - 1) / b;
     h->fsym_stride = (h->max_frame_syms + 63u) & ~63u;
-    h->frames_cap = std::max<uint32_t>(4096u, n_channels * 32u);
-    h->bytes_cap = std::max<uint32_t>(1u << 20, n_channels * 2048u);
+    /* frames / payload bytes that may accumulate between two collects (about 2 minutes of back-to-back
+     * short frames per channel); overflow drops frames and is reported by anm_demod_overflowed() */
+    h->frames_cap = (uint32_t)std::min<uint64_t>(1ull << 24, std::max<uint64_t>(4096u, (uint64_t)n_channels * 256u));
+    h->bytes_cap = (uint32_t)std::min<uint64_t>(1ull << 30, std::max<uint64_t>(1u << 20, (uint64_t)n_channels * 16384u));
     h->osym_cap = (flags & ANM_FLAG_SYMBOLS) ? 4096u : 0u;
     CK(cudaMalloc(&h->d_state, (size_t)n_channels * var->state_bytes));
     CK(cudaMalloc(&h->d_fsyms, (size_t)n_channels * h->fsym_stride));
@@ -444,6 +446,9 @@ extern "C" int anm_demod_stats(anm_demod_t *h, anm_chan_stats_t *out) {
 }
 
 extern "C" uint64_t anm_demod_launch_count(const anm_demod_t *h) { return h ? h->launches : 0; }
+
+/* 1 if a frame/symbol queue overflowed since create/reset (frames were dropped) */
+extern "C" int anm_demod_overflowed(const anm_demod_t *h) { return h ? h->overflow : 0; }
 
 /* sums the device time of the kernels launched since the last call (at most 64 are
  * tracked between calls); returns the number of launches summed */

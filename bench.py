@@ -333,7 +333,7 @@ def main():
     for i in range(args.warmup):
         step(i)
     dm.collect()
-    dm.read_frames()
+    dm.read_frames(cap=1 << 22, bytes_cap=1 << 28)   # drop the warm-up's frames
     dm.kernel_time()
     l0 = dm.launch_count()
     barrier()
@@ -350,7 +350,8 @@ def main():
     launches = dm.launch_count() - l0
     k_ms, k_n = dm.kernel_time()
     dm.collect()
-    recs, by = dm.read_frames(cap=1 << 22, bytes_cap=1 << 28)
+    recs, by = dm.read_frames(cap=1 << 22, bytes_cap=1 << 30)
+    assert not dm.overflowed(), "frame queue overflowed inside the timed region: use fewer --steps"
     bits_ok = int(recs["len"][recs["crc_ok"] == 1].sum()) * 8
     frames_ok = int((recs["crc_ok"] == 1).sum())
 
@@ -374,7 +375,7 @@ def main():
         dm2 = anm.Demod(cfg, n_ch, device=local)
         dm2.feed_host_ptr(host[0].data_ptr(), chunk, chunk)   # warm-up (allocates the staging buffer)
         dm2.collect()
-        dm2.read_frames()
+        dm2.read_frames(cap=1 << 20, bytes_cap=1 << 26)
         barrier()
         t0 = time.perf_counter()
         d2h = 0

@@ -155,11 +155,21 @@ size_t anm_demod_read_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8
 /* Pops up to cap decided symbols (tone indices) of one channel. */
 size_t anm_demod_read_symbols(anm_demod_t *h, uint32_t channel, uint8_t *out, size_t cap);
 int anm_demod_stats(anm_demod_t *h, anm_chan_stats_t *out /*[n_channels]*/);
+/* 1 if an output queue overflowed since create/reset: frames or symbols were dropped.  Queues hold
+ * 256 frames / 16 KiB of payload per channel between two collects. */
+int anm_demod_overflowed(const anm_demod_t *h);
 /* number of kernels this handle has launched (bench.py's gpu_launches) */
 uint64_t anm_demod_launch_count(const anm_demod_t *h);
 /* duration in ms of the most recent feed's kernel, measured with CUDA events on
  * the launching stream (waits for it). */
 float anm_demod_last_kernel_ms(anm_demod_t *h);
+/* Sums the device time (ms, CUDA events on the launching stream) of the kernels launched since the
+ * previous call (at most 64 are tracked between calls); returns the number of launches summed. */
+int anm_demod_kernel_time(anm_demod_t *h, float *sum_ms);
+/* persistent-grid geometry chosen for this handle */
+int anm_demod_launch_geometry(const anm_demod_t *h, uint32_t *grid, uint32_t *warps_per_cta, uint32_t *smem_bytes);
+/* fills anm_tx_params_t.reserved with the Q20 noise scale anm_tx_render_device reads */
+void anm_tx_params_prepare(anm_tx_params_t *p, size_t n);
 const char *anm_last_error(void);
 const char *anm_version(void);
 
