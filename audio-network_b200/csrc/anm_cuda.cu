@@ -108,6 +108,12 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
         any |= cfg->tone_bin[t] & 3u;
     }
     k->rot_mode = (any == 0) ? 0u : ((any & 1u) ? 2u : 1u);
+    /* CRC-16 lane constants of the lane-parallel frame check: x^(8(31-lane)+16) mod 0x11021 */
+    for (int lane = 0; lane < 32; ++lane) {
+        uint32_t v = 1;
+        for (int i = 0; i < 8 * (31 - lane) + 16; ++i) v = ((v << 1) ^ ((v & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
+        k->crc_pow[lane] = (uint16_t)v;
+    }
 }
 
 static int set_device(const anm_demod *h) {

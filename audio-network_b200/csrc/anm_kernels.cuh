@@ -65,6 +65,7 @@ struct KParams {
     uint8_t preamble[ANM_MAX_PREAMBLE];
     const float2 *tw_global;      /* [N][T] (cos, sin) twiddle table in HBM; its first N/NQ rows are staged per CTA */
     unsigned long long tw_rot[2];  /* 2 bits per tone: tone_bin mod 4 (quarter-period rotation code) */
+    uint16_t crc_pow[32];          /* x^(8(31-lane)+16) mod the CRC-16 polynomial, per lane */
 };
 
 __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
@@ -197,11 +198,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     const uint32_t cp_chunk = (uint32_t)lane % (uint32_t)CPS;
 
     /* CRC-16 lane constant: x^(8(31-lane)+16) mod p (see frame assembly) */
-    uint32_t crc_k = 1;
-    if (MODE == 0) {
-        const int nsh = 8 * (31 - lane) + 16;
-        for (int i = 0; i < nsh; ++i) crc_k = ((crc_k << 1) ^ ((crc_k & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
-    }
+    const uint32_t crc_k = (MODE == 0) ? (uint32_t)p.crc_pow[lane] : 0u; /* computed once on the host */
 
     const uint32_t n_steps = (p.n_syms + 31u) / 32u;
     const uint32_t total_warps = gridDim.x * wpb;
@@ -286,11 +283,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                     uint32_t twa = stw + (uint32_t)((pass * H) * T + g * TG) * 8u;
 #pragma unroll 1
                     for (int c = 0; c < TL / 8 / GR; ++c, twa += 8 * T * 8) {
+                        /* swizzled chunk address ((hop*CPH + c) ^ sw) << 4, split into a loop-invariant hop
+                         * part and a per-iteration chunk part (the XOR never carries between them) */
+                        constexpr uint32_t LOWM = (uint32_t)(CPH - 1) & 7u;
+                        const uint32_t cpart = (((uint32_t)c ^ (sw & LOWM))) << 4;
                         uint4 v[NQ];
 #pragma unroll
                         for (int q = 0; q < NQ; ++q) {
-                            const uint32_t cc = (uint32_t)((pass + q * GR) * CPH + c);
-                            v[q] = lds128(row + ((cc ^ sw) << 4));
+                            const uint32_t hpart = row + ((((uint32_t)((pass + q * GR) * CPH)) ^ (sw & 7u & ~LOWM)) << 4);
+                            v[q] = lds128(hpart + cpart);
                         }
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -450,11 +451,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
             /* publish this step's hop records in the ring (slots of lanes past a ragged end keep their
              * older content: they are never addressed) */
             if (active) {
+                const uint32_t idx0 = (hic + (uint32_t)(lane * S)) & RM; /* S consecutive, S-aligned ring entries */
+                if (S == 4) {
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(se + idx0 * 4u), "f"(ec[0]), "f"(ec[1]), "f"(ec[2 % S]), "f"(ec[3 % S]) : "memory");
+                    const uint32_t pk = (dc[0] & 0xffu) | ((dc[1] & 0xffu) << 8) | ((dc[2 % S] & 0xffu) << 16) | (dc[3 % S] << 24);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sd + idx0), "r"(pk) : "memory");
+                } else {
 #pragma unroll
-                for (int i = 0; i < S; ++i) {
-                    const uint32_t idx = (hic + (uint32_t)(lane * S + i)) & RM;
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + idx * 4u), "f"(ec[i]) : "memory");
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + idx), "r"(dc[i]) : "memory");
+                    for (int i = 0; i < S; ++i) {
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (idx0 + i) * 4u), "f"(ec[i]) : "memory");
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + idx0 + i), "r"(dc[i]) : "memory");
+                    }
                 }
             }
             __syncwarp();
@@ -596,7 +603,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                         const uint32_t be = __ballot_sync(FULL, voter && (sjm != sj) && ve > e_on);
                         /* tracker epochs inside the run: only an actual timing move ends the run early */
                         int adj = 0;
-                        {
+                        if ((bl | be) == 0u && sc.acc < (int)p.trk_thresh && sc.acc > -(int)p.trk_thresh) {
+                            /* no vote in this run and the carried sum cannot trip: epochs just tick over */
+                            if (cnt < sc.ep_left) {
+                                sc.ep_left -= cnt;
+                            } else {
+                                uint32_t rem = cnt - sc.ep_left;
+                                while (rem >= p.trk_epoch) rem -= p.trk_epoch;
+                                sc.ep_left = p.trk_epoch - rem;
+                                sc.acc = 0;
+                            }
+                        } else {
                             const uint32_t s0 = (uint32_t)(first >> LV);
                             uint32_t pos = 0;
                             while (true) {
