@@ -300,3 +300,84 @@ def test_pb_istream_seam_on_gpu_frames():
     assert bytes(got) == total
     assert not s.callback(C.addressof(s), got, 1)   # drained: fails like a closed socket
     L.demod_destroy(d)
+
+
+def _gpu_render(cfg, progs, lens, params, n, first=0):
+    torch = _torch()
+    n_ch = progs.shape[0]
+    d_prog = torch.from_numpy(progs).cuda()
+    d_len = torch.from_numpy(lens.astype(np.int32)).cuda()
+    d_par = torch.from_numpy(params.view(np.uint8).copy()).cuda()
+    d_pcm = torch.empty((n_ch, n), dtype=torch.int16, device="cuda")
+    anm.tx_render_device(cfg, d_prog.data_ptr(), progs.shape[1], d_len.data_ptr(), d_par.data_ptr(), n_ch, first, d_pcm.data_ptr(), n, n)
+    torch.cuda.synchronize()
+    return d_pcm
+
+
+def _programs(cfg, n_ch, seed, snr_db, ppm_max, offset_max, payload=(8, 64), max_len=1024):
+    from sigutil import make_program
+
+    progs = np.full((n_ch, max_len), anm.ANM_SILENCE, dtype=np.uint8)
+    lens = np.zeros(n_ch, dtype=np.int32)
+    plist = []
+    rng = np.random.default_rng(seed)
+    for c in range(n_ch):
+        prog, _ = make_program(cfg, rng, max_len // 2, payload_len=payload, gap=(2, 30))
+        prog = prog[:max_len]
+        progs[c, : len(prog)] = prog
+        lens[c] = len(prog)
+        plist.append(anm.tx_params(seed=seed * 7919 + c, start_offset=-int(rng.integers(0, offset_max + 1)), amplitude=0.5,
+                                   snr_db=snr_db if not callable(snr_db) else snr_db(c),
+                                   ppm=float(rng.uniform(-ppm_max, ppm_max)) if ppm_max else 0.0))
+    return progs, lens, anm.tx_params_array(plist)
+
+
+def test_config2_1024_channels_10s_clean_bit_exact():
+    """BASELINE.json configs[1]: 1,024 channels x 10 s (3,445 symbol periods = 440,960 samples) of clean FSK
+    at the reference tone set on one B200; every frame and CRC verdict equals the oracle's (compared through
+    the order-independent digest of oracle/anm_oracle_batch.c, plus exact counts)."""
+    import os
+
+    from oracle_binding import frames_digest, run_batch
+
+    torch = _torch()
+    cfg = anm.config_preset("ref4")
+    n_ch, n = 1024, 3445 * cfg.sym_len
+    progs, lens, params = _programs(cfg, n_ch, seed=101, snr_db=None, ppm_max=0.0, offset_max=3000)
+    d_pcm = _gpu_render(cfg, progs, lens, params, n)
+    dm = anm.Demod(cfg, n_ch, device=0)
+    chunk = 345 * cfg.sym_len
+    pos = 0
+    while pos < n:
+        ln = min(chunk, n - pos)
+        dm.feed_device(d_pcm.data_ptr() + pos * 2, n, ln, torch.cuda.current_stream().cuda_stream)
+        pos += ln
+    dm.collect()
+    frames = anm.frames_to_list(*dm.read_frames(cap=1 << 20, bytes_cap=1 << 26))
+    assert not dm.overflowed()
+    dm.close()
+    pcm = d_pcm.cpu().numpy()
+    sec, ok, bad, nbytes, dg = run_batch(cfg, pcm, os.cpu_count() or 1)
+    assert len(frames) == ok + bad and ok > 15 * n_ch and bad == 0
+    assert sum(f[2] for f in frames) == ok
+    assert sum(len(f[3]) for f in frames if f[2]) == nbytes
+    assert frames_digest(frames) == dg
+
+
+def test_config5_low_snr_drift_sweep_bit_exact():
+    """BASELINE.json configs[4]: 0-3 dB SNR, +/-200 ppm clock error, random frame offsets.  Bit-exact against the
+    oracle channel by channel; detection and CRC-pass rates are printed for the record."""
+    torch = _torch()
+    cfg = anm.config_preset("ref4")
+    n_ch, n = 128, 1500 * cfg.sym_len
+    progs, lens, params = _programs(cfg, n_ch, seed=55, snr_db=lambda c: float(c % 4), ppm_max=200.0, offset_max=5000, payload=(16, 200))
+    d_pcm = _gpu_render(cfg, progs, lens, params, n)
+    pcm = d_pcm.cpu().numpy()
+    frames = _check_against_oracle(cfg, pcm, [211, 64])
+    by_snr = {}
+    for ch, _s, ok, _p in frames:
+        k = ch % 4
+        a, b = by_snr.get(k, (0, 0))
+        by_snr[k] = (a + 1, b + ok)
+    print("config5 frames detected / CRC ok by SNR dB:", by_snr)
+    assert all(b >= 0.9 * a and a > 0 for a, b in by_snr.values())
