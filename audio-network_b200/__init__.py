@@ -105,7 +105,8 @@ EXPORTS = [
     "anm_config_preset", "anm_config_validate", "anm_twiddles", "anm_crc16", "anm_crc8",
     "anm_frame_num_symbols", "anm_frame_symbols", "anm_tx_render", "anm_tx_render_device",
     "anm_tone_energies_device", "anm_demod_create", "anm_demod_destroy", "anm_demod_reset",
-    "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_collect", "anm_demod_read_frames",
+    "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_feed_host_async", "anm_demod_wait_input",
+    "anm_demod_collect", "anm_demod_collect_upto", "anm_demod_read_frames",
     "anm_demod_read_symbols", "anm_demod_stats", "anm_demod_launch_count", "anm_demod_overflowed", "anm_demod_last_kernel_ms",
     "anm_last_error", "anm_version", "demod_initialize", "demod_create", "demod_feed",
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
@@ -141,6 +142,9 @@ def lib():
         "anm_demod_reset": (C.c_int, [vp]),
         "anm_demod_feed_device": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp]),
         "anm_demod_feed_host": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
+        "anm_demod_feed_host_async": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
+        "anm_demod_wait_input": (C.c_int, [vp]),
+        "anm_demod_collect_upto": (C.c_long, [vp, C.c_uint32]),
         "anm_demod_collect": (C.c_long, [vp]),
         "anm_demod_read_frames": (C.c_size_t, [vp, vp, C.c_size_t, vp, C.c_size_t]),
         "anm_demod_read_symbols": (C.c_size_t, [vp, C.c_uint32, vp, C.c_size_t]),
@@ -282,6 +286,16 @@ class Demod:
 
     def feed_host_ptr(self, ptr, ch_stride, n_samples):
         _check(lib().anm_demod_feed_host(self._h, ptr, ch_stride, n_samples))
+
+    def feed_host_async_ptr(self, ptr, ch_stride, n_samples):
+        """Enqueue copy + kernel and return; the host buffer must stay untouched until wait_input()."""
+        _check(lib().anm_demod_feed_host_async(self._h, ptr, ch_stride, n_samples))
+
+    def wait_input(self):
+        _check(lib().anm_demod_wait_input(self._h))
+
+    def collect_upto(self, lag):
+        return _check(lib().anm_demod_collect_upto(self._h, lag))
 
     def collect(self):
         return _check(lib().anm_demod_collect(self._h))

@@ -63,6 +63,14 @@ struct EvPair {
     cudaEvent_t a, b;
 };
 
+constexpr size_t kSnapSlots = 64; /* per-launch snapshots of the queue counters kept in pinned memory */
+
+uint32_t pow2_ceil(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+
 } /* namespace */
 
 struct anm_demod {
@@ -90,6 +98,13 @@ struct anm_demod {
     uint64_t samples_fed, syms_since_collect, launches;
     std::vector<EvPair> evs;
     size_t ev_used;
+    uint32_t read_f, read_b;           /* frames / payload bytes consumed by the host (mod 2^32) */
+    uint32_t *snap;                    /* pinned [kSnapSlots][4] counter snapshots */
+    cudaEvent_t snap_ev[kSnapSlots];
+    bool snap_valid[kSnapSlots];
+    bool want_snapshot;                /* set by the pipelined host feed around its launch */
+    cudaEvent_t h2d_done;
+    cudaStream_t d2h_stream;
     /* host-side result queues */
     std::vector<anm_frame_t> q_frames;
     std::vector<uint8_t> q_bytes;
@@ -183,8 +198,8 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     h->fsym_stride = (h->max_frame_syms + 63u) & ~63u;
     /* frames / payload bytes that may accumulate between two collects (about 2 minutes of back-to-back
      * short frames per channel); overflow drops frames and is reported by anm_demod_overflowed() */
-    h->frames_cap = (uint32_t)std::min<uint64_t>(1ull << 24, std::max<uint64_t>(4096u, (uint64_t)n_channels * 256u));
-    h->bytes_cap = (uint32_t)std::min<uint64_t>(1ull << 30, std::max<uint64_t>(1u << 20, (uint64_t)n_channels * 16384u));
+    h->frames_cap = pow2_ceil(std::min<uint64_t>(1ull << 24, std::max<uint64_t>(4096u, (uint64_t)n_channels * 256u)));
+    h->bytes_cap = pow2_ceil(std::min<uint64_t>(1ull << 30, std::max<uint64_t>(1u << 20, (uint64_t)n_channels * 16384u)));
     h->osym_cap = (flags & ANM_FLAG_SYMBOLS) ? 4096u : 0u;
     CK(cudaMalloc(&h->d_state, (size_t)n_channels * var->state_bytes));
     CK(cudaMalloc(&h->d_fsyms, (size_t)n_channels * h->fsym_stride));
@@ -203,6 +218,11 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
         CK(cudaEventCreate(&e.a));
         CK(cudaEventCreate(&e.b));
     }
+    CK(cudaHostAlloc(&h->snap, kSnapSlots * 16, cudaHostAllocDefault));
+    memset(h->snap, 0, kSnapSlots * 16);
+    for (size_t i = 0; i < kSnapSlots; ++i) CK(cudaEventCreateWithFlags(&h->snap_ev[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->h2d_done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     h->q_syms.resize((flags & ANM_FLAG_SYMBOLS) ? n_channels : 0);
     /* constant part of the kernel parameters */
     KParams &k = h->kp;
@@ -258,6 +278,7 @@ extern "C" int anm_demod_reset(anm_demod_t *h) {
     h->samples_fed = 0;
     h->syms_since_collect = 0;
     h->ev_used = 0;
+    h->read_f = h->read_b = 0;
     h->q_frames.clear();
     h->q_bytes.clear();
     for (auto &q : h->q_syms) q.clear();
@@ -281,18 +302,81 @@ extern "C" void anm_demod_destroy(anm_demod_t *h) {
         if (e.a) cudaEventDestroy(e.a);
         if (e.b) cudaEventDestroy(e.b);
     }
+    for (size_t i = 0; i < kSnapSlots; ++i)
+        if (h->snap_ev[i]) cudaEventDestroy(h->snap_ev[i]);
+    if (h->h2d_done) cudaEventDestroy(h->h2d_done);
+    if (h->snap) cudaFreeHost(h->snap);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
-static int launch(anm_demod *h, const KParams &k, cudaStream_t s, bool timed) {
+static int launch(anm_demod *h, KParams &k, cudaStream_t s, bool timed, bool snapshot) {
     EvPair *ev = nullptr;
     if (timed && h->ev_used < h->evs.size()) ev = &h->evs[h->ev_used++];
+    /* frame / byte queues are rings addressed by monotonically increasing counters; the kernel may
+     * fill them up to one capacity beyond what the host has consumed so far */
+    k.base_f = h->read_f;
+    k.base_b = h->read_b;
     if (ev) CK(cudaEventRecord(ev->a, s));
     void *args[] = {(void *)&k};
     CK(cudaLaunchKernel((const void *)h->var->fn, dim3(h->grid), dim3(h->warps_per_cta * 32), args, h->smem_bytes, s));
     if (ev) CK(cudaEventRecord(ev->b, s));
+    /* pipelined host feeds: stream-ordered snapshot of the queue counters as they stand after this
+     * launch, so that a later drain can stop exactly there while newer launches are in flight */
+    const size_t slot = (size_t)(h->launches % kSnapSlots);
+    h->snap_valid[slot] = snapshot;
+    if (snapshot) {
+        CK(cudaMemcpyAsync(h->snap + slot * 4, h->d_counters, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(h->snap_ev[slot], s));
+    }
     h->launches++;
+    return ANM_OK;
+}
+
+/* Moves the frames produced up to (and including) launch number `seq` into the host queues.  Waits only
+ * for that launch; later launches may still be running or queued behind a host->device copy. */
+static int drain_frames(anm_demod *h, uint64_t seq) {
+    const size_t slot = (size_t)(seq % kSnapSlots);
+    uint32_t wf, wb, ovf;
+    if (h->snap_valid[slot]) {
+        CK(cudaEventSynchronize(h->snap_ev[slot]));
+        wf = h->snap[slot * 4 + 0], wb = h->snap[slot * 4 + 1], ovf = h->snap[slot * 4 + 2];
+    } else {
+        /* no snapshot was taken for this launch: everything must have completed */
+        CK(cudaStreamSynchronize(h->last_stream));
+        uint32_t cnt[4];
+        CK(cudaMemcpy(cnt, h->d_counters, 16, cudaMemcpyDeviceToHost));
+        wf = cnt[0], wb = cnt[1], ovf = cnt[2];
+    }
+    const uint32_t nf = wf - h->read_f, nb = wb - h->read_b; /* modulo 2^32 */
+    if (ovf || nf > h->frames_cap || nb > h->bytes_cap) {
+        /* records of dropped frames were never written: discard what is pending and resynchronise */
+        h->overflow = 1;
+        h->read_f = wf;
+        h->read_b = wb;
+        CK(cudaMemsetAsync(h->d_counters + 2, 0, 4, h->d2h_stream));
+        CK(cudaStreamSynchronize(h->d2h_stream));
+        return ANM_OK;
+    }
+    if (nf) {
+        const size_t f0 = h->q_frames.size(), b0 = h->q_bytes.size();
+        h->q_frames.resize(f0 + nf);
+        h->q_bytes.resize(b0 + nb);
+        const uint32_t fpos = h->read_f & (h->frames_cap - 1), f1 = std::min(nf, h->frames_cap - fpos);
+        CK(cudaMemcpyAsync(h->q_frames.data() + f0, h->d_frames + fpos, (size_t)f1 * sizeof(anm_frame_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (nf > f1)
+            CK(cudaMemcpyAsync(h->q_frames.data() + f0 + f1, h->d_frames, (size_t)(nf - f1) * sizeof(anm_frame_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (nb) {
+            const uint32_t bpos = h->read_b & (h->bytes_cap - 1), b1 = std::min(nb, h->bytes_cap - bpos);
+            CK(cudaMemcpyAsync(h->q_bytes.data() + b0, h->d_bytes + bpos, b1, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (nb > b1) CK(cudaMemcpyAsync(h->q_bytes.data() + b0 + b1, h->d_bytes, nb - b1, cudaMemcpyDeviceToHost, h->d2h_stream));
+        }
+        CK(cudaStreamSynchronize(h->d2h_stream));
+        for (size_t i = f0; i < f0 + nf; ++i) h->q_frames[i].offset = (uint32_t)b0 + (h->q_frames[i].offset - h->read_b);
+        h->read_f = wf;
+        h->read_b = wb;
+    }
     return ANM_OK;
 }
 
@@ -319,7 +403,7 @@ extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_
     k.ch_stride = ch_stride;
     k.n_syms = (uint32_t)nsyms;
     k.hop_base = h->samples_fed / (N / h->cfg.hops_per_sym);
-    int rc = launch(h, k, s, true);
+    int rc = launch(h, k, s, true, h->want_snapshot);
     if (rc) return rc;
     h->last_stream = s;
     h->samples_fed += n_samples;
@@ -327,7 +411,7 @@ extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_
     return ANM_OK;
 }
 
-extern "C" int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples) {
+static int feed_host_impl(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples, bool async) {
     if (!h || (!h_pcm && n_samples)) return ANM_ERR_ARG;
     if (n_samples == 0) return ANM_OK;
     if (n_samples % h->cfg.sym_len) return ANM_ERR_ALIGN;
@@ -348,10 +432,39 @@ extern "C" int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t 
     else
         CK(cudaMemcpy2DAsync(h->d_stage, n_samples * 2, h_pcm, ch_stride * 2, n_samples * 2, h->n_ch,
                              cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(h->h2d_done, s));
+    h->want_snapshot = async;
     int rc = anm_demod_feed_device(h, h->d_stage, n_samples, n_samples, s);
+    h->want_snapshot = false;
     if (rc) return rc;
-    CK(cudaStreamSynchronize(s));
+    if (!async) CK(cudaStreamSynchronize(s));
     return ANM_OK;
+}
+
+extern "C" int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples) {
+    return feed_host_impl(h, h_pcm, ch_stride, n_samples, false);
+}
+
+extern "C" int anm_demod_feed_host_async(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples) {
+    return feed_host_impl(h, h_pcm, ch_stride, n_samples, true);
+}
+
+extern "C" int anm_demod_wait_input(anm_demod_t *h) {
+    if (!h) return ANM_ERR_ARG;
+    if (set_device(h)) return ANM_ERR_CUDA;
+    CK(cudaEventSynchronize(h->h2d_done));
+    return ANM_OK;
+}
+
+extern "C" long anm_demod_collect_upto(anm_demod_t *h, uint32_t lag) {
+    if (!h) return ANM_ERR_ARG;
+    if (set_device(h)) return ANM_ERR_CUDA;
+    if (lag >= kSnapSlots - 1) return ANM_ERR_ARG;
+    if (h->launches > lag) {
+        int rc = drain_frames(h, h->launches - 1 - lag);
+        if (rc) return rc;
+    }
+    return (long)h->q_frames.size();
 }
 
 extern "C" long anm_demod_collect(anm_demod_t *h) {
@@ -359,20 +472,10 @@ extern "C" long anm_demod_collect(anm_demod_t *h) {
     if (set_device(h)) return ANM_ERR_CUDA;
     cudaStream_t s = h->last_stream;
     CK(cudaStreamSynchronize(s));
-    uint32_t cnt[4] = {0, 0, 0, 0};
-    CK(cudaMemcpy(cnt, h->d_counters, 16, cudaMemcpyDeviceToHost));
-    const uint32_t nf = std::min(cnt[0], h->frames_cap);
-    const uint32_t nb = std::min(cnt[1], h->bytes_cap);
-    if (cnt[2] || cnt[0] > h->frames_cap || cnt[1] > h->bytes_cap) h->overflow = 1;
-    if (nf) {
-        const size_t f0 = h->q_frames.size(), b0 = h->q_bytes.size();
-        h->q_frames.resize(f0 + nf);
-        h->q_bytes.resize(b0 + nb);
-        CK(cudaMemcpy(h->q_frames.data() + f0, h->d_frames, (size_t)nf * sizeof(anm_frame_t), cudaMemcpyDeviceToHost));
-        if (nb) CK(cudaMemcpy(h->q_bytes.data() + b0, h->d_bytes, nb, cudaMemcpyDeviceToHost));
-        for (size_t i = f0; i < f0 + nf; ++i) h->q_frames[i].offset += (uint32_t)b0;
+    if (h->launches) {
+        int rc = drain_frames(h, h->launches - 1);
+        if (rc) return rc;
     }
-    CK(cudaMemset(h->d_counters, 0, 16));
     if (h->osym_cap && h->syms_since_collect) {
         std::vector<uint32_t> oc(h->n_ch);
         const size_t off = offsetof(ChanScalars, osym_cnt);

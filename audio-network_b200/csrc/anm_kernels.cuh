@@ -57,7 +57,8 @@ struct KParams {
     anm_frame_t *frames;
     uint8_t *bytes;
     uint32_t *counters;           /* [0]=n_frames [1]=n_bytes [2]=overflow flags */
-    uint32_t frames_cap, bytes_cap;
+    uint32_t frames_cap, bytes_cap; /* powers of two: the queues are rings */
+    uint32_t base_f, base_b;        /* counters as of what the host has consumed (mod 2^32) */
     uint8_t *osyms;               /* [n_ch][osym_cap] or NULL */
     uint32_t osym_cap;
     uint32_t P, tol, max_payload, trk_epoch, trk_thresh, hdr_syms;
@@ -678,7 +679,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                             }
                             fidx = __shfl_sync(FULL, fidx, 0);
                             boff = __shfl_sync(FULL, boff, 0);
-                            const bool fits = fidx < p.frames_cap && boff + len <= p.bytes_cap;
+                            const bool fits = (fidx - p.base_f) < p.frames_cap && (boff + len - p.base_b) <= p.bytes_cap;
                             const uint8_t *bs = fs + p.hdr_syms;
                             /* body byte byi (payload, then the two CRC bytes) from its symbols */
                             auto body_byte = [&](uint32_t byi) -> uint32_t {
@@ -718,7 +719,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                         v8 = (mi == 0) ? (len >> 8) : (len & 0xffu);
                                     } else {
                                         v8 = body_byte(mi - 2);
-                                        if (fits) p.bytes[boff + mi - 2] = (uint8_t)v8;
+                                        if (fits) p.bytes[(boff + mi - 2) & (p.bytes_cap - 1u)] = (uint8_t)v8;
                                     }
                                     if (li == 0) v8 ^= crc >> 8;
                                     if (li == 1) v8 ^= crc & 0xffu;
@@ -750,7 +751,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                     f.start_sample = (sc.t0 + 1 - (unsigned long long)p.P * S) * H;
                                     f.crc_ok = ok;
                                     f.offset = boff;
-                                    p.frames[fidx] = f;
+                                    p.frames[fidx & (p.frames_cap - 1u)] = f;
                                 }
                                 if (ok) sc.stats.frames_ok++; else sc.stats.frames_bad++;
                             } else if (lane == 0) {

@@ -145,6 +145,15 @@ int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride
 /* PCM in host memory (pinned for full speed): copies to an internal HBM staging
  * buffer, demodulates, and waits for completion. */
 int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples);
+/* Pipelined form: enqueues the copy and the kernel on the handle's stream and returns.  h_pcm must
+ * stay untouched until anm_demod_wait_input() (or a later collect) returns.  Together with
+ * anm_demod_collect_upto(h, 1) this overlaps the host-side handling of chunk k with the PCIe
+ * transfer of chunk k+1. */
+int anm_demod_feed_host_async(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples);
+int anm_demod_wait_input(anm_demod_t *h);
+/* Like anm_demod_collect for frames only, but waits just for the launch that is `lag` launches
+ * behind the most recent one (lag 0 = the latest). */
+long anm_demod_collect_upto(anm_demod_t *h, uint32_t lag);
 /* Waits for outstanding work and moves newly produced frames/symbols to the
  * host queues.  Returns number of frames now queued, or a negative error. */
 long anm_demod_collect(anm_demod_t *h);
