@@ -205,7 +205,7 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     CK(cudaMalloc(&h->d_fsyms, (size_t)n_channels * h->fsym_stride));
     CK(cudaMalloc(&h->d_frames, (size_t)h->frames_cap * sizeof(anm_frame_t)));
     CK(cudaMalloc(&h->d_bytes, h->bytes_cap));
-    CK(cudaMalloc(&h->d_counters, 16));
+    CK(cudaMalloc(&h->d_counters, 32));
     if (h->osym_cap) CK(cudaMalloc(&h->d_osyms, (size_t)n_channels * h->osym_cap));
     h->h_tw.resize((size_t)cfg->sym_len * cfg->n_tones * 2);
     anm_twiddles(cfg, h->h_tw.data());
@@ -273,7 +273,7 @@ extern "C" int anm_demod_reset(anm_demod_t *h) {
     CK(cudaStreamSynchronize(h->last_stream));
     int rc = init_state(h->var, h->d_state, h->n_ch, h->own_stream);
     if (rc) return rc;
-    CK(cudaMemsetAsync(h->d_counters, 0, 16, h->own_stream));
+    CK(cudaMemsetAsync(h->d_counters, 0, 32, h->own_stream));
     CK(cudaStreamSynchronize(h->own_stream));
     h->samples_fed = 0;
     h->syms_since_collect = 0;

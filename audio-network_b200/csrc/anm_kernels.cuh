@@ -56,7 +56,7 @@ struct KParams {
     unsigned long long tr_hops;
     anm_frame_t *frames;
     uint8_t *bytes;
-    uint32_t *counters;           /* [0]=n_frames [1]=n_bytes [2]=overflow flags */
+    uint32_t *counters;           /* [0]=n_frames [1]=n_bytes [2]=overflow flags [4]=next channel [5]=warps done */
     uint32_t frames_cap, bytes_cap; /* powers of two: the queues are rings */
     uint32_t base_f, base_b;        /* counters as of what the host has consumed (mod 2^32) */
     uint8_t *osyms;               /* [n_ch][osym_cap] or NULL */
@@ -138,8 +138,12 @@ template <int T, int S>
 __host__ __device__ constexpr uint32_t state_carry_offset() { return state_rec_d_offset<T, S>() + ((32u * S + 15u) & ~15u); }
 template <int T, int S>
 __host__ __device__ constexpr uint32_t state_bytes() { return state_carry_offset<T, S>() + (uint32_t)(S - 1) * T * 8u; }
+/* PCM stage: one row per lane (= symbol period), padded to an odd number of 16-byte chunks so that
+ * the lanes' LDS.128 of the same chunk index fall into different banks */
 template <int N>
-__host__ __device__ constexpr uint32_t stage_bytes() { return 32u * N * 2u; }
+__host__ __device__ constexpr uint32_t stage_row_bytes() { return 2u * N + 16u; }
+template <int N>
+__host__ __device__ constexpr uint32_t stage_bytes() { return 32u * stage_row_bytes<N>(); }
 /* Per-warp shared memory: PCM stage | emax ring[64 slots][S] | d ring[64 slots][S] | scalars | tree carry */
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t warp_smem_bytes() {
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     constexpr int NG = T / TG;
     constexpr int LV = Log2<S>::v;
     constexpr int CPH = H / 8; /* 16-byte chunks per hop */
-    constexpr int CPS = N / 8; /* 16-byte chunks per symbol period */
+    
     constexpr uint32_t RM = 64u * S - 1u; /* record ring mask (hops) */
     constexpr uint32_t FULL = 0xffffffffu;
     static_assert(N >= 64 && (H % 8) == 0 && S >= 2, "unsupported geometry");
@@ -192,11 +196,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     ChanScalars *ssc = reinterpret_cast<ChanScalars *>(wsm + stage_bytes<N>() + 64u * S * 5u);
     float2 *carry = reinterpret_cast<float2 *>(wsm + stage_bytes<N>() + 64u * S * 5u + 128u); /* [(S-1)*T] */
 
-    const uint32_t sw = lane & 7u;
-    /* cp.async: lane copies 16-byte chunk (q*32 + lane) of the step */
-    constexpr int LPS = (CPS >= 32) ? 1 : 32 / CPS; /* symbol slots covered by one cp.async instruction */
-    const uint32_t cp_slot = (CPS >= 32) ? 0u : (uint32_t)lane / (uint32_t)CPS;
-    const uint32_t cp_chunk = (uint32_t)lane % (uint32_t)CPS;
+    constexpr uint32_t RS = stage_row_bytes<N>();
+    constexpr int CPS = N / 8; /* 16-byte chunks per symbol period */
+    /* cp.async: per instruction the warp copies 32 consecutive 16-byte chunks (512 contiguous bytes);
+     * lane l lands in row cp_row (+ rows per instruction), chunk cp_col of the padded stage */
+    constexpr int LPS = (CPS >= 32) ? 1 : 32 / CPS; /* stage rows covered by one cp.async instruction */
+    const uint32_t cp_row = (CPS >= 32) ? 0u : (uint32_t)lane / (uint32_t)CPS;
+    const uint32_t cp_col = (uint32_t)lane % (uint32_t)CPS;
 
     /* CRC-16 lane constant: x^(8(31-lane)+16) mod p (see frame assembly) */
     const uint32_t crc_k = (MODE == 0) ? (uint32_t)p.crc_pow[lane] : 0u; /* computed once on the host */
@@ -204,7 +210,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     const uint32_t n_steps = (p.n_syms + 31u) / 32u;
     const uint32_t total_warps = gridDim.x * wpb;
 
-    for (uint32_t ch = blockIdx.x * wpb + wib; ch < p.n_ch; ch += total_warps) {
+    uint32_t ch = blockIdx.x * wpb + wib; /* first channel static, further ones from the work queue */
+    while (ch < p.n_ch) {
         unsigned char *stp = p.state + (size_t)ch * p.state_stride;
         float *grec_e = reinterpret_cast<float *>(stp + sizeof(ChanScalars));
         uint8_t *grec_d = stp + state_rec_d_offset<T, S>();
@@ -228,23 +235,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
             const uint32_t nv = min(32u, p.n_syms - step * 32u);
             const char *g = src + (size_t)step * (32u * N * 2u) + (size_t)lane * 16u;
             if (CPS >= 32) {
-                constexpr uint32_t IPS = (CPS >= 32) ? CPS / 32 : 1; /* instructions per slot */
+                constexpr uint32_t IPS = (CPS >= 32) ? CPS / 32 : 1; /* instructions per row */
 #pragma unroll 4
-                for (uint32_t q = 0; q < (uint32_t)CPS; ++q) {
-                    const uint32_t sl = q / IPS, c = (q % IPS) * 32u + lane;
-                    if (sl < nv) cp_async16(stage + sl * (2 * N) + ((c ^ (sl & 7u)) << 4), g + (size_t)q * 512u);
-                }
-            } else if (nv == 32u) {
-#pragma unroll
-                for (int q = 0; q < CPS; ++q) {
-                    const uint32_t sl7 = ((uint32_t)(q * LPS) & 7u) | (cp_slot & 7u);
-                    cp_async16(stage + (uint32_t)(q * LPS) * (2 * N) + cp_slot * (2 * N) + ((cp_chunk ^ sl7) << 4), g + (size_t)q * 512u);
+                for (uint32_t q = 0; q < 32u * IPS; ++q) {
+                    const uint32_t r = q / IPS, c = (q % IPS) * 32u + lane;
+                    if (r < nv) cp_async16(stage + r * RS + (c << 4), g + (size_t)q * 512u);
                 }
             } else {
+                const uint32_t d0 = stage + cp_row * RS + (cp_col << 4);
+                if (nv == 32u) {
+#pragma unroll
+                    for (int q = 0; q < CPS; ++q) cp_async16(d0 + (uint32_t)(q * LPS) * RS, g + (size_t)q * 512u);
+                } else {
 #pragma unroll 4
-                for (int q = 0; q < CPS; ++q) {
-                    const uint32_t sl = (uint32_t)(q * LPS) + cp_slot;
-                    if (sl < nv) cp_async16(stage + sl * (2 * N) + ((cp_chunk ^ (sl & 7u)) << 4), g + (size_t)q * 512u);
+                    for (int q = 0; q < CPS; ++q)
+                        if ((uint32_t)(q * LPS) + cp_row < nv) cp_async16(d0 + (uint32_t)(q * LPS) * RS, g + (size_t)q * 512u);
                 }
             }
             cp_async_commit();
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
         for (uint32_t step = 0; step < n_steps; ++step) {
             cp_async_wait<0>();
             __syncwarp();
-            const uint32_t row = stage + (uint32_t)lane * (2 * N);
+            const uint32_t row = stage + (uint32_t)lane * RS;
             const int nvalid = (int)min(32u, p.n_syms - step * 32u);
             const bool active = lane < nvalid;
             const unsigned long long hbs = p.hop_base + (unsigned long long)step * 32u * S;
@@ -284,16 +289,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                     uint32_t twa = stw + (uint32_t)((pass * H) * T + g * TG) * 8u;
 #pragma unroll 1
                     for (int c = 0; c < TL / 8 / GR; ++c, twa += 8 * T * 8) {
-                        /* swizzled chunk address ((hop*CPH + c) ^ sw) << 4, split into a loop-invariant hop
-                         * part and a per-iteration chunk part (the XOR never carries between them) */
-                        constexpr uint32_t LOWM = (uint32_t)(CPH - 1) & 7u;
-                        const uint32_t cpart = (((uint32_t)c ^ (sw & LOWM))) << 4;
                         uint4 v[NQ];
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q) {
-                            const uint32_t hpart = row + ((((uint32_t)((pass + q * GR) * CPH)) ^ (sw & 7u & ~LOWM)) << 4);
-                            v[q] = lds128(hpart + cpart);
-                        }
+                        for (int q = 0; q < NQ; ++q) v[q] = lds128(row + (uint32_t)(((pass + q * GR) * CPH + c) * 16));
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float x[NQ];
@@ -782,6 +780,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
         for (int i = lane; i < (S - 1) * T; i += 32) gcarry[i] = carry[i];
         if (MODE == 0) reinterpret_cast<uint32_t *>(stp)[lane] = reinterpret_cast<const uint32_t *>(ssc)[lane];
         __syncwarp();
+        if (MODE == 0) {
+            uint32_t nx = 0;
+            if (lane == 0) nx = atomicAdd(&p.counters[4], 1u);
+            ch = total_warps + __shfl_sync(FULL, nx, 0);
+        } else {
+            ch += total_warps;
+        }
+    }
+    /* the last warp to leave re-arms the work queue for the next launch */
+    if (MODE == 0 && lane == 0) {
+        if (atomicAdd(&p.counters[5], 1u) == total_warps - 1u) {
+            p.counters[4] = 0u;
+            p.counters[5] = 0u;
+        }
     }
 }
 
