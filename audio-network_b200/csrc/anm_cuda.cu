@@ -41,12 +41,12 @@ struct Variant {
     uint32_t T, N, S;
     kern_fn fn;       /* streaming demodulator */
     kern_fn fn_trace; /* stateless tone-energy pass */
-    uint32_t warp_smem, cta_smem, state_bytes, rec_d_off;
+    uint32_t warp_smem, cta_smem, state_bytes;
 };
 
 #define VARIANT(T_, N_, S_)                                                                       \
     {T_, N_, S_, (kern_fn)k_demod<T_, N_, S_, 0>, (kern_fn)k_demod<T_, N_, S_, 1>, warp_smem_bytes<T_, N_, S_>(), \
-     cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>(), state_rec_d_offset<T_, S_>()}
+     cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
 
 const Variant kVariants[] = {
     VARIANT(4, 128, 4),  VARIANT(2, 128, 4),  VARIANT(8, 128, 4), VARIANT(16, 128, 4),
@@ -261,9 +261,10 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
 }
 
 static int init_state(const Variant *var, unsigned char *d_state, uint32_t n_ch, cudaStream_t s) {
-    /* zero everything, then set the hop-decision history to 0xFF ("before the stream") */
-    CK(cudaMemsetAsync(d_state, 0, (size_t)n_ch * var->state_bytes, s));
-    CK(cudaMemset2DAsync(d_state + var->rec_d_off, var->state_bytes, 0xFF, 32u * var->S, n_ch, s));
+    /* zero everything, hop-decision history = 0xFF ("before the stream") */
+    const size_t words = (size_t)n_ch * (var->state_bytes / 4u);
+    k_init_state<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_state, var->state_bytes, n_ch, 32u * var->S);
+    CK(cudaGetLastError());
     return ANM_OK;
 }
 

@@ -24,19 +24,27 @@ namespace anm {
 
 enum : uint32_t { ST_SEARCH = 0, ST_PEAK = 1, ST_HEADER = 2, ST_BODY = 3 };
 
-/* Uniform (per-channel) part of the carried state; lane-distributed parts follow it. */
+/* Uniform (per-channel) part of the carried state; lane-distributed parts follow it.  Hop indices are
+ * 32-bit wrapping counters: every difference the state machine takes is far below 2^31 hops. */
 struct ChanScalars {
-    uint64_t peak_end, best_h, t0, next, prev_hop;
-    float best_q;
     uint32_t state, nsym, total, flen;
+    uint32_t next, prev_hop, best_h, peak_end;
+    float best_q;
     int32_t acc;
     uint32_t s_prev, s_prev2;
+    uint32_t ep_left;  /* symbols until the next tracker epoch boundary */
     uint32_t osym_cnt;
+    unsigned long long t0; /* absolute hop of the lock (frame start_sample) */
     anm_chan_stats_t stats; /* 32 bytes */
-    uint32_t ep_left;       /* symbols until the next tracker epoch boundary */
-    uint32_t pad[3];
+    uint32_t pad[8];
 };
 static_assert(sizeof(ChanScalars) == 128, "ChanScalars layout");
+
+/* hop record: energy of the strongest tone and its index (0xFF before the stream) */
+struct HopRec {
+    float e;
+    uint32_t d;
+};
 
 struct KParams {
     const int16_t *pcm;
@@ -131,11 +139,9 @@ struct Log2 { static constexpr int v = 1 + Log2<T / 2>::v; };
 template <>
 struct Log2<1> { static constexpr int v = 0; };
 
-/* Per-channel state in HBM: ChanScalars | emax[32 slots][S] | d[32 slots][S] (bytes) | tree carry */
+/* Per-channel state in HBM: ChanScalars | HopRec[32 slots][S] | tree carry */
 template <int T, int S>
-__host__ __device__ constexpr uint32_t state_rec_d_offset() { return (uint32_t)sizeof(ChanScalars) + 32u * S * 4u; }
-template <int T, int S>
-__host__ __device__ constexpr uint32_t state_carry_offset() { return state_rec_d_offset<T, S>() + ((32u * S + 15u) & ~15u); }
+__host__ __device__ constexpr uint32_t state_carry_offset() { return (uint32_t)sizeof(ChanScalars) + 32u * S * 8u; }
 template <int T, int S>
 __host__ __device__ constexpr uint32_t state_bytes() { return state_carry_offset<T, S>() + (uint32_t)(S - 1) * T * 8u; }
 /* PCM stage: one row per lane (= symbol period), padded to an odd number of 16-byte chunks so that
@@ -144,10 +150,10 @@ template <int N>
 __host__ __device__ constexpr uint32_t stage_row_bytes() { return 2u * N + 16u; }
 template <int N>
 __host__ __device__ constexpr uint32_t stage_bytes() { return 32u * stage_row_bytes<N>(); }
-/* Per-warp shared memory: PCM stage | emax ring[64 slots][S] | d ring[64 slots][S] | scalars | tree carry */
+/* Per-warp shared memory: PCM stage | HopRec ring[64 slots][S] | scalars | tree carry */
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t warp_smem_bytes() {
-    return stage_bytes<N>() + 64u * S * 4u + 64u * S + 128u + (uint32_t)(S - 1) * T * 8u;
+    return stage_bytes<N>() + 64u * S * 8u + 128u + (uint32_t)(S - 1) * T * 8u;
 }
 /* Hops that share one pass over the twiddle table: the table holds the first 1/NQ of a symbol
  * period; hop offsets that differ by N/NQ rotate every twiddle by an exact multiple of 90 degrees. */
@@ -191,10 +197,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     const uint32_t stw = (uint32_t)__cvta_generic_to_shared(smem_raw);
     unsigned char *wsm = smem_raw + cta_smem_bytes<T, N, S>() + (size_t)wib * warp_smem_bytes<T, N, S>();
     const uint32_t stage = (uint32_t)__cvta_generic_to_shared(wsm);
-    const uint32_t se = stage + stage_bytes<N>();   /* float emax ring [64*S] */
-    const uint32_t sd = se + 64u * S * 4u;           /* u8 d ring [64*S] */
-    ChanScalars *ssc = reinterpret_cast<ChanScalars *>(wsm + stage_bytes<N>() + 64u * S * 5u);
-    float2 *carry = reinterpret_cast<float2 *>(wsm + stage_bytes<N>() + 64u * S * 5u + 128u); /* [(S-1)*T] */
+    const uint32_t sr = stage + stage_bytes<N>(); /* HopRec ring [64*S] */
+    ChanScalars *ssc = reinterpret_cast<ChanScalars *>(wsm + stage_bytes<N>() + 64u * S * 8u);
+    float2 *carry = reinterpret_cast<float2 *>(wsm + stage_bytes<N>() + 64u * S * 8u + 128u); /* [(S-1)*T] */
 
     constexpr uint32_t RS = stage_row_bytes<N>();
     constexpr int CPS = N / 8; /* 16-byte chunks per symbol period */
@@ -213,18 +218,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     uint32_t ch = blockIdx.x * wpb + wib; /* first channel static, further ones from the work queue */
     while (ch < p.n_ch) {
         unsigned char *stp = p.state + (size_t)ch * p.state_stride;
-        float *grec_e = reinterpret_cast<float *>(stp + sizeof(ChanScalars));
-        uint8_t *grec_d = stp + state_rec_d_offset<T, S>();
+        uint2 *grec = reinterpret_cast<uint2 *>(stp + sizeof(ChanScalars));
         float2 *gcarry = reinterpret_cast<float2 *>(stp + state_carry_offset<T, S>());
 
         /* ---- restore carried state: the last 32 symbol slots go to ring slots 32..63 ---- */
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            const float ev = grec_e[lane * S + i];
-            const uint32_t dv = grec_d[lane * S + i];
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (uint32_t)((32 + lane) * S + i) * 4u), "f"(ev) : "memory");
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + (uint32_t)((32 + lane) * S + i)), "r"(dv) : "memory");
+            const uint2 rv = grec[lane * S + i];
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + (uint32_t)((32 + lane) * S + i) * 8u), "r"(rv.x), "r"(rv.y) : "memory");
         }
         for (int i = lane; i < (S - 1) * T; i += 32) carry[i] = gcarry[i];
         if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = reinterpret_cast<const uint32_t *>(stp)[lane];
@@ -263,7 +265,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
             const uint32_t row = stage + (uint32_t)lane * RS;
             const int nvalid = (int)min(32u, p.n_syms - step * 32u);
             const bool active = lane < nvalid;
-            const unsigned long long hbs = p.hop_base + (unsigned long long)step * 32u * S;
             const uint32_t hic = step * 32u * S; /* hop index of the step start within the chunk (ring position) */
 
             /* ================= tone energies (SPEC 3) ================= */
@@ -450,17 +451,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
             /* publish this step's hop records in the ring (slots of lanes past a ragged end keep their
              * older content: they are never addressed) */
             if (active) {
-                const uint32_t idx0 = (hic + (uint32_t)(lane * S)) & RM; /* S consecutive, S-aligned ring entries */
-                if (S == 4) {
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(se + idx0 * 4u), "f"(ec[0]), "f"(ec[1]), "f"(ec[2 % S]), "f"(ec[3 % S]) : "memory");
-                    const uint32_t pk = (dc[0] & 0xffu) | ((dc[1] & 0xffu) << 8) | ((dc[2 % S] & 0xffu) << 16) | (dc[3 % S] << 24);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sd + idx0), "r"(pk) : "memory");
+                const uint32_t a0 = sr + (((hic + (uint32_t)(lane * S)) & RM) << 3); /* S consecutive ring entries */
+                if (S % 2 == 0) {
+#pragma unroll
+                    for (int i = 0; i < S; i += 2)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]),
+                                     "r"(__float_as_uint(ec[(i + 1) % S])), "r"(dc[(i + 1) % S]) : "memory");
                 } else {
 #pragma unroll
-                    for (int i = 0; i < S; ++i) {
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(se + (idx0 + i) * 4u), "f"(ec[i]) : "memory");
-                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(sd + idx0 + i), "r"(dc[i]) : "memory");
-                    }
+                    for (int i = 0; i < S; ++i)
+                        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
                 }
             }
             __syncwarp();
@@ -477,15 +477,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 
             /* ================= sync / slicing / framing (SPEC 5) ================= */
             if (MODE == 0) {
-                /* hop records by hop index r relative to the step start, r in [-32S, 32S) */
-                auto RD = [&](int r) -> uint32_t {
-                    uint32_t v;
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sd + ((hic + (uint32_t)r) & RM)) : "memory");
-                    return v;
-                };
-                auto RE = [&](int r) -> float {
-                    float v;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(se + ((hic + (uint32_t)r) & RM) * 4u) : "memory");
+                const uint32_t hb = (uint32_t)p.hop_base + hic; /* wrapping index of the step's first hop */
+                /* hop record by hop index r relative to the step start, r in [-32S, 32S): .x = emax bits, .y = d */
+                auto REC = [&](int r) -> uint2 {
+                    uint2 v;
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + (((hic + (uint32_t)r) & RM) << 3)) : "memory");
                     return v;
                 };
                 ChanScalars sc = *ssc; /* warp-uniform broadcast loads */
@@ -499,24 +495,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                 /* quality of the alignment whose last preamble symbol ends at relative hop h: SPEC 5 q(h) */
                 auto quality = [&](int h) -> float {
                     const int pl = min(lane, (int)p.P - 1);
-                    const int r = h - ((int)p.P - 1 - pl) * S;
-                    const uint32_t dv = RD(r);
-                    const float ev = RE(r);
-                    float leaf = (lane < (int)p.P && dv == (uint32_t)p.preamble[pl]) ? ev : 0.0f;
+                    const uint2 rv = REC(h - ((int)p.P - 1 - pl) * S);
+                    float leaf = (lane < (int)p.P && rv.y == (uint32_t)p.preamble[pl]) ? __uint_as_float(rv.x) : 0.0f;
                     for (uint32_t w = 1; w < p.P; w <<= 1) leaf = __fadd_rn(leaf, __shfl_xor_sync(FULL, leaf, w));
                     return __shfl_sync(FULL, leaf, 0);
                 };
 
 #pragma unroll 1
                 while (cur < endh) {
-                    if (sc.state == ST_SEARCH || sc.state == ST_PEAK) {
+                    if (sc.state <= ST_PEAK) {
                         if (!have_cand) {
                             /* preamble correlation on bit-planes of the hop decisions */
                             const int sh = 32 + lane - (int)(p.P - 1); /* bit of preamble symbol 0 in the 64-bit history */
                             const uint32_t pmask = (p.P >= 32) ? 0xffffffffu : ((1u << p.P) - 1u);
 #pragma unroll
                             for (int i = 0; i < S; ++i) {
-                                const uint32_t dprev = RD((lane - 32) * S + i); /* same lane, previous step */
+                                const uint32_t dprev = REC((lane - 32) * S + i).y; /* same lane, previous step */
                                 uint32_t mism = 0;
 #pragma unroll
                                 for (int j = 0; j <= B; ++j) {
@@ -539,45 +533,45 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                 const uint32_t mk = (smin >= 32) ? 0u : (cand[i] & (0xffffffffu << smin));
                                 if (mk) h0 = min(h0, ((__ffs(mk) - 1) << LV) + i);
                             }
-                            if (h0 == 0x7fffffff) { cur = endh; break; }
+                            if (h0 == 0x7fffffff) break;
                             sc.best_q = quality(h0);
-                            sc.best_h = hbs + h0;
-                            sc.peak_end = hbs + h0 + S - 1;
+                            sc.best_h = hb + (uint32_t)h0;
+                            sc.peak_end = hb + (uint32_t)(h0 + S - 1);
                             sc.state = ST_PEAK;
                             cur = h0 + 1;
                         } else {
-                            const long long pend = (long long)(sc.peak_end - hbs);
+                            const int pend = (int)(sc.peak_end - hb);
                             while (cur < endh && cur <= pend) {
                                 if ((pick<S>(cand, cur & (S - 1)) >> (cur >> LV)) & 1u) {
                                     const float q = quality(cur);
-                                    if (q > sc.best_q) { sc.best_q = q; sc.best_h = hbs + cur; }
+                                    if (q > sc.best_q) { sc.best_q = q; sc.best_h = hb + (uint32_t)cur; }
                                 }
                                 ++cur;
                             }
                             if (cur > pend) {
-                                sc.t0 = sc.best_h;
-                                sc.next = sc.t0 + S;
+                                sc.t0 = p.hop_base + (unsigned long long)hic + (long long)(int)(sc.best_h - hb);
+                                sc.next = sc.best_h + S;
                                 sc.nsym = 0;
                                 sc.acc = 0;
                                 sc.ep_left = p.trk_epoch;
                                 sc.s_prev = p.preamble[p.P - 1];
                                 sc.s_prev2 = 0xFFu;
-                                sc.prev_hop = sc.t0;
+                                sc.prev_hop = sc.best_h;
                                 sc.state = ST_HEADER;
                                 sc.stats.locks++;
                             }
                         }
                     } else {
-                        /* ---- locked: slice up to 32 symbols at once ---- */
-                        const long long firstl = (long long)(sc.next - hbs);
-                        if (firstl >= endh) { cur = endh; break; }
-                        const int first = (int)firstl;
+                        /* ---- locked: slice up to 32 symbols at once (lane = symbol) ---- */
+                        const int first = (int)(sc.next - hb);
+                        if (first >= endh) break;
                         const uint32_t until_evt = (sc.state == ST_HEADER ? p.hdr_syms : sc.total) - sc.nsym;
                         uint32_t cnt = min(until_evt, (uint32_t)(((endh - 1 - first) >> LV) + 1));
-                        const int e = lane - (first >> LV);          /* index of this lane's symbol in the run */
-                        const bool part = e >= 0 && e < (int)cnt;
-                        const int hr = part ? first + (e << LV) : first; /* relative hop of this lane's symbol */
-                        const uint32_t sym = RD(hr);
+                        const int s0 = first >> LV;
+                        const int e = lane - s0;                 /* index of this lane's symbol in the run */
+                        const int hr = first + (e << LV);        /* its relative hop (ring-addressed for every lane) */
+                        const bool part = (uint32_t)e < cnt;
+                        const uint32_t sym = REC(hr).y;
                         uint8_t *fs = p.fsyms + (size_t)ch * p.fsym_stride;
                         if (part) {
                             fs[sc.nsym + e] = (uint8_t)sym;
@@ -587,19 +581,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                             }
                         }
                         /* tracker votes (SPEC 5): the lane of symbol n votes for symbol n-1, whose hop is one
-                         * symbol back -- or, for the first symbol of the run, the carried prev_hop */
-                        const int r0 = (int)((long long)(sc.prev_hop - hbs));
-                        const int hj = (e <= 0) ? r0 : hr - S;
-                        /* tones of symbols n-1 and n-2; for the first symbols of a frame these are the carried
-                         * values (s_{-1} is the nominal last preamble tone, not a decision) */
-                        const uint32_t sj = (e <= 0) ? sc.s_prev : RD(hr - S);
-                        const uint32_t sjm = (e >= 2) ? RD(hr - 2 * S) : ((e == 1) ? sc.s_prev : sc.s_prev2);
-                        const float e_on = RE(hj);
-                        const float ve = (RD(hj - 1) == sj) ? RE(hj - 1) : 0.0f;
-                        const float vl = (RD(hj + 1) == sj) ? RE(hj + 1) : 0.0f;
-                        const bool voter = part && (sc.nsym + e >= 1);
-                        const uint32_t bl = __ballot_sync(FULL, voter && (sym != sj) && vl > e_on);
-                        const uint32_t be = __ballot_sync(FULL, voter && (sjm != sj) && ve > e_on);
+                         * symbol back -- or, for the first symbol of the run, the carried prev_hop.  Its tone
+                         * s_j is the decision at that hop (the nominal s_{-1} never is the subject of a vote). */
+                        const int hj = (e <= 0) ? (int)(sc.prev_hop - hb) : hr - S;
+                        const uint2 rj = REC(hj), rje = REC(hj - 1), rjl = REC(hj + 1);
+                        const uint32_t sj2 = REC(hr - 2 * S).y;
+                        const uint32_t sj = rj.y;
+                        /* tone of symbol n-2: for the first symbols of a run the carried values */
+                        const uint32_t sjm = (e >= 2) ? sj2 : ((e == 1) ? sc.s_prev : sc.s_prev2);
+                        const float e_on = __uint_as_float(rj.x);
+                        const bool early = rje.y == sj && __uint_as_float(rje.x) > e_on;
+                        const bool late = rjl.y == sj && __uint_as_float(rjl.x) > e_on;
+                        const bool voter = part && (sc.nsym + (uint32_t)e >= 1u);
+                        const uint32_t bl = __ballot_sync(FULL, voter && (sym != sj) && late);
+                        const uint32_t be = __ballot_sync(FULL, voter && (sjm != sj) && early);
                         /* tracker epochs inside the run: only an actual timing move ends the run early */
                         int adj = 0;
                         if ((bl | be) == 0u && sc.acc < (int)p.trk_thresh && sc.acc > -(int)p.trk_thresh) {
@@ -613,13 +608,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                 sc.acc = 0;
                             }
                         } else {
-                            const uint32_t s0 = (uint32_t)(first >> LV);
                             uint32_t pos = 0;
                             while (true) {
                                 const uint32_t eb = pos + sc.ep_left; /* symbols of the run up to the next boundary */
                                 const uint32_t hi = min(eb, cnt);
-                                const uint32_t lo_m = 0xffffffffu << (s0 + pos);
-                                const uint32_t hi_m = (s0 + hi >= 32u) ? 0xffffffffu : ((1u << (s0 + hi)) - 1u);
+                                const uint32_t lo_m = 0xffffffffu << ((uint32_t)s0 + pos);
+                                const uint32_t hi_m = ((uint32_t)s0 + hi >= 32u) ? 0xffffffffu : ((1u << ((uint32_t)s0 + hi)) - 1u);
                                 sc.acc += __popc(bl & lo_m & hi_m) - __popc(be & lo_m & hi_m);
                                 if (eb > cnt) { sc.ep_left -= (cnt - pos); break; }
                                 pos = eb;
@@ -632,12 +626,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                             }
                         }
                         const int lasth = first + (int)((cnt - 1) << LV);
-                        sc.s_prev2 = (cnt >= 2) ? RD(lasth - S) : sc.s_prev;
-                        sc.s_prev = RD(lasth);
-                        sc.prev_hop = hbs + lasth;
+                        sc.s_prev2 = (cnt >= 2) ? REC(lasth - S).y : sc.s_prev;
+                        sc.s_prev = REC(lasth).y;
+                        sc.prev_hop = hb + (uint32_t)lasth;
                         sc.nsym += cnt;
                         sc.osym_cnt += cnt;
-                        sc.next += ((unsigned long long)cnt << LV) + adj;
+                        sc.next += (cnt << LV) + (uint32_t)adj;
                         sc.stats.symbols += cnt;
                         sc.stats.trk_moves += adj;
                         cur = lasth + 1;
@@ -770,12 +764,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             const uint32_t idx = ((p.n_syms - 32u + (uint32_t)lane) * S + (uint32_t)i) & RM;
-            float ev;
-            uint32_t dv;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ev) : "r"(se + idx * 4u) : "memory");
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(dv) : "r"(sd + idx) : "memory");
-            grec_e[lane * S + i] = ev;
-            grec_d[lane * S + i] = (uint8_t)dv;
+            uint2 rv;
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + idx * 8u) : "memory");
+            grec[lane * S + i] = rv;
         }
         for (int i = lane; i < (S - 1) * T; i += 32) gcarry[i] = carry[i];
         if (MODE == 0) reinterpret_cast<uint32_t *>(stp)[lane] = reinterpret_cast<const uint32_t *>(ssc)[lane];
@@ -795,6 +786,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
             p.counters[5] = 0u;
         }
     }
+}
+
+/* fresh per-channel state: everything zero, hop records "before the stream" (d = 0xFF, emax = 0) */
+__global__ void k_init_state(unsigned char *state, uint32_t state_stride, uint32_t n_ch, uint32_t n_rec) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t words = state_stride / 4u;
+    if (i >= (size_t)n_ch * words) return;
+    const uint32_t w = (uint32_t)(i % words);
+    uint32_t v = 0u;
+    if (w >= sizeof(ChanScalars) / 4u && w < sizeof(ChanScalars) / 4u + 2u * n_rec && (w & 1u)) v = 0xFFu;
+    reinterpret_cast<uint32_t *>(state)[i] = v;
 }
 
 } /* namespace anm */
