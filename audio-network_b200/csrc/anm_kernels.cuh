@@ -163,7 +163,7 @@ __host__ __device__ constexpr int quad_hops() { return S >= 4 ? 4 : 2; }
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t cta_smem_bytes() { return (uint32_t)(N / quad_hops<S>()) * T * 8u; }
 
-constexpr int kMaxWarps = 19; /* 19 warps x 104 registers fill the register file; 3 passes cover 8,192 channels on 148 SMs */
+constexpr int kMaxWarps = 20; /* registers are allocated per 4 warps: 20 warps x 96 registers fit the file; 24 would cap at 80 */
 
 /* MODE 0: streaming demodulator (sync, slicing, framing; no trace output).
  * MODE 1: stateless tone-energy pass (trace outputs only; parity / debug). */
