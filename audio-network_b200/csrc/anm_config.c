@@ -64,6 +64,8 @@ int anm_config_validate(const anm_config_t *c) {
     if (c->sync_tol >= c->preamble_len) return ANM_ERR_ARG;
     if (c->max_payload == 0 || c->max_payload > 4104) return ANM_ERR_ARG;
     if (c->trk_epoch == 0 || c->trk_thresh == 0) return ANM_ERR_ARG;
+    /* dense (integer) arithmetic: |window sum| <= N * 32768 * 127 must fit a signed 32-bit integer */
+    if (c->n_tones >= 32u && c->sym_len > 512u) return ANM_ERR_ARG;
     return ANM_OK;
 }
 
@@ -85,6 +87,31 @@ int anm_twiddles(const anm_config_t *c, float *out) {
                 float sq = r == 0 ? si : r == 1 ? co : r == 2 ? -si : -co;
                 out[((m + q * (N / 4)) * T + k) * 2 + 0] = cq;
                 out[((m + q * (N / 4)) * T + k) * 2 + 1] = sq;
+            }
+        }
+    return ANM_OK;
+}
+
+/* SPEC 3b: configurations with a dense tone set (T >= 32) compute tone energies from an 8-bit
+ * integer basis with exact integer accumulation (the tensor-core contraction of the CUDA path). */
+int anm_config_dense(const anm_config_t *c) { return c && c->n_tones >= 32u; }
+
+int anm_basis_q7(const anm_config_t *c, int8_t *out) {
+    if (anm_config_validate(c) != ANM_OK || !out) return ANM_ERR_ARG;
+    const double two_pi = 6.283185307179586476925286766559;
+    const uint32_t N = c->sym_len, T = c->n_tones;
+    /* first quarter rounded from libm, the other quarters by the exact (-j)^{b q} symmetry (as anm_twiddles) */
+    for (uint32_t m = 0; m < N / 4; ++m)
+        for (uint32_t k = 0; k < T; ++k) {
+            uint32_t r0 = (c->tone_bin[k] * m) % N;
+            double a = two_pi * (double)r0 / (double)N;
+            int co = (int)lround(127.0 * cos(a)), si = (int)lround(127.0 * sin(a));
+            for (uint32_t q = 0; q < 4; ++q) {
+                uint32_t r = (c->tone_bin[k] * q) & 3u;
+                int cq = r == 0 ? co : r == 1 ? -si : r == 2 ? -co : si;
+                int sq = r == 0 ? si : r == 1 ? co : r == 2 ? -si : -co;
+                out[((m + q * (N / 4)) * T + k) * 2 + 0] = (int8_t)cq;
+                out[((m + q * (N / 4)) * T + k) * 2 + 1] = (int8_t)sq;
             }
         }
     return ANM_OK;

@@ -19,7 +19,7 @@
 #include <new>
 #include <vector>
 
-#include "anm_kernels.cuh"
+#include "anm_kernels_tc.cuh"
 #include "../../include/anmodem_pb.h"
 
 using namespace anm;
@@ -42,20 +42,24 @@ struct Variant {
     kern_fn fn;       /* streaming demodulator */
     kern_fn fn_trace; /* stateless tone-energy pass */
     uint32_t warp_smem, cta_smem, state_bytes;
+    bool dense; /* SPEC 3b: tensor-core contraction kernel, 4 channels per CTA */
 };
 
 #define VARIANT(T_, N_, S_)                                                                       \
     {T_, N_, S_, (kern_fn)k_demod<T_, N_, S_, 0>, (kern_fn)k_demod<T_, N_, S_, 1>, warp_smem_bytes<T_, N_, S_>(), \
-     cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>()}
+     cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>(), false}
+#define VARIANT_TC(T_, N_, S_)                                                                    \
+    {T_, N_, S_, (kern_fn)k_demod_tc<T_, N_, S_, 0>, (kern_fn)k_demod_tc<T_, N_, S_, 1>, 0u, tc::smem_bytes<T_, N_, S_>(), \
+     state_bytes<T_, S_>(), true}
 
 const Variant kVariants[] = {
     VARIANT(4, 128, 4),  VARIANT(2, 128, 4),  VARIANT(8, 128, 4), VARIANT(16, 128, 4),
-    VARIANT(64, 256, 4), VARIANT(4, 128, 8),  VARIANT(4, 128, 2), VARIANT(4, 64, 4),
+    VARIANT_TC(64, 256, 4), VARIANT(4, 128, 8),  VARIANT(4, 128, 2), VARIANT(4, 64, 4),
 };
 
 const Variant *find_variant(const anm_config_t *c) {
     for (const Variant &v : kVariants)
-        if (v.T == c->n_tones && v.N == c->sym_len && v.S == c->hops_per_sym) return &v;
+        if (v.T == c->n_tones && v.N == c->sym_len && v.S == c->hops_per_sym && v.dense == (anm_config_dense(c) != 0)) return &v;
     return nullptr;
 }
 
@@ -92,6 +96,7 @@ struct anm_demod {
     uint32_t osym_cap;
     float2 *d_tw;
     std::vector<float> h_tw;
+    uint8_t *d_basis; /* dense tone sets: int8 basis panels */
     int16_t *d_stage;
     size_t stage_cap;
     cudaStream_t own_stream, last_stream;
@@ -131,12 +136,36 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
     }
 }
 
+/* int8 basis of a dense configuration in the panel order the MMA descriptors of k_demod_tc address:
+ * [tone group][16-sample K chunk][column = 2*tone_in_group + (0: cos, 1: sin)][sample in chunk] */
+static int upload_basis_panels(const anm_config_t *cfg, uint8_t **d_out) {
+    const uint32_t N = cfg->sym_len, T = cfg->n_tones, H = N / cfg->hops_per_sym, KC = H / 16;
+    std::vector<int8_t> q7((size_t)N * T * 2);
+    if (anm_basis_q7(cfg, q7.data()) != ANM_OK) return ANM_ERR_ARG;
+    std::vector<uint8_t> pan((size_t)(T / tc::kTG) * KC * tc::kBPanel);
+    for (uint32_t g = 0; g < T / tc::kTG; ++g)
+        for (uint32_t kc = 0; kc < KC; ++kc)
+            for (uint32_t n = 0; n < tc::kNcol; ++n)
+                for (uint32_t kk = 0; kk < 16; ++kk)
+                    pan[((size_t)(g * KC + kc) * tc::kNcol + n) * 16 + kk] =
+                        (uint8_t)q7[((size_t)(kc * 16 + kk) * T + (g * tc::kTG + n / 2)) * 2 + (n & 1u)];
+    CK(cudaMalloc(d_out, pan.size()));
+    CK(cudaMemcpy(*d_out, pan.data(), pan.size(), cudaMemcpyHostToDevice));
+    return ANM_OK;
+}
+
 static int set_device(const anm_demod *h) {
     CK(cudaSetDevice(h->device));
     return ANM_OK;
 }
 
 static void choose_launch(anm_demod *h) {
+    if (h->var->dense) {
+        h->warps_per_cta = 4;
+        h->grid = (h->n_ch + 3u) / 4u;
+        h->smem_bytes = h->var->cta_smem;
+        return;
+    }
     const uint32_t per_warp = h->var->warp_smem;
     const uint32_t smem_max = 227u * 1024u - h->var->cta_smem;
     uint32_t wmax = std::min<uint32_t>((uint32_t)kMaxWarps, smem_max / per_warp);
@@ -147,14 +176,9 @@ static void choose_launch(anm_demod *h) {
         W = std::max<uint32_t>(1u, (h->n_ch + sms - 1) / sms);
         h->grid = (h->n_ch + W - 1) / W;
     } else {
-        /* passes x (latency floor + per-warp issue time): measured per-pass time grows as ~(7 + W) */
-        double best = 1e30;
-        for (uint32_t w = wmax; w >= std::max<uint32_t>(1u, wmax / 2); --w) {
-            const uint64_t slots = (uint64_t)sms * w;
-            const uint64_t passes = (h->n_ch + slots - 1) / slots;
-            const double cost = (double)passes * (7.0 + (double)w);
-            if (cost < best - 1e-9) { best = cost; W = w; }
-        }
+        /* channels beyond the first wave are handed out by the kernel's work queue: more resident warps
+         * only add latency hiding */
+        W = wmax;
         h->grid = sms;
     }
     if (const char *env = getenv("ANM_WARPS")) { /* experiment knob: force warps per CTA */
@@ -254,6 +278,11 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     memcpy(k.preamble, cfg->preamble, ANM_MAX_PREAMBLE);
     k.tw_global = h->d_tw;
     set_tw_sign(cfg, &k);
+    if (var->dense) {
+        int rcb = upload_basis_panels(cfg, &h->d_basis);
+        if (rcb != ANM_OK) { anm_demod_destroy(h); return rcb; }
+        k.tc_basis = h->d_basis;
+    }
     int rc = anm_demod_reset(h);
     if (rc != ANM_OK) { anm_demod_destroy(h); return rc; }
     *out = h;
@@ -298,6 +327,7 @@ extern "C" void anm_demod_destroy(anm_demod_t *h) {
     cudaFree(h->d_counters);
     cudaFree(h->d_osyms);
     cudaFree(h->d_tw);
+    cudaFree(h->d_basis);
     cudaFree(h->d_stage);
     for (EvPair &e : h->evs) {
         if (e.a) cudaEventDestroy(e.a);
@@ -635,12 +665,28 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
         k.tr_hops = n_samples / (cfg->sym_len / cfg->hops_per_sym);
         k.P = cfg->preamble_len;
         k.tw_global = d_tw;
-        const uint32_t W = std::min<uint32_t>(8u, (227u * 1024u - var->cta_smem) / var->warp_smem);
-        const uint32_t grid = (n_ch + W - 1) / W;
+        uint8_t *d_basis = nullptr;
+        uint32_t W, grid;
+        size_t smem;
+        if (var->dense) {
+            rc = upload_basis_panels(cfg, &d_basis);
+            k.tc_basis = d_basis;
+            W = 4;
+            grid = (n_ch + 3u) / 4u;
+            smem = var->cta_smem;
+        } else {
+            W = std::min<uint32_t>(8u, (227u * 1024u - var->cta_smem) / var->warp_smem);
+            grid = std::min<uint32_t>((n_ch + W - 1) / W, (uint32_t)sms * 4u);
+            smem = (size_t)W * var->warp_smem + var->cta_smem;
+        }
         cudaFuncSetAttribute((const void *)var->fn_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         void *args[] = {(void *)&k};
-        cudaError_t e = cudaLaunchKernel((const void *)var->fn_trace, dim3(std::min<uint32_t>(grid, (uint32_t)sms * 4u)), dim3(W * 32), args,
-                                         (size_t)W * var->warp_smem + var->cta_smem, s);
+        cudaError_t e = rc == ANM_OK ? cudaLaunchKernel((const void *)var->fn_trace, dim3(grid), dim3(W * 32), args, smem, s) : cudaSuccess;
+        if (rc == ANM_OK && e == cudaSuccess) {
+            const cudaError_t es = cudaStreamSynchronize(s);
+            if (es != cudaSuccess) { anm_set_error("tone pass: %s", cudaGetErrorString(es)); rc = ANM_ERR_CUDA; }
+        }
+        cudaFree(d_basis);
         if (e != cudaSuccess) { anm_set_error("launch: %s", cudaGetErrorString(e)); rc = ANM_ERR_CUDA; }
     }
     cudaError_t e2 = cudaStreamSynchronize(s);

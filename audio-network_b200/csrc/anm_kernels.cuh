@@ -75,6 +75,7 @@ struct KParams {
     const float2 *tw_global;      /* [N][T] (cos, sin) twiddle table in HBM; its first N/NQ rows are staged per CTA */
     unsigned long long tw_rot[2];  /* 2 bits per tone: tone_bin mod 4 (quarter-period rotation code) */
     uint16_t crc_pow[32];          /* x^(8(31-lane)+16) mod the CRC-16 polynomial, per lane */
+    const uint8_t *tc_basis;       /* dense tone sets: int8 basis panels [group][K chunk][32 columns][16] (anm_kernels_tc.cuh) */
 };
 
 __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
@@ -162,6 +163,300 @@ __host__ __device__ constexpr int quad_hops() { return S >= 4 ? 4 : 2; }
 /* CTA-shared twiddle table: (N / NQ) positions x T tones x (cos, sin) */
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t cta_smem_bytes() { return (uint32_t)(N / quad_hops<S>()) * T * 8u; }
+
+/* ================= sync / slicing / framing (SPEC 5) =================
+ * One call per step (32 symbol periods) and channel, by the whole warp.  The step's hop records are
+ * already in the ring `sr` (HopRec[64*S], indexed by hop-in-chunk & RM); dc[] are this lane's own
+ * decisions of the step (lane = symbol period). */
+template <int T, int N, int S>
+__device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, const int lane, const uint32_t sr,
+                                        const uint32_t hic, const int nvalid, const bool active,
+                                        const uint32_t (&dc)[S], ChanScalars *ssc, const uint32_t crc_k) {
+    constexpr int H = N / S;
+    constexpr int B = Log2<T>::v;
+    constexpr int LV = Log2<S>::v;
+    constexpr uint32_t RM = 64u * S - 1u;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t hb = (uint32_t)p.hop_base + hic; /* wrapping index of the step's first hop */
+    /* hop record by hop index r relative to the step start, r in [-32S, 32S): .x = emax bits, .y = d */
+    auto REC = [&](int r) -> uint2 {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + (((hic + (uint32_t)r) & RM) << 3)) : "memory");
+        return v;
+    };
+    ChanScalars sc = *ssc; /* warp-uniform broadcast loads */
+    const int endh = nvalid * S;
+    int cur = 0;
+    bool have_cand = false;
+    uint32_t cand[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) cand[i] = 0;
+
+    /* quality of the alignment whose last preamble symbol ends at relative hop h: SPEC 5 q(h) */
+    auto quality = [&](int h) -> float {
+        const int pl = min(lane, (int)p.P - 1);
+        const uint2 rv = REC(h - ((int)p.P - 1 - pl) * S);
+        float leaf = (lane < (int)p.P && rv.y == (uint32_t)p.preamble[pl]) ? __uint_as_float(rv.x) : 0.0f;
+        for (uint32_t w = 1; w < p.P; w <<= 1) leaf = __fadd_rn(leaf, __shfl_xor_sync(FULL, leaf, w));
+        return __shfl_sync(FULL, leaf, 0);
+    };
+
+#pragma unroll 1
+    while (cur < endh) {
+        if (sc.state <= ST_PEAK) {
+            if (!have_cand) {
+                /* preamble correlation on bit-planes of the hop decisions */
+                const int sh = 32 + lane - (int)(p.P - 1); /* bit of preamble symbol 0 in the 64-bit history */
+                const uint32_t pmask = (p.P >= 32) ? 0xffffffffu : ((1u << p.P) - 1u);
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const uint32_t dprev = REC((lane - 32) * S + i).y; /* same lane, previous step */
+                    uint32_t mism = 0;
+#pragma unroll
+                    for (int j = 0; j <= B; ++j) {
+                        const uint32_t bc = (j < B) ? ((dc[i] >> j) & 1u) : (dc[i] > (uint32_t)(T - 1));
+                        const uint32_t bp = (j < B) ? ((dprev >> j) & 1u) : (dprev > (uint32_t)(T - 1));
+                        const unsigned long long hist = ((unsigned long long)__ballot_sync(FULL, bc) << 32) | __ballot_sync(FULL, bp);
+                        const uint32_t w = (uint32_t)(hist >> sh);
+                        mism |= (j < B) ? (w ^ p.pre_plane[j]) : w;
+                    }
+                    const uint32_t m = p.P - __popc(mism & pmask);
+                    cand[i] = __ballot_sync(FULL, active && m >= p.P - p.tol);
+                }
+                have_cand = true;
+            }
+            if (sc.state == ST_SEARCH) {
+                int h0 = 0x7fffffff;
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const int smin = (cur > i) ? ((cur - i + S - 1) >> LV) : 0;
+                    const uint32_t mk = (smin >= 32) ? 0u : (cand[i] & (0xffffffffu << smin));
+                    if (mk) h0 = min(h0, ((__ffs(mk) - 1) << LV) + i);
+                }
+                if (h0 == 0x7fffffff) break;
+                sc.best_q = quality(h0);
+                sc.best_h = hb + (uint32_t)h0;
+                sc.peak_end = hb + (uint32_t)(h0 + S - 1);
+                sc.state = ST_PEAK;
+                cur = h0 + 1;
+            } else {
+                const int pend = (int)(sc.peak_end - hb);
+                while (cur < endh && cur <= pend) {
+                    if ((pick<S>(cand, cur & (S - 1)) >> (cur >> LV)) & 1u) {
+                        const float q = quality(cur);
+                        if (q > sc.best_q) { sc.best_q = q; sc.best_h = hb + (uint32_t)cur; }
+                    }
+                    ++cur;
+                }
+                if (cur > pend) {
+                    sc.t0 = p.hop_base + (unsigned long long)hic + (long long)(int)(sc.best_h - hb);
+                    sc.next = sc.best_h + S;
+                    sc.nsym = 0;
+                    sc.acc = 0;
+                    sc.ep_left = p.trk_epoch;
+                    sc.s_prev = p.preamble[p.P - 1];
+                    sc.s_prev2 = 0xFFu;
+                    sc.prev_hop = sc.best_h;
+                    sc.state = ST_HEADER;
+                    sc.stats.locks++;
+                }
+            }
+        } else {
+            /* ---- locked: slice up to 32 symbols at once (lane = symbol) ---- */
+            const int first = (int)(sc.next - hb);
+            if (first >= endh) break;
+            const uint32_t until_evt = (sc.state == ST_HEADER ? p.hdr_syms : sc.total) - sc.nsym;
+            uint32_t cnt = min(until_evt, (uint32_t)(((endh - 1 - first) >> LV) + 1));
+            const int s0 = first >> LV;
+            const int e = lane - s0;                 /* index of this lane's symbol in the run */
+            const int hr = first + (e << LV);        /* its relative hop (ring-addressed for every lane) */
+            const bool part = (uint32_t)e < cnt;
+            const uint32_t sym = REC(hr).y;
+            uint8_t *fs = p.fsyms + (size_t)ch * p.fsym_stride;
+            if (part) {
+                fs[sc.nsym + e] = (uint8_t)sym;
+                if (p.osyms) {
+                    const uint32_t oi = sc.osym_cnt + e;
+                    if (oi < p.osym_cap) p.osyms[(size_t)ch * p.osym_cap + oi] = (uint8_t)sym;
+                }
+            }
+            /* tracker votes (SPEC 5): the lane of symbol n votes for symbol n-1, whose hop is one
+             * symbol back -- or, for the first symbol of the run, the carried prev_hop.  Its tone
+             * s_j is the decision at that hop (the nominal s_{-1} never is the subject of a vote). */
+            const int hj = (e <= 0) ? (int)(sc.prev_hop - hb) : hr - S;
+            const uint2 rj = REC(hj), rje = REC(hj - 1), rjl = REC(hj + 1);
+            const uint32_t sj2 = REC(hr - 2 * S).y;
+            const uint32_t sj = rj.y;
+            /* tone of symbol n-2: for the first symbols of a run the carried values */
+            const uint32_t sjm = (e >= 2) ? sj2 : ((e == 1) ? sc.s_prev : sc.s_prev2);
+            const float e_on = __uint_as_float(rj.x);
+            const bool early = rje.y == sj && __uint_as_float(rje.x) > e_on;
+            const bool late = rjl.y == sj && __uint_as_float(rjl.x) > e_on;
+            const bool voter = part && (sc.nsym + (uint32_t)e >= 1u);
+            const uint32_t bl = __ballot_sync(FULL, voter && (sym != sj) && late);
+            const uint32_t be = __ballot_sync(FULL, voter && (sjm != sj) && early);
+            /* tracker epochs inside the run: only an actual timing move ends the run early */
+            int adj = 0;
+            if ((bl | be) == 0u && sc.acc < (int)p.trk_thresh && sc.acc > -(int)p.trk_thresh) {
+                /* no vote in this run and the carried sum cannot trip: epochs just tick over */
+                if (cnt < sc.ep_left) {
+                    sc.ep_left -= cnt;
+                } else {
+                    uint32_t rem = cnt - sc.ep_left;
+                    while (rem >= p.trk_epoch) rem -= p.trk_epoch;
+                    sc.ep_left = p.trk_epoch - rem;
+                    sc.acc = 0;
+                }
+            } else {
+                uint32_t pos = 0;
+                while (true) {
+                    const uint32_t eb = pos + sc.ep_left; /* symbols of the run up to the next boundary */
+                    const uint32_t hi = min(eb, cnt);
+                    const uint32_t lo_m = 0xffffffffu << ((uint32_t)s0 + pos);
+                    const uint32_t hi_m = ((uint32_t)s0 + hi >= 32u) ? 0xffffffffu : ((1u << ((uint32_t)s0 + hi)) - 1u);
+                    sc.acc += __popc(bl & lo_m & hi_m) - __popc(be & lo_m & hi_m);
+                    if (eb > cnt) { sc.ep_left -= (cnt - pos); break; }
+                    pos = eb;
+                    sc.ep_left = p.trk_epoch;
+                    if (sc.acc >= (int)p.trk_thresh) adj = 1;
+                    else if (sc.acc <= -(int)p.trk_thresh) adj = -1;
+                    sc.acc = 0;
+                    if (adj) { cnt = pos; break; }
+                    if (pos == cnt) break;
+                }
+            }
+            const int lasth = first + (int)((cnt - 1) << LV);
+            sc.s_prev2 = (cnt >= 2) ? REC(lasth - S).y : sc.s_prev;
+            sc.s_prev = REC(lasth).y;
+            sc.prev_hop = hb + (uint32_t)lasth;
+            sc.nsym += cnt;
+            sc.osym_cnt += cnt;
+            sc.next += (cnt << LV) + (uint32_t)adj;
+            sc.stats.symbols += cnt;
+            sc.stats.trk_moves += adj;
+            cur = lasth + 1;
+            if (sc.state == ST_HEADER && sc.nsym == p.hdr_syms) {
+                __syncwarp();
+                /* 24 header bits from hdr_syms symbols, one symbol per lane, OR-reduced */
+                uint32_t contrib = 0;
+                if (lane < (int)p.hdr_syms) {
+                    const uint32_t v = gray_inv(fs[lane]);
+                    const int pos = 24 - B * (lane + 1);
+                    contrib = (pos >= 0) ? (v << pos) : (v >> (-pos));
+                }
+                const uint32_t hdr = __reduce_or_sync(FULL, contrib);
+                const uint32_t len = hdr >> 8;
+                uint32_t c8 = 0;
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    c8 ^= (hdr >> (16 - 8 * z)) & 0xffu;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) c8 = (c8 & 0x80u) ? (((c8 << 1) ^ 0x07u) & 0xffu) : ((c8 << 1) & 0xffu);
+                }
+                if (len == 0 || len > p.max_payload || c8 != (hdr & 0xffu)) {
+                    sc.stats.header_fail++;
+                    sc.state = ST_SEARCH;
+                } else {
+                    sc.flen = len;
+                    sc.total = p.hdr_syms + ((len + 2) * 8 + B - 1) / B;
+                    sc.state = ST_BODY;
+                }
+            } else if (sc.state == ST_BODY && sc.nsym == sc.total) {
+                __syncwarp();
+                const uint32_t len = sc.flen;
+                uint32_t fidx = 0, boff = 0;
+                if (lane == 0) {
+                    fidx = atomicAdd(&p.counters[0], 1u);
+                    boff = atomicAdd(&p.counters[1], len);
+                }
+                fidx = __shfl_sync(FULL, fidx, 0);
+                boff = __shfl_sync(FULL, boff, 0);
+                const bool fits = (fidx - p.base_f) < p.frames_cap && (boff + len - p.base_b) <= p.bytes_cap;
+                const uint8_t *bs = fs + p.hdr_syms;
+                /* body byte byi (payload, then the two CRC bytes) from its symbols */
+                auto body_byte = [&](uint32_t byi) -> uint32_t {
+                    uint32_t v8 = 0;
+                    if (8 % B == 0) {
+                        constexpr int SPB = (8 % B == 0) ? 8 / B : 1;
+#pragma unroll
+                        for (int j = 0; j < SPB; ++j) v8 |= gray_inv(bs[byi * SPB + j]) << (B * (SPB - 1 - j));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t bit = byi * 8 + k;
+                            const uint32_t v = gray_inv(bs[bit / B]);
+                            v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
+                        }
+                    }
+                    return v8;
+                };
+                /* bits -> bytes and CRC-16, both lane-parallel.  The message (LEN bytes +
+                 * payload) is consumed 32 bytes per round, right-aligned: lane l holds the byte
+                 * that is 31-l positions from the end of the round, multiplies it by
+                 * x^(8(31-l)+16) mod p (crc_k, a lane constant) in GF(2)[x], and the round is the
+                 * XOR of all lanes; the running CRC enters the next round through its first two
+                 * bytes (a CRC register R equals XORing R into the next two message bytes). */
+                const uint32_t mlen = len + 2; /* CRC'd bytes: LEN hi, LEN lo, payload */
+                uint32_t crc = 0xFFFFu;
+                uint32_t done = 0;
+                uint32_t take = mlen & 31u; /* first (short) round */
+                if (take == 0) take = 32;
+#pragma unroll 1
+                while (done < mlen) {
+                    const int li = lane - (32 - (int)take); /* index within the round */
+                    uint32_t v8 = 0;
+                    if (li >= 0) {
+                        const uint32_t mi = done + li; /* index in the CRC'd message */
+                        if (mi < 2) {
+                            v8 = (mi == 0) ? (len >> 8) : (len & 0xffu);
+                        } else {
+                            v8 = body_byte(mi - 2);
+                            if (fits) p.bytes[(boff + mi - 2) & (p.bytes_cap - 1u)] = (uint8_t)v8;
+                        }
+                        if (li == 0) v8 ^= crc >> 8;
+                        if (li == 1) v8 ^= crc & 0xffu;
+                    }
+                    /* v8 * crc_k mod p, Horner over the 8 bits */
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int k = 7; k >= 0; --k) {
+                        acc = ((acc << 1) ^ ((acc & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
+                        if ((v8 >> k) & 1u) acc ^= crc_k;
+                    }
+                    acc = __reduce_xor_sync(FULL, acc);
+                    /* a 1-byte round has no second byte to carry the register's low byte:
+                     * R_lo * x^(8n) with n = 1 is R_lo << 8 */
+                    if (take == 1) acc ^= (crc & 0xffu) << 8;
+                    crc = acc;
+                    done += take;
+                    take = 32;
+                }
+                /* received CRC-16: the two bytes after the payload */
+                const uint32_t rx = (lane < 2) ? (body_byte(len + lane) << (8 * (1 - lane))) : 0u;
+                const uint32_t crc_rx = __reduce_or_sync(FULL, rx);
+                const uint32_t ok = crc == crc_rx;
+                if (fits) {
+                    if (lane == 0) {
+                        anm_frame_t f;
+                        f.channel = ch;
+                        f.len = len;
+                        f.start_sample = (sc.t0 + 1 - (unsigned long long)p.P * S) * H;
+                        f.crc_ok = ok;
+                        f.offset = boff;
+                        p.frames[fidx & (p.frames_cap - 1u)] = f;
+                    }
+                    if (ok) sc.stats.frames_ok++; else sc.stats.frames_bad++;
+                } else if (lane == 0) {
+                    atomicOr(&p.counters[2], 1u);
+                }
+                sc.state = ST_SEARCH;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *ssc = sc;
+    __syncwarp();
+}
 
 constexpr int kMaxWarps = 20; /* registers are allocated per 4 warps: 20 warps x 96 registers fit the file; 24 would cap at 80 */
 
@@ -475,288 +770,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                 }
             }
 
-            /* ================= sync / slicing / framing (SPEC 5) ================= */
-            if (MODE == 0) {
-                const uint32_t hb = (uint32_t)p.hop_base + hic; /* wrapping index of the step's first hop */
-                /* hop record by hop index r relative to the step start, r in [-32S, 32S): .x = emax bits, .y = d */
-                auto REC = [&](int r) -> uint2 {
-                    uint2 v;
-                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + (((hic + (uint32_t)r) & RM) << 3)) : "memory");
-                    return v;
-                };
-                ChanScalars sc = *ssc; /* warp-uniform broadcast loads */
-                const int endh = nvalid * S;
-                int cur = 0;
-                bool have_cand = false;
-                uint32_t cand[S];
-#pragma unroll
-                for (int i = 0; i < S; ++i) cand[i] = 0;
-
-                /* quality of the alignment whose last preamble symbol ends at relative hop h: SPEC 5 q(h) */
-                auto quality = [&](int h) -> float {
-                    const int pl = min(lane, (int)p.P - 1);
-                    const uint2 rv = REC(h - ((int)p.P - 1 - pl) * S);
-                    float leaf = (lane < (int)p.P && rv.y == (uint32_t)p.preamble[pl]) ? __uint_as_float(rv.x) : 0.0f;
-                    for (uint32_t w = 1; w < p.P; w <<= 1) leaf = __fadd_rn(leaf, __shfl_xor_sync(FULL, leaf, w));
-                    return __shfl_sync(FULL, leaf, 0);
-                };
-
-#pragma unroll 1
-                while (cur < endh) {
-                    if (sc.state <= ST_PEAK) {
-                        if (!have_cand) {
-                            /* preamble correlation on bit-planes of the hop decisions */
-                            const int sh = 32 + lane - (int)(p.P - 1); /* bit of preamble symbol 0 in the 64-bit history */
-                            const uint32_t pmask = (p.P >= 32) ? 0xffffffffu : ((1u << p.P) - 1u);
-#pragma unroll
-                            for (int i = 0; i < S; ++i) {
-                                const uint32_t dprev = REC((lane - 32) * S + i).y; /* same lane, previous step */
-                                uint32_t mism = 0;
-#pragma unroll
-                                for (int j = 0; j <= B; ++j) {
-                                    const uint32_t bc = (j < B) ? ((dc[i] >> j) & 1u) : (dc[i] > (uint32_t)(T - 1));
-                                    const uint32_t bp = (j < B) ? ((dprev >> j) & 1u) : (dprev > (uint32_t)(T - 1));
-                                    const unsigned long long hist = ((unsigned long long)__ballot_sync(FULL, bc) << 32) | __ballot_sync(FULL, bp);
-                                    const uint32_t w = (uint32_t)(hist >> sh);
-                                    mism |= (j < B) ? (w ^ p.pre_plane[j]) : w;
-                                }
-                                const uint32_t m = p.P - __popc(mism & pmask);
-                                cand[i] = __ballot_sync(FULL, active && m >= p.P - p.tol);
-                            }
-                            have_cand = true;
-                        }
-                        if (sc.state == ST_SEARCH) {
-                            int h0 = 0x7fffffff;
-#pragma unroll
-                            for (int i = 0; i < S; ++i) {
-                                const int smin = (cur > i) ? ((cur - i + S - 1) >> LV) : 0;
-                                const uint32_t mk = (smin >= 32) ? 0u : (cand[i] & (0xffffffffu << smin));
-                                if (mk) h0 = min(h0, ((__ffs(mk) - 1) << LV) + i);
-                            }
-                            if (h0 == 0x7fffffff) break;
-                            sc.best_q = quality(h0);
-                            sc.best_h = hb + (uint32_t)h0;
-                            sc.peak_end = hb + (uint32_t)(h0 + S - 1);
-                            sc.state = ST_PEAK;
-                            cur = h0 + 1;
-                        } else {
-                            const int pend = (int)(sc.peak_end - hb);
-                            while (cur < endh && cur <= pend) {
-                                if ((pick<S>(cand, cur & (S - 1)) >> (cur >> LV)) & 1u) {
-                                    const float q = quality(cur);
-                                    if (q > sc.best_q) { sc.best_q = q; sc.best_h = hb + (uint32_t)cur; }
-                                }
-                                ++cur;
-                            }
-                            if (cur > pend) {
-                                sc.t0 = p.hop_base + (unsigned long long)hic + (long long)(int)(sc.best_h - hb);
-                                sc.next = sc.best_h + S;
-                                sc.nsym = 0;
-                                sc.acc = 0;
-                                sc.ep_left = p.trk_epoch;
-                                sc.s_prev = p.preamble[p.P - 1];
-                                sc.s_prev2 = 0xFFu;
-                                sc.prev_hop = sc.best_h;
-                                sc.state = ST_HEADER;
-                                sc.stats.locks++;
-                            }
-                        }
-                    } else {
-                        /* ---- locked: slice up to 32 symbols at once (lane = symbol) ---- */
-                        const int first = (int)(sc.next - hb);
-                        if (first >= endh) break;
-                        const uint32_t until_evt = (sc.state == ST_HEADER ? p.hdr_syms : sc.total) - sc.nsym;
-                        uint32_t cnt = min(until_evt, (uint32_t)(((endh - 1 - first) >> LV) + 1));
-                        const int s0 = first >> LV;
-                        const int e = lane - s0;                 /* index of this lane's symbol in the run */
-                        const int hr = first + (e << LV);        /* its relative hop (ring-addressed for every lane) */
-                        const bool part = (uint32_t)e < cnt;
-                        const uint32_t sym = REC(hr).y;
-                        uint8_t *fs = p.fsyms + (size_t)ch * p.fsym_stride;
-                        if (part) {
-                            fs[sc.nsym + e] = (uint8_t)sym;
-                            if (p.osyms) {
-                                const uint32_t oi = sc.osym_cnt + e;
-                                if (oi < p.osym_cap) p.osyms[(size_t)ch * p.osym_cap + oi] = (uint8_t)sym;
-                            }
-                        }
-                        /* tracker votes (SPEC 5): the lane of symbol n votes for symbol n-1, whose hop is one
-                         * symbol back -- or, for the first symbol of the run, the carried prev_hop.  Its tone
-                         * s_j is the decision at that hop (the nominal s_{-1} never is the subject of a vote). */
-                        const int hj = (e <= 0) ? (int)(sc.prev_hop - hb) : hr - S;
-                        const uint2 rj = REC(hj), rje = REC(hj - 1), rjl = REC(hj + 1);
-                        const uint32_t sj2 = REC(hr - 2 * S).y;
-                        const uint32_t sj = rj.y;
-                        /* tone of symbol n-2: for the first symbols of a run the carried values */
-                        const uint32_t sjm = (e >= 2) ? sj2 : ((e == 1) ? sc.s_prev : sc.s_prev2);
-                        const float e_on = __uint_as_float(rj.x);
-                        const bool early = rje.y == sj && __uint_as_float(rje.x) > e_on;
-                        const bool late = rjl.y == sj && __uint_as_float(rjl.x) > e_on;
-                        const bool voter = part && (sc.nsym + (uint32_t)e >= 1u);
-                        const uint32_t bl = __ballot_sync(FULL, voter && (sym != sj) && late);
-                        const uint32_t be = __ballot_sync(FULL, voter && (sjm != sj) && early);
-                        /* tracker epochs inside the run: only an actual timing move ends the run early */
-                        int adj = 0;
-                        if ((bl | be) == 0u && sc.acc < (int)p.trk_thresh && sc.acc > -(int)p.trk_thresh) {
-                            /* no vote in this run and the carried sum cannot trip: epochs just tick over */
-                            if (cnt < sc.ep_left) {
-                                sc.ep_left -= cnt;
-                            } else {
-                                uint32_t rem = cnt - sc.ep_left;
-                                while (rem >= p.trk_epoch) rem -= p.trk_epoch;
-                                sc.ep_left = p.trk_epoch - rem;
-                                sc.acc = 0;
-                            }
-                        } else {
-                            uint32_t pos = 0;
-                            while (true) {
-                                const uint32_t eb = pos + sc.ep_left; /* symbols of the run up to the next boundary */
-                                const uint32_t hi = min(eb, cnt);
-                                const uint32_t lo_m = 0xffffffffu << ((uint32_t)s0 + pos);
-                                const uint32_t hi_m = ((uint32_t)s0 + hi >= 32u) ? 0xffffffffu : ((1u << ((uint32_t)s0 + hi)) - 1u);
-                                sc.acc += __popc(bl & lo_m & hi_m) - __popc(be & lo_m & hi_m);
-                                if (eb > cnt) { sc.ep_left -= (cnt - pos); break; }
-                                pos = eb;
-                                sc.ep_left = p.trk_epoch;
-                                if (sc.acc >= (int)p.trk_thresh) adj = 1;
-                                else if (sc.acc <= -(int)p.trk_thresh) adj = -1;
-                                sc.acc = 0;
-                                if (adj) { cnt = pos; break; }
-                                if (pos == cnt) break;
-                            }
-                        }
-                        const int lasth = first + (int)((cnt - 1) << LV);
-                        sc.s_prev2 = (cnt >= 2) ? REC(lasth - S).y : sc.s_prev;
-                        sc.s_prev = REC(lasth).y;
-                        sc.prev_hop = hb + (uint32_t)lasth;
-                        sc.nsym += cnt;
-                        sc.osym_cnt += cnt;
-                        sc.next += (cnt << LV) + (uint32_t)adj;
-                        sc.stats.symbols += cnt;
-                        sc.stats.trk_moves += adj;
-                        cur = lasth + 1;
-                        if (sc.state == ST_HEADER && sc.nsym == p.hdr_syms) {
-                            __syncwarp();
-                            /* 24 header bits from hdr_syms symbols, one symbol per lane, OR-reduced */
-                            uint32_t contrib = 0;
-                            if (lane < (int)p.hdr_syms) {
-                                const uint32_t v = gray_inv(fs[lane]);
-                                const int pos = 24 - B * (lane + 1);
-                                contrib = (pos >= 0) ? (v << pos) : (v >> (-pos));
-                            }
-                            const uint32_t hdr = __reduce_or_sync(FULL, contrib);
-                            const uint32_t len = hdr >> 8;
-                            uint32_t c8 = 0;
-#pragma unroll
-                            for (int z = 0; z < 2; ++z) {
-                                c8 ^= (hdr >> (16 - 8 * z)) & 0xffu;
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) c8 = (c8 & 0x80u) ? (((c8 << 1) ^ 0x07u) & 0xffu) : ((c8 << 1) & 0xffu);
-                            }
-                            if (len == 0 || len > p.max_payload || c8 != (hdr & 0xffu)) {
-                                sc.stats.header_fail++;
-                                sc.state = ST_SEARCH;
-                            } else {
-                                sc.flen = len;
-                                sc.total = p.hdr_syms + ((len + 2) * 8 + B - 1) / B;
-                                sc.state = ST_BODY;
-                            }
-                        } else if (sc.state == ST_BODY && sc.nsym == sc.total) {
-                            __syncwarp();
-                            const uint32_t len = sc.flen;
-                            uint32_t fidx = 0, boff = 0;
-                            if (lane == 0) {
-                                fidx = atomicAdd(&p.counters[0], 1u);
-                                boff = atomicAdd(&p.counters[1], len);
-                            }
-                            fidx = __shfl_sync(FULL, fidx, 0);
-                            boff = __shfl_sync(FULL, boff, 0);
-                            const bool fits = (fidx - p.base_f) < p.frames_cap && (boff + len - p.base_b) <= p.bytes_cap;
-                            const uint8_t *bs = fs + p.hdr_syms;
-                            /* body byte byi (payload, then the two CRC bytes) from its symbols */
-                            auto body_byte = [&](uint32_t byi) -> uint32_t {
-                                uint32_t v8 = 0;
-                                if (8 % B == 0) {
-                                    constexpr int SPB = (8 % B == 0) ? 8 / B : 1;
-#pragma unroll
-                                    for (int j = 0; j < SPB; ++j) v8 |= gray_inv(bs[byi * SPB + j]) << (B * (SPB - 1 - j));
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) {
-                                        const uint32_t bit = byi * 8 + k;
-                                        const uint32_t v = gray_inv(bs[bit / B]);
-                                        v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
-                                    }
-                                }
-                                return v8;
-                            };
-                            /* bits -> bytes and CRC-16, both lane-parallel.  The message (LEN bytes +
-                             * payload) is consumed 32 bytes per round, right-aligned: lane l holds the byte
-                             * that is 31-l positions from the end of the round, multiplies it by
-                             * x^(8(31-l)+16) mod p (crc_k, a lane constant) in GF(2)[x], and the round is the
-                             * XOR of all lanes; the running CRC enters the next round through its first two
-                             * bytes (a CRC register R equals XORing R into the next two message bytes). */
-                            const uint32_t mlen = len + 2; /* CRC'd bytes: LEN hi, LEN lo, payload */
-                            uint32_t crc = 0xFFFFu;
-                            uint32_t done = 0;
-                            uint32_t take = mlen & 31u; /* first (short) round */
-                            if (take == 0) take = 32;
-#pragma unroll 1
-                            while (done < mlen) {
-                                const int li = lane - (32 - (int)take); /* index within the round */
-                                uint32_t v8 = 0;
-                                if (li >= 0) {
-                                    const uint32_t mi = done + li; /* index in the CRC'd message */
-                                    if (mi < 2) {
-                                        v8 = (mi == 0) ? (len >> 8) : (len & 0xffu);
-                                    } else {
-                                        v8 = body_byte(mi - 2);
-                                        if (fits) p.bytes[(boff + mi - 2) & (p.bytes_cap - 1u)] = (uint8_t)v8;
-                                    }
-                                    if (li == 0) v8 ^= crc >> 8;
-                                    if (li == 1) v8 ^= crc & 0xffu;
-                                }
-                                /* v8 * crc_k mod p, Horner over the 8 bits */
-                                uint32_t acc = 0;
-#pragma unroll
-                                for (int k = 7; k >= 0; --k) {
-                                    acc = ((acc << 1) ^ ((acc & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
-                                    if ((v8 >> k) & 1u) acc ^= crc_k;
-                                }
-                                acc = __reduce_xor_sync(FULL, acc);
-                                /* a 1-byte round has no second byte to carry the register's low byte:
-                                 * R_lo * x^(8n) with n = 1 is R_lo << 8 */
-                                if (take == 1) acc ^= (crc & 0xffu) << 8;
-                                crc = acc;
-                                done += take;
-                                take = 32;
-                            }
-                            /* received CRC-16: the two bytes after the payload */
-                            const uint32_t rx = (lane < 2) ? (body_byte(len + lane) << (8 * (1 - lane))) : 0u;
-                            const uint32_t crc_rx = __reduce_or_sync(FULL, rx);
-                            const uint32_t ok = crc == crc_rx;
-                            if (fits) {
-                                if (lane == 0) {
-                                    anm_frame_t f;
-                                    f.channel = ch;
-                                    f.len = len;
-                                    f.start_sample = (sc.t0 + 1 - (unsigned long long)p.P * S) * H;
-                                    f.crc_ok = ok;
-                                    f.offset = boff;
-                                    p.frames[fidx & (p.frames_cap - 1u)] = f;
-                                }
-                                if (ok) sc.stats.frames_ok++; else sc.stats.frames_bad++;
-                            } else if (lane == 0) {
-                                atomicOr(&p.counters[2], 1u);
-                            }
-                            sc.state = ST_SEARCH;
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) *ssc = sc;
-                __syncwarp();
-            }
+            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, ssc, crc_k);
         }
 
         /* ---- save carried state: the last 32 symbol slots of the chunk ---- */

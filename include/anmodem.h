@@ -99,6 +99,10 @@ int anm_config_preset(const char *name, anm_config_t *out); /* "ref4", "bfsk2", 
 int anm_config_validate(const anm_config_t *cfg);
 /* twiddle table [sym_len][n_tones][2] = (cos, sin)(2*pi*bin*m/N) rounded to fp32 */
 int anm_twiddles(const anm_config_t *cfg, float *out);
+/* SPEC 3b: 1 if the configuration uses the dense integer basis (n_tones >= 32) */
+int anm_config_dense(const anm_config_t *cfg);
+/* SPEC 3b: int8 basis out[sym_len][n_tones][2] = (round(127 cos), round(127 sin)) with the quarter-period symmetry */
+int anm_basis_q7(const anm_config_t *cfg, int8_t *out);
 uint16_t anm_crc16(const uint8_t *data, size_t len, uint16_t crc);
 uint8_t anm_crc8(const uint8_t *data, size_t len, uint8_t crc);
 /* number of symbols (preamble + header + body) of a frame carrying len bytes */

@@ -37,6 +37,10 @@ struct anm_oracle {
     uint64_t hop; /* index of the hop being assembled */
     /* tree history: hist[l][h & 7][k][2]; level 0 = hop partials */
     float hist[MAXLVL + 1][8][MAXT][2];
+    /* SPEC 3b (dense tone sets, T >= 32): int8 basis and exact integer hop partials / window sums */
+    int dense;
+    int8_t *bq; /* [N][T][2] */
+    int32_t ihist[MAXLVL + 1][8][MAXT][2];
     /* hop records */
     uint8_t rd[RING];
     float re[RING];
@@ -99,6 +103,28 @@ anm_oracle_t *anm_oracle_create(const anm_config_t *cfg, const float *twiddles) 
     o->tw = (float *)malloc(ntw * sizeof(float));
     memcpy(o->tw, twiddles, ntw * sizeof(float));
     o->fsyms = (uint8_t *)malloc(((size_t)cfg->max_payload + 8) * 8 + 64);
+    o->dense = o->T >= 32;
+    if (o->dense) {
+        /* SPEC 3b: first quarter = round(127 cos), round(127 sin) of the reduced angle; the other
+         * quarters by the exact rotation (-j)^(bin q) */
+        const double two_pi = 6.283185307179586476925286766559;
+        o->bq = (int8_t *)malloc((size_t)o->N * o->T * 2);
+        for (uint32_t m = 0; m < o->N / 4; ++m)
+            for (uint32_t k = 0; k < o->T; ++k) {
+                double a = two_pi * (double)((cfg->tone_bin[k] * m) % o->N) / (double)o->N;
+                int co = (int)lround(127.0 * cos(a)), si = (int)lround(127.0 * sin(a));
+                for (uint32_t q = 0; q < 4; ++q) {
+                    int cq = co, sq = si;
+                    for (uint32_t t = 0; t < ((cfg->tone_bin[k] * q) & 3u); ++t) { /* multiply (c - j s) by -j */
+                        int nc = -sq, ns = cq;
+                        cq = nc;
+                        sq = ns;
+                    }
+                    o->bq[((size_t)(m + q * (o->N / 4)) * o->T + k) * 2 + 0] = (int8_t)cq;
+                    o->bq[((size_t)(m + q * (o->N / 4)) * o->T + k) * 2 + 1] = (int8_t)sq;
+                }
+            }
+    }
     anm_oracle_reset(o);
     return o;
 }
@@ -107,6 +133,7 @@ void anm_oracle_reset(anm_oracle_t *o) {
     o->nbuf = 0;
     o->hop = 0;
     memset(o->hist, 0, sizeof o->hist);
+    memset(o->ihist, 0, sizeof o->ihist);
     memset(o->rd, 0xFF, sizeof o->rd);
     memset(o->re, 0, sizeof o->re);
     o->state = ST_SEARCH;
@@ -117,6 +144,7 @@ void anm_oracle_reset(anm_oracle_t *o) {
 void anm_oracle_destroy(anm_oracle_t *o) {
     if (!o) return;
     free(o->tw);
+    free(o->bq);
     free(o->fsyms);
     free(o->frames);
     free(o->bytes);
@@ -276,40 +304,78 @@ static void state_step(anm_oracle_t *o, uint64_t h) {
     }
 }
 
-/* SPEC 3: one complete hop of H samples */
-static void process_hop(anm_oracle_t *o) {
-    const uint64_t h = o->hop;
+/* SPEC 3b: hop partials, window sums (exact integers) and energies of a dense tone set */
+static void dense_energies(anm_oracle_t *o, uint64_t h, float *E) {
     const uint32_t T = o->T, H = o->H;
     const uint32_t m0 = (uint32_t)((h * H) % o->N);
-    float(*P)[2] = o->hist[0][h & 7];
+    int32_t(*P)[2] = o->ihist[0][h & 7];
     for (uint32_t k = 0; k < T; ++k) {
-        const float *tw = o->tw + ((size_t)m0 * T + k) * 2;
-        float x = (float)o->hopbuf[0];
-        float I = x * tw[0], Q = x * tw[1];
-        for (uint32_t j = 1; j < H; ++j) {
-            tw += (size_t)T * 2;
-            x = (float)o->hopbuf[j];
-            I = fmaf(x, tw[0], I);
-            Q = fmaf(x, tw[1], Q);
+        int32_t I = 0, Q = 0;
+        for (uint32_t j = 0; j < H; ++j) {
+            const int8_t *b = o->bq + ((size_t)(m0 + j) * T + k) * 2;
+            I += (int32_t)o->hopbuf[j] * b[0];
+            Q += (int32_t)o->hopbuf[j] * b[1];
         }
         P[k][0] = I;
         P[k][1] = Q;
     }
     for (uint32_t l = 1; l <= o->lvl; ++l) {
         uint32_t d = 1u << (l - 1);
-        float(*cur)[2] = o->hist[l][h & 7];
-        float(*a)[2] = o->hist[l - 1][(h - d) & 7]; /* zero before the stream (hist zero-initialised) */
-        float(*bb)[2] = o->hist[l - 1][h & 7];
+        int32_t(*cur)[2] = o->ihist[l][h & 7];
+        int32_t(*a)[2] = o->ihist[l - 1][(h - d) & 7];
+        int32_t(*bb)[2] = o->ihist[l - 1][h & 7];
         for (uint32_t k = 0; k < T; ++k) {
             cur[k][0] = a[k][0] + bb[k][0];
             cur[k][1] = a[k][1] + bb[k][1];
         }
     }
-    float(*W)[2] = o->hist[o->lvl][h & 7];
+    int32_t(*W)[2] = o->ihist[o->lvl][h & 7];
+    for (uint32_t k = 0; k < T; ++k) {
+        float fi = (float)W[k][0], fq = (float)W[k][1]; /* round to nearest */
+        E[k] = fmaf(fi, fi, fq * fq);
+    }
+}
+
+/* SPEC 3: one complete hop of H samples */
+static void process_hop(anm_oracle_t *o) {
+    const uint64_t h = o->hop;
+    const uint32_t T = o->T, H = o->H;
+    float Eh[MAXT];
+    if (o->dense) {
+        dense_energies(o, h, Eh);
+    } else {
+        const uint32_t m0 = (uint32_t)((h * H) % o->N);
+        float(*P)[2] = o->hist[0][h & 7];
+        for (uint32_t k = 0; k < T; ++k) {
+            const float *tw = o->tw + ((size_t)m0 * T + k) * 2;
+            float x = (float)o->hopbuf[0];
+            float I = x * tw[0], Q = x * tw[1];
+            for (uint32_t j = 1; j < H; ++j) {
+                tw += (size_t)T * 2;
+                x = (float)o->hopbuf[j];
+                I = fmaf(x, tw[0], I);
+                Q = fmaf(x, tw[1], Q);
+            }
+            P[k][0] = I;
+            P[k][1] = Q;
+        }
+        for (uint32_t l = 1; l <= o->lvl; ++l) {
+            uint32_t d = 1u << (l - 1);
+            float(*cur)[2] = o->hist[l][h & 7];
+            float(*a)[2] = o->hist[l - 1][(h - d) & 7]; /* zero before the stream (hist zero-initialised) */
+            float(*bb)[2] = o->hist[l - 1][h & 7];
+            for (uint32_t k = 0; k < T; ++k) {
+                cur[k][0] = a[k][0] + bb[k][0];
+                cur[k][1] = a[k][1] + bb[k][1];
+            }
+        }
+        float(*W)[2] = o->hist[o->lvl][h & 7];
+        for (uint32_t k = 0; k < T; ++k) Eh[k] = fmaf(W[k][0], W[k][0], W[k][1] * W[k][1]);
+    }
     uint32_t best = 0;
     float emax = 0.0f;
     for (uint32_t k = 0; k < T; ++k) {
-        float E = fmaf(W[k][0], W[k][0], W[k][1] * W[k][1]);
+        float E = Eh[k];
         if (o->trE && h < o->trcap) o->trE[h * T + k] = E;
         if (k == 0 || E > emax) {
             emax = E;
