@@ -137,18 +137,19 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
 }
 
 /* int8 basis of a dense configuration in the panel order the MMA descriptors of k_demod_tc address:
- * [tone group][16-sample K chunk][column = 2*tone_in_group + (0: cos, 1: sin)][sample in chunk] */
+ * [hop phase q][tone group][16-sample K chunk][column = 2*tone_in_group + (0: cos, 1: sin)][sample in chunk] */
 static int upload_basis_panels(const anm_config_t *cfg, uint8_t **d_out) {
-    const uint32_t N = cfg->sym_len, T = cfg->n_tones, H = N / cfg->hops_per_sym, KC = H / 16;
+    const uint32_t N = cfg->sym_len, T = cfg->n_tones, S = cfg->hops_per_sym, H = N / S, KC = H / 16, NG = T / tc::kTG;
     std::vector<int8_t> q7((size_t)N * T * 2);
     if (anm_basis_q7(cfg, q7.data()) != ANM_OK) return ANM_ERR_ARG;
-    std::vector<uint8_t> pan((size_t)(T / tc::kTG) * KC * tc::kBPanel);
-    for (uint32_t g = 0; g < T / tc::kTG; ++g)
-        for (uint32_t kc = 0; kc < KC; ++kc)
-            for (uint32_t n = 0; n < tc::kNcol; ++n)
-                for (uint32_t kk = 0; kk < 16; ++kk)
-                    pan[((size_t)(g * KC + kc) * tc::kNcol + n) * 16 + kk] =
-                        (uint8_t)q7[((size_t)(kc * 16 + kk) * T + (g * tc::kTG + n / 2)) * 2 + (n & 1u)];
+    std::vector<uint8_t> pan((size_t)S * NG * KC * tc::kBPanel);
+    for (uint32_t q = 0; q < S; ++q)
+        for (uint32_t g = 0; g < NG; ++g)
+            for (uint32_t kc = 0; kc < KC; ++kc)
+                for (uint32_t n = 0; n < tc::kNcol; ++n)
+                    for (uint32_t kk = 0; kk < 16; ++kk)
+                        pan[((size_t)((q * NG + g) * KC + kc) * tc::kNcol + n) * 16 + kk] =
+                            (uint8_t)q7[((size_t)(q * H + kc * 16 + kk) * T + (g * tc::kTG + n / 2)) * 2 + (n & 1u)];
     CK(cudaMalloc(d_out, pan.size()));
     CK(cudaMemcpy(*d_out, pan.data(), pan.size(), cudaMemcpyHostToDevice));
     return ANM_OK;

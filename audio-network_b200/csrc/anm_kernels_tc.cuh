@@ -9,11 +9,11 @@
  *   PCM (int16, HBM) --LDG.128, coalesced--> byte split (PRMT): high bytes (s8), low bytes (u8)
  *        --> A operand panels in shared memory, K-major, no swizzle: row = symbol period (128 rows =
  *            4 warps x 32 lanes), K = the H samples of one hop; one panel set per hop phase q and plane
- *   basis (int8, first quarter period only) --> B operand panels, 16 tones (32 columns) per group
+ *   basis (int8, one panel set per hop phase) --> B operand panels, 16 tones (32 columns) per group
  *   D[q][plane] (128 x 32, s32, TMEM) = A[q][plane] . B^T        2 x tcgen05.mma (K = 32 each) per D
  *   hop partial = 256 * D[q][hi] + D[q][lo]                       exact integer (x = 256 hi + lo)
- *   rotation by (-j)^(bin q) (the basis' quarter-period symmetry), window sums (exact integer adds,
- *   tails of the previous symbol period by shuffle / carry), E = fma(fI, fI, fQ fQ), argmax over tones.
+ *   window sums (exact integer adds, tails of the previous symbol period by shuffle / carry),
+ *   E = fma(fI, fI, fQ fQ), argmax over tones.
  *
  * There is no reference kernel for this; behaviour is SPEC.md's.
  */
@@ -32,8 +32,10 @@ constexpr uint32_t kTmemCols = 256;                /* 4 hop phases x 2 byte plan
 
 template <int N, int S>
 __host__ __device__ constexpr uint32_t a_bytes() { return 2u * S * (uint32_t)(N / S / 16) * kPanel; }
+/* basis panels [hop phase q][tone group][K chunk]: the basis of hop phase q is the first-quarter basis
+ * rotated by (-j)^(bin q); keeping all S phases removes every rotation from the epilogue */
 template <int T, int N, int S>
-__host__ __device__ constexpr uint32_t b_bytes() { return (uint32_t)(T / kTG) * (uint32_t)(N / S / 16) * kBPanel; }
+__host__ __device__ constexpr uint32_t b_bytes() { return (uint32_t)S * (uint32_t)(T / kTG) * (uint32_t)(N / S / 16) * kBPanel; }
 template <int T, int S>
 __host__ __device__ constexpr uint32_t warp_bytes() { return 64u * S * 8u + 128u + (uint32_t)(S - 1) * T * 8u; }
 template <int T, int N, int S>
@@ -62,6 +64,12 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, int32_t (&v)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             const uint64_t ad = smem_desc(sA + (uint32_t)((pl * S + q) * KC + 2 * ks) * kPanel, kPanel, 128u);
-                            const uint64_t bd = smem_desc(sB + (uint32_t)(g * KC + 2 * ks) * kBPanel, kBPanel, 128u);
+                            const uint64_t bd = smem_desc(sB + (uint32_t)((q * NG + g) * KC + 2 * ks) * kBPanel, kBPanel, 128u);
                             mma_i8(tmem_base + (uint32_t)(q * 2 + pl) * kNcol, ad, bd, idesc_i8(pl == 0), ks > 0 ? 1u : 0u);
                         }
                 mma_commit(mbar);
@@ -210,36 +218,33 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
             mph ^= 1u;
             tc_fence_after();
 
-            /* ---- epilogue: two tones at a time ---- */
+            /* ---- epilogue: eight tones (16 accumulator columns) at a time ---- */
             if (have_ch) {
+                constexpr int TN = 8;
 #pragma unroll 1
-                for (int tp = 0; tp < kTG / 2; ++tp) {
-                    int32_t v[S][2][4];
+                for (int tb = 0; tb < kTG / TN; ++tb) {
+                    int32_t v[S][2][2 * TN];
 #pragma unroll
                     for (int q = 0; q < S; ++q)
 #pragma unroll
-                        for (int pl = 0; pl < 2; ++pl) tmem_ld4(tmem_lane + (uint32_t)((q * 2 + pl) * (int)kNcol + 4 * tp), v[q][pl]);
+                        for (int pl = 0; pl < 2; ++pl) tmem_ld16(tmem_lane + (uint32_t)((q * 2 + pl) * (int)kNcol + 2 * TN * tb), v[q][pl]);
                     tmem_ld_wait();
+                    const int tone0 = g * kTG + tb * TN;
+                    /* hop partials, their suffix sums (hops i..S-1) and the window sums:
+                     * W_i = (suffix sum of the previous symbol period from hop i+1) + (prefix sum to hop i) */
+                    int32_t cI[TN][S - 1], cQ[TN][S - 1]; /* this lane's suffix sums, next step's carry */
 #pragma unroll
-                    for (int tt = 0; tt < 2; ++tt) {
-                        const int tone = g * kTG + 2 * tp + tt;
-                        const uint32_t rot = (uint32_t)(p.tw_rot[tone >> 5] >> (2 * (tone & 31))) & 3u;
+                    for (int tt = 0; tt < TN; ++tt) {
                         int32_t PI[S], PQ[S];
 #pragma unroll
                         for (int q = 0; q < S; ++q) {
-                            const int32_t I0 = v[q][0][2 * tt] * 256 + v[q][1][2 * tt];
-                            const int32_t Q0 = v[q][0][2 * tt + 1] * 256 + v[q][1][2 * tt + 1];
-                            /* basis at m + q N/4 = (-j)^(bin q) x basis at m (SPEC 3b): exact swap / negate */
-                            const uint32_t r = (rot * (uint32_t)q) & 3u;
-                            PI[q] = (r == 0u) ? I0 : (r == 1u) ? -Q0 : (r == 2u) ? -I0 : Q0;
-                            PQ[q] = (r == 0u) ? Q0 : (r == 1u) ? I0 : (r == 2u) ? -Q0 : -I0;
+                            PI[q] = v[q][0][2 * tt] * 256 + v[q][1][2 * tt];
+                            PQ[q] = v[q][0][2 * tt + 1] * 256 + v[q][1][2 * tt + 1];
                         }
-                        /* window sums: W_i = (suffix sum of the previous symbol period from hop i+1) + (prefix sum to hop i) */
-                        int32_t SI[S], SQ[S]; /* suffix sums of this symbol period: hops i..S-1 */
-                        SI[S - 1] = PI[S - 1];
-                        SQ[S - 1] = PQ[S - 1];
+                        cI[tt][S - 2] = PI[S - 1];
+                        cQ[tt][S - 2] = PQ[S - 1];
 #pragma unroll
-                        for (int i = S - 2; i >= 1; --i) { SI[i] = PI[i] + SI[i + 1]; SQ[i] = PQ[i] + SQ[i + 1]; }
+                        for (int i = S - 2; i >= 1; --i) { cI[tt][i - 1] = PI[i] + cI[tt][i]; cQ[tt][i - 1] = PQ[i] + cQ[tt][i]; }
                         int32_t fI = 0, fQ = 0;
 #pragma unroll
                         for (int i = 0; i < S; ++i) {
@@ -247,8 +252,8 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
                             fQ += PQ[i];
                             int32_t wI = fI, wQ = fQ;
                             if (i < S - 1) {
-                                int32_t pI = __shfl_up_sync(FULL, SI[i + 1], 1), pQ = __shfl_up_sync(FULL, SQ[i + 1], 1);
-                                if (lane == 0) { const int2 cv = carry[tone * (S - 1) + i]; pI = cv.x; pQ = cv.y; }
+                                int32_t pI = __shfl_up_sync(FULL, cI[tt][i], 1), pQ = __shfl_up_sync(FULL, cQ[tt][i], 1);
+                                if (lane == 0) { const int2 cv = carry[(tone0 + tt) * (S - 1) + i]; pI = cv.x; pQ = cv.y; }
                                 wI += pI;
                                 wQ += pQ;
                             }
@@ -257,16 +262,18 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
                             if (MODE == 1) {
                                 if (p.trE && active) {
                                     const size_t hop = ((size_t)step * 32 + lane) * S + i;
-                                    p.trE[((size_t)ch * p.tr_hops + hop) * T + tone] = E;
+                                    p.trE[((size_t)ch * p.tr_hops + hop) * T + tone0 + tt] = E;
                                 }
                             }
-                            if (tone == 0 || E > ec[i]) { ec[i] = E; dc[i] = (uint32_t)tone; }
+                            if ((g == 0 && tb == 0 && tt == 0) || E > ec[i]) { ec[i] = E; dc[i] = (uint32_t)(tone0 + tt); }
                         }
-                        __syncwarp(); /* lane 0 has read the old carry */
-                        if (lane == nvalid - 1) {
+                    }
+                    __syncwarp(); /* lane 0 has read the old carry */
+                    if (lane == nvalid - 1) {
 #pragma unroll
-                            for (int i = 0; i < S - 1; ++i) carry[tone * (S - 1) + i] = make_int2(SI[i + 1], SQ[i + 1]);
-                        }
+                        for (int tt = 0; tt < TN; ++tt)
+#pragma unroll
+                            for (int i = 0; i < S - 1; ++i) carry[(tone0 + tt) * (S - 1) + i] = make_int2(cI[tt][i], cQ[tt][i]);
                     }
                 }
             }
