@@ -15,7 +15,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 CU = ["anm_cuda.cu", "anm_tx.cu"]
 C = ["anm_config.c", "anm_tx.c", "anm_pb.c"]
-DEPS = ["anm_kernels.cuh", "anm_internal.h", "../../include/anmodem.h", "../../include/anmodem_pb.h"]
+DEPS = ["anm_kernels.cuh", "anm_kernels_tc.cuh", "anm_internal.h", "../../include/anmodem.h", "../../include/anmodem_pb.h"]
 
 
 def _newer(target, sources):

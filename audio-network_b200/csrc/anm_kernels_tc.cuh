@@ -169,21 +169,38 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
         const bool active = have_ch && lane < nvalid;
         const uint32_t hic = step * 32u * S;
 
-        /* ---- PCM -> byte planes in the A panels (this warp's 32 rows) ---- */
+        /* ---- PCM -> byte planes in the A panels (this warp's 32 rows).  All loads of the step are issued
+         * before the first split so that the DRAM / L2 latency is paid once; the next step's lines are
+         * pulled into L2 meanwhile. ---- */
         if (have_ch) {
             const char *g = src + (size_t)step * (32u * N * 2u) + (size_t)lane * 16u;
             constexpr int IT = CPS; /* CPS * 32 chunks of 16 bytes per step and warp, 32 per instruction */
             static_assert(CPS % 32 == 0 || 32 % CPS == 0, "chunk geometry");
-#pragma unroll 8
-            for (int it = 0; it < IT; ++it) {
-                const uint32_t idx = (uint32_t)it * 32u + (uint32_t)lane;
-                const uint32_t r = idx / (uint32_t)CPS, c = idx % (uint32_t)CPS; /* symbol period in the step, chunk in it */
-                if ((int)r < nvalid) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)it * 512u));
+            constexpr int BATCH = 32;
+            static_assert(IT % BATCH == 0, "load batch");
+#pragma unroll 1
+            for (int b0 = 0; b0 < IT; b0 += BATCH) {
+                uint4 v[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const uint32_t idx = (uint32_t)(b0 + j) * 32u + (uint32_t)lane;
+                    v[j] = make_uint4(0u, 0u, 0u, 0u);
+                    if ((int)(idx / (uint32_t)CPS) < nvalid) v[j] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)(b0 + j) * 512u));
+                }
+                if (b0 == 0 && step + 1 < n_steps) {
+                    /* next step: 32 * N * 2 bytes per warp = N / 2 lines of 128 bytes, N / 64 per lane */
+                    const char *nx = src + (size_t)(step + 1) * (32u * N * 2u) + (size_t)lane * 128u;
+#pragma unroll
+                    for (int j = 0; j < N / 64; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * 4096u));
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    const uint32_t idx = (uint32_t)(b0 + j) * 32u + (uint32_t)lane;
+                    const uint32_t r = idx / (uint32_t)CPS, c = idx % (uint32_t)CPS; /* symbol period in the step, chunk in it */
                     const uint32_t q = c / (uint32_t)(H / 8), hc = c % (uint32_t)(H / 8);
                     const uint32_t off = (q * KC + (hc >> 1)) * kPanel + ((uint32_t)(32 * w) + r) * 16u + (hc & 1u) * 8u;
-                    const uint32_t lo0 = prmt(v.x, v.y, 0x6420u), lo1 = prmt(v.z, v.w, 0x6420u);
-                    const uint32_t hi0 = prmt(v.x, v.y, 0x7531u), hi1 = prmt(v.z, v.w, 0x7531u);
+                    const uint32_t lo0 = prmt(v[j].x, v[j].y, 0x6420u), lo1 = prmt(v[j].z, v[j].w, 0x6420u);
+                    const uint32_t hi0 = prmt(v[j].x, v[j].y, 0x7531u), hi1 = prmt(v[j].z, v[j].w, 0x7531u);
                     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sA + off), "r"(hi0), "r"(hi1) : "memory");
                     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sA + (uint32_t)(S * KC) * kPanel + off), "r"(lo0), "r"(lo1) : "memory");
                 }
