@@ -2,9 +2,12 @@
  * anm_kernels_tc.cuh -- dense tone sets (SPEC 3b, T >= 32): the windows-by-basis contraction on the
  * 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
  *
- * A CTA of four warps owns four channels; warp w owns channel 4*blockIdx.x + w and, within a step of
- * 32 symbol periods, lane l owns symbol period l -- the same ownership as k_demod, so the hop-record
- * ring, the carried state and the whole sync / slicing / framing state machine (sm_step) are shared.
+ * A CTA owns four channels; two warps serve each channel c = 4*blockIdx.x + (w & 3): within a step of
+ * 32 symbol periods lane l owns symbol period l (the same ownership as k_demod, so the hop-record
+ * ring, the carried state and the whole sync / slicing / framing state machine sm_step are shared).
+ * Both warps of a channel read the same TMEM lanes (rows) and split the tones of every group; warp
+ * c ("front") merges the two argmax candidates and runs the state machine while warp c + 4 ("back")
+ * already loads and byte-splits the next step's PCM.
  *
  *   PCM (int16, HBM) --LDG.128, coalesced--> byte split (PRMT): high bytes (s8), low bytes (u8)
  *        --> A operand panels in shared memory, K-major, no swizzle: row = symbol period (128 rows =
@@ -71,6 +74,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
                    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -94,32 +102,84 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 /* MODE 0: streaming demodulator; MODE 1: stateless tone-energy pass (trace outputs). */
 template <int T, int N, int S, int MODE>
-__global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(256, 2) k_demod_tc(const __grid_constant__ KParams p) {
     using namespace tc;
     constexpr int H = N / S;
     constexpr int KC = H / 16;          /* 16-byte K chunks per hop */
     constexpr int KS = H / 32;          /* MMAs (K = 32) per hop */
     constexpr int NG = T / kTG;         /* tone groups */
     constexpr int CPS = N / 8;          /* 16-byte PCM chunks per symbol period */
+    constexpr int TH = kTG / 2;         /* tones of a group per warp of the pair */
+    constexpr int TN = 4;               /* tones per epilogue iteration */
     constexpr uint32_t RM = 64u * S - 1u;
     constexpr uint32_t FULL = 0xffffffffu;
-    static_assert(S == 4 && (H % 32) == 0 && (T % kTG) == 0, "unsupported dense geometry");
+    static_assert(S == 4 && (H % 32) == 0 && (T % kTG) == 0 && (TH % TN) == 0, "unsupported dense geometry");
     static_assert(2u * S * kNcol == kTmemCols, "TMEM column budget");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
+    const int c4 = w & 3;               /* channel slot of the CTA = TMEM lane quadrant */
+    const bool front = w < 4;           /* front: merge + state machine; back: next step's PCM */
     const uint32_t sA = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t sB = sA + a_bytes<N, S>();
-    unsigned char *wsm = smem_raw + a_bytes<N, S>() + b_bytes<T, N, S>() + (size_t)w * warp_bytes<T, S>();
-    const uint32_t sr = (uint32_t)__cvta_generic_to_shared(wsm); /* HopRec ring [64*S] */
+    unsigned char *wsm = smem_raw + a_bytes<N, S>() + b_bytes<T, N, S>() + (size_t)c4 * warp_bytes<T, S>();
+    const uint32_t sr = (uint32_t)__cvta_generic_to_shared(wsm); /* HopRec ring [64*S] of the channel */
     ChanScalars *ssc = reinterpret_cast<ChanScalars *>(wsm + 64u * S * 8u);
     int2 *carry = reinterpret_cast<int2 *>(wsm + 64u * S * 8u + 128u); /* [T][S-1] suffix sums of the last symbol period */
     unsigned char *tail = smem_raw + a_bytes<N, S>() + b_bytes<T, N, S>() + 4u * warp_bytes<T, S>();
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(tail);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tail + 8);
 
-    /* ---- one-time setup: basis panels, mbarrier, TMEM ---- */
+    const uint32_t crc_k = (MODE == 0) ? (uint32_t)p.crc_pow[lane] : 0u;
+    const uint32_t n_steps = (p.n_syms + 31u) / 32u;
+    const uint32_t ch = blockIdx.x * 4u + (uint32_t)c4;
+    const bool have_ch = ch < p.n_ch;
+    unsigned char *stp = p.state + (size_t)(have_ch ? ch : 0u) * p.state_stride;
+    uint2 *grec = reinterpret_cast<uint2 *>(stp + sizeof(ChanScalars));
+    int2 *gcarry = reinterpret_cast<int2 *>(stp + state_carry_offset<T, S>());
+    const char *src = reinterpret_cast<const char *>(p.pcm + (size_t)(have_ch ? ch : 0u) * p.ch_stride);
+
+    /* PCM of one step -> byte planes in the A panels (rows 32*c4 ..).  All loads are issued before the
+     * first split so that the DRAM / L2 latency is paid once; the following step is pulled into L2. */
+    auto load_step = [&](uint32_t step) {
+        const int nv = (int)min(32u, p.n_syms - step * 32u);
+        const char *g = src + (size_t)step * (32u * N * 2u) + (size_t)lane * 16u;
+        constexpr int IT = CPS; /* CPS * 32 chunks of 16 bytes per step and channel, 32 per instruction */
+        static_assert(CPS % 32 == 0 || 32 % CPS == 0, "chunk geometry");
+        constexpr int BATCH = 16;
+        static_assert(IT % BATCH == 0, "load batch");
+#pragma unroll 1
+        for (int b0 = 0; b0 < IT; b0 += BATCH) {
+            uint4 v[BATCH];
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                const uint32_t idx = (uint32_t)(b0 + j) * 32u + (uint32_t)lane;
+                v[j] = make_uint4(0u, 0u, 0u, 0u);
+                if ((int)(idx / (uint32_t)CPS) < nv) v[j] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)(b0 + j) * 512u));
+            }
+            if (b0 == 0 && step + 1 < n_steps) {
+                /* next step: 32 * N * 2 bytes per channel = N / 2 lines of 128 bytes, N / 64 per lane */
+                const char *nx = src + (size_t)(step + 1) * (32u * N * 2u) + (size_t)lane * 128u;
+#pragma unroll
+                for (int j = 0; j < N / 64; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * 4096u));
+            }
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                const uint32_t idx = (uint32_t)(b0 + j) * 32u + (uint32_t)lane;
+                const uint32_t r = idx / (uint32_t)CPS, c = idx % (uint32_t)CPS; /* symbol period in the step, chunk in it */
+                const uint32_t q = c / (uint32_t)(H / 8), hc = c % (uint32_t)(H / 8);
+                const uint32_t off = (q * KC + (hc >> 1)) * kPanel + ((uint32_t)(32 * c4) + r) * 16u + (hc & 1u) * 8u;
+                const uint32_t lo0 = prmt(v[j].x, v[j].y, 0x6420u), lo1 = prmt(v[j].z, v[j].w, 0x6420u);
+                const uint32_t hi0 = prmt(v[j].x, v[j].y, 0x7531u), hi1 = prmt(v[j].z, v[j].w, 0x7531u);
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sA + off), "r"(hi0), "r"(hi1) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sA + (uint32_t)(S * KC) * kPanel + off), "r"(lo0), "r"(lo1) : "memory");
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* panels -> visible to the MMA's async proxy */
+    };
+
+    /* ---- one-time setup: basis panels, mbarrier, TMEM, carried state, first step's PCM ---- */
     {
         const uint4 *gsrc = reinterpret_cast<const uint4 *>(p.tc_basis);
         uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + a_bytes<N, S>());
@@ -133,24 +193,7 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* basis panels -> visible to the MMA's async proxy */
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * w) << 16);
-    uint32_t mph = 0;
-
-    const uint32_t crc_k = (MODE == 0) ? (uint32_t)p.crc_pow[lane] : 0u;
-    const uint32_t n_steps = (p.n_syms + 31u) / 32u;
-    const uint32_t ch = blockIdx.x * 4u + (uint32_t)w;
-    const bool have_ch = ch < p.n_ch;
-    unsigned char *stp = p.state + (size_t)(have_ch ? ch : 0u) * p.state_stride;
-    uint2 *grec = reinterpret_cast<uint2 *>(stp + sizeof(ChanScalars));
-    int2 *gcarry = reinterpret_cast<int2 *>(stp + state_carry_offset<T, S>());
-
-    /* ---- restore carried state ---- */
-    if (have_ch) {
+    if (have_ch && front) {
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             const uint2 rv = grec[lane * S + i];
@@ -159,55 +202,20 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
         for (int i = lane; i < (S - 1) * T; i += 32) carry[i] = gcarry[i];
         if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = reinterpret_cast<const uint32_t *>(stp)[lane];
     }
-    __syncwarp();
-
-    const char *src = reinterpret_cast<const char *>(p.pcm + (size_t)(have_ch ? ch : 0u) * p.ch_stride);
+    if (have_ch && !front && n_steps) load_step(0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* basis panels */
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * c4) << 16) + (front ? 0u : (uint32_t)(2 * TH)); /* this warp's columns of every accumulator */
+    uint32_t mph = 0;
 
 #pragma unroll 1
     for (uint32_t step = 0; step < n_steps; ++step) {
         const int nvalid = (int)min(32u, p.n_syms - step * 32u);
         const bool active = have_ch && lane < nvalid;
         const uint32_t hic = step * 32u * S;
-
-        /* ---- PCM -> byte planes in the A panels (this warp's 32 rows).  All loads of the step are issued
-         * before the first split so that the DRAM / L2 latency is paid once; the next step's lines are
-         * pulled into L2 meanwhile. ---- */
-        if (have_ch) {
-            const char *g = src + (size_t)step * (32u * N * 2u) + (size_t)lane * 16u;
-            constexpr int IT = CPS; /* CPS * 32 chunks of 16 bytes per step and warp, 32 per instruction */
-            static_assert(CPS % 32 == 0 || 32 % CPS == 0, "chunk geometry");
-            constexpr int BATCH = 32;
-            static_assert(IT % BATCH == 0, "load batch");
-#pragma unroll 1
-            for (int b0 = 0; b0 < IT; b0 += BATCH) {
-                uint4 v[BATCH];
-#pragma unroll
-                for (int j = 0; j < BATCH; ++j) {
-                    const uint32_t idx = (uint32_t)(b0 + j) * 32u + (uint32_t)lane;
-                    v[j] = make_uint4(0u, 0u, 0u, 0u);
-                    if ((int)(idx / (uint32_t)CPS) < nvalid) v[j] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)(b0 + j) * 512u));
-                }
-                if (b0 == 0 && step + 1 < n_steps) {
-                    /* next step: 32 * N * 2 bytes per warp = N / 2 lines of 128 bytes, N / 64 per lane */
-                    const char *nx = src + (size_t)(step + 1) * (32u * N * 2u) + (size_t)lane * 128u;
-#pragma unroll
-                    for (int j = 0; j < N / 64; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * 4096u));
-                }
-#pragma unroll
-                for (int j = 0; j < BATCH; ++j) {
-                    const uint32_t idx = (uint32_t)(b0 + j) * 32u + (uint32_t)lane;
-                    const uint32_t r = idx / (uint32_t)CPS, c = idx % (uint32_t)CPS; /* symbol period in the step, chunk in it */
-                    const uint32_t q = c / (uint32_t)(H / 8), hc = c % (uint32_t)(H / 8);
-                    const uint32_t off = (q * KC + (hc >> 1)) * kPanel + ((uint32_t)(32 * w) + r) * 16u + (hc & 1u) * 8u;
-                    const uint32_t lo0 = prmt(v[j].x, v[j].y, 0x6420u), lo1 = prmt(v[j].z, v[j].w, 0x6420u);
-                    const uint32_t hi0 = prmt(v[j].x, v[j].y, 0x7531u), hi1 = prmt(v[j].z, v[j].w, 0x7531u);
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sA + off), "r"(hi0), "r"(hi1) : "memory");
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sA + (uint32_t)(S * KC) * kPanel + off), "r"(lo0), "r"(lo1) : "memory");
-                }
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
 
         uint32_t dc[S];
         float ec[S];
@@ -216,8 +224,8 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
 
 #pragma unroll 1
         for (int g = 0; g < NG; ++g) {
-            /* ---- contraction of tone group g: D[q][plane] = A[q][plane] . B_g^T ---- */
-            if (threadIdx.x == 0) {
+            /* ---- contraction of tone group g: D[q][plane] = A[q][plane] . B[q][g]^T (one thread of a back warp) ---- */
+            if (w == 4 + (g & 3) && lane == 0) {
                 tc_fence_after();
 #pragma unroll
                 for (int q = 0; q < S; ++q)
@@ -235,18 +243,17 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
             mph ^= 1u;
             tc_fence_after();
 
-            /* ---- epilogue: eight tones (16 accumulator columns) at a time ---- */
+            /* ---- epilogue: this warp's TH tones of the group, TN at a time ---- */
             if (have_ch) {
-                constexpr int TN = 8;
 #pragma unroll 1
-                for (int tb = 0; tb < kTG / TN; ++tb) {
+                for (int tb = 0; tb < TH / TN; ++tb) {
                     int32_t v[S][2][2 * TN];
 #pragma unroll
                     for (int q = 0; q < S; ++q)
 #pragma unroll
-                        for (int pl = 0; pl < 2; ++pl) tmem_ld16(tmem_lane + (uint32_t)((q * 2 + pl) * (int)kNcol + 2 * TN * tb), v[q][pl]);
+                        for (int pl = 0; pl < 2; ++pl) tmem_ld8(tmem_lane + (uint32_t)((q * 2 + pl) * (int)kNcol + 2 * TN * tb), v[q][pl]);
                     tmem_ld_wait();
-                    const int tone0 = g * kTG + tb * TN;
+                    const int tone0 = g * kTG + (front ? 0 : TH) + tb * TN;
                     /* hop partials, their suffix sums (hops i..S-1) and the window sums:
                      * W_i = (suffix sum of the previous symbol period from hop i+1) + (prefix sum to hop i) */
                     int32_t cI[TN][S - 1], cQ[TN][S - 1]; /* this lane's suffix sums, next step's carry */
@@ -299,17 +306,35 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
             __syncthreads();
         }
 
-        if (have_ch) {
-            if (!active) {
+        /* ---- the back warp hands its argmax candidates to the front warp through the ring slots of this
+         * step (their old content, two steps back, is dead) and moves on to the next step's PCM ---- */
+        const uint32_t a0 = sr + (((hic + (uint32_t)(lane * S)) & RM) << 3);
+        if (have_ch && !front && active) {
 #pragma unroll
-                for (int i = 0; i < S; ++i) { dc[i] = 0xFFu; ec[i] = 0.0f; }
-            }
+            for (int i = 0; i < S; i += 2)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]),
+                             "r"(__float_as_uint(ec[i + 1])), "r"(dc[i + 1]) : "memory");
+        }
+        __syncthreads();
+        if (have_ch && front) {
             if (active) {
-                const uint32_t a0 = sr + (((hic + (uint32_t)(lane * S)) & RM) << 3);
+#pragma unroll
+                for (int i = 0; i < S; i += 2) {
+                    uint32_t e0, d0, e1, d1;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e0), "=r"(d0), "=r"(e1), "=r"(d1) : "r"(a0 + (uint32_t)i * 8u) : "memory");
+                    /* lowest tone index wins a tie (SPEC 3): the back warp's tones of a group are the higher ones,
+                     * but a later group of the front warp is higher still */
+                    const float f0 = __uint_as_float(e0), f1 = __uint_as_float(e1);
+                    if (f0 > ec[i] || (f0 == ec[i] && d0 < dc[i])) { ec[i] = f0; dc[i] = d0; }
+                    if (f1 > ec[i + 1] || (f1 == ec[i + 1] && d1 < dc[i + 1])) { ec[i + 1] = f1; dc[i + 1] = d1; }
+                }
 #pragma unroll
                 for (int i = 0; i < S; i += 2)
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]),
                                  "r"(__float_as_uint(ec[i + 1])), "r"(dc[i + 1]) : "memory");
+            } else {
+#pragma unroll
+                for (int i = 0; i < S; ++i) { dc[i] = 0xFFu; ec[i] = 0.0f; }
             }
             __syncwarp();
             if (MODE == 1) {
@@ -324,10 +349,12 @@ __global__ void __launch_bounds__(128, 2) k_demod_tc(const __grid_constant__ KPa
             }
             if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, ssc, crc_k);
         }
+        if (have_ch && !front && step + 1 < n_steps) load_step(step + 1);
+        __syncthreads(); /* next step's panels complete; the ring is the state machine's again */
     }
 
     /* ---- save carried state ---- */
-    if (have_ch) {
+    if (have_ch && front) {
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < S; ++i) {

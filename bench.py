@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--preset", default="ref4")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the dense-tone-set (tensor-core) leg")
     ap.add_argument("--cpu-channels", type=int, default=0, help="channels in the CPU sample (0 = 4 per core)")
     return ap.parse_args()
 
@@ -230,6 +231,58 @@ def cpu_baseline(cfg, pcm, n_threads, chunk_samples):
     }
 
 
+def kernel_name(cfg, anm):
+    return ("k_demod_tc<%d,%d,%d>" if anm.config_dense(cfg) else "k_demod<%d,%d,%d>") % (cfg.n_tones, cfg.sym_len, cfg.hops_per_sym)
+
+
+def tensor_profile():
+    """Tensor-pipe utilisation of k_demod_tc from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r1_tc_pipe.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+def cfg4_leg(anm, torch, dev, local, stream, steps=12, warmup=3, n_ch=2048):
+    """BASELINE config 4: the 64-tone preset through the tcgen05 contraction kernel (k_demod_tc),
+    same chunking and SNR as the headline workload; PCM resident in HBM, inputs larger than L2."""
+    cfg = anm.config_preset("wide64")
+    chunk = CHUNK_SYMS * cfg.sym_len
+    resident = min(steps + warmup, 8)
+    total = resident * chunk
+    progs, lens, params = build_programs(cfg, anm, n_ch, 1 << 20)
+    d_prog, d_len = torch.from_numpy(progs).to(dev), torch.from_numpy(lens).to(dev)
+    d_par = torch.from_numpy(params.view(np.uint8).copy()).to(dev)
+    d_pcm = torch.empty((n_ch, total), dtype=torch.int16, device=dev)
+    anm.tx_render_device(cfg, d_prog.data_ptr(), progs.shape[1], d_len.data_ptr(), d_par.data_ptr(), n_ch, 0,
+                         d_pcm.data_ptr(), total, total, stream)
+    torch.cuda.synchronize()
+    dm = anm.Demod(cfg, n_ch, device=local)
+    for i in range(warmup):
+        dm.feed_device(d_pcm.data_ptr() + (i % resident) * chunk * 2, total, chunk, stream)
+    dm.collect()
+    dm.read_frames(cap=1 << 22, bytes_cap=1 << 28)
+    dm.kernel_time()
+    for i in range(steps):
+        dm.feed_device(d_pcm.data_ptr() + ((warmup + i) % resident) * chunk * 2, total, chunk, stream)
+    torch.cuda.synchronize()
+    k_ms, k_n = dm.kernel_time()
+    dm.collect()
+    recs, _ = dm.read_frames(cap=1 << 22, bytes_cap=1 << 30)
+    avg_ms = k_ms / max(1, k_n)
+    peak, _ = peaks()
+    gbs = n_ch * chunk * 2 / (avg_ms * 1e-3) / 1e9
+    out = {"workload": "cfg4: %d channels x %d-sample chunks, preset wide64 (64 tones, N=256), 10 dB SNR" % (n_ch, chunk),
+           "kernel": kernel_name(cfg, anm), "value": round(n_ch * chunk / (avg_ms * 1e-3) / 1e6, 2), "unit": "Msamples/s",
+           "avg_kernel_ms": round(avg_ms, 4), "launches_timed": k_n, "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / peak, 4),
+           "frames_ok": int((recs["crc_ok"] == 1).sum()), "arith": "s8/u8 x s8 -> s32 (tcgen05.mma kind::i8), exact",
+           "ncu": tensor_profile()}
+    dm.close()
+    del d_pcm
+    return out
+
+
 def reference_arm(args):
     """--impl reference: the CPU oracle with all host threads on bounded samples of the workload."""
     import audio_network_b200 as anm
@@ -407,6 +460,12 @@ def main():
         sample = d_pcm[:cch, : nchunks * chunk].cpu().numpy()
         cpu = cpu_baseline(cfg, np.ascontiguousarray(sample), cores, nchunks * chunk)
 
+    cfg4 = None
+    if rank == 0 and world == 1 and not args.no_cfg4 and args.preset == "ref4":
+        del d_pcm
+        torch.cuda.empty_cache()
+        cfg4 = cfg4_leg(anm, torch, dev, local, stream)
+
     if rank == 0:
         peak, peak_src = peaks()
         per_launch_bytes = n_ch * chunk * 2
@@ -426,7 +485,7 @@ def main():
             "gpu_launches": int(agg[2].item()),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": measured_traffic() if (n_ch == CH_PER_GPU and args.preset == "ref4") else None, "peak_source": peak_src,
-                         "kernel": "k_demod<%d,%d,%d>" % (cfg.n_tones, cfg.sym_len, cfg.hops_per_sym),
+                         "kernel": kernel_name(cfg, anm),
                          "avg_kernel_ms": round(avg_ms, 4), "launches_timed": k_n,
                          "algorithmic_bytes_per_launch": per_launch_bytes},
             "clocks": clocks,
@@ -435,6 +494,8 @@ def main():
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if cfg4:
+            line["cfg4"] = cfg4
         print(json.dumps(line), flush=True)
     dm.close()
     if world > 1:

@@ -1,0 +1,2 @@
+timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -k "wide64" 2>&1 | tail -3
+timeout 200 python bench.py --preset wide64 --channels 4096 --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 0 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('wide64', d['ms_per_step'], d['value'], d['roofline']['frac'], d['frames_ok'])"
