@@ -156,6 +156,8 @@ def lib():
         "anm_demod_last_kernel_ms": (C.c_float, [vp]),
         "anm_demod_kernel_time": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "anm_demod_launch_geometry": (C.c_int, [vp, u32p, u32p, u32p]),
+        "anm_pb_deframe_device": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
+        "anm_pb_deframe_host": (C.c_int, [vp, C.c_size_t, vp, C.c_size_t, vp]),
         "anm_last_error": (C.c_char_p, []),
         "anm_version": (C.c_char_p, []),
         "demod_initialize": (C.c_int, [cfgp]),
@@ -193,6 +195,21 @@ def config_preset(name):
 def twiddles(cfg):
     out = np.empty((cfg.sym_len, cfg.n_tones, 2), dtype=np.float32)
     _check(lib().anm_twiddles(C.byref(cfg), _ptr(out)))
+    return out
+
+
+PB_SPAN_DTYPE = np.dtype([("status", "<u4"), ("consumed", "<u4"), ("audio_offset", "<u4"), ("audio_len", "<u4")])
+ANM_PB_OK, ANM_PB_FAIL, ANM_PB_NO_AUDIO, ANM_PB_CRC = 0, 1, 2, 3
+
+
+def pb_deframe(recs, payload_bytes):
+    """Batched GPU deframer (include/anmodem_pb.h): frame records + byte arena as returned by
+    Demod.read_frames() -> one span record per frame locating the Opus bytes of its ToReceiver message."""
+    recs = np.ascontiguousarray(recs, dtype=FRAME_DTYPE)
+    by = np.ascontiguousarray(payload_bytes, dtype=np.uint8)
+    out = np.zeros(len(recs), dtype=PB_SPAN_DTYPE)
+    _check(lib().anm_pb_deframe_host(_ptr(recs) if len(recs) else None, len(recs), _ptr(by) if len(by) else None, len(by),
+                                     _ptr(out) if len(recs) else None))
     return out
 
 

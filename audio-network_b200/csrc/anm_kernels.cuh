@@ -465,7 +465,6 @@ constexpr int kMaxWarps = 20; /* registers are allocated per 4 warps: 20 warps x
 template <int T, int N, int S, int MODE>
 __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant__ KParams p) {
     constexpr int H = N / S;
-    constexpr int B = Log2<T>::v;
     constexpr int NQ = quad_hops<S>(); /* hops per table pass */
     constexpr int TL = N / NQ;         /* table positions */
     constexpr int GR = S / NQ;         /* passes per symbol period (hop = pass + q*GR) */

@@ -64,6 +64,33 @@ size_t anm_pb_encode_broadcast_request(uint32_t magic, uint8_t *out, size_t cap)
  * malformed input (bad varint, truncated field, unknown wire type). */
 size_t anm_pb_scan_to_receiver_audio(const uint8_t *buf, size_t len, const uint8_t **payload, size_t *payload_len);
 
+/* ---- batched deframer on the GPU ----------------------------
+ * The decode step of the reference's receive loop (hardware/src/network.cpp:406-430) for many
+ * frames at once: every CRC-valid frame payload is walked as one varint-delimited ToReceiver
+ * message with the semantics of pb_decode_delimited(&stream, ToReceiver_fields, &msg)
+ * (hardware/lib/nanopb/src/pb_decode.c:1142-1168) and of the field callback
+ * network_pb_callback_audio_data (hardware/src/network.cpp:212-249, 4096-byte limit at :223).
+ * Instead of copying the Opus bytes into two heap blocks per frame it reports where they lie. */
+enum {
+    ANM_PB_OK = 0,       /* decoded, audio_data present: [audio_offset, audio_offset + audio_len) */
+    ANM_PB_FAIL = 1,     /* pb_decode_delimited would return false */
+    ANM_PB_NO_AUDIO = 2, /* decoded, but the oneof does not hold audio_data */
+    ANM_PB_CRC = 3       /* frame failed its CRC-16: never handed to the decoder */
+};
+typedef struct anm_pb_span {
+    uint32_t status;
+    uint32_t consumed;     /* bytes of the payload the decoder consumed (length varint + message) */
+    uint32_t audio_offset; /* position in the byte arena (same space as anm_frame_t.offset) */
+    uint32_t audio_len;
+} anm_pb_span_t;
+/* frames / bytes / out in device memory; bytes_mask = arena size - 1 for a power-of-two ring,
+ * 0xFFFFFFFF for a linear array; stream is a cudaStream_t (NULL = default stream) */
+int anm_pb_deframe_device(const anm_frame_t *d_frames, uint32_t n_frames, const uint8_t *d_bytes,
+                          uint32_t bytes_mask, anm_pb_span_t *d_out, void *stream);
+/* host arrays as returned by anm_demod_read_frames(); copies in, runs the kernel, copies out */
+int anm_pb_deframe_host(const anm_frame_t *frames, size_t n_frames, const uint8_t *bytes, size_t n_bytes,
+                        anm_pb_span_t *out);
+
 #ifdef __cplusplus
 }
 #endif
