@@ -25,18 +25,22 @@ namespace anm {
 enum : uint32_t { ST_SEARCH = 0, ST_PEAK = 1, ST_HEADER = 2, ST_BODY = 3 };
 
 /* Uniform (per-channel) part of the carried state; lane-distributed parts follow it.  Hop indices are
- * 32-bit wrapping counters: every difference the state machine takes is far below 2^31 hops. */
+ * 32-bit wrapping counters: every difference the state machine takes is far below 2^31 hops.  The
+ * first 48 bytes are the working set of every step (three 16-byte loads / stores); the rest is touched
+ * on events only. */
 struct ChanScalars {
     uint32_t state, nsym, total, flen;
-    uint32_t next, prev_hop, best_h, peak_end;
-    float best_q;
+    uint32_t next, prev_hop;
     int32_t acc;
-    uint32_t s_prev, s_prev2;
     uint32_t ep_left;  /* symbols until the next tracker epoch boundary */
-    uint32_t osym_cnt;
+    uint32_t s_prev, s_prev2, osym_cnt, pad0;
+    uint32_t best_h, peak_end; /* SEARCH / PEAK only */
+    float best_q;
+    uint32_t pad1;
     unsigned long long t0; /* absolute hop of the lock (frame start_sample) */
+    uint32_t pad2[2];
     anm_chan_stats_t stats; /* 32 bytes */
-    uint32_t pad[8];
+    uint32_t pad3[4];
 };
 static_assert(sizeof(ChanScalars) == 128, "ChanScalars layout");
 
@@ -171,7 +175,7 @@ __host__ __device__ constexpr uint32_t cta_smem_bytes() { return (uint32_t)(N / 
 template <int T, int N, int S>
 __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, const int lane, const uint32_t sr,
                                         const uint32_t hic, const int nvalid, const bool active,
-                                        const uint32_t (&dc)[S], ChanScalars *ssc, const uint32_t crc_k) {
+                                        const uint32_t (&dc)[S], const uint32_t ssa, const uint32_t crc_k) {
     constexpr int H = N / S;
     constexpr int B = Log2<T>::v;
     constexpr int LV = Log2<S>::v;
@@ -184,7 +188,31 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
         asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + (((hic + (uint32_t)r) & RM) << 3)) : "memory");
         return v;
     };
-    ChanScalars sc = *ssc; /* warp-uniform broadcast loads */
+    /* warp-uniform working set: three broadcast LDS.128; everything else of ChanScalars is read / written
+     * in shared memory (address ssa) when an event needs it */
+    struct {
+        uint32_t state, nsym, total, flen, next, prev_hop;
+        int32_t acc;
+        uint32_t ep_left, s_prev, s_prev2, osym_cnt, pad0;
+    } sc;
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *>(&sc);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4 * i]), "=r"(w[4 * i + 1]), "=r"(w[4 * i + 2]), "=r"(w[4 * i + 3]) : "r"(ssa + 16u * i) : "memory");
+    }
+    auto cold_ld = [&](uint32_t off) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ssa + off) : "memory");
+        return v;
+    };
+    auto cold_st = [&](uint32_t off, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(ssa + off), "r"(v) : "memory"); }; /* every lane, same value */
+    constexpr uint32_t O_BEST_H = offsetof(ChanScalars, best_h), O_PEAK_END = offsetof(ChanScalars, peak_end), O_BEST_Q = offsetof(ChanScalars, best_q),
+                       O_T0 = offsetof(ChanScalars, t0), O_STATS = offsetof(ChanScalars, stats);
+    constexpr uint32_t O_LOCKS = O_STATS + offsetof(anm_chan_stats_t, locks), O_HFAIL = O_STATS + offsetof(anm_chan_stats_t, header_fail),
+                       O_FOK = O_STATS + offsetof(anm_chan_stats_t, frames_ok), O_FBAD = O_STATS + offsetof(anm_chan_stats_t, frames_bad),
+                       O_SYMS = O_STATS + offsetof(anm_chan_stats_t, symbols), O_TRK = O_STATS + offsetof(anm_chan_stats_t, trk_moves);
+    uint32_t syms_step = 0; /* symbols decided in this step, folded into stats.symbols at the end */
     const int endh = nvalid * S;
     int cur = 0;
     bool have_cand = false;
@@ -197,7 +225,11 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
         const int pl = min(lane, (int)p.P - 1);
         const uint2 rv = REC(h - ((int)p.P - 1 - pl) * S);
         float leaf = (lane < (int)p.P && rv.y == (uint32_t)p.preamble[pl]) ? __uint_as_float(rv.x) : 0.0f;
-        for (uint32_t w = 1; w < p.P; w <<= 1) leaf = __fadd_rn(leaf, __shfl_xor_sync(FULL, leaf, w));
+#pragma unroll
+        for (uint32_t w = 1; w < (uint32_t)ANM_MAX_PREAMBLE; w <<= 1) {
+            const float o = __shfl_xor_sync(FULL, leaf, w);
+            if (w < p.P) leaf = __fadd_rn(leaf, o);
+        }
         return __shfl_sync(FULL, leaf, 0);
     };
 
@@ -234,31 +266,37 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                     if (mk) h0 = min(h0, ((__ffs(mk) - 1) << LV) + i);
                 }
                 if (h0 == 0x7fffffff) break;
-                sc.best_q = quality(h0);
-                sc.best_h = hb + (uint32_t)h0;
-                sc.peak_end = hb + (uint32_t)(h0 + S - 1);
+                cold_st(O_BEST_Q, __float_as_uint(quality(h0)));
+                cold_st(O_BEST_H, hb + (uint32_t)h0);
+                cold_st(O_PEAK_END, hb + (uint32_t)(h0 + S - 1));
                 sc.state = ST_PEAK;
                 cur = h0 + 1;
             } else {
-                const int pend = (int)(sc.peak_end - hb);
+                const int pend = (int)(cold_ld(O_PEAK_END) - hb);
+                float best_q = __uint_as_float(cold_ld(O_BEST_Q));
+                uint32_t best_h = cold_ld(O_BEST_H);
                 while (cur < endh && cur <= pend) {
                     if ((pick<S>(cand, cur & (S - 1)) >> (cur >> LV)) & 1u) {
                         const float q = quality(cur);
-                        if (q > sc.best_q) { sc.best_q = q; sc.best_h = hb + (uint32_t)cur; }
+                        if (q > best_q) { best_q = q; best_h = hb + (uint32_t)cur; }
                     }
                     ++cur;
                 }
+                cold_st(O_BEST_Q, __float_as_uint(best_q));
+                cold_st(O_BEST_H, best_h);
                 if (cur > pend) {
-                    sc.t0 = p.hop_base + (unsigned long long)hic + (long long)(int)(sc.best_h - hb);
-                    sc.next = sc.best_h + S;
+                    const unsigned long long t0 = p.hop_base + (unsigned long long)hic + (long long)(int)(best_h - hb);
+                    cold_st(O_T0, (uint32_t)t0);
+                    cold_st(O_T0 + 4u, (uint32_t)(t0 >> 32));
+                    sc.next = best_h + S;
                     sc.nsym = 0;
                     sc.acc = 0;
                     sc.ep_left = p.trk_epoch;
                     sc.s_prev = p.preamble[p.P - 1];
                     sc.s_prev2 = 0xFFu;
-                    sc.prev_hop = sc.best_h;
+                    sc.prev_hop = best_h;
                     sc.state = ST_HEADER;
-                    sc.stats.locks++;
+                    cold_st(O_LOCKS, cold_ld(O_LOCKS) + 1u);
                 }
             }
         } else {
@@ -332,8 +370,8 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
             sc.nsym += cnt;
             sc.osym_cnt += cnt;
             sc.next += (cnt << LV) + (uint32_t)adj;
-            sc.stats.symbols += cnt;
-            sc.stats.trk_moves += adj;
+            syms_step += cnt;
+            if (adj) cold_st(O_TRK, cold_ld(O_TRK) + (uint32_t)adj);
             cur = lasth + 1;
             if (sc.state == ST_HEADER && sc.nsym == p.hdr_syms) {
                 __syncwarp();
@@ -354,7 +392,7 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                     for (int k = 0; k < 8; ++k) c8 = (c8 & 0x80u) ? (((c8 << 1) ^ 0x07u) & 0xffu) : ((c8 << 1) & 0xffu);
                 }
                 if (len == 0 || len > p.max_payload || c8 != (hdr & 0xffu)) {
-                    sc.stats.header_fail++;
+                    cold_st(O_HFAIL, cold_ld(O_HFAIL) + 1u);
                     sc.state = ST_SEARCH;
                 } else {
                     sc.flen = len;
@@ -440,12 +478,13 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                         anm_frame_t f;
                         f.channel = ch;
                         f.len = len;
-                        f.start_sample = (sc.t0 + 1 - (unsigned long long)p.P * S) * H;
+                        const unsigned long long t0 = (unsigned long long)cold_ld(O_T0) | ((unsigned long long)cold_ld(O_T0 + 4u) << 32);
+                        f.start_sample = (t0 + 1 - (unsigned long long)p.P * S) * H;
                         f.crc_ok = ok;
                         f.offset = boff;
                         p.frames[fidx & (p.frames_cap - 1u)] = f;
                     }
-                    if (ok) sc.stats.frames_ok++; else sc.stats.frames_bad++;
+                    cold_st(ok ? O_FOK : O_FBAD, cold_ld(ok ? O_FOK : O_FBAD) + 1u);
                 } else if (lane == 0) {
                     atomicOr(&p.counters[2], 1u);
                 }
@@ -453,8 +492,17 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
             }
         }
     }
-    __syncwarp();
-    if (lane == 0) *ssc = sc;
+    if (syms_step) {
+        const unsigned long long n = ((unsigned long long)cold_ld(O_SYMS) | ((unsigned long long)cold_ld(O_SYMS + 4u) << 32)) + syms_step;
+        cold_st(O_SYMS, (uint32_t)n);
+        cold_st(O_SYMS + 4u, (uint32_t)(n >> 32));
+    }
+    {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&sc);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ssa + 16u * i), "r"(w[4 * i]), "r"(w[4 * i + 1]), "r"(w[4 * i + 2]), "r"(w[4 * i + 3]) : "memory");
+    }
     __syncwarp();
 }
 
@@ -769,7 +817,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                 }
             }
 
-            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, ssc, crc_k);
+            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k);
         }
 
         /* ---- save carried state: the last 32 symbol slots of the chunk ---- */

@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256, 2) k_demod_tc(const __grid_constant__ KPa
                     for (int i = 0; i < S; ++i) p.trEmax[(size_t)ch * p.tr_hops + ((size_t)step * 32 + lane) * S + i] = ec[i];
                 }
             }
-            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, ssc, crc_k);
+            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k);
         }
         if (have_ch && !front && step + 1 < n_steps) load_step(step + 1);
         __syncthreads(); /* next step's panels complete; the ring is the state machine's again */
