@@ -102,7 +102,7 @@ STATS_DTYPE = np.dtype(
 
 # every symbol include/anmodem.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "anm_config_preset", "anm_config_validate", "anm_twiddles", "anm_config_dense", "anm_basis_q7", "anm_crc16", "anm_crc8",
+    "anm_config_preset", "anm_config_validate", "anm_twiddles", "anm_config_dense", "anm_basis_q7", "anm_config_foldable", "anm_fold_twiddles", "anm_crc16", "anm_crc8",
     "anm_frame_num_symbols", "anm_frame_symbols", "anm_tx_render", "anm_tx_render_device",
     "anm_tone_energies_device", "anm_demod_create", "anm_demod_destroy", "anm_demod_reset",
     "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_feed_host_async", "anm_demod_wait_input",
@@ -130,6 +130,8 @@ def lib():
         "anm_config_validate": (C.c_int, [cfgp]),
         "anm_twiddles": (C.c_int, [cfgp, vp]),
         "anm_config_dense": (C.c_int, [cfgp]),
+        "anm_config_foldable": (C.c_int, [cfgp]),
+        "anm_fold_twiddles": (C.c_int, [cfgp, vp]),
         "anm_basis_q7": (C.c_int, [cfgp, vp]),
         "anm_crc16": (C.c_uint16, [vp, C.c_size_t, C.c_uint16]),
         "anm_crc8": (C.c_uint8, [vp, C.c_size_t, C.c_uint8]),
@@ -216,6 +218,17 @@ def pb_deframe(recs, payload_bytes):
 def config_dense(cfg):
     """SPEC 3b: True if the configuration uses the dense integer basis (tensor-core contraction path)."""
     return bool(lib().anm_config_dense(C.byref(cfg)))
+
+
+def config_foldable(cfg):
+    """SPEC 3: True if the hop partials are computed by centre folding."""
+    return bool(lib().anm_config_foldable(C.byref(cfg)))
+
+
+def fold_twiddles(cfg):
+    out = np.empty((cfg.hop // 2, cfg.n_tones, 2), dtype=np.float32)
+    _check(lib().anm_fold_twiddles(C.byref(cfg), _ptr(out)))
+    return out
 
 
 def basis_q7(cfg):

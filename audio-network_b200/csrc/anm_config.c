@@ -92,6 +92,32 @@ int anm_twiddles(const anm_config_t *c, float *out) {
     return ANM_OK;
 }
 
+/* SPEC 3: the hop partials are computed by centre folding when every tone bin is a multiple of S/2
+ * (then the centre of every hop sits at a multiple of a quarter turn of every tone) */
+int anm_config_foldable(const anm_config_t *c) {
+    if (!c || anm_config_validate(c) != ANM_OK || c->n_tones >= 32u) return 0;
+    if ((c->sym_len / c->hops_per_sym) % 16u) return 0;
+    for (uint32_t k = 0; k < c->n_tones; ++k)
+        if ((2u * c->tone_bin[k]) % c->hops_per_sym) return 0;
+    return 1;
+}
+
+/* out[k][tone] = (cos, sin)(2 pi bin (k + 1/2) / N), k < H/2: the twiddles of the sample pairs at
+ * distance k + 1/2 on either side of a hop centre */
+int anm_fold_twiddles(const anm_config_t *c, float *out) {
+    if (!anm_config_foldable(c) || !out) return ANM_ERR_ARG;
+    const double two_pi = 6.283185307179586476925286766559;
+    const uint32_t N = c->sym_len, T = c->n_tones, H2 = N / c->hops_per_sym / 2;
+    for (uint32_t k = 0; k < H2; ++k)
+        for (uint32_t t = 0; t < T; ++t) {
+            uint32_t r = (c->tone_bin[t] * (2u * k + 1u)) % (2u * N); /* angle reduced exactly in integers */
+            double a = two_pi * (double)r / (double)(2u * N);
+            out[(k * T + t) * 2 + 0] = (float)cos(a);
+            out[(k * T + t) * 2 + 1] = (float)sin(a);
+        }
+    return ANM_OK;
+}
+
 /* SPEC 3b: configurations with a dense tone set (T >= 32) compute tone energies from an 8-bit
  * integer basis with exact integer accumulation (the tensor-core contraction of the CUDA path). */
 int anm_config_dense(const anm_config_t *c) { return c && c->n_tones >= 32u; }

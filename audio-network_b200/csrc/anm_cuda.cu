@@ -122,6 +122,11 @@ struct anm_demod {
  * sample position advances by N/4 (anm_twiddles builds the table with exactly this symmetry) */
 static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
     k->tw_rot[0] = k->tw_rot[1] = 0;
+    k->fold = anm_config_foldable(cfg) ? 1u : 0u;
+    k->fold_odd = 0;
+    if (k->fold)
+        for (uint32_t t = 0; t < cfg->n_tones; ++t)
+            if ((2u * cfg->tone_bin[t] / cfg->hops_per_sym) & 1u) k->fold_odd |= 1ull << t;
     uint32_t any = 0;
     for (uint32_t t = 0; t < cfg->n_tones; ++t) {
         k->tw_rot[t >> 5] |= (unsigned long long)(cfg->tone_bin[t] & 3u) << (2 * (t & 31));
@@ -233,7 +238,8 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     CK(cudaMalloc(&h->d_counters, 32));
     if (h->osym_cap) CK(cudaMalloc(&h->d_osyms, (size_t)n_channels * h->osym_cap));
     h->h_tw.resize((size_t)cfg->sym_len * cfg->n_tones * 2);
-    anm_twiddles(cfg, h->h_tw.data());
+    if (anm_config_foldable(cfg)) anm_fold_twiddles(cfg, h->h_tw.data()); /* [H/2][T][2], a prefix of the buffer */
+    else anm_twiddles(cfg, h->h_tw.data());
     CK(cudaMalloc(&h->d_tw, h->h_tw.size() * sizeof(float)));
     CK(cudaMemcpy(h->d_tw, h->h_tw.data(), h->h_tw.size() * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -644,7 +650,8 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
     unsigned char *d_state = nullptr;
     float2 *d_tw = nullptr;
     std::vector<float> tw((size_t)cfg->sym_len * cfg->n_tones * 2);
-    anm_twiddles(cfg, tw.data());
+    if (anm_config_foldable(cfg)) anm_fold_twiddles(cfg, tw.data());
+    else anm_twiddles(cfg, tw.data());
     CK(cudaMalloc(&d_state, (size_t)n_ch * var->state_bytes));
     CK(cudaMalloc(&d_tw, tw.size() * sizeof(float)));
     int rc = init_state(var, d_state, n_ch, s);

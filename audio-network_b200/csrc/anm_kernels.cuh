@@ -79,12 +79,22 @@ struct KParams {
     const float2 *tw_global;      /* [N][T] (cos, sin) twiddle table in HBM; its first N/NQ rows are staged per CTA */
     unsigned long long tw_rot[2];  /* 2 bits per tone: tone_bin mod 4 (quarter-period rotation code) */
     uint16_t crc_pow[32];          /* x^(8(31-lane)+16) mod the CRC-16 polynomial, per lane */
+    uint32_t fold;                 /* 1: centre-folded hop partials (SPEC 3); tw_global then holds the folded twiddles [H/2][T] */
+    unsigned long long fold_odd;   /* bit per tone: 2*tone_bin/S is odd (odd hops of that tone change sign) */
     const uint8_t *tc_basis;       /* dense tone sets: int8 basis panels [group][K chunk][32 columns][16] (anm_kernels_tc.cuh) */
 };
 
 __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
     unsigned long long rb, rc, rd, ra;
     ra = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
+    rb = ((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x);
+    rc = ((unsigned long long)__float_as_uint(c.y) << 32) | __float_as_uint(c.x);
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return make_float2(__uint_as_float((uint32_t)rd), __uint_as_float((uint32_t)(rd >> 32)));
+}
+__device__ __forceinline__ float2 ffma2vv(float2 a, float2 b, float2 c) {
+    unsigned long long ra, rb, rc, rd;
+    ra = ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
     rb = ((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x);
     rc = ((unsigned long long)__float_as_uint(c.y) << 32) | __float_as_uint(c.x);
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
@@ -533,7 +543,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     {
         const float4 *gsrc = reinterpret_cast<const float4 *>(p.tw_global);
         float4 *dst = reinterpret_cast<float4 *>(smem_raw);
-        for (int i = threadIdx.x; i < TL * T / 2; i += blockDim.x) dst[i] = __ldg(&gsrc[i]);
+        const int n4 = p.fold ? (H / 2) * T / 2 : TL * T / 2; /* folded twiddles [H/2][T] or first quarter period [TL][T] */
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(&gsrc[i]);
         __syncthreads();
     }
     const uint32_t stw = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -622,6 +633,64 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                  * memory; their results are discarded below).  One pass accumulates the NQ hops whose
                  * offsets differ by N/NQ: they see the same twiddle sequence up to an exact rotation by
                  * multiples of 90 degrees, applied once after the chain. */
+                if ((H % 16) == 0 && p.fold) {
+                    /* Centre folding (SPEC 3): the samples k + 1/2 after and before a hop centre share a twiddle
+                     * up to conjugation, so their exact sum and difference feed ONE packed FMA per tone:
+                     * (A, Bq) += (a + b, a - b) * (cos, sin).  Every hop uses the same H/2 twiddles. */
+#pragma unroll
+                    for (int pass = 0; pass < GR; ++pass) {
+                        float2 acc[NQ][TG];
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                            for (int t = 0; t < TG; ++t) acc[q][t] = make_float2(0.f, 0.f);
+                        uint32_t twa = stw + (uint32_t)(g * TG) * 8u;
+#pragma unroll 1
+                        for (int i = 0; i < H / 16; ++i, twa += 8 * T * 8) {
+                            uint4 vf[NQ], vb[NQ];
+#pragma unroll
+                            for (int q = 0; q < NQ; ++q) {
+                                const uint32_t hb2 = row + (uint32_t)((pass + q * GR) * 2 * H + H);
+                                vf[q] = lds128(hb2 + (uint32_t)(16 * i));
+                                vb[q] = lds128(hb2 - (uint32_t)(16 * (i + 1)));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float2 xs[NQ];
+#pragma unroll
+                                for (int q = 0; q < NQ; ++q) {
+                                    const uint32_t wa = (j < 2) ? vf[q].x : (j < 4) ? vf[q].y : (j < 6) ? vf[q].z : vf[q].w;
+                                    const uint32_t wb = (j < 2) ? vb[q].w : (j < 4) ? vb[q].z : (j < 6) ? vb[q].y : vb[q].x;
+                                    const float a = (j & 1) ? cvt_s16<1>(wa) : cvt_s16<0>(wa);
+                                    const float b = (j & 1) ? cvt_s16<0>(wb) : cvt_s16<1>(wb); /* element 7 - j */
+                                    xs[q] = make_float2(__fadd_rn(a, b), __fsub_rn(a, b));
+                                }
+#pragma unroll
+                                for (int t = 0; t < TG; t += 2) {
+                                    float4 w2;
+                                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                        : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w)
+                                        : "r"(twa + (uint32_t)(j * T + t) * 8u));
+#pragma unroll
+                                    for (int q = 0; q < NQ; ++q) {
+                                        acc[q][t] = ffma2vv(xs[q], make_float2(w2.x, w2.y), acc[q][t]);
+                                        acc[q][t + 1] = ffma2vv(xs[q], make_float2(w2.z, w2.w), acc[q][t + 1]);
+                                    }
+                                }
+                            }
+                        }
+                        /* relative quarter turns between hop centres: a sign flip on odd hops of "odd" tones */
+                        const uint32_t odd = (uint32_t)(p.fold_odd >> (g * TG));
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                            for (int t = 0; t < TG; ++t) {
+                                const uint32_t mk = (((pass + q * GR) & 1) && ((odd >> t) & 1u)) ? 0x80000000u : 0u;
+                                Pp[pass + q * GR][t] = make_float2(__uint_as_float(__float_as_uint(acc[q][t].x) ^ mk),
+                                                                   __uint_as_float(__float_as_uint(acc[q][t].y) ^ mk));
+                            }
+                    }
+                } else
 #pragma unroll
                 for (int pass = 0; pass < GR; ++pass) {
                     float2 acc[NQ][TG];

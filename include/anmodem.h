@@ -99,6 +99,10 @@ int anm_config_preset(const char *name, anm_config_t *out); /* "ref4", "bfsk2", 
 int anm_config_validate(const anm_config_t *cfg);
 /* twiddle table [sym_len][n_tones][2] = (cos, sin)(2*pi*bin*m/N) rounded to fp32 */
 int anm_twiddles(const anm_config_t *cfg, float *out);
+/* SPEC 3: 1 if the hop partials are computed by centre folding (every tone bin a multiple of S/2) */
+int anm_config_foldable(const anm_config_t *cfg);
+/* SPEC 3: folded twiddles out[H/2][n_tones][2] = (cos, sin)(2 pi bin (k + 1/2) / N) */
+int anm_fold_twiddles(const anm_config_t *cfg, float *out);
 /* SPEC 3b: 1 if the configuration uses the dense integer basis (n_tones >= 32) */
 int anm_config_dense(const anm_config_t *cfg);
 /* SPEC 3b: int8 basis out[sym_len][n_tones][2] = (round(127 cos), round(127 sin)) with the quarter-period symmetry */

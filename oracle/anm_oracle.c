@@ -37,6 +37,9 @@ struct anm_oracle {
     uint64_t hop; /* index of the hop being assembled */
     /* tree history: hist[l][h & 7][k][2]; level 0 = hop partials */
     float hist[MAXLVL + 1][8][MAXT][2];
+    /* SPEC 3 (every tone bin a multiple of S/2): centre-folded hop partials */
+    int fold;
+    float *ftw; /* [H/2][T][2] */
     /* SPEC 3b (dense tone sets, T >= 32): int8 basis and exact integer hop partials / window sums */
     int dense;
     int8_t *bq; /* [N][T][2] */
@@ -104,6 +107,20 @@ anm_oracle_t *anm_oracle_create(const anm_config_t *cfg, const float *twiddles) 
     memcpy(o->tw, twiddles, ntw * sizeof(float));
     o->fsyms = (uint8_t *)malloc(((size_t)cfg->max_payload + 8) * 8 + 64);
     o->dense = o->T >= 32;
+    o->fold = !o->dense && (o->H % 16) == 0;
+    for (uint32_t k = 0; k < o->T; ++k)
+        if ((2 * cfg->tone_bin[k]) % o->S) o->fold = 0;
+    if (o->fold) {
+        /* twiddles of the sample pairs k + 1/2 away from a hop centre, angle reduced exactly first */
+        const double two_pi = 6.283185307179586476925286766559;
+        o->ftw = (float *)malloc((size_t)(o->H / 2) * o->T * 2 * sizeof(float));
+        for (uint32_t k = 0; k < o->H / 2; ++k)
+            for (uint32_t t = 0; t < o->T; ++t) {
+                double a = two_pi * (double)((cfg->tone_bin[t] * (2 * k + 1)) % (2 * o->N)) / (double)(2 * o->N);
+                o->ftw[(k * o->T + t) * 2 + 0] = (float)cos(a);
+                o->ftw[(k * o->T + t) * 2 + 1] = (float)sin(a);
+            }
+    }
     if (o->dense) {
         /* SPEC 3b: first quarter = round(127 cos), round(127 sin) of the reduced angle; the other
          * quarters by the exact rotation (-j)^(bin q) */
@@ -145,6 +162,7 @@ void anm_oracle_destroy(anm_oracle_t *o) {
     if (!o) return;
     free(o->tw);
     free(o->bq);
+    free(o->ftw);
     free(o->fsyms);
     free(o->frames);
     free(o->bytes);
@@ -344,20 +362,38 @@ static void process_hop(anm_oracle_t *o) {
     if (o->dense) {
         dense_energies(o, h, Eh);
     } else {
-        const uint32_t m0 = (uint32_t)((h * H) % o->N);
         float(*P)[2] = o->hist[0][h & 7];
-        for (uint32_t k = 0; k < T; ++k) {
-            const float *tw = o->tw + ((size_t)m0 * T + k) * 2;
-            float x = (float)o->hopbuf[0];
-            float I = x * tw[0], Q = x * tw[1];
-            for (uint32_t j = 1; j < H; ++j) {
-                tw += (size_t)T * 2;
-                x = (float)o->hopbuf[j];
-                I = fmaf(x, tw[0], I);
-                Q = fmaf(x, tw[1], Q);
+        if (o->fold) {
+            /* SPEC 3, centre folding: the samples k + 1/2 after and before the hop centre share a twiddle
+             * up to conjugation; their sum and difference are exact in fp32 */
+            for (uint32_t k = 0; k < T; ++k) {
+                float A = 0.0f, Bq = 0.0f;
+                for (uint32_t j = 0; j < H / 2; ++j) {
+                    float a = (float)o->hopbuf[H / 2 + j], b = (float)o->hopbuf[H / 2 - 1 - j];
+                    const float *tw = o->ftw + ((size_t)j * T + k) * 2;
+                    A = fmaf(a + b, tw[0], A);
+                    Bq = fmaf(a - b, tw[1], Bq);
+                }
+                /* relative quarter turns between hop centres: a sign flip on odd hops of "odd" tones */
+                if (((2 * o->cfg.tone_bin[k] / o->S) & 1u) && (h & 1u)) { A = -A; Bq = -Bq; }
+                P[k][0] = A;
+                P[k][1] = Bq;
             }
-            P[k][0] = I;
-            P[k][1] = Q;
+        } else {
+            const uint32_t m0 = (uint32_t)((h * H) % o->N);
+            for (uint32_t k = 0; k < T; ++k) {
+                const float *tw = o->tw + ((size_t)m0 * T + k) * 2;
+                float x = (float)o->hopbuf[0];
+                float I = x * tw[0], Q = x * tw[1];
+                for (uint32_t j = 1; j < H; ++j) {
+                    tw += (size_t)T * 2;
+                    x = (float)o->hopbuf[j];
+                    I = fmaf(x, tw[0], I);
+                    Q = fmaf(x, tw[1], Q);
+                }
+                P[k][0] = I;
+                P[k][1] = Q;
+            }
         }
         for (uint32_t l = 1; l <= o->lvl; ++l) {
             uint32_t d = 1u << (l - 1);
