@@ -645,24 +645,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 #pragma unroll
                             for (int t = 0; t < TG; ++t) acc[q][t] = make_float2(0.f, 0.f);
                         uint32_t twa = stw + (uint32_t)(g * TG) * 8u;
+                        uint32_t fwd = row + (uint32_t)(pass * 2 * H + H), bwd = fwd; /* walk away from the hop centres */
 #pragma unroll 1
-                        for (int i = 0; i < H / 16; ++i, twa += 8 * T * 8) {
-                            uint4 vf[NQ], vb[NQ];
+                        for (int i = 0; i < H / 8; ++i, twa += 4 * T * 8, fwd += 8u) {
+                            bwd -= 8u;
+                            uint2 vf[NQ], vb[NQ]; /* four samples after / before the centre of each hop */
 #pragma unroll
                             for (int q = 0; q < NQ; ++q) {
-                                const uint32_t hb2 = row + (uint32_t)((pass + q * GR) * 2 * H + H);
-                                vf[q] = lds128(hb2 + (uint32_t)(16 * i));
-                                vb[q] = lds128(hb2 - (uint32_t)(16 * (i + 1)));
+                                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(vf[q].x), "=r"(vf[q].y) : "r"(fwd + (uint32_t)(q * GR * 2 * H)));
+                                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(vb[q].x), "=r"(vb[q].y) : "r"(bwd + (uint32_t)(q * GR * 2 * H)));
                             }
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
+                            for (int j = 0; j < 4; ++j) {
                                 float2 xs[NQ];
 #pragma unroll
                                 for (int q = 0; q < NQ; ++q) {
-                                    const uint32_t wa = (j < 2) ? vf[q].x : (j < 4) ? vf[q].y : (j < 6) ? vf[q].z : vf[q].w;
-                                    const uint32_t wb = (j < 2) ? vb[q].w : (j < 4) ? vb[q].z : (j < 6) ? vb[q].y : vb[q].x;
+                                    const uint32_t wa = (j < 2) ? vf[q].x : vf[q].y;
+                                    const uint32_t wb = (j < 2) ? vb[q].y : vb[q].x;
                                     const float a = (j & 1) ? cvt_s16<1>(wa) : cvt_s16<0>(wa);
-                                    const float b = (j & 1) ? cvt_s16<0>(wb) : cvt_s16<1>(wb); /* element 7 - j */
+                                    const float b = (j & 1) ? cvt_s16<0>(wb) : cvt_s16<1>(wb); /* element 3 - j */
                                     xs[q] = make_float2(__fadd_rn(a, b), __fsub_rn(a, b));
                                 }
 #pragma unroll
