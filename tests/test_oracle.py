@@ -97,3 +97,25 @@ def test_empty_and_tiny_inputs():
     o.feed(np.zeros(0, dtype=np.int16))
     o.feed(np.zeros(5, dtype=np.int16))
     assert o.frames() == [] and len(o.symbols()) == 0
+
+
+@pytest.mark.parametrize("name,S", [("ref4", 4), ("ref4", 2), ("ref4", 8), ("mfsk16", 4), ("bfsk2", 4)])
+def test_energies_equal_the_sliding_dft(name, S):
+    """SPEC 3 (centre-folded or direct form) is the sliding DFT at the tone bins: |W|^2 of a float64
+    restatement, within fp32 rounding -- the folding signs and twiddle phases are right for every S."""
+    cfg = anm.config_preset(name)
+    cfg.hops_per_sym = S
+    N, T, H = cfg.sym_len, cfg.n_tones, cfg.sym_len // S
+    assert anm.config_foldable(cfg) == (S != 8)          # bins 10, 14 are not multiples of 8/2
+    rng = np.random.default_rng(3)
+    x = rng.integers(-20000, 20000, size=5 * N).astype(np.int16)
+    hops = len(x) // H
+    o = Oracle(cfg, trace_hops=hops)
+    o.feed(x)
+    xx = np.concatenate([np.zeros(N), x.astype(np.float64)])
+    bins = np.array(cfg.tone_bin[:T], dtype=np.float64)
+    for h in range(hops):
+        n = np.arange((h + 1) * H - N, (h + 1) * H)
+        w = (xx[N + n][:, None] * np.exp(-2j * np.pi * bins[None, :] * n[:, None] / N)).sum(axis=0)
+        e64 = np.abs(w) ** 2
+        assert np.max(np.abs(o.E[h] - e64)) <= 1e-5 * e64.max()
