@@ -227,16 +227,17 @@ __global__ void __launch_bounds__(256, 2) k_demod_tc(const __grid_constant__ KPa
             /* ---- contraction of tone group g: D[q][plane] = A[q][plane] . B[q][g]^T (one thread of a back warp) ---- */
             if (w == 4 + (g & 3) && lane == 0) {
                 tc_fence_after();
+                /* descriptors differ only in their start-address field: base + a compile-time offset */
+                const uint64_t a0 = smem_desc(sA, kPanel, 128u);
+                const uint64_t b0 = smem_desc(sB + (uint32_t)(g * KC) * kBPanel, kBPanel, 128u);
 #pragma unroll
                 for (int q = 0; q < S; ++q)
 #pragma unroll
                     for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
-                        for (int ks = 0; ks < KS; ++ks) {
-                            const uint64_t ad = smem_desc(sA + (uint32_t)((pl * S + q) * KC + 2 * ks) * kPanel, kPanel, 128u);
-                            const uint64_t bd = smem_desc(sB + (uint32_t)((q * NG + g) * KC + 2 * ks) * kBPanel, kBPanel, 128u);
-                            mma_i8(tmem_base + (uint32_t)(q * 2 + pl) * kNcol, ad, bd, idesc_i8(pl == 0), ks > 0 ? 1u : 0u);
-                        }
+                        for (int ks = 0; ks < KS; ++ks)
+                            mma_i8(tmem_base + (uint32_t)(q * 2 + pl) * kNcol, a0 + (uint64_t)(((uint32_t)((pl * S + q) * KC + 2 * ks) * kPanel) >> 4),
+                                   b0 + (uint64_t)(((uint32_t)(q * NG * KC + 2 * ks) * kBPanel) >> 4), idesc_i8(pl == 0), ks > 0 ? 1u : 0u);
                 mma_commit(mbar);
             }
             mbar_wait(mbar, mph);
