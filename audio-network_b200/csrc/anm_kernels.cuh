@@ -664,7 +664,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                     const uint32_t wb = (j < 2) ? vb[q].y : vb[q].x;
                                     const float a = (j & 1) ? cvt_s16<1>(wa) : cvt_s16<0>(wa);
                                     const float b = (j & 1) ? cvt_s16<0>(wb) : cvt_s16<1>(wb); /* element 3 - j */
-                                    xs[q] = make_float2(__fadd_rn(a, b), __fsub_rn(a, b));
+                                    /* (a + b, a - b) as one packed FMA: (a, b) * (1, -1) + (b, a); both halves exact */
+                                    xs[q] = ffma2vv(make_float2(a, b), make_float2(1.0f, -1.0f), make_float2(b, a));
                                 }
 #pragma unroll
                                 for (int t = 0; t < TG; t += 2) {
