@@ -139,6 +139,10 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
         for (int i = 0; i < 8 * (31 - lane) + 16; ++i) v = ((v << 1) ^ ((v & 0x8000u) ? 0x1021u : 0u)) & 0xffffu;
         k->crc_pow[lane] = (uint16_t)v;
     }
+    for (uint32_t b = 0; b < 256; ++b) {
+        const uint8_t one = (uint8_t)b;
+        k->crc8_tab[b] = anm_crc8(&one, 1, 0);
+    }
 }
 
 /* int8 basis of a dense configuration in the panel order the MMA descriptors of k_demod_tc address:

@@ -79,6 +79,7 @@ struct KParams {
     const float2 *tw_global;      /* [N][T] (cos, sin) twiddle table in HBM; its first N/NQ rows are staged per CTA */
     unsigned long long tw_rot[2];  /* 2 bits per tone: tone_bin mod 4 (quarter-period rotation code) */
     uint16_t crc_pow[32];          /* x^(8(31-lane)+16) mod the CRC-16 polynomial, per lane */
+    uint8_t crc8_tab[256];         /* CRC-8 (poly 0x07) of one byte, for the 2-byte header check */
     uint32_t fold;                 /* 1: centre-folded hop partials (SPEC 3); tw_global then holds the folded twiddles [H/2][T] */
     unsigned long long fold_odd;   /* bit per tone: 2*tone_bin/S is odd (odd hops of that tone change sign) */
     const uint8_t *tc_basis;       /* dense tone sets: int8 basis panels [group][K chunk][32 columns][16] (anm_kernels_tc.cuh) */
@@ -394,13 +395,8 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                 }
                 const uint32_t hdr = __reduce_or_sync(FULL, contrib);
                 const uint32_t len = hdr >> 8;
-                uint32_t c8 = 0;
-#pragma unroll
-                for (int z = 0; z < 2; ++z) {
-                    c8 ^= (hdr >> (16 - 8 * z)) & 0xffu;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) c8 = (c8 & 0x80u) ? (((c8 << 1) ^ 0x07u) & 0xffu) : ((c8 << 1) & 0xffu);
-                }
+                /* CRC-8 of the two LEN bytes: two look-ups in the host-built byte table */
+                const uint32_t c8 = p.crc8_tab[p.crc8_tab[(hdr >> 16) & 0xffu] ^ ((hdr >> 8) & 0xffu)];
                 if (len == 0 || len > p.max_payload || c8 != (hdr & 0xffu)) {
                     cold_st(O_HFAIL, cold_ld(O_HFAIL) + 1u);
                     sc.state = ST_SEARCH;
