@@ -134,6 +134,18 @@ __device__ __forceinline__ float cvt_s16(uint32_t w) {
     return f;
 }
 
+/* the same conversion on the ALU pipe (PRMT sign extension + I2FP): two issue slots instead of one, but it
+ * takes load off the quarter-rate XU pipe that I2F.S16 runs on */
+template <int HI>
+__device__ __forceinline__ float cvt_s16_alu(uint32_t w) {
+    uint32_t x;
+    float f;
+    if (HI) asm("prmt.b32 %0, %1, 0, 0xBB32;" : "=r"(x) : "r"(w));
+    else asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(x) : "r"(w));
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(x));
+    return f;
+}
+
 /* select element ph (warp-uniform, runtime) of a register array without local memory */
 template <int S, typename V>
 __device__ __forceinline__ V pick(const V (&r)[S], int ph) {
@@ -658,8 +670,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                 for (int q = 0; q < NQ; ++q) {
                                     const uint32_t wa = (j < 2) ? vf[q].x : vf[q].y;
                                     const uint32_t wb = (j < 2) ? vb[q].y : vb[q].x;
-                                    const float a = (j & 1) ? cvt_s16<1>(wa) : cvt_s16<0>(wa);
-                                    const float b = (j & 1) ? cvt_s16<0>(wb) : cvt_s16<1>(wb); /* element 3 - j */
+                                    const float a = (j & 1) ? cvt_s16<1>(wa) : cvt_s16<0>(wa);               /* XU pipe */
+                                    const float b = (j & 1) ? cvt_s16_alu<0>(wb) : cvt_s16_alu<1>(wb);       /* element 3 - j, ALU pipe */
                                     /* (a + b, a - b) as one packed FMA: (a, b) * (1, -1) + (b, a); both halves exact */
                                     xs[q] = ffma2vv(make_float2(a, b), make_float2(1.0f, -1.0f), make_float2(b, a));
                                 }
