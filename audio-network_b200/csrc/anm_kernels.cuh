@@ -3,13 +3,15 @@
  *
  * One warp owns one channel.  Within a step of 32 symbol periods, lane l owns symbol
  * period l (N samples = S hops), so all per-sample work is lane-private register
- * arithmetic (SPEC 3's FMA chains as packed fma.rn.f32x2), the S-hop window tree needs
- * S-1 shuffles per tone per step, the preamble correlation is ballots + popc over
- * bit-planes of the hop decisions, and symbol slicing / tracking / framing are
- * lane-parallel over up to 32 symbols at a time.  PCM moves HBM -> shared memory with
- * coalesced 16-byte cp.async into an XOR-swizzled stage (refilled for the next step as soon
- * as the arithmetic of this step has consumed it), and is read back with conflict-free
- * LDS.128.
+ * arithmetic (SPEC 3: centre-folded hop partials, one packed fma.rn.f32x2 per tone and
+ * sample pair; the direct FMA chains for tone sets that do not fold), the tails of the
+ * S-hop window tree travel to the next lane through the dead PCM stage, the preamble
+ * correlation is ballots + popc over bit-planes of the hop decisions, and symbol
+ * slicing / tracking / framing (sm_step, shared with the tensor-core kernel of
+ * anm_kernels_tc.cuh) are lane-parallel over up to 32 symbols at a time.  PCM moves
+ * HBM -> shared memory with coalesced 16-byte cp.async into a stage of padded rows
+ * (refilled for the next step as soon as the arithmetic of this step has consumed it)
+ * and is read back conflict-free.
  *
  * There is no reference kernel for any of this; the behaviour is
  * SPEC.md's, the structure is B200-first.
