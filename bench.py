@@ -246,9 +246,10 @@ def tensor_profile():
     return None
 
 
-def cfg4_leg(anm, torch, dev, local, stream, steps=12, warmup=3, n_ch=2048):
+def cfg4_leg(anm, torch, dev, local, stream, steps=12, warmup=3, n_ch=4736):
     """BASELINE config 4: the 64-tone preset through the tcgen05 contraction kernel (k_demod_tc),
-    same chunking and SNR as the headline workload; PCM resident in HBM, inputs larger than L2."""
+    same chunking and SNR as the headline workload; PCM resident in HBM, inputs larger than L2.
+    4,736 channels = 148 SMs x 2 resident CTAs x 4 channels per CTA x 4 waves."""
     cfg = anm.config_preset("wide64")
     chunk = CHUNK_SYMS * cfg.sym_len
     resident = min(steps + warmup, 8)
