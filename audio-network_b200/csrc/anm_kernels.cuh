@@ -434,7 +434,12 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                 /* body byte byi (payload, then the two CRC bytes) from its symbols */
                 auto body_byte = [&](uint32_t byi) -> uint32_t {
                     uint32_t v8 = 0;
-                    if (8 % B == 0) {
+                    if (B == 2 && (p.hdr_syms & 3u) == 0u) {
+                        /* four 2-bit symbols in one aligned word: Gray-decode all four at once */
+                        const uint32_t wv = *reinterpret_cast<const uint32_t *>(bs + byi * 4u);
+                        const uint32_t v = wv ^ ((wv >> 1) & 0x01010101u);
+                        v8 = ((v & 3u) << 6) | (((v >> 8) & 3u) << 4) | (((v >> 16) & 3u) << 2) | ((v >> 24) & 3u);
+                    } else if (8 % B == 0) {
                         constexpr int SPB = (8 % B == 0) ? 8 / B : 1;
 #pragma unroll
                         for (int j = 0; j < SPB; ++j) v8 |= gray_inv(bs[byi * SPB + j]) << (B * (SPB - 1 - j));
@@ -783,22 +788,24 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                  * dead by now and serves as the exchange buffer; otherwise the tails travel by shuffle.
                  * Once the last group has consumed the stage, the next step's PCM starts streaming in. */
                 float2 pin[TG][S - 1];
+                /* V[t][lv][i]: level-lv tree value of hop i.  Entries with i >= 2^lv - 1 depend on this lane
+                 * only and are computed now (their top ones are the tails the next lane needs); the others
+                 * follow after the exchange, from the previous lane's tails.  Every add has the operands and
+                 * the order of SPEC 3's tree. */
+                float2 V[TG][LV + 1][S];
                 {
                     float2 tails[TG][S - 1];
 #pragma unroll
                     for (int t = 0; t < TG; ++t) {
-                        float2 Lc[S];
 #pragma unroll
-                        for (int i = 0; i < S; ++i) Lc[i] = Pp[i][t];
+                        for (int i = 0; i < S; ++i) V[t][0][i] = Pp[i][t];
 #pragma unroll
                         for (int lv = 1; lv <= LV; ++lv) {
                             const int d = 1 << (lv - 1);
 #pragma unroll
-                            for (int j = 0; j < d; ++j) tails[t][d - 1 + j] = Lc[S - d + j];
-                            if (lv < LV) {
+                            for (int j = 0; j < d; ++j) tails[t][d - 1 + j] = V[t][lv - 1][S - d + j];
 #pragma unroll
-                                for (int i = S - 1; i >= 2 * d - 1; --i) Lc[i] = fadd2(Lc[i - d], Lc[i]);
-                            }
+                            for (int i = (1 << lv) - 1; i < S; ++i) V[t][lv][i] = fadd2(V[t][lv - 1][i - d], V[t][lv - 1][i]);
                         }
                     }
                     float2 *cg = carry + g * TG * (S - 1);
@@ -844,16 +851,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                     const int tg = g * TG + t;
                     float2 L[S];
 #pragma unroll
-                    for (int i = 0; i < S; ++i) L[i] = Pp[i][t];
-#pragma unroll
                     for (int lv = 1; lv <= LV; ++lv) {
                         const int d = 1 << (lv - 1);
-                        float2 Nw[S];
 #pragma unroll
-                        for (int i = 0; i < S; ++i) Nw[i] = fadd2((i >= d) ? L[(i >= d) ? i - d : 0] : pin[t][d - 1 + i], L[i]);
-#pragma unroll
-                        for (int i = 0; i < S; ++i) L[i] = Nw[i];
+                        for (int i = 0; i < (1 << lv) - 1 && i < S; ++i)
+                            V[t][lv][i] = fadd2((i >= d) ? V[t][lv - 1][(i >= d) ? i - d : 0] : pin[t][d - 1 + i], V[t][lv - 1][i]);
                     }
+#pragma unroll
+                    for (int i = 0; i < S; ++i) L[i] = V[t][LV][i];
 #pragma unroll
                     for (int i = 0; i < S; ++i) {
                         const float E = __fmaf_rn(L[i].x, L[i].x, __fmul_rn(L[i].y, L[i].y));
