@@ -171,7 +171,7 @@ static int set_device(const anm_demod *h) {
 
 static void choose_launch(anm_demod *h) {
     if (h->var->dense) {
-        h->warps_per_cta = 8; /* two warps per channel, four channels per CTA */
+        h->warps_per_cta = tc::kWorkerWarps + 1; /* two worker warps per TMEM quadrant (four channels per CTA) + the MMA issuer */
         h->grid = (h->n_ch + 3u) / 4u;
         h->smem_bytes = h->var->cta_smem;
         return;
@@ -683,7 +683,7 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
         if (var->dense) {
             rc = upload_basis_panels(cfg, &d_basis);
             k.tc_basis = d_basis;
-            W = 8;
+            W = tc::kWorkerWarps + 1;
             grid = (n_ch + 3u) / 4u;
             smem = var->cta_smem;
         } else {
