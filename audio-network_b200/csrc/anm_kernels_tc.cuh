@@ -411,8 +411,11 @@ __global__ void __launch_bounds__(288, 2) k_demod_tc(const __grid_constant__ KPa
             if (have_ch && step + 1 < n_steps) load_step(step + 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* carry rows and panels -> async proxy */
         }
-        __syncthreads(); /* next step's panels complete; the rings are the state machines' again */
+        /* next step's panels complete: only the loaders and the issuer meet here; the front warps join the
+         * next step's rounds whenever their state machine is done (full / empty mbarriers keep them in step) */
+        if (!front) asm volatile("bar.sync 2, 160;" ::: "memory");
     }
+    __syncthreads();
 
     /* ---- save carried state ---- */
     if (have_ch) {
