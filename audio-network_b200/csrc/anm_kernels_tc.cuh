@@ -339,11 +339,11 @@ __global__ void __launch_bounds__(288, 2) k_demod_tc(const __grid_constant__ KPa
                 }
             }
         }
-        __syncthreads(); /* every contraction of the step is complete and consumed */
-
-        /* ---- the back warps move this step's last symbol period into the carry rows, hand their argmax
-         * candidates to the front warps through the ring slots of the step (their old content, two steps
-         * back, is dead) and load the next step's PCM ---- */
+        /* ---- a worker that has waited for the last round knows every contraction of the step is complete: the
+         * A panels are free.  The back warps move this step's last symbol period into the carry rows, hand their
+         * argmax candidates to their front warp through the ring slots of the step (their old content, two
+         * steps back, was last read by the previous step's state machine, which every front warp has left by
+         * now: no worker is more than two rounds ahead of another) and load the next step's PCM ---- */
         const uint32_t a0r = esr + (((hic + (uint32_t)(esp * S)) & RM) << 3);
         if (back) {
             {
@@ -359,9 +359,10 @@ __global__ void __launch_bounds__(288, 2) k_demod_tc(const __grid_constant__ KPa
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0r + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]),
                                  "r"(__float_as_uint(ec[i + 1])), "r"(dc[i + 1]) : "memory");
             }
+            asm volatile("bar.arrive %0, 64;" ::"r"(3 + c4) : "memory"); /* candidates of this quadrant are in the rings */
         }
-        __syncthreads();
         if (front) {
+            asm volatile("bar.sync %0, 64;" ::"r"(3 + c4) : "memory");
             if (eactive) {
 #pragma unroll
                 for (int i = 0; i < S; i += 2) {
