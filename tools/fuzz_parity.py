@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised differential test: CUDA path (through the C ABI) vs the CPU oracle on seeded channels
 with random preset, SNR, clock error, offsets, payload lengths and chunking.  Test infrastructure.
-Usage: python tools/fuzz_parity.py [seconds] [first_seed]"""
+Usage: python tools/fuzz_parity.py [seconds] [first_seed] [preset]"""
 import os
 import sys
 import time
@@ -18,14 +18,17 @@ from test_gpu_parity import _check_against_oracle  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+only = sys.argv[3] if len(sys.argv) > 3 else None
 t0, n, frames_total = time.time(), 0, 0
 while time.time() - t0 < budget:
     rng = np.random.default_rng(seed)
     name = ["ref4", "ref4", "bfsk2", "mfsk8", "mfsk16", "wide64"][int(rng.integers(0, 6))]
+    if only:
+        name = only
     cfg = anm.config_preset(name)
     if name == "ref4" and rng.integers(0, 4) == 0:
         cfg.hops_per_sym = int(rng.choice([2, 8]))
-    n_ch = int(rng.integers(1, 9))
+    n_ch = int(rng.integers(1, 9)) if name != "wide64" else int(rng.integers(1, 40))
     n_sym = int(rng.integers(40, 400))
     snr = [None, 12.0, 6.0, 3.0, 1.0, 0.0][int(rng.integers(0, 6))]
     ppm = float(rng.choice([0.0, 50.0, 200.0]))
