@@ -41,21 +41,29 @@ struct Variant {
     uint32_t T, N, S;
     kern_fn fn;       /* streaming demodulator */
     kern_fn fn_trace; /* stateless tone-energy pass */
+    kern_fn fn_fold, fn_trace_fold; /* the same for foldable configurations (SPEC 3, centre-folded hop partials) */
     uint32_t warp_smem, cta_smem, state_bytes;
     bool dense; /* SPEC 3b: tensor-core contraction kernel, 4 channels per CTA */
 };
 
 #define VARIANT(T_, N_, S_)                                                                       \
-    {T_, N_, S_, (kern_fn)k_demod<T_, N_, S_, 0>, (kern_fn)k_demod<T_, N_, S_, 1>, warp_smem_bytes<T_, N_, S_>(), \
+    {T_, N_, S_, (kern_fn)k_demod<T_, N_, S_, 0, 0>, (kern_fn)k_demod<T_, N_, S_, 1, 0>,                     \
+     (kern_fn)k_demod<T_, N_, S_, 0, 1>, (kern_fn)k_demod<T_, N_, S_, 1, 1>, warp_smem_bytes<T_, N_, S_>(), \
      cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>(), false}
 #define VARIANT_TC(T_, N_, S_)                                                                    \
-    {T_, N_, S_, (kern_fn)k_demod_tc<T_, N_, S_, 0>, (kern_fn)k_demod_tc<T_, N_, S_, 1>, 0u, tc::smem_bytes<T_, N_, S_>(), \
+    {T_, N_, S_, (kern_fn)k_demod_tc<T_, N_, S_, 0>, (kern_fn)k_demod_tc<T_, N_, S_, 1>, nullptr, nullptr, 0u, tc::smem_bytes<T_, N_, S_>(), \
      state_bytes<T_, S_>(), true}
 
 const Variant kVariants[] = {
     VARIANT(4, 128, 4),  VARIANT(2, 128, 4),  VARIANT(8, 128, 4), VARIANT(16, 128, 4),
     VARIANT_TC(64, 256, 4), VARIANT(4, 128, 8),  VARIANT(4, 128, 2), VARIANT(4, 64, 4),
 };
+
+/* the kernel of a configuration: the folded instantiation when SPEC 3's centre folding applies */
+kern_fn variant_fn(const Variant *v, const anm_config_t *c, bool trace) {
+    const bool fold = !v->dense && anm_config_foldable(c);
+    return trace ? (fold ? v->fn_trace_fold : v->fn_trace) : (fold ? v->fn_fold : v->fn);
+}
 
 const Variant *find_variant(const anm_config_t *c) {
     for (const Variant &v : kVariants)
@@ -127,6 +135,10 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
     if (k->fold)
         for (uint32_t t = 0; t < cfg->n_tones; ++t)
             if ((2u * cfg->tone_bin[t] / cfg->hops_per_sym) & 1u) k->fold_odd |= 1ull << t;
+    for (uint32_t t = 0; t < 16; ++t) {
+        const float sg = ((k->fold_odd >> t) & 1ull) ? -1.0f : 1.0f;
+        k->fold_sg[t] = make_float2(sg, sg);
+    }
     uint32_t any = 0;
     for (uint32_t t = 0; t < cfg->n_tones; ++t) {
         k->tw_rot[t >> 5] |= (unsigned long long)(cfg->tone_bin[t] & 3u) << (2 * (t & 31));
@@ -225,7 +237,7 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     choose_launch(h);
-    CK(cudaFuncSetAttribute((const void *)var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CK(cudaFuncSetAttribute((const void *)variant_fn(var, cfg, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     const uint32_t b = anm_bits_per_sym(cfg);
     const uint32_t hdr_syms = (24 + b - 1) / b;
     h->max_frame_syms = hdr_syms + ((cfg->max_payload + 2) * 8 + b - 1) / b;
@@ -362,7 +374,7 @@ static int launch(anm_demod *h, KParams &k, cudaStream_t s, bool timed, bool sna
     k.base_b = h->read_b;
     if (ev) CK(cudaEventRecord(ev->a, s));
     void *args[] = {(void *)&k};
-    CK(cudaLaunchKernel((const void *)h->var->fn, dim3(h->grid), dim3(h->warps_per_cta * 32), args, h->smem_bytes, s));
+    CK(cudaLaunchKernel((const void *)variant_fn(h->var, &h->cfg, false), dim3(h->grid), dim3(h->warps_per_cta * 32), args, h->smem_bytes, s));
     if (ev) CK(cudaEventRecord(ev->b, s));
     /* pipelined host feeds: stream-ordered snapshot of the queue counters as they stand after this
      * launch, so that a later drain can stop exactly there while newer launches are in flight */
@@ -691,9 +703,9 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
             grid = std::min<uint32_t>((n_ch + W - 1) / W, (uint32_t)sms * 4u);
             smem = (size_t)W * var->warp_smem + var->cta_smem;
         }
-        cudaFuncSetAttribute((const void *)var->fn_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        cudaFuncSetAttribute((const void *)variant_fn(var, cfg, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         void *args[] = {(void *)&k};
-        cudaError_t e = rc == ANM_OK ? cudaLaunchKernel((const void *)var->fn_trace, dim3(grid), dim3(W * 32), args, smem, s) : cudaSuccess;
+        cudaError_t e = rc == ANM_OK ? cudaLaunchKernel((const void *)variant_fn(var, cfg, true), dim3(grid), dim3(W * 32), args, smem, s) : cudaSuccess;
         if (rc == ANM_OK && e == cudaSuccess) {
             const cudaError_t es = cudaStreamSynchronize(s);
             if (es != cudaSuccess) { anm_set_error("tone pass: %s", cudaGetErrorString(es)); rc = ANM_ERR_CUDA; }

@@ -84,31 +84,36 @@ struct KParams {
     uint8_t crc8_tab[256];         /* CRC-8 (poly 0x07) of one byte, for the 2-byte header check */
     uint32_t fold;                 /* 1: centre-folded hop partials (SPEC 3); tw_global then holds the folded twiddles [H/2][T] */
     unsigned long long fold_odd;   /* bit per tone: 2*tone_bin/S is odd (odd hops of that tone change sign) */
+    float2 fold_sg[16];            /* (-1, -1) for those tones, (1, 1) otherwise (and always when not folding): the factor the
+                                    * first tree level applies to its odd-hop operand */
     const uint8_t *tc_basis;       /* dense tone sets: int8 basis panels [group][K chunk][32 columns][16] (anm_kernels_tc.cuh) */
 };
 
+/* packed pairs of fp32 travel as 64-bit registers; mov.b64 keeps the halves in a register pair (no shifts / ORs) */
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
 __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
-    unsigned long long rb, rc, rd, ra;
-    ra = ((unsigned long long)__float_as_uint(a) << 32) | __float_as_uint(a);
-    rb = ((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x);
-    rc = ((unsigned long long)__float_as_uint(c.y) << 32) | __float_as_uint(c.x);
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return make_float2(__uint_as_float((uint32_t)rd), __uint_as_float((uint32_t)(rd >> 32)));
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk2(a, a)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+    return upk2(rd);
 }
 __device__ __forceinline__ float2 ffma2vv(float2 a, float2 b, float2 c) {
-    unsigned long long ra, rb, rc, rd;
-    ra = ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
-    rb = ((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x);
-    rc = ((unsigned long long)__float_as_uint(c.y) << 32) | __float_as_uint(c.x);
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return make_float2(__uint_as_float((uint32_t)rd), __uint_as_float((uint32_t)(rd >> 32)));
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+    return upk2(rd);
 }
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    unsigned long long ra, rb, rd;
-    ra = ((unsigned long long)__float_as_uint(a.y) << 32) | __float_as_uint(a.x);
-    rb = ((unsigned long long)__float_as_uint(b.y) << 32) | __float_as_uint(b.x);
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-    return make_float2(__uint_as_float((uint32_t)rd), __uint_as_float((uint32_t)(rd >> 32)));
+    unsigned long long rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(rd);
 }
 __device__ __forceinline__ float2 shfl2(float2 v, int src) {
     return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
@@ -534,8 +539,9 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
 constexpr int kMaxWarps = 20; /* registers are allocated per 4 warps: 20 warps x 96 registers fit the file; 24 would cap at 80 */
 
 /* MODE 0: streaming demodulator (sync, slicing, framing; no trace output).
- * MODE 1: stateless tone-energy pass (trace outputs only; parity / debug). */
-template <int T, int N, int S, int MODE>
+ * MODE 1: stateless tone-energy pass (trace outputs only; parity / debug).
+ * FOLD 1: centre-folded hop partials (configurations for which anm_config_foldable holds), 0: direct form. */
+template <int T, int N, int S, int MODE, int FOLD>
 __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant__ KParams p) {
     constexpr int H = N / S;
     constexpr int NQ = quad_hops<S>(); /* hops per table pass */
@@ -558,7 +564,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     {
         const float4 *gsrc = reinterpret_cast<const float4 *>(p.tw_global);
         float4 *dst = reinterpret_cast<float4 *>(smem_raw);
-        const int n4 = p.fold ? (H / 2) * T / 2 : TL * T / 2; /* folded twiddles [H/2][T] or first quarter period [TL][T] */
+        const int n4 = FOLD ? (H / 2) * T / 2 : TL * T / 2; /* folded twiddles [H/2][T] or first quarter period [TL][T] */
         for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(&gsrc[i]);
         __syncthreads();
     }
@@ -648,7 +654,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                  * memory; their results are discarded below).  One pass accumulates the NQ hops whose
                  * offsets differ by N/NQ: they see the same twiddle sequence up to an exact rotation by
                  * multiples of 90 degrees, applied once after the chain. */
-                if ((H % 16) == 0 && p.fold) {
+                if ((H % 16) == 0 && FOLD) {
                     /* Centre folding (SPEC 3): the samples k + 1/2 after and before a hop centre share a twiddle
                      * up to conjugation, so their exact sum and difference feed ONE packed FMA per tone:
                      * (A, Bq) += (a + b, a - b) * (cos, sin).  Every hop uses the same H/2 twiddles. */
@@ -696,16 +702,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                 }
                             }
                         }
-                        /* relative quarter turns between hop centres: a sign flip on odd hops of "odd" tones */
-                        const uint32_t odd = (uint32_t)(p.fold_odd >> (g * TG));
+                        /* relative quarter turns between hop centres: a sign flip on odd hops of "odd" tones; the first
+                         * level of the window tree applies it (every level-1 add pairs one odd and one even hop) */
 #pragma unroll
                         for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                            for (int t = 0; t < TG; ++t) {
-                                const uint32_t mk = (((pass + q * GR) & 1) && ((odd >> t) & 1u)) ? 0x80000000u : 0u;
-                                Pp[pass + q * GR][t] = make_float2(__uint_as_float(__float_as_uint(acc[q][t].x) ^ mk),
-                                                                   __uint_as_float(__float_as_uint(acc[q][t].y) ^ mk));
-                            }
+                            for (int t = 0; t < TG; ++t) Pp[pass + q * GR][t] = acc[q][t];
                     }
                 } else
 #pragma unroll
@@ -805,7 +807,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 #pragma unroll
                             for (int j = 0; j < d; ++j) tails[t][d - 1 + j] = V[t][lv - 1][S - d + j];
 #pragma unroll
-                            for (int i = (1 << lv) - 1; i < S; ++i) V[t][lv][i] = fadd2(V[t][lv - 1][i - d], V[t][lv - 1][i]);
+                            for (int i = (1 << lv) - 1; i < S; ++i)
+                                V[t][lv][i] = (lv == 1) ? ffma2vv(V[t][0][(i & 1) ? i : i - 1], p.fold_sg[g * TG + t], V[t][0][(i & 1) ? i - 1 : i])
+                                                        : fadd2(V[t][lv - 1][i - d], V[t][lv - 1][i]);
                         }
                     }
                     float2 *cg = carry + g * TG * (S - 1);
@@ -855,7 +859,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                         const int d = 1 << (lv - 1);
 #pragma unroll
                         for (int i = 0; i < (1 << lv) - 1 && i < S; ++i)
-                            V[t][lv][i] = fadd2((i >= d) ? V[t][lv - 1][(i >= d) ? i - d : 0] : pin[t][d - 1 + i], V[t][lv - 1][i]);
+                            V[t][lv][i] = (lv == 1) ? ffma2vv(pin[t][0], p.fold_sg[g * TG + t], V[t][0][0]) /* the previous lane's hop S-1 is odd */
+                                                    : fadd2((i >= d) ? V[t][lv - 1][(i >= d) ? i - d : 0] : pin[t][d - 1 + i], V[t][lv - 1][i]);
                     }
 #pragma unroll
                     for (int i = 0; i < S; ++i) L[i] = V[t][LV][i];
