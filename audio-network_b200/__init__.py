@@ -24,7 +24,7 @@ ANM_SILENCE = 0xFF
 ANM_SNR_CLEAN = 2**31 - 1
 ANM_FLAG_SYMBOLS = 1
 
-ANM_OK, ANM_ERR_ARG, ANM_ERR_CUDA, ANM_ERR_NOMEM, ANM_ERR_ALIGN, ANM_ERR_OVERFLOW, ANM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
+ANM_OK, ANM_ERR_ARG, ANM_ERR_CUDA, ANM_ERR_NOMEM, ANM_ERR_ALIGN, ANM_ERR_OVERFLOW, ANM_ERR_UNSUPPORTED, ANM_ERR_FORMAT = 0, -1, -2, -3, -4, -5, -6, -7
 
 
 class AnmError(RuntimeError):
@@ -100,6 +100,68 @@ STATS_DTYPE = np.dtype(
     [("locks", "<u4"), ("header_fail", "<u4"), ("frames_ok", "<u4"), ("frames_bad", "<u4"), ("symbols", "<u8"), ("trk_moves", "<i4"), ("reserved", "<u4")]
 )
 
+
+class PbDiscovery(C.Structure):
+    """anm_pb_discovery_t (include/anmodem_pb.h): DiscoveryResponse of protocol/ip.proto:20-27"""
+    _fields_ = [
+        ("protocol_version", C.c_uint32),
+        ("currently_streaming", C.c_uint8),
+        ("pad", C.c_uint8 * 3),
+        ("mac_address", C.c_uint64),
+        ("device_name", C.c_char * 128),
+        ("opus_version", C.c_char * 128),
+    ]
+
+
+class PbBroadcast(C.Structure):
+    _fields_ = [
+        ("magic_word", C.c_uint32),
+        ("which", C.c_uint32),
+        ("discovery_request", C.c_uint8),
+        ("pad", C.c_uint8 * 7),
+        ("discovery_response", PbDiscovery),
+    ]
+
+
+class PbToTransmitter(C.Structure):
+    _fields_ = [
+        ("which", C.c_uint32),
+        ("max_encoded_frame_size", C.c_uint32),
+        ("max_decoded_frame_size", C.c_uint32),
+        ("audio_underflow", C.c_uint8),
+        ("audio_decode_error", C.c_uint8),
+        ("pad", C.c_uint8 * 2),
+        ("discovery_data", PbDiscovery),
+    ]
+
+
+class Pacer(C.Structure):
+    """anm_pacer_t (include/anmodem.h): the reference transmitter's LeakyBucket with an explicit clock"""
+    _fields_ = [("capacity", C.c_int64), ("drain_rate_per_second", C.c_int64), ("last_value", C.c_int64), ("last_value_at_ns", C.c_int64)]
+
+    def __init__(self, capacity=1200, drain_rate_per_second=1000, now_ns=0):
+        super().__init__()
+        _check(lib().anm_pacer_init(C.byref(self), capacity, drain_rate_per_second, now_ns))
+
+    def level(self, now_ns):
+        return lib().anm_pacer_level(C.byref(self), now_ns)
+
+    def try_put(self, amount, now_ns):
+        """None when added (as LeakyBucket.tryPut), else the nanoseconds to wait; AnmError where the reference throws."""
+        r = lib().anm_pacer_try_put(C.byref(self), amount, now_ns)
+        if r < 0:
+            raise AnmError(int(r), "amount exceeds the bucket capacity")
+        return None if r == 0 else int(r)
+
+    def wait_for_capacity(self, amount, now_ns):
+        """Virtual-clock waitForCapacity: returns (now_ns after the waits, total ns waited)."""
+        t = C.c_int64(now_ns)
+        r = lib().anm_pacer_wait_for_capacity(C.byref(self), amount, C.byref(t))
+        if r < 0:
+            raise AnmError(int(r), "amount exceeds the bucket capacity")
+        return t.value, int(r)
+
+
 # every symbol include/anmodem.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "anm_config_preset", "anm_config_validate", "anm_twiddles", "anm_config_dense", "anm_basis_q7", "anm_config_foldable", "anm_fold_twiddles", "anm_crc16", "anm_crc8",
@@ -110,6 +172,7 @@ EXPORTS = [
     "anm_demod_read_symbols", "anm_demod_stats", "anm_demod_launch_count", "anm_demod_overflowed", "anm_demod_last_kernel_ms",
     "anm_last_error", "anm_version", "demod_initialize", "demod_create", "demod_feed",
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
+    "anm_pacer_init", "anm_pacer_level", "anm_pacer_try_put", "anm_pacer_wait_for_capacity",
 ]
 
 _lib = None
@@ -160,6 +223,15 @@ def lib():
         "anm_demod_launch_geometry": (C.c_int, [vp, u32p, u32p, u32p]),
         "anm_pb_deframe_device": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "anm_pb_deframe_host": (C.c_int, [vp, C.c_size_t, vp, C.c_size_t, vp]),
+        "anm_pb_encode_broadcast": (C.c_size_t, [C.POINTER(PbBroadcast), vp, C.c_size_t]),
+        "anm_pb_encode_to_transmitter": (C.c_size_t, [C.POINTER(PbToTransmitter), vp, C.c_size_t]),
+        "anm_pb_decode_broadcast": (C.c_int, [vp, C.c_size_t, C.POINTER(PbBroadcast), C.POINTER(C.c_size_t)]),
+        "anm_pb_decode_to_transmitter": (C.c_int, [vp, C.c_size_t, C.POINTER(PbToTransmitter), C.POINTER(C.c_size_t)]),
+        "anm_pb_firmware_discovery": (None, [C.c_uint64, C.c_char_p, C.POINTER(PbBroadcast)]),
+        "anm_pacer_init": (C.c_int, [C.POINTER(Pacer), C.c_int64, C.c_int64, C.c_int64]),
+        "anm_pacer_level": (C.c_int64, [C.POINTER(Pacer), C.c_int64]),
+        "anm_pacer_try_put": (C.c_int64, [C.POINTER(Pacer), C.c_int64, C.c_int64]),
+        "anm_pacer_wait_for_capacity": (C.c_int64, [C.POINTER(Pacer), C.c_int64, C.POINTER(C.c_int64)]),
         "anm_last_error": (C.c_char_p, []),
         "anm_version": (C.c_char_p, []),
         "demod_initialize": (C.c_int, [cfgp]),
@@ -213,6 +285,33 @@ def pb_deframe(recs, payload_bytes):
     _check(lib().anm_pb_deframe_host(_ptr(recs) if len(recs) else None, len(recs), _ptr(by) if len(by) else None, len(by),
                                      _ptr(out) if len(recs) else None))
     return out
+
+
+def pb_encode_broadcast(m):
+    buf = (C.c_uint8 * 512)()
+    n = lib().anm_pb_encode_broadcast(C.byref(m), buf, 512)
+    return bytes(buf[:n])
+
+
+def pb_encode_to_transmitter(m):
+    buf = (C.c_uint8 * 512)()
+    n = lib().anm_pb_encode_to_transmitter(C.byref(m), buf, 512)
+    return bytes(buf[:n])
+
+
+def pb_decode_broadcast(data):
+    """-> (PbBroadcast, consumed) or None where the reference's pb_decode_delimited returns false"""
+    m, used = PbBroadcast(), C.c_size_t(0)
+    b = (C.c_uint8 * max(1, len(data))).from_buffer_copy(bytes(data) or b"\0")
+    rc = lib().anm_pb_decode_broadcast(b, len(data), C.byref(m), C.byref(used))
+    return (m, used.value) if rc == ANM_OK else None
+
+
+def pb_decode_to_transmitter(data):
+    m, used = PbToTransmitter(), C.c_size_t(0)
+    b = (C.c_uint8 * max(1, len(data))).from_buffer_copy(bytes(data) or b"\0")
+    rc = lib().anm_pb_decode_to_transmitter(b, len(data), C.byref(m), C.byref(used))
+    return (m, used.value) if rc == ANM_OK else None
 
 
 def config_dense(cfg):

@@ -45,7 +45,8 @@ enum {
     ANM_ERR_NOMEM = -3,    /* host or device allocation failed */
     ANM_ERR_ALIGN = -4,    /* buffer not 16-byte aligned / length not a multiple of sym_len */
     ANM_ERR_OVERFLOW = -5, /* an output queue overflowed; results were dropped */
-    ANM_ERR_UNSUPPORTED = -6
+    ANM_ERR_UNSUPPORTED = -6,
+    ANM_ERR_FORMAT = -7    /* malformed message: the reference's decoder would return false */
 };
 
 /* Modem configuration (SPEC.md section 2). */
@@ -205,6 +206,19 @@ int demod_feed(demod_t *d, const int16_t *pcm, size_t n_samples); /* borrowed in
 size_t demod_read_symbols(demod_t *d, uint8_t *out, size_t cap);
 size_t demod_read_frames(demod_t *d, demod_frame_t *out, size_t cap);
 void demod_destroy(demod_t *d);
+
+/* ---- chunk pacing of a real-time streaming feed -----------------------
+ * The reference transmitter's leaky bucket (transmitter/.../LeakyBucket.kt:9-64; instance "1200 ms of
+ * receiver buffer draining 1000 ms per second", MulticastAudioOutput.kt:85) with the clock as a
+ * parameter.  Amounts are in the caller's unit (the reference: milliseconds of audio). */
+typedef struct anm_pacer {
+    int64_t capacity, drain_rate_per_second;
+    int64_t last_value, last_value_at_ns;
+} anm_pacer_t;
+int anm_pacer_init(anm_pacer_t *p, int64_t capacity, int64_t drain_rate_per_second, int64_t now_ns);
+int64_t anm_pacer_level(const anm_pacer_t *p, int64_t now_ns);              /* LeakyBucket.currentValue */
+int64_t anm_pacer_try_put(anm_pacer_t *p, int64_t amount, int64_t now_ns); /* 0 added, > 0 ns to wait, ANM_ERR_ARG */
+int64_t anm_pacer_wait_for_capacity(anm_pacer_t *p, int64_t amount, int64_t *now_ns); /* virtual-clock waitForCapacity */
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,43 @@ size_t anm_pb_encode_broadcast_request(uint32_t magic, uint8_t *out, size_t cap)
  * malformed input (bad varint, truncated field, unknown wire type). */
 size_t anm_pb_scan_to_receiver_audio(const uint8_t *buf, size_t len, const uint8_t **payload, size_t *payload_len);
 
+/* ---- discovery / handshake messages --------------------------------
+ * BroadcastMessage and ToTransmitter of protocol/ip.proto:9-64 as flat structs (the nanopb structs
+ * of hardware/src/protogen/ip.pb.h:18-68 without the unions).  decode = the verdict and the fields of
+ * pb_decode_delimited(&stream, BroadcastMessage_fields / ToTransmitter_fields, &msg) over a buffer
+ * (hardware/src/network.cpp:475); encode = the bytes pb_encode_delimited writes (network.cpp:394). */
+#define ANM_PB_MAGIC_WORD 0x2C5DA044u /* protocol/ip.proto:10, network.cpp:369 */
+typedef struct anm_pb_discovery {
+    uint32_t protocol_version;
+    uint8_t currently_streaming;
+    uint8_t pad[3];
+    uint64_t mac_address;
+    char device_name[128]; /* zero-terminated, at most 127 characters (protobuf_ip.options:1-2) */
+    char opus_version[128];
+} anm_pb_discovery_t;
+typedef struct anm_pb_broadcast {
+    uint32_t magic_word;
+    uint32_t which;            /* 0: oneof not set, 2: discovery_request, 3: discovery_response */
+    uint8_t discovery_request; /* valid when which == 2 */
+    uint8_t pad[7];
+    anm_pb_discovery_t discovery_response; /* valid when which == 3 */
+} anm_pb_broadcast_t;
+typedef struct anm_pb_to_transmitter {
+    uint32_t which; /* 0: not set, 1: receiver_information, 2: error */
+    uint32_t max_encoded_frame_size, max_decoded_frame_size; /* which == 1 */
+    uint8_t audio_underflow, audio_decode_error;             /* which == 2 */
+    uint8_t pad[2];
+    anm_pb_discovery_t discovery_data; /* which == 1 */
+} anm_pb_to_transmitter_t;
+/* return the encoded length (length varint included), 0 if it does not fit or the struct is invalid */
+size_t anm_pb_encode_broadcast(const anm_pb_broadcast_t *m, uint8_t *out, size_t cap);
+size_t anm_pb_encode_to_transmitter(const anm_pb_to_transmitter_t *m, uint8_t *out, size_t cap);
+/* ANM_OK, or ANM_ERR_FORMAT where pb_decode_delimited returns false; *consumed (optional) = bytes read */
+int anm_pb_decode_broadcast(const uint8_t *buf, size_t len, anm_pb_broadcast_t *out, size_t *consumed);
+int anm_pb_decode_to_transmitter(const uint8_t *buf, size_t len, anm_pb_to_transmitter_t *out, size_t *consumed);
+/* the discovery response the firmware sends (network.cpp:356-378): protocol version 1, not streaming */
+void anm_pb_firmware_discovery(uint64_t mac, const char *opus_version, anm_pb_broadcast_t *out);
+
 /* ---- batched deframer on the GPU ----------------------------
  * The decode step of the reference's receive loop (hardware/src/network.cpp:406-430) for many
  * frames at once: every CRC-valid frame payload is walked as one varint-delimited ToReceiver
