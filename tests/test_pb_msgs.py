@@ -128,3 +128,55 @@ def test_live_differential_against_the_reference():
             _check("broadcast", w, pc.ref_decode_broadcast(R, w))
         for w in pc.to_transmitter_corpus(seed + 100):
             _check("to_transmitter", w, pc.ref_decode_to_transmitter(R, w))
+
+
+def _handshake_capture(cfg, n_ch=6):
+    """one channel per accepted golden message (both kinds), each carried as the payload of one frame"""
+    wires = []
+    for kind in ("broadcast", "to_transmitter"):
+        ok = [r for r in GOLD[kind] if r["ref"] is not None and 0 < len(r["wire"]) // 2 <= 300]
+        for r in ok[:: max(1, len(ok) // (n_ch // 2))][: n_ch // 2]:
+            wires.append((kind, bytes.fromhex(r["wire"]), r["ref"]))
+    n_sym = max(len(anm.frame_symbols(cfg, w)) for _, w, _ in wires) + 12
+    pcm = np.zeros((len(wires), n_sym * cfg.sym_len), dtype=np.int16)
+    for c, (_, w, _) in enumerate(wires):
+        fs = anm.frame_symbols(cfg, w)
+        prog = np.concatenate([np.full(3 + c, 255, np.uint8), fs, np.full(n_sym + 8 - len(fs), 255, np.uint8)])  # silence to the end of the capture
+        pcm[c] = anm.tx_render(cfg, prog, anm.tx_params(seed=40 + c, amplitude=0.5, snr_db=10.0), 0, pcm.shape[1])
+    return wires, pcm
+
+
+def test_handshake_messages_survive_the_modem_oracle():
+    """row f3: discovery / hello messages as known-answer frame payloads (CPU oracle as the demodulator)"""
+    from oracle_binding import Oracle
+
+    cfg = anm.config_preset("ref4")
+    wires, pcm = _handshake_capture(cfg)
+    for c, (kind, w, ref) in enumerate(wires):
+        o = Oracle(cfg)
+        o.feed(pcm[c])
+        (_, _, ok, payload), = o.frames()
+        assert ok and payload == w
+        assert _check(kind, payload, ref) == 1
+
+
+@pytest.mark.gpu
+def test_handshake_messages_survive_the_modem_gpu():
+    """the same capture through the CUDA demodulator (C ABI): payload bytes, then the product decoder's fields
+    against the reference nanopb's committed fields"""
+    import torch
+
+    cfg = anm.config_preset("ref4")
+    wires, pcm = _handshake_capture(cfg)
+    dm = anm.Demod(cfg, len(wires), device=0)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    dm.feed_device(d_pcm.data_ptr(), pcm.shape[1], pcm.shape[1], torch.cuda.current_stream().cuda_stream)
+    dm.collect()
+    frames = anm.frames_to_list(*dm.read_frames())
+    dm.close()
+    assert len(frames) == len(wires)
+    by_ch = {f[0]: f for f in frames}
+    for c, (kind, w, ref) in enumerate(wires):
+        ch, _start, ok, payload = by_ch[c]
+        assert ok and payload == w
+        assert _check(kind, payload, ref) == 1
