@@ -403,3 +403,45 @@ def test_pipelined_host_feed_equals_oracle_and_queue_wraps():
     got.sort(key=lambda f: (f[0], f[1]))
     want = oracle_frames_batch(cfg, pcm)
     assert got == want and len(got) > 400
+
+
+def test_config3_one_gpu_share_streamed_10db():
+    """BASELINE.json configs[2] at one GPU's share of the 8-GPU run: 8,192 channels with AWGN at 10 dB SNR, streamed in
+    1-second chunks.  At this size the oracle checks a sample of channels frame for frame; the whole batch is held to
+    size-independent properties: streaming in chunks == one shot (every frame, byte and CRC verdict), every detected
+    frame passes its CRC at 10 dB, and every channel delivers at least the frames its program holds completely."""
+    torch = _torch()
+    cfg = anm.config_preset("ref4")
+    n_ch, chunk, n_chunks = 8192, 344 * cfg.sym_len, 3
+    n = chunk * n_chunks
+    progs, lens, params = _programs(cfg, n_ch, seed=303, snr_db=10.0, ppm_max=0.0, offset_max=2000, payload=(24, 40), max_len=2200)
+    d_pcm = _gpu_render(cfg, progs, lens, params, n)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(pieces):
+        dm = anm.Demod(cfg, n_ch, device=0)
+        pos = 0
+        for ln in pieces:
+            dm.feed_device(d_pcm.data_ptr() + pos * 2, n, ln, stream)
+            pos += ln
+        dm.collect()
+        recs, by = dm.read_frames(cap=1 << 21, bytes_cap=1 << 27)
+        assert not dm.overflowed()
+        stats = dm.stats()
+        dm.close()
+        return recs, by, stats
+
+    recs, by, stats = run([chunk] * n_chunks)
+    recs1, by1, stats1 = run([n])
+    fr = sorted(anm.frames_to_list(recs, by), key=lambda f: (f[0], f[1]))
+    fr1 = sorted(anm.frames_to_list(recs1, by1), key=lambda f: (f[0], f[1]))
+    assert fr == fr1 and len(fr) > 5 * n_ch
+    assert np.array_equal(stats["frames_ok"], stats1["frames_ok"]) and np.array_equal(stats["symbols"], stats1["symbols"])
+    assert all(f[2] == 1 for f in fr)                      # 10 dB: no CRC failure among the detected frames
+    per_ch = np.bincount([f[0] for f in fr], minlength=n_ch)
+    assert per_ch.min() >= 4                                # 1,032 symbol periods hold at least 4 whole frames of <= 196 + 30 symbols
+    sample = list(range(0, n_ch, 128))                      # 64 channels against the oracle
+    pcm = d_pcm[sample].cpu().numpy()
+    want = oracle_frames_batch(cfg, pcm)
+    got = [(sample.index(f[0]), f[1], f[2], f[3]) for f in fr if f[0] in set(sample)]
+    assert got == want
