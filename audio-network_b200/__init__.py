@@ -173,6 +173,7 @@ EXPORTS = [
     "anm_last_error", "anm_version", "demod_initialize", "demod_create", "demod_feed",
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
     "anm_pacer_init", "anm_pacer_level", "anm_pacer_try_put", "anm_pacer_wait_for_capacity",
+    "anm_opus_parse_device", "anm_opus_parse_host",
 ]
 
 _lib = None
@@ -223,6 +224,8 @@ def lib():
         "anm_demod_launch_geometry": (C.c_int, [vp, u32p, u32p, u32p]),
         "anm_pb_deframe_device": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "anm_pb_deframe_host": (C.c_int, [vp, C.c_size_t, vp, C.c_size_t, vp]),
+        "anm_opus_parse_device": (C.c_int, [vp, C.c_uint32, vp, C.c_uint32, C.c_int32, vp, vp]),
+        "anm_opus_parse_host": (C.c_int, [vp, C.c_size_t, vp, C.c_size_t, C.c_int32, vp]),
         "anm_pb_encode_broadcast": (C.c_size_t, [C.POINTER(PbBroadcast), vp, C.c_size_t]),
         "anm_pb_encode_to_transmitter": (C.c_size_t, [C.POINTER(PbToTransmitter), vp, C.c_size_t]),
         "anm_pb_decode_broadcast": (C.c_int, [vp, C.c_size_t, C.POINTER(PbBroadcast), C.POINTER(C.c_size_t)]),
@@ -284,6 +287,23 @@ def pb_deframe(recs, payload_bytes):
     out = np.zeros(len(recs), dtype=PB_SPAN_DTYPE)
     _check(lib().anm_pb_deframe_host(_ptr(recs) if len(recs) else None, len(recs), _ptr(by) if len(by) else None, len(by),
                                      _ptr(out) if len(recs) else None))
+    return out
+
+
+OPUS_PACKET_DTYPE = np.dtype([("count", "<i4"), ("toc", "u1"), ("channels", "u1"), ("pad", "u1", (2,)), ("mode", "<i4"), ("bandwidth", "<i4"),
+                              ("samples_per_frame", "<i4"), ("payload_offset", "<i4"), ("nb_frames", "<i4"), ("nb_samples", "<i4"),
+                              ("size", "<i2", (48,))])  # anm_opus_packet_t (include/anmodem_opus.h), 128 bytes
+ANM_OPUS_BAD_ARG, ANM_OPUS_INVALID_PACKET = -1, -4
+
+
+def opus_parse(spans, payload_bytes, fs=48000):
+    """Batched Opus packet parse on the GPU (include/anmodem_opus.h): span records as returned by pb_deframe() + the byte
+    arena -> one anm_opus_packet_t per span (TOC fields, frame count, frame sizes) as libopus' opus_packet_parse gives them."""
+    spans = np.ascontiguousarray(spans, dtype=PB_SPAN_DTYPE)
+    by = np.ascontiguousarray(payload_bytes, dtype=np.uint8)
+    out = np.zeros(len(spans), dtype=OPUS_PACKET_DTYPE)
+    _check(lib().anm_opus_parse_host(_ptr(spans) if len(spans) else None, len(spans), _ptr(by) if len(by) else None, len(by), fs,
+                                     _ptr(out) if len(spans) else None))
     return out
 
 
