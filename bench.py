@@ -29,7 +29,7 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-CHUNK_SYMS = 344          # symbol periods per chunk (~1 s at N=128)
+CHUNK_SYMS = int(os.environ.get("ANM_BENCH_CHUNK_SYMS", "344"))   # symbol periods per chunk (~1 s at N=128)
 CH_PER_GPU = 8192         # 65,536 channels / 8 GPUs
 SNR_DB = 10.0
 PAYLOAD = 32              # payload bytes per frame
@@ -479,8 +479,8 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg3 weak-scaled: %d channels/GPU x %d-sample chunks (344 symbol periods), 10 dB SNR, "
-                                   "preset %s, %d-byte payload frames" % (n_ch, chunk, args.preset, PAYLOAD),
+            "config": {"workload": "cfg3 weak-scaled: %d channels/GPU x %d-sample chunks (%d symbol periods), 10 dB SNR, "
+                                   "preset %s, %d-byte payload frames" % (n_ch, chunk, CHUNK_SYMS, args.preset, PAYLOAD),
                        "channels_total": world * n_ch, "chunk_samples": chunk, "l2_policy": "inputs larger than L2 (%.0f MB per step, %d distinct chunks resident)" % (per_launch_bytes / 1e6, resident),
                        "launch": {"grid": grid, "warps_per_cta": wpc, "smem_bytes": smem}},
             "decoded_bits_per_s": round(float(agg[0].item()) / (ms_max * 1e-3), 1),
