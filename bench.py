@@ -69,8 +69,59 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def frame_payload(rng):
+    """PAYLOAD bytes: one varint-delimited ToReceiver{AudioData{opus_encoded_frame}} (protocol/ip.proto:29-33, 62-64) whose
+    Opus bytes are a code-0 CELT fullband stereo 20 ms packet (TOC 0xFC) with random contents -- what the reference's
+    receive loop would hand to pb_decode_delimited and then to opus_decode."""
+    n = PAYLOAD - 5
+    opus = bytes([0xFC]) + rng.integers(0, 256, size=n - 1, dtype=np.uint8).tobytes()
+    return bytes([n + 4, 0x0A, n + 2, 0x0A, n]) + opus
+
+
+def decode_chain_leg(anm, torch, dev, recs, by, reps=20):
+    """The steps after frame assembly on the frames of the timed region (rows f2 / f1 first stage): k_pb_deframe locates the
+    Opus bytes of every frame's ToReceiver message, k_opus_parse reads the packets' framing; device-resident, CUDA events."""
+    n = len(recs)
+    if n == 0:
+        return None
+    d_recs = torch.from_numpy(recs.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_by = torch.from_numpy(np.ascontiguousarray(by)).to(dev)
+    d_spans = torch.zeros(n * anm.PB_SPAN_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_pk = torch.zeros(n * anm.OPUS_PACKET_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    L = anm.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_def = t_par = 0.0
+    for r in range(reps + 2):
+        ev[0].record()
+        assert L.anm_pb_deframe_device(d_recs.data_ptr(), n, d_by.data_ptr(), 0xFFFFFFFF, d_spans.data_ptr(), stream) == 0
+        ev[1].record()
+        assert L.anm_opus_parse_device(d_spans.data_ptr(), n, d_by.data_ptr(), 0xFFFFFFFF, 48000, d_pk.data_ptr(), stream) == 0
+        ev[2].record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            t_def += ev[0].elapsed_time(ev[1])
+            t_par += ev[1].elapsed_time(ev[2])
+    spans = d_spans.cpu().numpy().view(anm.PB_SPAN_DTYPE)
+    pk = d_pk.cpu().numpy().view(anm.OPUS_PACKET_DTYPE)
+    ok = recs["crc_ok"] == 1
+    peak, _src = peaks()
+    # algorithmic bytes per frame: k_pb_deframe = 24 (frame record) + 32 (the sector holding the message header) + 16 (span out);
+    # k_opus_parse = 16 (span) + 32 (the sector holding the TOC / size bytes) + 128 (packet record out)
+    gbs_def = n * 72 / (t_def / reps * 1e-3) / 1e9
+    gbs_par = n * 176 / (t_par / reps * 1e-3) / 1e9
+    return {"frames": int(n), "payload_bytes": int(len(by)), "k_pb_deframe_ms": round(t_def / reps, 4), "k_opus_parse_ms": round(t_par / reps, 4),
+            "k_pb_deframe_hbm": {"algorithmic_bytes_per_frame": 72, "achieved_gbs": round(gbs_def, 1), "frac": round(gbs_def / peak, 4)},
+            "k_opus_parse_hbm": {"algorithmic_bytes_per_frame": 176, "achieved_gbs": round(gbs_par, 1), "frac": round(gbs_par / peak, 4)},
+            "Mframes_per_s": round(n / ((t_def + t_par) / reps * 1e-3) / 1e6, 1), "gpu_launches": 2 * reps,
+            "audio_located": int((spans["status"] == anm.ANM_PB_OK).sum()), "crc_ok_frames": int(ok.sum()),
+            "opus_packets_parsed": int((pk["count"] == 1).sum()),
+            "all_crc_ok_frames_decode": bool(((spans["status"] == anm.ANM_PB_OK) == ok).all() and ((pk["count"] == 1) == ok).all()
+                                              and (pk["size"][ok, 0] == PAYLOAD - 6).all())}
+
+
 def build_programs(cfg, anm, n_ch, ch0, max_len=512):
-    """Per-channel cyclic symbol programs: frames of PAYLOAD random bytes (seed = global
+    """Per-channel cyclic symbol programs: frames of PAYLOAD bytes (frame_payload; seed = global
     channel id) separated by 4..16 symbols of silence."""
     progs = np.full((n_ch, max_len), anm.ANM_SILENCE, dtype=np.uint8)
     lens = np.zeros(n_ch, dtype=np.int32)
@@ -79,7 +130,7 @@ def build_programs(cfg, anm, n_ch, ch0, max_len=512):
         rng = np.random.default_rng(ch0 + c)
         parts, total = [], 0
         while True:
-            pl = rng.integers(0, 256, size=PAYLOAD, dtype=np.uint8).tobytes()
+            pl = frame_payload(rng)
             syms = anm.frame_symbols(cfg, pl)
             gap = int(rng.integers(4, 17))
             if total + len(syms) + gap > max_len:
@@ -463,6 +514,8 @@ def main():
         sample = d_pcm[:cch, : nchunks * chunk].cpu().numpy()
         cpu = cpu_baseline(cfg, np.ascontiguousarray(sample), cores, nchunks * chunk)
 
+    chain = decode_chain_leg(anm, torch, dev, recs, by) if rank == 0 else None
+
     cfg4 = None
     if rank == 0 and world == 1 and not args.no_cfg4 and args.preset == "ref4":
         del d_pcm
@@ -497,6 +550,8 @@ def main():
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if chain:
+            line["decode_chain"] = chain
         if cfg4:
             line["cfg4"] = cfg4
         print(json.dumps(line), flush=True)
