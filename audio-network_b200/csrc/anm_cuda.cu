@@ -135,6 +135,12 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
     if (k->fold)
         for (uint32_t t = 0; t < cfg->n_tones; ++t)
             if ((2u * cfg->tone_bin[t] / cfg->hops_per_sym) & 1u) k->fold_odd |= 1ull << t;
+    memset(k->fold_tw, 0, sizeof k->fold_tw);
+    if (k->fold && (cfg->sym_len / cfg->hops_per_sym / 2) * cfg->n_tones <= 256u) {
+        std::vector<float> ft((size_t)cfg->sym_len * cfg->n_tones * 2);
+        anm_fold_twiddles(cfg, ft.data());
+        memcpy(k->fold_tw, ft.data(), (size_t)(cfg->sym_len / cfg->hops_per_sym / 2) * cfg->n_tones * 8u);
+    }
     for (uint32_t t = 0; t < 16; ++t) {
         const float sg = ((k->fold_odd >> t) & 1ull) ? -1.0f : 1.0f;
         k->fold_sg[t] = make_float2(sg, sg);

@@ -84,6 +84,7 @@ struct KParams {
     uint8_t crc8_tab[256];         /* CRC-8 (poly 0x07) of one byte, for the 2-byte header check */
     uint32_t fold;                 /* 1: centre-folded hop partials (SPEC 3); tw_global then holds the folded twiddles [H/2][T] */
     unsigned long long fold_odd;   /* bit per tone: 2*tone_bin/S is odd (odd hops of that tone change sign) */
+    float2 fold_tw[256];           /* folded twiddles [H/2][T] when they fit (constant-bank operands of the arithmetic loop) */
     float2 fold_sg[16];            /* (-1, -1) for those tones, (1, 1) otherwise (and always when not folding): the factor the
                                     * first tree level applies to its odd-hop operand */
     const uint8_t *tc_basis;       /* dense tone sets: int8 basis panels [group][K chunk][32 columns][16] (anm_kernels_tc.cuh) */
@@ -667,7 +668,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                             for (int t = 0; t < TG; ++t) acc[q][t] = make_float2(0.f, 0.f);
                         uint32_t twa = stw + (uint32_t)(g * TG) * 8u;
                         uint32_t fwd = row + (uint32_t)(pass * 2 * H + H), bwd = fwd; /* walk away from the hop centres */
-#pragma unroll 1
+#pragma unroll
                         for (int i = 0; i < H / 8; ++i, twa += 4 * T * 8, fwd += 8u) {
                             bwd -= 8u;
                             uint2 vf[NQ], vb[NQ]; /* four samples after / before the centre of each hop */
@@ -691,9 +692,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 #pragma unroll
                                 for (int t = 0; t < TG; t += 2) {
                                     float4 w2;
-                                    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                        : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w)
-                                        : "r"(twa + (uint32_t)(j * T + t) * 8u));
+                                    if ((H / 2) * T <= 256) {
+                                        /* warp-uniform twiddles straight from the kernel parameters (constant bank / uniform registers) */
+                                        const float2 wa = p.fold_tw[(i * 4 + j) * T + g * TG + t], wb = p.fold_tw[(i * 4 + j) * T + g * TG + t + 1];
+                                        w2 = make_float4(wa.x, wa.y, wb.x, wb.y);
+                                    } else {
+                                        asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                            : "=f"(w2.x), "=f"(w2.y), "=f"(w2.z), "=f"(w2.w)
+                                            : "r"(twa + (uint32_t)(j * T + t) * 8u));
+                                    }
 #pragma unroll
                                     for (int q = 0; q < NQ; ++q) {
                                         acc[q][t] = ffma2vv(xs[q], make_float2(w2.x, w2.y), acc[q][t]);
