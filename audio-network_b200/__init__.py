@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libanmodem.so")
+LIB_PATH = os.environ.get("ANM_LIB_PATH") or os.path.join(_HERE, "libanmodem.so")   # ANM_LIB_PATH: experiment knob (variant builds)
 
 ANM_MAX_TONES = 64
 ANM_MAX_PREAMBLE = 32

@@ -22,6 +22,12 @@
 
 #include "anm_internal.h"
 
+/* which of the four "before the centre" samples of an 8-sample group are converted on the ALU pipe (PRMT + I2FP, two issue
+ * slots) instead of the XU pipe (I2F.S16, one issue slot at a quarter of the rate); the "after" samples always take XU */
+#ifndef ANM_CVT_ALU_MASK
+#define ANM_CVT_ALU_MASK 0xF
+#endif
+
 namespace anm {
 
 enum : uint32_t { ST_SEARCH = 0, ST_PEAK = 1, ST_HEADER = 2, ST_BODY = 3 };
@@ -109,6 +115,11 @@ __device__ __forceinline__ float2 ffma2(float a, float2 b, float2 c) {
 __device__ __forceinline__ float2 ffma2vv(float2 a, float2 b, float2 c) {
     unsigned long long rd;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+    return upk2(rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
     return upk2(rd);
 }
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
@@ -668,7 +679,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                             for (int t = 0; t < TG; ++t) acc[q][t] = make_float2(0.f, 0.f);
                         uint32_t twa = stw + (uint32_t)(g * TG) * 8u;
                         uint32_t fwd = row + (uint32_t)(pass * 2 * H + H), bwd = fwd; /* walk away from the hop centres */
-#pragma unroll
+#pragma unroll(NG == 1 ? H / 8 : 1) /* one tone group: straight-line loop, every twiddle address an immediate */
                         for (int i = 0; i < H / 8; ++i, twa += 4 * T * 8, fwd += 8u) {
                             bwd -= 8u;
                             uint2 vf[NQ], vb[NQ]; /* four samples after / before the centre of each hop */
@@ -685,14 +696,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                     const uint32_t wa = (j < 2) ? vf[q].x : vf[q].y;
                                     const uint32_t wb = (j < 2) ? vb[q].y : vb[q].x;
                                     const float a = (j & 1) ? cvt_s16<1>(wa) : cvt_s16<0>(wa);               /* XU pipe */
-                                    const float b = (j & 1) ? cvt_s16_alu<0>(wb) : cvt_s16_alu<1>(wb);       /* element 3 - j, ALU pipe */
+                                    const float b = ((ANM_CVT_ALU_MASK >> j) & 1) ? ((j & 1) ? cvt_s16_alu<0>(wb) : cvt_s16_alu<1>(wb))   /* element 3 - j, ALU pipe */
+                                                                                  : ((j & 1) ? cvt_s16<0>(wb) : cvt_s16<1>(wb));
                                     /* (a + b, a - b) as one packed FMA: (a, b) * (1, -1) + (b, a); both halves exact */
                                     xs[q] = ffma2vv(make_float2(a, b), make_float2(1.0f, -1.0f), make_float2(b, a));
                                 }
 #pragma unroll
                                 for (int t = 0; t < TG; t += 2) {
                                     float4 w2;
-                                    if ((H / 2) * T <= 256) {
+                                    if ((H / 2) * T <= 256 && NG == 1) {
                                         /* warp-uniform twiddles straight from the kernel parameters (constant bank / uniform registers) */
                                         const float2 wa = p.fold_tw[(i * 4 + j) * T + g * TG + t], wb = p.fold_tw[(i * 4 + j) * T + g * TG + t + 1];
                                         w2 = make_float4(wa.x, wa.y, wb.x, wb.y);
@@ -703,8 +715,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                                     }
 #pragma unroll
                                     for (int q = 0; q < NQ; ++q) {
-                                        acc[q][t] = ffma2vv(xs[q], make_float2(w2.x, w2.y), acc[q][t]);
-                                        acc[q][t + 1] = ffma2vv(xs[q], make_float2(w2.z, w2.w), acc[q][t + 1]);
+                                        if (NG == 1 && i == 0 && j == 0) {
+                                            /* straight-line form: the chain starts with a product instead of 0 + product (the only
+                                             * difference, the sign of an all-zero sum, cannot reach an energy: E = fma(I, I, Q * Q)) */
+                                            acc[q][t] = fmul2(xs[q], make_float2(w2.x, w2.y));
+                                            acc[q][t + 1] = fmul2(xs[q], make_float2(w2.z, w2.w));
+                                        } else {
+                                            acc[q][t] = ffma2vv(xs[q], make_float2(w2.x, w2.y), acc[q][t]);
+                                            acc[q][t + 1] = ffma2vv(xs[q], make_float2(w2.z, w2.w), acc[q][t + 1]);
+                                        }
                                     }
                                 }
                             }
