@@ -12,10 +12,12 @@
  */
 #include "../../include/anmodem.h"
 
+#include <stdint.h>
+
 #define NANOS_PER_SECOND 1000000000LL
 
 int anm_pacer_init(anm_pacer_t *p, int64_t capacity, int64_t drain_rate_per_second, int64_t now_ns) {
-    if (!p || capacity < 0 || drain_rate_per_second <= 0) return ANM_ERR_ARG;
+    if (!p || capacity < 0 || capacity > INT64_MAX / 2 || drain_rate_per_second <= 0) return ANM_ERR_ARG; /* level + amount must fit */
     p->capacity = capacity;
     p->drain_rate_per_second = drain_rate_per_second;
     p->last_value = 0;
@@ -26,9 +28,10 @@ int anm_pacer_init(anm_pacer_t *p, int64_t capacity, int64_t drain_rate_per_seco
 /* LeakyBucket.currentValue, LeakyBucket.kt:21-26 */
 int64_t anm_pacer_level(const anm_pacer_t *p, int64_t now_ns) {
     const int64_t since = now_ns - p->last_value_at_ns;
-    const int64_t drained = p->drain_rate_per_second * since / NANOS_PER_SECOND;
-    const int64_t v = p->last_value - drained;
-    return v < 0 ? 0 : v;
+    /* the reference multiplies in 64 bits (and silently wraps after long idle times at high rates); 128 bits here */
+    const __int128 drained = (__int128)p->drain_rate_per_second * since / NANOS_PER_SECOND;
+    const __int128 v = (__int128)p->last_value - drained;
+    return v < 0 ? 0 : (v > INT64_MAX ? INT64_MAX : (int64_t)v);
 }
 
 /* LeakyBucket.tryPut, LeakyBucket.kt:33-51: 0 = added; > 0 = nanoseconds to wait before retrying (the
@@ -38,8 +41,8 @@ int64_t anm_pacer_try_put(anm_pacer_t *p, int64_t amount, int64_t now_ns) {
     const int64_t cur = anm_pacer_level(p, now_ns);
     const int64_t nv = cur + amount;
     if (nv > p->capacity) {
-        const int64_t wait = (nv - p->capacity) * NANOS_PER_SECOND / p->drain_rate_per_second;
-        return wait > 0 ? wait : 1; /* a sub-nanosecond overshoot still has to wait */
+        const __int128 wait = (__int128)(nv - p->capacity) * NANOS_PER_SECOND / p->drain_rate_per_second;
+        return wait > INT64_MAX ? INT64_MAX : (wait > 0 ? (int64_t)wait : 1); /* a sub-nanosecond overshoot still has to wait */
     }
     p->last_value = nv;
     p->last_value_at_ns = now_ns;
