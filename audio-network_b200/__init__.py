@@ -168,7 +168,7 @@ EXPORTS = [
     "anm_frame_num_symbols", "anm_frame_symbols", "anm_tx_render", "anm_tx_render_device",
     "anm_tone_energies_device", "anm_demod_create", "anm_demod_destroy", "anm_demod_reset",
     "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_feed_host_async", "anm_demod_wait_input",
-    "anm_demod_collect", "anm_demod_collect_upto", "anm_demod_read_frames",
+    "anm_demod_collect", "anm_demod_collect_upto", "anm_demod_read_frames", "anm_demod_take_frames", "anm_demod_frame_rings", "demod_create_cfg", "anm_frames_digest",
     "anm_demod_read_symbols", "anm_demod_stats", "anm_demod_launch_count", "anm_demod_overflowed", "anm_demod_last_kernel_ms",
     "anm_last_error", "anm_version", "demod_initialize", "demod_create", "demod_feed",
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
@@ -215,6 +215,10 @@ def lib():
         "anm_demod_collect_upto": (C.c_long, [vp, C.c_uint32]),
         "anm_demod_collect": (C.c_long, [vp]),
         "anm_demod_read_frames": (C.c_size_t, [vp, vp, C.c_size_t, vp, C.c_size_t]),
+        "anm_demod_take_frames": (C.c_size_t, [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "anm_demod_frame_rings": (C.c_int, [vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "demod_create_cfg": (vp, [cfgp]),
+        "anm_frames_digest": (C.c_uint64, [vp, C.c_size_t, vp]),
         "anm_demod_read_symbols": (C.c_size_t, [vp, C.c_uint32, vp, C.c_size_t]),
         "anm_demod_stats": (C.c_int, [vp, vp]),
         "anm_demod_launch_count": (C.c_uint64, [vp]),
@@ -471,6 +475,18 @@ class Demod:
         used = int(recs["len"].sum()) if n else 0
         return recs, by[:used]
 
+    def take_frames(self, recs, by):
+        """Everything queued, arrival order, into caller-owned arrays (FRAME_DTYPE records, uint8 bytes); -> (n_frames, n_bytes)."""
+        nb = C.c_size_t(0)
+        n = lib().anm_demod_take_frames(self._h, _ptr(recs), len(recs), _ptr(by), len(by), C.byref(nb))
+        return int(n), int(nb.value)
+
+    def frame_rings(self):
+        """(d_frames ptr, frames_mask, d_bytes ptr, bytes_mask) of the device-resident rings."""
+        f, b, fm, bm = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint32()
+        _check(lib().anm_demod_frame_rings(self._h, C.byref(f), C.byref(fm), C.byref(b), C.byref(bm)))
+        return f.value, fm.value, b.value, bm.value
+
     def read_symbols(self, channel, cap=1 << 20):
         out = np.zeros(cap, dtype=np.uint8)
         n = lib().anm_demod_read_symbols(self._h, channel, _ptr(out), cap)
@@ -497,6 +513,13 @@ class Demod:
         g, w, s = C.c_uint32(), C.c_uint32(), C.c_uint32()
         _check(lib().anm_demod_launch_geometry(self._h, C.byref(g), C.byref(w), C.byref(s)))
         return g.value, w.value, s.value
+
+
+def frames_digest(recs, by):
+    """anm_frames_digest over read_frames / take_frames output (order-independent)."""
+    recs = np.ascontiguousarray(recs, dtype=FRAME_DTYPE)
+    by = np.ascontiguousarray(by, dtype=np.uint8)
+    return int(lib().anm_frames_digest(_ptr(recs) if len(recs) else None, len(recs), _ptr(by) if len(by) else None))
 
 
 def frames_to_list(recs, by):

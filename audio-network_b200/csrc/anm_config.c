@@ -206,3 +206,20 @@ size_t anm_frame_symbols(const anm_config_t *c, const uint8_t *payload, size_t l
     n += pack_section(body, len + 2, b, syms + n);
     return n;
 }
+
+/* Order-independent checksum of a set of frames: FNV-1a over (channel-seeded) start_sample, len, crc_ok and the payload of each
+ * frame, summed modulo 2^64 over the frames.  A host-side gather (several devices / processes) uses it to check that what
+ * arrived is what was decoded; the test oracle computes the same quantity independently (oracle/anm_oracle_batch.c). */
+uint64_t anm_frames_digest(const anm_frame_t *frames, size_t n, const uint8_t *bytes) {
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t h = 0xCBF29CE484222325ull ^ frames[i].channel;
+        const uint8_t *parts[4] = {(const uint8_t *)&frames[i].start_sample, (const uint8_t *)&frames[i].len,
+                                   (const uint8_t *)&frames[i].crc_ok, bytes ? bytes + frames[i].offset : NULL};
+        const size_t lens[4] = {8, 4, 4, bytes ? frames[i].len : 0};
+        for (int k = 0; k < 4; ++k)
+            for (size_t j = 0; j < lens[k]; ++j) h = (h ^ parts[k][j]) * 0x100000001B3ull;
+        total += h;
+    }
+    return total;
+}

@@ -19,6 +19,7 @@
 #include <new>
 #include <vector>
 
+#include "anm_host_queue.h"
 #include "anm_kernels_tc.cuh"
 #include "../../include/anmodem_pb.h"
 
@@ -105,22 +106,25 @@ struct anm_demod {
     float2 *d_tw;
     std::vector<float> h_tw;
     uint8_t *d_basis; /* dense tone sets: int8 basis panels */
-    int16_t *d_stage;
+    /* host feeds: two staging buffers, so that the copy of chunk k+1 crosses PCIe while the kernel of chunk k runs */
+    int16_t *d_stage[2];
     size_t stage_cap;
-    cudaStream_t own_stream, last_stream;
-    uint64_t samples_fed, syms_since_collect, launches;
+    uint32_t stage_next;
+    cudaStream_t own_stream, h2d_stream, last_stream;
+    cudaEvent_t stage_free[2]; /* recorded behind the kernel that read the staging buffer */
+    cudaEvent_t h2d_done, order_ev;
+    uint64_t samples_fed, syms_since_collect;
+    uint64_t launches;             /* launches of the streaming kernel since create (bench.py's gpu_launches) */
+    uint64_t launches_since_reset; /* the work-queue / snapshot sequence restarts with the state */
+    uint64_t drained_upto;         /* launches (since reset) whose frames are in the host queue */
     std::vector<EvPair> evs;
     size_t ev_used;
-    uint32_t read_f, read_b;           /* frames / payload bytes consumed by the host (mod 2^32) */
-    uint32_t *snap;                    /* pinned [kSnapSlots][4] counter snapshots */
+    uint32_t read_f, read_b;       /* frames / payload bytes consumed by the host (mod 2^32) */
+    uint32_t seen_drops;           /* value of the device's drop counter the host has accounted for */
+    uint32_t *snap;                /* pinned, device-visible [kSnapSlots][4]: written by each launch's last warp */
     cudaEvent_t snap_ev[kSnapSlots];
-    bool snap_valid[kSnapSlots];
-    bool want_snapshot;                /* set by the pipelined host feed around its launch */
-    cudaEvent_t h2d_done;
     cudaStream_t d2h_stream;
-    /* host-side result queues */
-    std::vector<anm_frame_t> q_frames;
-    std::vector<uint8_t> q_bytes;
+    anm::FrameQueue q;             /* host-side result queue (pinned storage; device-to-host copies land in it) */
     std::vector<std::deque<uint8_t>> q_syms;
     int overflow;
     KParams kp;
@@ -165,7 +169,7 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
 
 /* int8 basis of a dense configuration in the panel order the MMA descriptors of k_demod_tc address:
  * [hop phase q][tone group][16-sample K chunk][column = 2*tone_in_group + (0: cos, 1: sin)][sample in chunk] */
-static int upload_basis_panels(const anm_config_t *cfg, uint8_t **d_out) {
+static int upload_basis_panels(const anm_config_t *cfg, uint8_t **d_out, cudaStream_t stream) {
     const uint32_t N = cfg->sym_len, T = cfg->n_tones, S = cfg->hops_per_sym, H = N / S, KC = H / 16, NG = T / tc::kTG;
     std::vector<int8_t> q7((size_t)N * T * 2);
     if (anm_basis_q7(cfg, q7.data()) != ANM_OK) return ANM_ERR_ARG;
@@ -178,7 +182,9 @@ static int upload_basis_panels(const anm_config_t *cfg, uint8_t **d_out) {
                         pan[((size_t)((q * NG + g) * KC + kc) * tc::kNcol + n) * 16 + kk] =
                             (uint8_t)q7[((size_t)(q * H + kc * 16 + kk) * T + (g * tc::kTG + n / 2)) * 2 + (n & 1u)];
     CK(cudaMalloc(d_out, pan.size()));
-    CK(cudaMemcpy(*d_out, pan.data(), pan.size(), cudaMemcpyHostToDevice));
+    /* pageable source: the runtime stages it before the call returns, the copy itself is ordered on `stream` */
+    CK(cudaMemcpyAsync(*d_out, pan.data(), pan.size(), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
     return ANM_OK;
 }
 
@@ -217,24 +223,7 @@ static void choose_launch(anm_demod *h) {
     h->smem_bytes = (size_t)W * per_warp + h->var->cta_smem;
 }
 
-extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, int device, uint32_t flags,
-                                anm_demod_t **out) {
-    if (!cfg || !out || n_channels == 0) return ANM_ERR_ARG;
-    if (anm_config_validate(cfg) != ANM_OK) { anm_set_error("invalid configuration"); return ANM_ERR_ARG; }
-    const Variant *var = find_variant(cfg);
-    if (!var) {
-        anm_set_error("no kernel instance for T=%u N=%u S=%u", cfg->n_tones, cfg->sym_len, cfg->hops_per_sym);
-        return ANM_ERR_UNSUPPORTED;
-    }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        anm_set_error("no CUDA device: the demodulator has no CPU fallback");
-        return ANM_ERR_CUDA;
-    }
-    if (device < 0 || device >= ndev) return ANM_ERR_ARG;
-    anm_demod *h = new (std::nothrow) anm_demod();
-    if (!h) return ANM_ERR_NOMEM;
+static int create_impl(anm_demod *h, const anm_config_t *cfg, const Variant *var, uint32_t n_channels, int device, uint32_t flags) {
     h->cfg = *cfg;
     h->var = var;
     h->device = device;
@@ -248,11 +237,15 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     const uint32_t hdr_syms = (24 + b - 1) / b;
     h->max_frame_syms = hdr_syms + ((cfg->max_payload + 2) * 8 + b - 1) / b;
     h->fsym_stride = (h->max_frame_syms + 63u) & ~63u;
-    /* frames / payload bytes that may accumulate between two collects (about 2 minutes of back-to-back
-     * short frames per channel); overflow drops frames and is reported by anm_demod_overflowed() */
-    h->frames_cap = pow2_ceil(std::min<uint64_t>(1ull << 24, std::max<uint64_t>(4096u, (uint64_t)n_channels * 256u)));
-    h->bytes_cap = pow2_ceil(std::min<uint64_t>(1ull << 30, std::max<uint64_t>(1u << 20, (uint64_t)n_channels * 16384u)));
+    /* frames / payload bytes that may accumulate between two collects (about 4 minutes of back-to-back short frames per
+     * channel); overflow drops frames and is reported by anm_demod_overflowed() */
+    h->frames_cap = pow2_ceil(std::min<uint64_t>(1ull << 24, std::max<uint64_t>(4096u, (uint64_t)n_channels * 512u)));
+    h->bytes_cap = pow2_ceil(std::min<uint64_t>(1ull << 30, std::max<uint64_t>(1u << 20, (uint64_t)n_channels * 32768u)));
     h->osym_cap = (flags & ANM_FLAG_SYMBOLS) ? 4096u : 0u;
+    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    h->last_stream = h->own_stream;
     CK(cudaMalloc(&h->d_state, (size_t)n_channels * var->state_bytes));
     CK(cudaMalloc(&h->d_fsyms, (size_t)n_channels * h->fsym_stride));
     CK(cudaMalloc(&h->d_frames, (size_t)h->frames_cap * sizeof(anm_frame_t)));
@@ -263,9 +256,9 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     if (anm_config_foldable(cfg)) anm_fold_twiddles(cfg, h->h_tw.data()); /* [H/2][T][2], a prefix of the buffer */
     else anm_twiddles(cfg, h->h_tw.data());
     CK(cudaMalloc(&h->d_tw, h->h_tw.size() * sizeof(float)));
-    CK(cudaMemcpy(h->d_tw, h->h_tw.data(), h->h_tw.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    h->last_stream = h->own_stream;
+    /* uploads go through the handle's own stream: it is non-blocking, so the legacy default stream would not order them
+     * before the first kernel (h_tw lives as long as the handle) */
+    CK(cudaMemcpyAsync(h->d_tw, h->h_tw.data(), h->h_tw.size() * sizeof(float), cudaMemcpyHostToDevice, h->own_stream));
     h->evs.resize(64);
     for (EvPair &e : h->evs) {
         CK(cudaEventCreate(&e.a));
@@ -275,7 +268,8 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     memset(h->snap, 0, kSnapSlots * 16);
     for (size_t i = 0; i < kSnapSlots; ++i) CK(cudaEventCreateWithFlags(&h->snap_ev[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->h2d_done, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&h->stage_free[i], cudaEventDisableTiming));
     h->q_syms.resize((flags & ANM_FLAG_SYMBOLS) ? n_channels : 0);
     /* constant part of the kernel parameters */
     KParams &k = h->kp;
@@ -308,12 +302,36 @@ extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, in
     k.tw_global = h->d_tw;
     set_tw_sign(cfg, &k);
     if (var->dense) {
-        int rcb = upload_basis_panels(cfg, &h->d_basis);
-        if (rcb != ANM_OK) { anm_demod_destroy(h); return rcb; }
+        int rcb = upload_basis_panels(cfg, &h->d_basis, h->own_stream);
+        if (rcb != ANM_OK) return rcb;
         k.tc_basis = h->d_basis;
     }
-    int rc = anm_demod_reset(h);
-    if (rc != ANM_OK) { anm_demod_destroy(h); return rc; }
+    return anm_demod_reset(h); /* synchronises own_stream: every upload above is complete when create returns */
+}
+
+extern "C" int anm_demod_create(const anm_config_t *cfg, uint32_t n_channels, int device, uint32_t flags,
+                                anm_demod_t **out) {
+    if (!cfg || !out || n_channels == 0) return ANM_ERR_ARG;
+    if (anm_config_validate(cfg) != ANM_OK) { anm_set_error("invalid configuration"); return ANM_ERR_ARG; }
+    const Variant *var = find_variant(cfg);
+    if (!var) {
+        anm_set_error("no kernel instance for T=%u N=%u S=%u", cfg->n_tones, cfg->sym_len, cfg->hops_per_sym);
+        return ANM_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        anm_set_error("no CUDA device: the demodulator has no CPU fallback");
+        return ANM_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) return ANM_ERR_ARG;
+    anm_demod *h = new (std::nothrow) anm_demod();
+    if (!h) return ANM_ERR_NOMEM;
+    const int rc = create_impl(h, cfg, var, n_channels, device, flags);
+    if (rc != ANM_OK) {
+        anm_demod_destroy(h); /* releases whatever was allocated before the failure */
+        return rc;
+    }
     *out = h;
     return ANM_OK;
 }
@@ -330,16 +348,21 @@ extern "C" int anm_demod_reset(anm_demod_t *h) {
     if (!h) return ANM_ERR_ARG;
     if (set_device(h)) return ANM_ERR_CUDA;
     CK(cudaStreamSynchronize(h->last_stream));
+    CK(cudaStreamSynchronize(h->h2d_stream));
+    CK(cudaStreamSynchronize(h->d2h_stream));
     int rc = init_state(h->var, h->d_state, h->n_ch, h->own_stream);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->d_counters, 0, 32, h->own_stream));
     CK(cudaStreamSynchronize(h->own_stream));
+    h->last_stream = h->own_stream;
     h->samples_fed = 0;
     h->syms_since_collect = 0;
     h->ev_used = 0;
     h->read_f = h->read_b = 0;
-    h->q_frames.clear();
-    h->q_bytes.clear();
+    h->seen_drops = 0;
+    h->launches_since_reset = 0;
+    h->drained_upto = 0;
+    h->q.clear();
     for (auto &q : h->q_syms) q.clear();
     h->overflow = 0;
     return ANM_OK;
@@ -357,83 +380,105 @@ extern "C" void anm_demod_destroy(anm_demod_t *h) {
     cudaFree(h->d_osyms);
     cudaFree(h->d_tw);
     cudaFree(h->d_basis);
-    cudaFree(h->d_stage);
+    cudaFree(h->d_stage[0]);
+    cudaFree(h->d_stage[1]);
     for (EvPair &e : h->evs) {
         if (e.a) cudaEventDestroy(e.a);
         if (e.b) cudaEventDestroy(e.b);
     }
     for (size_t i = 0; i < kSnapSlots; ++i)
         if (h->snap_ev[i]) cudaEventDestroy(h->snap_ev[i]);
+    for (int i = 0; i < 2; ++i)
+        if (h->stage_free[i]) cudaEventDestroy(h->stage_free[i]);
     if (h->h2d_done) cudaEventDestroy(h->h2d_done);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
+    h->q.frames.release(); /* pinned storage: free it while the context is current */
+    h->q.bytes.release();
     if (h->snap) cudaFreeHost(h->snap);
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
-static int launch(anm_demod *h, KParams &k, cudaStream_t s, bool timed, bool snapshot) {
+static int launch(anm_demod *h, KParams &k, cudaStream_t s, bool timed) {
     EvPair *ev = nullptr;
     if (timed && h->ev_used < h->evs.size()) ev = &h->evs[h->ev_used++];
+    /* One launch of a handle at a time: a launch on another stream than the previous one is ordered behind it (the
+     * per-channel state, the work-queue tickets and the snapshot sequence all assume it). */
+    if (s != h->last_stream) {
+        CK(cudaEventRecord(h->order_ev, h->last_stream));
+        CK(cudaStreamWaitEvent(s, h->order_ev, 0));
+    }
     /* frame / byte queues are rings addressed by monotonically increasing counters; the kernel may
      * fill them up to one capacity beyond what the host has consumed so far */
     k.base_f = h->read_f;
     k.base_b = h->read_b;
+    const uint64_t seq = h->launches_since_reset;
+    const size_t slot = (size_t)(seq % kSnapSlots);
+    k.q_base = (uint32_t)(seq * h->n_ch);
+    k.done_base = (uint32_t)(seq * (uint64_t)h->grid * h->warps_per_cta);
+    k.snap = h->snap + slot * 4;
+    k.seq1 = (uint32_t)(seq + 1);
     if (ev) CK(cudaEventRecord(ev->a, s));
     void *args[] = {(void *)&k};
     CK(cudaLaunchKernel((const void *)variant_fn(h->var, &h->cfg, false), dim3(h->grid), dim3(h->warps_per_cta * 32), args, h->smem_bytes, s));
     if (ev) CK(cudaEventRecord(ev->b, s));
-    /* pipelined host feeds: stream-ordered snapshot of the queue counters as they stand after this
-     * launch, so that a later drain can stop exactly there while newer launches are in flight */
-    const size_t slot = (size_t)(h->launches % kSnapSlots);
-    h->snap_valid[slot] = snapshot;
-    if (snapshot) {
-        CK(cudaMemcpyAsync(h->snap + slot * 4, h->d_counters, 16, cudaMemcpyDeviceToHost, s));
-        CK(cudaEventRecord(h->snap_ev[slot], s));
-    }
+    /* the kernel's last warp writes the queue counters as they stand after this launch into snap[slot] (pinned host
+     * memory); the event tells the host when that has happened.  A later drain can therefore stop exactly behind this
+     * launch while newer launches are in flight -- no extra copy in the stream. */
+    CK(cudaEventRecord(h->snap_ev[slot], s));
     h->launches++;
+    h->launches_since_reset++;
+    h->last_stream = s;
     return ANM_OK;
 }
 
-/* Moves the frames produced up to (and including) launch number `seq` into the host queues.  Waits only
- * for that launch; later launches may still be running or queued behind a host->device copy. */
+/* Moves the frames produced up to (and including) launch number `seq` (counted since reset) into the host queue.  Waits
+ * only for that launch; later launches may still be running or queued behind a host->device copy. */
 static int drain_frames(anm_demod *h, uint64_t seq) {
-    const size_t slot = (size_t)(seq % kSnapSlots);
-    uint32_t wf, wb, ovf;
-    if (h->snap_valid[slot]) {
-        CK(cudaEventSynchronize(h->snap_ev[slot]));
-        wf = h->snap[slot * 4 + 0], wb = h->snap[slot * 4 + 1], ovf = h->snap[slot * 4 + 2];
-    } else {
-        /* no snapshot was taken for this launch: everything must have completed */
-        CK(cudaStreamSynchronize(h->last_stream));
-        uint32_t cnt[4];
-        CK(cudaMemcpy(cnt, h->d_counters, 16, cudaMemcpyDeviceToHost));
-        wf = cnt[0], wb = cnt[1], ovf = cnt[2];
+    if (seq + 1 <= h->drained_upto) return ANM_OK; /* an older launch than what was already handed out: nothing new */
+    if (h->launches_since_reset - seq > kSnapSlots) {
+        /* the launch's snapshot slot has been reused: fall back to the state after everything submitted so far */
+        seq = h->launches_since_reset - 1;
     }
+    const size_t slot = (size_t)(seq % kSnapSlots);
+    CK(cudaEventSynchronize(h->snap_ev[slot]));
+    volatile const uint32_t *sn = h->snap + slot * 4;
+    if (sn[3] != (uint32_t)(seq + 1)) {
+        anm_set_error("internal: snapshot of launch %llu holds sequence %u", (unsigned long long)seq, sn[3] - 1u);
+        return ANM_ERR_CUDA;
+    }
+    const uint32_t wf = sn[0], wb = sn[1], drops = sn[2];
+    h->drained_upto = seq + 1;
     const uint32_t nf = wf - h->read_f, nb = wb - h->read_b; /* modulo 2^32 */
-    if (ovf || nf > h->frames_cap || nb > h->bytes_cap) {
-        /* records of dropped frames were never written: discard what is pending and resynchronise */
+    if (drops != h->seen_drops || nf > h->frames_cap || nb > h->bytes_cap) {
+        /* Records of dropped frames were never written: discard what is pending and resynchronise on the snapshot.  The
+         * device's drop counter only ever counts up and is never cleared while launches may be in flight; launches
+         * submitted after this point take the new read positions as their base. */
         h->overflow = 1;
+        h->seen_drops = drops;
         h->read_f = wf;
         h->read_b = wb;
-        CK(cudaMemsetAsync(h->d_counters + 2, 0, 4, h->d2h_stream));
-        CK(cudaStreamSynchronize(h->d2h_stream));
         return ANM_OK;
     }
     if (nf) {
-        const size_t f0 = h->q_frames.size(), b0 = h->q_bytes.size();
-        h->q_frames.resize(f0 + nf);
-        h->q_bytes.resize(b0 + nb);
+        anm_frame_t *fdst;
+        uint8_t *bdst;
+        const size_t b0 = h->q.bytes.n;
+        if (!h->q.grow(nf, nb, &fdst, &bdst)) { anm_set_error("out of host memory for %u frames", nf); return ANM_ERR_NOMEM; }
+        const size_t b0q = (h->q.bytes.n - nb); /* grow() may have restarted the queue at the front */
+        (void)b0;
         const uint32_t fpos = h->read_f & (h->frames_cap - 1), f1 = std::min(nf, h->frames_cap - fpos);
-        CK(cudaMemcpyAsync(h->q_frames.data() + f0, h->d_frames + fpos, (size_t)f1 * sizeof(anm_frame_t), cudaMemcpyDeviceToHost, h->d2h_stream));
-        if (nf > f1)
-            CK(cudaMemcpyAsync(h->q_frames.data() + f0 + f1, h->d_frames, (size_t)(nf - f1) * sizeof(anm_frame_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        CK(cudaMemcpyAsync(fdst, h->d_frames + fpos, (size_t)f1 * sizeof(anm_frame_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (nf > f1) CK(cudaMemcpyAsync(fdst + f1, h->d_frames, (size_t)(nf - f1) * sizeof(anm_frame_t), cudaMemcpyDeviceToHost, h->d2h_stream));
         if (nb) {
             const uint32_t bpos = h->read_b & (h->bytes_cap - 1), b1 = std::min(nb, h->bytes_cap - bpos);
-            CK(cudaMemcpyAsync(h->q_bytes.data() + b0, h->d_bytes + bpos, b1, cudaMemcpyDeviceToHost, h->d2h_stream));
-            if (nb > b1) CK(cudaMemcpyAsync(h->q_bytes.data() + b0 + b1, h->d_bytes, nb - b1, cudaMemcpyDeviceToHost, h->d2h_stream));
+            CK(cudaMemcpyAsync(bdst, h->d_bytes + bpos, b1, cudaMemcpyDeviceToHost, h->d2h_stream));
+            if (nb > b1) CK(cudaMemcpyAsync(bdst + b1, h->d_bytes, nb - b1, cudaMemcpyDeviceToHost, h->d2h_stream));
         }
         CK(cudaStreamSynchronize(h->d2h_stream));
-        for (size_t i = f0; i < f0 + nf; ++i) h->q_frames[i].offset = (uint32_t)b0 + (h->q_frames[i].offset - h->read_b);
+        for (uint32_t i = 0; i < nf; ++i) fdst[i].offset = (uint32_t)b0q + (fdst[i].offset - h->read_b);
         h->read_f = wf;
         h->read_b = wb;
     }
@@ -463,9 +508,8 @@ extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_
     k.ch_stride = ch_stride;
     k.n_syms = (uint32_t)nsyms;
     k.hop_base = h->samples_fed / (N / h->cfg.hops_per_sym);
-    int rc = launch(h, k, s, true, h->want_snapshot);
+    int rc = launch(h, k, s, true);
     if (rc) return rc;
-    h->last_stream = s;
     h->samples_fed += n_samples;
     h->syms_since_collect += nsyms;
     return ANM_OK;
@@ -475,29 +519,38 @@ static int feed_host_impl(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride
     if (!h || (!h_pcm && n_samples)) return ANM_ERR_ARG;
     if (n_samples == 0) return ANM_OK;
     if (n_samples % h->cfg.sym_len) return ANM_ERR_ALIGN;
+    if (ch_stride < n_samples) return ANM_ERR_ARG;
     if (set_device(h)) return ANM_ERR_CUDA;
     const size_t need = (size_t)h->n_ch * n_samples;
     if (need > h->stage_cap) {
         CK(cudaStreamSynchronize(h->last_stream));
-        cudaFree(h->d_stage);
-        h->d_stage = nullptr;
+        CK(cudaStreamSynchronize(h->h2d_stream));
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->d_stage[i]);
+            h->d_stage[i] = nullptr;
+        }
         h->stage_cap = 0;
-        CK(cudaMalloc(&h->d_stage, need * sizeof(int16_t)));
+        for (int i = 0; i < 2; ++i) CK(cudaMalloc(&h->d_stage[i], need * sizeof(int16_t)));
         h->stage_cap = need;
+        /* fresh events: nothing has read the new buffers */
+        for (int i = 0; i < 2; ++i) CK(cudaEventRecord(h->stage_free[i], h->own_stream));
     }
-    cudaStream_t s = h->own_stream;
-    if (h->last_stream != s) CK(cudaStreamSynchronize(h->last_stream));
+    const uint32_t sb = h->stage_next;
+    h->stage_next ^= 1u;
+    int16_t *dst = h->d_stage[sb];
+    /* the copy runs on its own stream: it only waits for the kernel that last read this staging buffer (two feeds ago),
+     * so it overlaps the kernel of the previous chunk */
+    CK(cudaStreamWaitEvent(h->h2d_stream, h->stage_free[sb], 0));
     if (ch_stride == n_samples)
-        CK(cudaMemcpyAsync(h->d_stage, h_pcm, need * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(dst, h_pcm, need * sizeof(int16_t), cudaMemcpyHostToDevice, h->h2d_stream));
     else
-        CK(cudaMemcpy2DAsync(h->d_stage, n_samples * 2, h_pcm, ch_stride * 2, n_samples * 2, h->n_ch,
-                             cudaMemcpyHostToDevice, s));
-    CK(cudaEventRecord(h->h2d_done, s));
-    h->want_snapshot = async;
-    int rc = anm_demod_feed_device(h, h->d_stage, n_samples, n_samples, s);
-    h->want_snapshot = false;
+        CK(cudaMemcpy2DAsync(dst, n_samples * 2, h_pcm, ch_stride * 2, n_samples * 2, h->n_ch, cudaMemcpyHostToDevice, h->h2d_stream));
+    CK(cudaEventRecord(h->h2d_done, h->h2d_stream));
+    CK(cudaStreamWaitEvent(h->own_stream, h->h2d_done, 0));
+    int rc = anm_demod_feed_device(h, dst, n_samples, n_samples, h->own_stream);
     if (rc) return rc;
-    if (!async) CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(h->stage_free[sb], h->own_stream));
+    if (!async) CK(cudaStreamSynchronize(h->own_stream));
     return ANM_OK;
 }
 
@@ -520,11 +573,11 @@ extern "C" long anm_demod_collect_upto(anm_demod_t *h, uint32_t lag) {
     if (!h) return ANM_ERR_ARG;
     if (set_device(h)) return ANM_ERR_CUDA;
     if (lag >= kSnapSlots - 1) return ANM_ERR_ARG;
-    if (h->launches > lag) {
-        int rc = drain_frames(h, h->launches - 1 - lag);
+    if (h->launches_since_reset > lag) {
+        int rc = drain_frames(h, h->launches_since_reset - 1 - lag);
         if (rc) return rc;
     }
-    return (long)h->q_frames.size();
+    return (long)h->q.pending();
 }
 
 extern "C" long anm_demod_collect(anm_demod_t *h) {
@@ -532,68 +585,55 @@ extern "C" long anm_demod_collect(anm_demod_t *h) {
     if (set_device(h)) return ANM_ERR_CUDA;
     cudaStream_t s = h->last_stream;
     CK(cudaStreamSynchronize(s));
-    if (h->launches) {
-        int rc = drain_frames(h, h->launches - 1);
+    if (h->launches_since_reset) {
+        int rc = drain_frames(h, h->launches_since_reset - 1);
         if (rc) return rc;
     }
     if (h->osym_cap && h->syms_since_collect) {
         std::vector<uint32_t> oc(h->n_ch);
         const size_t off = offsetof(ChanScalars, osym_cnt);
-        CK(cudaMemcpy2D(oc.data(), 4, h->d_state + off, h->var->state_bytes, 4, h->n_ch, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2DAsync(oc.data(), 4, h->d_state + off, h->var->state_bytes, 4, h->n_ch, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
         uint32_t mx = 0;
         for (uint32_t c : oc) mx = std::max(mx, std::min(c, h->osym_cap));
         if (mx) {
             std::vector<uint8_t> tmp((size_t)h->n_ch * mx);
-            CK(cudaMemcpy2D(tmp.data(), mx, h->d_osyms, h->osym_cap, mx, h->n_ch, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy2DAsync(tmp.data(), mx, h->d_osyms, h->osym_cap, mx, h->n_ch, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
             for (uint32_t c = 0; c < h->n_ch; ++c) {
                 const uint32_t n = std::min(oc[c], h->osym_cap);
                 if (oc[c] > h->osym_cap) h->overflow = 1;
                 h->q_syms[c].insert(h->q_syms[c].end(), tmp.begin() + (size_t)c * mx, tmp.begin() + (size_t)c * mx + n);
             }
         }
-        CK(cudaMemset2D(h->d_state + off, h->var->state_bytes, 0, 4, h->n_ch));
+        /* on the launching stream (non-blocking streams are not ordered against the legacy default stream), and complete
+         * before the next kernel can read osym_cnt */
+        CK(cudaMemset2DAsync(h->d_state + off, h->var->state_bytes, 0, 4, h->n_ch, s));
+        CK(cudaStreamSynchronize(s));
     }
     h->syms_since_collect = 0;
     if (h->overflow) { anm_set_error("an output queue overflowed; some frames or symbols were dropped"); }
-    return (long)h->q_frames.size();
+    return (long)h->q.pending();
 }
 
 extern "C" size_t anm_demod_read_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8_t *bytes, size_t bytes_cap) {
     if (!h || !out || !cap) return 0;
-    /* deterministic order: (channel, start_sample) */
-    std::vector<size_t> idx(h->q_frames.size());
-    for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
-    std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
-        const anm_frame_t &x = h->q_frames[a], &y = h->q_frames[b];
-        if (x.channel != y.channel) return x.channel < y.channel;
-        return x.start_sample < y.start_sample;
-    });
-    size_t n = 0, bo = 0;
-    std::vector<char> taken(idx.size(), 0);
-    for (size_t ii = 0; ii < idx.size() && n < cap; ++ii) {
-        const anm_frame_t &f = h->q_frames[idx[ii]];
-        if (bo + f.len > bytes_cap) break;
-        out[n] = f;
-        out[n].offset = (uint32_t)bo;
-        if (bytes && f.len) memcpy(bytes + bo, h->q_bytes.data() + f.offset, f.len);
-        bo += f.len;
-        taken[idx[ii]] = 1;
-        ++n;
-    }
-    /* keep what was not taken (compact) */
-    std::vector<anm_frame_t> rest;
-    std::vector<uint8_t> rest_b;
-    for (size_t i = 0; i < h->q_frames.size(); ++i)
-        if (!taken[i]) {
-            anm_frame_t f = h->q_frames[i];
-            const uint32_t o = (uint32_t)rest_b.size();
-            rest_b.insert(rest_b.end(), h->q_bytes.begin() + f.offset, h->q_bytes.begin() + f.offset + f.len);
-            f.offset = o;
-            rest.push_back(f);
-        }
-    h->q_frames.swap(rest);
-    h->q_bytes.swap(rest_b);
-    return n;
+    return h->q.pop_sorted(h->n_ch, out, cap, bytes, bytes_cap);
+}
+
+extern "C" size_t anm_demod_take_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8_t *bytes, size_t bytes_cap, size_t *n_bytes) {
+    if (!h || !out) return 0;
+    return h->q.take_all(out, cap, bytes, bytes_cap, n_bytes);
+}
+
+extern "C" int anm_demod_frame_rings(const anm_demod_t *h, const anm_frame_t **d_frames, uint32_t *frames_mask, const uint8_t **d_bytes,
+                                     uint32_t *bytes_mask) {
+    if (!h) return ANM_ERR_ARG;
+    if (d_frames) *d_frames = h->d_frames;
+    if (frames_mask) *frames_mask = h->frames_cap - 1u;
+    if (d_bytes) *d_bytes = h->d_bytes;
+    if (bytes_mask) *bytes_mask = h->bytes_cap - 1u;
+    return ANM_OK;
 }
 
 extern "C" size_t anm_demod_read_symbols(anm_demod_t *h, uint32_t channel, uint8_t *out, size_t cap) {
@@ -675,7 +715,11 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
     if (anm_config_foldable(cfg)) anm_fold_twiddles(cfg, tw.data());
     else anm_twiddles(cfg, tw.data());
     CK(cudaMalloc(&d_state, (size_t)n_ch * var->state_bytes));
-    CK(cudaMalloc(&d_tw, tw.size() * sizeof(float)));
+    if (cudaMalloc(&d_tw, tw.size() * sizeof(float)) != cudaSuccess) {
+        cudaFree(d_state);
+        anm_set_error("tone pass: out of device memory");
+        return ANM_ERR_CUDA;
+    }
     int rc = init_state(var, d_state, n_ch, s);
     if (rc == ANM_OK && cudaMemcpyAsync(d_tw, tw.data(), tw.size() * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) rc = ANM_ERR_CUDA;
     if (rc == ANM_OK) {
@@ -699,7 +743,7 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
         uint32_t W, grid;
         size_t smem;
         if (var->dense) {
-            rc = upload_basis_panels(cfg, &d_basis);
+            rc = upload_basis_panels(cfg, &d_basis, s);
             k.tc_basis = d_basis;
             W = tc::kWorkerWarps + 1;
             grid = (n_ch + 3u) / 4u;
@@ -736,24 +780,40 @@ struct demod {
     anm_demod_t *h;
     std::vector<int16_t> pend; /* samples not yet forming a whole symbol period */
     anm_pb_queue_t *pbq;       /* CRC-valid payloads handed to the protobuf decoder */
+    std::vector<uint8_t> buf;  /* one frame's payload on its way out */
 };
+/* demod_initialize() follows the reference's `<module>_initialize()` idiom (hardware/README.md:10-14): it sets the
+ * DEFAULT configuration of demodulators created later with demod_create().  Every demodulator owns a copy of its
+ * configuration from then on (anm_demod.cfg); demod_create_cfg() takes one directly and needs no global at all. */
 static anm_config_t g_cfg;
 static bool g_cfg_set = false;
+static std::mutex g_cfg_mu;
 
 extern "C" int demod_initialize(const anm_config_t *cfg) {
     if (!cfg || anm_config_validate(cfg) != ANM_OK) return ANM_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
     g_cfg = *cfg;
     g_cfg_set = true;
     return ANM_OK;
 }
-extern "C" demod_t *demod_create(void) {
-    if (!g_cfg_set) { anm_set_error("demod_initialize() was not called"); return nullptr; }
+extern "C" demod_t *demod_create_cfg(const anm_config_t *cfg) {
+    if (!cfg) return nullptr;
     demod *d = new (std::nothrow) demod();
     if (!d) return nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (anm_demod_create(&g_cfg, 1, dev, ANM_FLAG_SYMBOLS, &d->h) != ANM_OK) { delete d; return nullptr; }
+    if (anm_demod_create(cfg, 1, dev, ANM_FLAG_SYMBOLS, &d->h) != ANM_OK) { delete d; return nullptr; }
+    d->buf.resize(4104);
     return d;
+}
+extern "C" demod_t *demod_create(void) {
+    anm_config_t cfg;
+    {
+        std::lock_guard<std::mutex> lk(g_cfg_mu);
+        if (!g_cfg_set) { anm_set_error("demod_initialize() was not called"); return nullptr; }
+        cfg = g_cfg;
+    }
+    return demod_create_cfg(&cfg);
 }
 extern "C" int demod_feed(demod_t *d, const int16_t *pcm, size_t n) {
     if (!d || (!pcm && n)) return ANM_ERR_ARG;
@@ -773,14 +833,13 @@ extern "C" size_t demod_read_symbols(demod_t *d, uint8_t *out, size_t cap) {
 extern "C" size_t demod_read_frames(demod_t *d, demod_frame_t *out, size_t cap) {
     if (!d || !out) return 0;
     size_t n = 0;
-    std::vector<uint8_t> buf(4104);
-    while (n < cap) {
+    while (n < cap) { /* one pop per frame from the queue's cursor: linear in the number of frames */
         anm_frame_t f;
-        if (anm_demod_read_frames(d->h, &f, 1, buf.data(), buf.size()) != 1) break;
+        if (anm_demod_read_frames(d->h, &f, 1, d->buf.data(), d->buf.size()) != 1) break;
         out[n].sample_offset = f.start_sample;
         out[n].len = f.len;
         out[n].crc_ok = f.crc_ok;
-        memcpy(out[n].bytes, buf.data(), f.len);
+        memcpy(out[n].bytes, d->buf.data(), f.len);
         ++n;
     }
     return n;
@@ -798,9 +857,8 @@ extern "C" anm_pb_istream_t demod_as_pb_istream(demod_t *d) {
     anm_pb_istream_t none = {nullptr, nullptr, 0, "no demodulator"};
     if (!d) return none;
     if (!d->pbq) d->pbq = anm_pb_queue_create();
-    std::vector<uint8_t> buf(4104);
     anm_frame_t f;
-    while (anm_demod_read_frames(d->h, &f, 1, buf.data(), buf.size()) == 1)
-        if (f.crc_ok) anm_pb_queue_push(d->pbq, buf.data(), f.len);
+    while (anm_demod_read_frames(d->h, &f, 1, d->buf.data(), d->buf.size()) == 1)
+        if (f.crc_ok) anm_pb_queue_push(d->pbq, d->buf.data(), f.len);
     return anm_pb_istream_from_queue(d->pbq);
 }

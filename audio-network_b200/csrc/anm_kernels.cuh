@@ -76,9 +76,14 @@ struct KParams {
     unsigned long long tr_hops;
     anm_frame_t *frames;
     uint8_t *bytes;
-    uint32_t *counters;           /* [0]=n_frames [1]=n_bytes [2]=overflow flags [4]=next channel [5]=warps done */
+    uint32_t *counters;           /* [0]=n_frames [1]=n_bytes [2]=frames dropped (queue full) [4]=channels handed out [5]=warps done;
+                                   * all free-running (mod 2^32) since create / reset: nothing is re-armed between launches */
     uint32_t frames_cap, bytes_cap; /* powers of two: the queues are rings */
     uint32_t base_f, base_b;        /* counters as of what the host has consumed (mod 2^32) */
+    uint32_t q_base, done_base;     /* values of counters[4] / counters[5] when this launch starts (launch index x n_ch / x warps) */
+    uint32_t *snap;                 /* pinned host memory: {n_frames, n_bytes, dropped, launch seq + 1} as they stand when this launch
+                                     * ends, written by the last warp to leave (a stream-ordered snapshot without a copy) */
+    uint32_t seq1;
     uint8_t *osyms;               /* [n_ch][osym_cap] or NULL */
     uint32_t osym_cap;
     uint32_t P, tol, max_payload, trk_epoch, trk_thresh, hdr_syms;
@@ -528,7 +533,7 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                     }
                     cold_st(ok ? O_FOK : O_FBAD, cold_ld(ok ? O_FOK : O_FBAD) + 1u);
                 } else if (lane == 0) {
-                    atomicOr(&p.counters[2], 1u);
+                    atomicAdd(&p.counters[2], 1u);
                 }
                 sc.state = ST_SEARCH;
             }
@@ -546,6 +551,23 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ssa + 16u * i), "r"(w[4 * i]), "r"(w[4 * i + 1]), "r"(w[4 * i + 2]), "r"(w[4 * i + 3]) : "memory");
     }
     __syncwarp();
+}
+
+/* The last warp of a launch to get here (every warp of the grid calls this once, lane 0) writes the queue counters as they
+ * stand at the end of the launch into pinned host memory.  All frame records and payload bytes of the launch were written
+ * before the counting atomics that precede this call, and the host reads the snapshot only after the launch's event. */
+__device__ __forceinline__ void publish_snapshot(const KParams &p, uint32_t total_warps) {
+    __threadfence();
+    if (atomicAdd(&p.counters[5], 1u) - p.done_base == total_warps - 1u) {
+        __threadfence();
+        volatile uint32_t *c = p.counters;
+        volatile uint32_t *s = p.snap;
+        s[0] = c[0];
+        s[1] = c[1];
+        s[2] = c[2];
+        s[3] = p.seq1;
+        __threadfence_system();
+    }
 }
 
 constexpr int kMaxWarps = 20; /* registers are allocated per 4 warps: 20 warps x 96 registers fit the file; 24 would cap at 80 */
@@ -950,20 +972,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
         if (MODE == 0) reinterpret_cast<uint32_t *>(stp)[lane] = reinterpret_cast<const uint32_t *>(ssc)[lane];
         __syncwarp();
         if (MODE == 0) {
+            /* every processed channel takes one ticket, so a launch advances the counter by exactly n_ch: the host knows the
+             * value it starts from (q_base) and nothing has to be reset between launches */
             uint32_t nx = 0;
             if (lane == 0) nx = atomicAdd(&p.counters[4], 1u);
-            ch = total_warps + __shfl_sync(FULL, nx, 0);
+            ch = total_warps + (__shfl_sync(FULL, nx, 0) - p.q_base);
         } else {
             ch += total_warps;
         }
     }
-    /* the last warp to leave re-arms the work queue for the next launch */
-    if (MODE == 0 && lane == 0) {
-        if (atomicAdd(&p.counters[5], 1u) == total_warps - 1u) {
-            p.counters[4] = 0u;
-            p.counters[5] = 0u;
-        }
-    }
+    if (MODE == 0 && lane == 0) publish_snapshot(p, total_warps);
 }
 
 /* fresh per-channel state: everything zero, hop records "before the stream" (d = 0xFF, emax = 0) */

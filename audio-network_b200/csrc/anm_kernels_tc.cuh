@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(288, 2) k_demod_tc(const __grid_constant__ KPa
             gcarry[lane] = cv;
         }
     }
+    if (MODE == 0 && lane == 0) publish_snapshot(p, gridDim.x * (blockDim.x >> 5));
     tc_fence_before();
     __syncthreads();
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");

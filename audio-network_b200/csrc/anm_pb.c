@@ -5,10 +5,12 @@
  * Follows the wire behaviour of the reference's decoder for the messages this path carries:
  * varint (hardware/lib/nanopb/src/pb_decode.c:170-232), tag split (pb_decode.c:288-303),
  * length-delimited substreams (pb_decode.c:359-387) and the delimited wrapper
- * (pb_decode.c:1142-1168); message shapes from protocol/ip.proto:9-64.  Written from the
- * protobuf wire format, not copied from nanopb.
+ * (pb_decode.c:1142-1168); message shapes from protocol/ip.proto:9-64.  The decode-side primitives live in
+ * anm_pb_wire.h (transcriptions of nanopb's rules, see the notice there); the encoders are written from the
+ * protobuf wire format.
  */
 #include "../../include/anmodem_pb.h"
+#include "anm_pb_wire.h"
 
 #include <stdlib.h>
 #include <string.h>
@@ -116,83 +118,16 @@ size_t anm_pb_encode_broadcast_request(uint32_t magic, uint8_t *out, size_t cap)
     return n;
 }
 
-/* returns bytes consumed, 0 on error; rejects encodings longer than 10 bytes and, like
- * pb_decode_varint32 (pb_decode.c:206-229), lengths that do not fit 32 bits */
-static size_t read_varint(const uint8_t *p, size_t len, uint64_t *out) {
-    uint64_t v = 0;
-    for (size_t i = 0; i < len && i < 10; ++i) {
-        v |= (uint64_t)(p[i] & 0x7F) << (7 * i);
-        if (!(p[i] & 0x80)) {
-            *out = v;
-            return i + 1;
-        }
-    }
-    return 0;
-}
-
-static size_t skip_field(const uint8_t *p, size_t len, uint32_t wt) {
-    uint64_t v;
-    size_t n;
-    switch (wt) {
-    case 0: return read_varint(p, len, &v);
-    case 1: return len >= 8 ? 8 : 0;
-    case 2:
-        n = read_varint(p, len, &v);
-        if (!n || v > len - n) return 0;
-        return n + (size_t)v;
-    case 5: return len >= 4 ? 4 : 0;
-    default: return 0;
-    }
-}
-
+/* Host twin of k_pb_deframe: the same walk (anm_pb_wire.h), so a payload is accepted on the host exactly when the GPU
+ * deframer and the reference decoder accept it -- including "wrong wire type" on field 1, the 32-bit varint rules and the
+ * callback's 4096-byte limit (hardware/src/network.cpp:223).  A message without audio_data is reported as 0 here. */
 size_t anm_pb_scan_to_receiver_audio(const uint8_t *buf, size_t len, const uint8_t **payload, size_t *payload_len) {
-    if (!buf || !payload || !payload_len) return 0;
-    uint64_t mlen;
-    size_t n = read_varint(buf, len, &mlen);
-    if (!n || mlen > 0xFFFFFFFFull || mlen > len - n) return 0;
-    const uint8_t *m = buf + n, *mend = m + mlen;
-    const uint8_t *found = NULL;
-    size_t found_len = 0;
-    while (m < mend) {
-        uint64_t tag;
-        size_t k = read_varint(m, (size_t)(mend - m), &tag);
-        if (!k || (tag >> 3) == 0) return 0;
-        m += k;
-        if ((tag >> 3) == 1 && (tag & 7) == 2) { /* audio_data submessage */
-            uint64_t sl;
-            k = read_varint(m, (size_t)(mend - m), &sl);
-            if (!k || sl > (uint64_t)(mend - m - k)) return 0;
-            const uint8_t *a = m + k, *aend = a + sl;
-            m = aend;
-            bool have = false;
-            while (a < aend) {
-                uint64_t t2;
-                size_t k2 = read_varint(a, (size_t)(aend - a), &t2);
-                if (!k2 || (t2 >> 3) == 0) return 0;
-                a += k2;
-                if ((t2 >> 3) == 1 && (t2 & 7) == 2) {
-                    uint64_t bl;
-                    k2 = read_varint(a, (size_t)(aend - a), &bl);
-                    if (!k2 || bl > (uint64_t)(aend - a - k2)) return 0;
-                    found = a + k2;
-                    found_len = (size_t)bl;
-                    a += k2 + bl;
-                    have = true;
-                } else {
-                    k2 = skip_field(a, (size_t)(aend - a), (uint32_t)(t2 & 7));
-                    if (!k2) return 0;
-                    a += k2;
-                }
-            }
-            if (!have) return 0; /* required field missing (pb_decode.c:1100-1138) */
-        } else {
-            k = skip_field(m, (size_t)(mend - m), (uint32_t)(tag & 7));
-            if (!k) return 0;
-            m += k;
-        }
-    }
-    if (!found) return 0;
-    *payload = found;
-    *payload_len = found_len;
-    return n + (size_t)mlen;
+    if (!buf || !payload || !payload_len || len > 0xFFFFFFFFu) return 0;
+    anm_wstream_t s = {buf, 0xFFFFFFFFu, 0u, (uint32_t)len};
+    bool have = false;
+    uint32_t a_off = 0, a_len = 0;
+    if (!anm_w_to_receiver(&s, &have, &a_off, &a_len) || !have) return 0;
+    *payload = buf + a_off;
+    *payload_len = a_len;
+    return s.pos;
 }

@@ -11,9 +11,10 @@
  *   oneof + submessage decode                :519-560, 1568-1618
  *   network_pb_callback_audio_data           hardware/src/network.cpp:212-249 (rejects > 4096 bytes, :223)
  * and reports where the Opus bytes lie instead of copying them into two mallocs per frame.
- * One thread per frame: frames are short (<= max_payload bytes) and independent.  Written from the
- * behaviour of the code above, not copied from it; parity is checked against the reference's own
- * nanopb compiled in place (oracle/_ref) on valid, truncated and mutated messages (tests/test_pb_gpu.py).
+ * One thread per frame: frames are short (<= max_payload bytes) and independent.  The wire primitives
+ * (anm_pb_wire.h) are transcriptions of nanopb's rules -- see the notice there; the message walk is written
+ * from the behaviour of the code above.  Parity is checked against the reference's own nanopb compiled in
+ * place (oracle/_ref) on valid, truncated and mutated messages (tests/test_pb_gpu.py).
  */
 #include <cuda_runtime.h>
 
@@ -21,139 +22,11 @@
 
 #include "../../include/anmodem_pb.h"
 #include "anm_internal.h"
+#include "anm_pb_wire.h"
 
 namespace {
 
-constexpr uint32_t kMaxEncodedFrame = 4096; /* MAX_ENCODED_FRAME_SIZE, hardware/src/network.cpp:24 */
-
-struct Stream {
-    const uint8_t *bytes;
-    uint32_t mask; /* arena ring mask, 0xFFFFFFFF for a linear array */
-    uint32_t pos;  /* absolute arena position of the next byte */
-    uint32_t left; /* bytes_left */
-};
-
-__device__ __forceinline__ bool rd(Stream &s, uint32_t &b) {
-    if (s.left == 0) return false; /* "end-of-stream" */
-    b = s.bytes[s.pos & s.mask];
-    ++s.pos;
-    --s.left;
-    return true;
-}
-__device__ __forceinline__ bool skip(Stream &s, uint32_t n) {
-    if (s.left < n) return false;
-    s.pos += n;
-    s.left -= n;
-    return true;
-}
-
-/* pb_decode_varint32_eof */
-__device__ bool varint32(Stream &s, uint32_t &out, bool *eof) {
-    uint32_t byte;
-    if (!rd(s, byte)) {
-        if (eof) *eof = true; /* bytes_left == 0 */
-        return false;
-    }
-    uint32_t result;
-    if ((byte & 0x80u) == 0) {
-        result = byte;
-    } else {
-        uint32_t bitpos = 7;
-        result = byte & 0x7Fu;
-        do {
-            if (!rd(s, byte)) return false;
-            if (bitpos >= 32) {
-                /* trailing 0x80 bytes, or the sign extension of a negative int32 */
-                const uint32_t sign_extension = (bitpos < 63) ? 0xFFu : 0x01u;
-                const bool valid = ((byte & 0x7Fu) == 0) || ((result >> 31) != 0 && byte == sign_extension);
-                if (bitpos >= 64 || !valid) return false; /* "varint overflow" */
-            } else {
-                result |= (byte & 0x7Fu) << bitpos;
-            }
-            bitpos += 7;
-        } while (byte & 0x80u);
-        if (bitpos == 35 && (byte & 0x70u) != 0) return false; /* only 4 bits of the fifth byte fit */
-    }
-    out = result;
-    return true;
-}
-
-/* pb_skip_field */
-__device__ bool skip_field(Stream &s, uint32_t wt) {
-    uint32_t b, len;
-    switch (wt) {
-    case 0: /* pb_skip_varint: no length limit */
-        do {
-            if (!rd(s, b)) return false;
-        } while (b & 0x80u);
-        return true;
-    case 1: return skip(s, 8);
-    case 2: return varint32(s, len, nullptr) && skip(s, len);
-    case 5: return skip(s, 4);
-    default: return false; /* "invalid wire_type" */
-    }
-}
-
-/* pb_make_string_substream: the parent keeps what follows the substream */
-__device__ bool substream(Stream &s, Stream &sub) {
-    uint32_t size;
-    if (!varint32(s, size, nullptr)) return false;
-    if (s.left < size) return false; /* "parent stream too short" */
-    sub = s;
-    sub.left = size;
-    s.pos += size;
-    s.left -= size;
-    return true;
-}
-
-/* AudioData: pb_decode_inner over {1: required bytes opus_encoded_frame (callback)} */
-__device__ bool decode_audio_data(Stream &s, uint32_t &a_off, uint32_t &a_len) {
-    bool seen = false;
-    while (s.left) {
-        uint32_t t;
-        bool eof = false;
-        if (!varint32(s, t, &eof)) {
-            if (eof) break;
-            return false;
-        }
-        const uint32_t tag = t >> 3, wt = t & 7u;
-        if (tag == 0) return false; /* "zero tag" */
-        if (tag != 1) {
-            if (!skip_field(s, wt)) return false;
-            continue;
-        }
-        seen = true;
-        if (wt == 2) { /* decode_callback_field, string: the callback sees the whole field */
-            Stream f;
-            if (!substream(s, f)) return false;
-            if (f.left > kMaxEncodedFrame) return false; /* "Encoded frame exceeds max size" */
-            a_off = f.pos;
-            a_len = f.left;
-        } else { /* scalar wire types reach the callback as their raw bytes (read_raw_value) */
-            uint32_t b;
-            const uint32_t p0 = s.pos;
-            if (wt == 0) {
-                uint32_t n = 0;
-                do {
-                    if (++n > 10) return false; /* "varint overflow" */
-                    if (!rd(s, b)) return false;
-                } while (b & 0x80u);
-                a_len = n;
-            } else if (wt == 1) {
-                if (!skip(s, 8)) return false;
-                a_len = 8;
-            } else if (wt == 5) {
-                if (!skip(s, 4)) return false;
-                a_len = 4;
-            } else {
-                return false; /* "invalid wire_type" */
-            }
-            a_off = p0;
-        }
-    }
-    return seen; /* "missing required field" */
-}
-
+/* wire primitives and the ToReceiver walk: anm_pb_wire.h (one implementation for the device and the host scanner) */
 __global__ void k_pb_deframe(const anm_frame_t *frames, uint32_t n, const uint8_t *bytes, uint32_t mask, anm_pb_span_t *out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -164,34 +37,10 @@ __global__ void k_pb_deframe(const anm_frame_t *frames, uint32_t n, const uint8_
         out[i] = r;
         return;
     }
-    Stream s = {bytes, mask, f.offset, f.len};
-    Stream m;
-    bool ok = substream(s, m); /* PB_DECODE_DELIMITED */
+    anm_wstream_t s = {bytes, mask, f.offset, f.len};
     bool have = false;
     uint32_t a_off = 0, a_len = 0;
-    if (ok) {
-        /* ToReceiver: pb_decode_inner over {oneof message {1: AudioData audio_data}} */
-        while (m.left) {
-            uint32_t t;
-            bool eof = false;
-            if (!varint32(m, t, &eof)) {
-                ok = eof;
-                break;
-            }
-            const uint32_t tag = t >> 3, wt = t & 7u;
-            if (tag == 0) { ok = false; break; }
-            if (tag != 1) {
-                if (!skip_field(m, wt)) { ok = false; break; }
-                continue;
-            }
-            if (wt != 2) { ok = false; break; } /* submessage: "wrong wire type" */
-            Stream a;
-            if (!substream(m, a)) { ok = false; break; }
-            have = true; /* which_message = audio_data */
-            if (!decode_audio_data(a, a_off, a_len)) { ok = false; break; }
-        }
-    }
-    if (ok) {
+    if (anm_w_to_receiver(&s, &have, &a_off, &a_len)) {
         r.status = have ? ANM_PB_OK : ANM_PB_NO_AUDIO;
         r.consumed = s.pos - f.offset; /* length varint + message, like len - bytes_left of the buffer stream */
         r.audio_offset = have ? a_off : 0u;

@@ -22,99 +22,16 @@
  * order, minimal varints).
  */
 #include "../../include/anmodem_pb.h"
+#include "anm_pb_wire.h"
 
 #include <string.h>
 
-typedef struct {
-    const uint8_t *p;
-    size_t left;
-} rs_t;
-
-static bool rd(rs_t *s, uint32_t *b) {
-    if (!s->left) return false; /* "end-of-stream" */
-    *b = *s->p++;
-    s->left--;
-    return true;
-}
-
-static bool skipn(rs_t *s, size_t n) {
-    if (s->left < n) return false;
-    s->p += n;
-    s->left -= n;
-    return true;
-}
-
-/* pb_decode_varint32_eof, pb_decode.c:170-232 */
-static bool varint32(rs_t *s, uint32_t *out, bool *eof) {
-    uint32_t byte, result;
-    if (!rd(s, &byte)) {
-        if (eof) *eof = true;
-        return false;
-    }
-    if (!(byte & 0x80u)) {
-        result = byte;
-    } else {
-        uint32_t bitpos = 7;
-        result = byte & 0x7Fu;
-        do {
-            if (!rd(s, &byte)) return false;
-            if (bitpos >= 32) {
-                const uint32_t sign_extension = (bitpos < 63) ? 0xFFu : 0x01u;
-                const bool valid = ((byte & 0x7Fu) == 0) || ((result >> 31) != 0 && byte == sign_extension);
-                if (bitpos >= 64 || !valid) return false; /* "varint overflow" */
-            } else {
-                result |= (byte & 0x7Fu) << bitpos;
-            }
-            bitpos += 7;
-        } while (byte & 0x80u);
-        if (bitpos == 35 && (byte & 0x70u)) return false;
-    }
-    *out = result;
-    return true;
-}
-
-/* pb_decode_varint, pb_decode.c:240-260 */
-static bool varint64(rs_t *s, uint64_t *out) {
-    uint32_t byte, bitpos = 0;
-    uint64_t result = 0;
-    do {
-        if (bitpos >= 64) return false; /* "varint overflow" */
-        if (!rd(s, &byte)) return false;
-        result |= (uint64_t)(byte & 0x7Fu) << bitpos;
-        bitpos += 7;
-    } while (byte & 0x80u);
-    *out = result;
-    return true;
-}
-
-/* pb_skip_field, pb_decode.c:305-315 */
-static bool skip_field(rs_t *s, uint32_t wt) {
-    uint32_t b, len;
-    switch (wt) {
-    case 0:
-        do {
-            if (!rd(s, &b)) return false;
-        } while (b & 0x80u);
-        return true;
-    case 1: return skipn(s, 8);
-    case 2: return varint32(s, &len, NULL) && skipn(s, len);
-    case 5: return skipn(s, 4);
-    default: return false; /* "invalid wire_type" */
-    }
-}
-
-/* pb_make_string_substream; closing it (pb_close_string_substream) is implicit: the parent already
- * points behind the substream */
-static bool substream(rs_t *s, rs_t *sub) {
-    uint32_t size;
-    if (!varint32(s, &size, NULL)) return false;
-    if (s->left < size) return false; /* "parent stream too short" */
-    sub->p = s->p;
-    sub->left = size;
-    s->p += size;
-    s->left -= size;
-    return true;
-}
+/* wire primitives: anm_pb_wire.h (shared with the GPU deframer and the host scanner) */
+typedef anm_wstream_t rs_t;
+#define varint32 anm_w_varint32
+#define varint64 anm_w_varint64
+#define skip_field anm_w_skip_field
+#define substream anm_w_substream
 
 static bool next_tag(rs_t *s, uint32_t *tag, uint32_t *wt, bool *done) {
     uint32_t t;
@@ -154,8 +71,8 @@ static bool dec_string(rs_t *s, uint32_t wt, char *dst) {
     if ((size_t)size + 1 > 128) return false;    /* "string overflow" */
     dst[size] = 0;
     if (s->left < size) return false;
-    memcpy(dst, s->p, size);
-    return skipn(s, size);
+    memcpy(dst, s->bytes + s->pos, size); /* linear host buffer (mask = 0xFFFFFFFF) */
+    return anm_w_skip(s, size);
 }
 
 /* DiscoveryResponse: five required fields; decoded on top of *d (PB_DECODE_NOINIT) */
@@ -183,8 +100,8 @@ static bool dec_discovery(rs_t *s, anm_pb_discovery_t *d) {
 }
 
 int anm_pb_decode_broadcast(const uint8_t *buf, size_t len, anm_pb_broadcast_t *out, size_t *consumed) {
-    if (!buf || !out) return ANM_ERR_ARG;
-    rs_t top = {buf, len}, s;
+    if (!buf || !out || len > 0xFFFFFFFFu) return ANM_ERR_ARG;
+    rs_t top = {buf, 0xFFFFFFFFu, 0u, (uint32_t)len}, s;
     anm_pb_broadcast_t m;
     memset(&m, 0, sizeof m);
     if (!substream(&top, &s)) return ANM_ERR_FORMAT;
@@ -219,8 +136,8 @@ int anm_pb_decode_broadcast(const uint8_t *buf, size_t len, anm_pb_broadcast_t *
 }
 
 int anm_pb_decode_to_transmitter(const uint8_t *buf, size_t len, anm_pb_to_transmitter_t *out, size_t *consumed) {
-    if (!buf || !out) return ANM_ERR_ARG;
-    rs_t top = {buf, len}, s;
+    if (!buf || !out || len > 0xFFFFFFFFu) return ANM_ERR_ARG;
+    rs_t top = {buf, 0xFFFFFFFFu, 0u, (uint32_t)len}, s;
     anm_pb_to_transmitter_t m;
     memset(&m, 0, sizeof m);
     if (!substream(&top, &s)) return ANM_ERR_FORMAT;

@@ -9,6 +9,8 @@
  * TCP and never produces modem PCM, so this generator is authored here.
  */
 #include "anm_internal.h"
+#define ANM_STR_(x) #x
+#define ANM_STR(x) ANM_STR_(x)
 
 #include <math.h>
 #include <pthread.h>
@@ -100,4 +102,4 @@ void anm_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 const char *anm_last_error(void) { return g_err; }
-const char *anm_version(void) { return "anmodem-b200 0.1 (SPEC.md rev 1)"; }
+const char *anm_version(void) { return "anmodem-b200 0.2 (SPEC.md rev " ANM_STR(ANM_SPEC_REVISION) ")"; }

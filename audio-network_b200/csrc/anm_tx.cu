@@ -55,14 +55,15 @@ __global__ void __launch_bounds__(256) k_tx_render(const __grid_constant__ TxK k
         for (int j = 0; j < 8; ++j) {
             const unsigned long long i = gidx * 8 + j;
             const unsigned long long nn = k.first_sample + i;
-            const long long tpos = (prm.start_offset << 32) + (long long)nn * step;
+            /* 128-bit like the CPU renderer (anm_tx.c): start_offset * 2^32 + n * step leaves 64 bits after 2^31 samples */
+            const __int128 tpos = (__int128)prm.start_offset * ((__int128)1 << 32) + (__int128)nn * (__int128)step;
             int sig = 0;
             if (tpos >= 0) {
-                const unsigned long long t = (unsigned long long)tpos >> 32;
+                const unsigned long long t = (unsigned long long)(tpos >> 32);
                 const unsigned long long sym = t >> k.lg;
                 const uint32_t e = prog[sym % plen];
                 if (e != ANM_SILENCE && e < k.n_tones) {
-                    const unsigned long long pos = (unsigned long long)tpos - ((sym << k.lg) << 32);
+                    const unsigned long long pos = (unsigned long long)(tpos - ((__int128)(sym << k.lg) << 32)); /* Q32, < N * 2^32 */
                     const uint32_t phase = (uint32_t)(((unsigned long long)k.bins[e] * pos) >> k.lg);
                     sig = ((int)prm.amplitude_q15 * (int)c_sine[phase >> 22]) >> 15;
                 }

@@ -34,6 +34,9 @@
 extern "C" {
 #endif
 
+/* revision of SPEC.md this library implements bit for bit (frozen: tests/golden/SPEC_VERSION.json) */
+#define ANM_SPEC_REVISION 2
+
 #define ANM_MAX_TONES 64
 #define ANM_MAX_PREAMBLE 32
 #define ANM_SILENCE 0xFF /* tx program entry: no tone during this symbol */
@@ -148,7 +151,9 @@ void anm_demod_destroy(anm_demod_t *h);
 int anm_demod_reset(anm_demod_t *h);
 /* PCM already in HBM: d_pcm[ch * ch_stride + i], i < n_samples; n_samples must be
  * a multiple of sym_len, d_pcm and ch_stride*2 multiples of 16 bytes.  Launches
- * on `stream` (a cudaStream_t, NULL = default) and returns without waiting. */
+ * on `stream` (a cudaStream_t, NULL = default) and returns without waiting; a launch on another stream than the
+ * handle's previous launch is ordered behind it.  Fastest when n_samples is a multiple of 32 * sym_len (the kernel
+ * works in steps of 32 symbol periods; a ragged last step costs a whole one). */
 int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride,
                           size_t n_samples, void *stream);
 /* PCM in host memory (pinned for full speed): copies to an internal HBM staging
@@ -161,7 +166,8 @@ int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, 
 int anm_demod_feed_host_async(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples);
 int anm_demod_wait_input(anm_demod_t *h);
 /* Like anm_demod_collect for frames only, but waits just for the launch that is `lag` launches
- * behind the most recent one (lag 0 = the latest). */
+ * behind the most recent one (lag 0 = the latest, lag < 63); works after any kind of feed.  A launch whose frames were
+ * already collected yields nothing new. */
 long anm_demod_collect_upto(anm_demod_t *h, uint32_t lag);
 /* Waits for outstanding work and moves newly produced frames/symbols to the
  * host queues.  Returns number of frames now queued, or a negative error. */
@@ -170,11 +176,23 @@ long anm_demod_collect(anm_demod_t *h);
  * appended to `bytes` (frame.offset indexes it).  Returns frames written. */
 size_t anm_demod_read_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8_t *bytes,
                              size_t bytes_cap);
+/* Moves out EVERYTHING that is queued, in arrival order (per channel still chronological), as two plain copies -- the
+ * cheapest way to hand a whole drain to a consumer that does not need the global order.  *n_bytes (optional) receives the
+ * payload bytes written.  Returns the number of frames; 0 (queue untouched) when a destination is too small or a sorted
+ * read is half way through what it had ordered. */
+size_t anm_demod_take_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8_t *bytes, size_t bytes_cap, size_t *n_bytes);
+/* The device-resident frame record / payload rings (powers of two; masks = size - 1) for consumers that stay on the GPU,
+ * e.g. anm_pb_deframe_device() directly on the rings (include/anmodem_pb.h). */
+int anm_demod_frame_rings(const anm_demod_t *h, const anm_frame_t **d_frames, uint32_t *frames_mask, const uint8_t **d_bytes,
+                          uint32_t *bytes_mask);
+/* Order-independent 64-bit checksum of frame records + their payload bytes (frame.offset indexes `bytes`): the same value
+ * whatever order or grouping the frames are gathered in (anm_config.c). */
+uint64_t anm_frames_digest(const anm_frame_t *frames, size_t n, const uint8_t *bytes);
 /* Pops up to cap decided symbols (tone indices) of one channel. */
 size_t anm_demod_read_symbols(anm_demod_t *h, uint32_t channel, uint8_t *out, size_t cap);
 int anm_demod_stats(anm_demod_t *h, anm_chan_stats_t *out /*[n_channels]*/);
 /* 1 if an output queue overflowed since create/reset: frames or symbols were dropped.  Queues hold
- * 256 frames / 16 KiB of payload per channel between two collects. */
+ * 512 frames / 32 KiB of payload per channel between two collects. */
 int anm_demod_overflowed(const anm_demod_t *h);
 /* number of kernels this handle has launched (bench.py's gpu_launches) */
 uint64_t anm_demod_launch_count(const anm_demod_t *h);
@@ -200,8 +218,9 @@ typedef struct demod_frame {
     uint8_t bytes[4104];
 } demod_frame_t;
 
-int demod_initialize(const anm_config_t *cfg); /* sets the process-wide configuration */
-demod_t *demod_create(void);
+int demod_initialize(const anm_config_t *cfg); /* sets the DEFAULT configuration of demodulators created later by demod_create() */
+demod_t *demod_create(void);                    /* a demodulator with (its own copy of) the default configuration */
+demod_t *demod_create_cfg(const anm_config_t *cfg); /* ... or with an explicit one: no process-wide state involved */
 int demod_feed(demod_t *d, const int16_t *pcm, size_t n_samples); /* borrowed input, any length */
 size_t demod_read_symbols(demod_t *d, uint8_t *out, size_t cap);
 size_t demod_read_frames(demod_t *d, demod_frame_t *out, size_t cap);

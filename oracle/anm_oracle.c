@@ -104,7 +104,28 @@ anm_oracle_t *anm_oracle_create(const anm_config_t *cfg, const float *twiddles) 
     o->hdr_syms = (24 + o->b - 1) / o->b;
     size_t ntw = (size_t)o->N * o->T * 2;
     o->tw = (float *)malloc(ntw * sizeof(float));
-    memcpy(o->tw, twiddles, ntw * sizeof(float));
+    if (twiddles) {
+        memcpy(o->tw, twiddles, ntw * sizeof(float)); /* a caller-supplied table (tests that perturb it) */
+    } else {
+        /* SPEC 3, the oracle's own table: first quarter from libm on the exactly reduced angle, the other three
+         * quarters by multiplying (C - j Sn) with -j once per quarter turn the tone advances */
+        const double two_pi = 6.283185307179586476925286766559;
+        for (uint32_t k = 0; k < o->T; ++k)
+            for (uint32_t m = 0; m < o->N / 4; ++m) {
+                double a = two_pi * (double)((cfg->tone_bin[k] * m) % o->N) / (double)o->N;
+                float c = (float)cos(a), s = (float)sin(a);
+                for (uint32_t q = 0; q < 4; ++q) {
+                    float cq = c, sq = s;
+                    for (uint32_t t = 0; t < ((cfg->tone_bin[k] * q) & 3u); ++t) { /* (c - j s) * (-j) = -s - j c */
+                        float nc = -sq, ns = cq;
+                        cq = nc;
+                        sq = ns;
+                    }
+                    o->tw[((size_t)(m + q * (o->N / 4)) * o->T + k) * 2 + 0] = cq;
+                    o->tw[((size_t)(m + q * (o->N / 4)) * o->T + k) * 2 + 1] = sq;
+                }
+            }
+    }
     o->fsyms = (uint8_t *)malloc(((size_t)cfg->max_payload + 8) * 8 + 64);
     o->dense = o->T >= 32;
     o->fold = !o->dense && (o->H % 16) == 0;

@@ -11,7 +11,8 @@
 extern "C" {
 #endif
 typedef struct anm_oracle anm_oracle_t;
-/* twiddles: [sym_len][n_tones][2] table (SPEC 3), an input of the oracle */
+/* twiddles: NULL = the oracle computes its own table from SPEC 3 (the normal case); a caller may pass a
+ * [sym_len][n_tones][2] table instead (tests that perturb it) */
 anm_oracle_t *anm_oracle_create(const anm_config_t *cfg, const float *twiddles);
 void anm_oracle_reset(anm_oracle_t *o);
 void anm_oracle_destroy(anm_oracle_t *o);
@@ -33,6 +34,17 @@ double anm_oracle_run_batch(const anm_config_t *cfg, const float *twiddles, cons
                             uint32_t n_ch, size_t ch_stride, size_t n_samples, uint32_t n_threads,
                             uint64_t *frames_ok, uint64_t *frames_bad, uint64_t *payload_bytes_ok,
                             uint64_t *digest);
+
+/* ---- the oracle's own transmit side (anm_oracle_tx.c): SPEC 2 presets, SPEC 4 frames, SPEC 6 transmitter.
+ * Independent restatements; tests hold the product's anm_config_preset / anm_frame_symbols / anm_tx_render
+ * against them, and bench.py --impl reference uses nothing else. */
+int anm_oracle_preset(const char *name, anm_config_t *out);
+size_t anm_oracle_frame_symbols(const anm_config_t *cfg, const uint8_t *payload, size_t len, uint8_t *syms, size_t cap);
+int anm_oracle_tx_render(const anm_config_t *cfg, const uint8_t *program, size_t prog_len, const anm_tx_params_t *p,
+                         uint64_t first_sample, int16_t *out, size_t n);
+int anm_oracle_tx_render_batch(const anm_config_t *cfg, const uint8_t *programs, size_t prog_stride, const uint32_t *prog_len,
+                               const anm_tx_params_t *params, uint32_t n_ch, uint64_t first_sample, int16_t *out,
+                               size_t ch_stride, size_t n, uint32_t n_threads);
 #ifdef __cplusplus
 }
 #endif

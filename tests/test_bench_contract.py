@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                          "--cpu-channels", "16"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--channels", "16"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -22,6 +22,18 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["config"]["chunk_samples"] == 352 * 128 and d["config"]["chunks_per_step"] == 60
+
+
+def test_both_arms_print_the_same_config():
+    """same_config: the CPU arm's `config` is the dict our arm prints (minus the launch details our arm adds)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    a = bench.workload_config("ref4", 8192, 1)
+    assert a["channels_per_gpu"] == 8192 and a["chunk_samples"] == 45056 and a["channels_total"] == 8192
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("workload_config(") >= 3          # definition + both arms
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -106,3 +106,41 @@ def test_dense_long_frames():
     pcm, _ = make_channels(cfg, 3, 1800 * cfg.sym_len, seed=41, snr_db=12.0, payload_len=(900, 1024), gap=(1, 5))
     frames = _gpu_vs_oracle(cfg, pcm, [344])
     assert any(len(f[3]) >= 900 and f[2] for f in frames)
+
+
+@pytest.mark.gpu
+def test_dense_config4_at_bench_scale_all_channels_vs_oracle():
+    """BASELINE.json configs[3] at the size bench.py's cfg4 leg runs: 4,736 channels (= 148 SMs x 2 resident CTAs x 4
+    channels x 4 waves of CTAs) x 2 chunks of 352 symbol periods through k_demod_tc, 10 dB SNR, with clock error and random
+    offsets.  Every frame of every channel equals the oracle's: count, CRC verdicts, payload bytes and the
+    order-independent digest of oracle/anm_oracle_batch.c; 37 channels also frame for frame."""
+    import os
+
+    import torch
+
+    from oracle_binding import frames_digest, oracle_frames_batch, run_batch
+    from test_gpu_parity import _gpu_render, _programs
+
+    cfg = anm.config_preset("wide64")
+    n_ch, chunk = 4736, 352 * cfg.sym_len
+    n = 2 * chunk
+    progs, lens, params = _programs(cfg, n_ch, seed=909, snr_db=10.0, ppm_max=150.0, offset_max=3000, payload=(16, 48), max_len=1024)
+    d_pcm = _gpu_render(cfg, progs, lens, params, n)
+    dm = anm.Demod(cfg, n_ch, device=0)
+    stream = torch.cuda.current_stream().cuda_stream
+    dm.feed_device(d_pcm.data_ptr(), n, chunk, stream)
+    dm.feed_device(d_pcm.data_ptr() + chunk * 2, n, chunk, stream)
+    dm.collect()
+    fr = anm.frames_to_list(*dm.read_frames(cap=1 << 20, bytes_cap=1 << 26))
+    assert not dm.overflowed()
+    dm.close()
+    pcm = d_pcm.cpu().numpy()
+    _sec, ok, bad, nbytes, dg = run_batch(cfg, pcm, os.cpu_count() or 1)
+    assert len(fr) == ok + bad and ok > 2 * n_ch
+    assert sum(f[2] for f in fr) == ok
+    assert sum(len(f[3]) for f in fr if f[2]) == nbytes
+    assert frames_digest(fr) == dg
+    sample = list(range(0, n_ch, 128))
+    want = oracle_frames_batch(cfg, pcm[sample])
+    got = [(sample.index(f[0]), f[1], f[2], f[3]) for f in fr if f[0] in set(sample)]
+    assert got == want

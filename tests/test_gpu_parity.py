@@ -440,8 +440,156 @@ def test_config3_one_gpu_share_streamed_10db():
     assert all(f[2] == 1 for f in fr)                      # 10 dB: no CRC failure among the detected frames
     per_ch = np.bincount([f[0] for f in fr], minlength=n_ch)
     assert per_ch.min() >= 4                                # 1,032 symbol periods hold at least 4 whole frames of <= 196 + 30 symbols
-    sample = list(range(0, n_ch, 128))                      # 64 channels against the oracle
-    pcm = d_pcm[sample].cpu().numpy()
-    want = oracle_frames_batch(cfg, pcm)
+    sample = list(range(0, n_ch, 128))                      # 64 channels against the oracle frame for frame
+    pcm = d_pcm.cpu().numpy()
+    want = oracle_frames_batch(cfg, pcm[sample])
     got = [(sample.index(f[0]), f[1], f[2], f[3]) for f in fr if f[0] in set(sample)]
     assert got == want
+    # ... and ALL 8,192 channels through the oracle's threaded batch runner: frame count, CRC verdicts, payload bytes and the
+    # order-independent digest over (channel, start_sample, len, crc_ok, payload) of every frame
+    import os
+
+    from oracle_binding import frames_digest, run_batch
+
+    _sec, ok, bad, nbytes, dg = run_batch(cfg, pcm, os.cpu_count() or 1)
+    assert len(fr) == ok + bad and bad == 0
+    assert sum(len(f[3]) for f in fr if f[2]) == nbytes
+    assert frames_digest(fr) == dg
+
+
+def test_pb_istream_seam_reference_decoder_reads_gpu_frames():
+    """BASELINE.json configs[0] closed end to end: ToReceiver{AudioData} messages -> frames -> PCM -> the CUDA demodulator
+    (demod_feed) -> demod_as_pb_istream() -> the REFERENCE's own pb_decode_delimited(&is, ToReceiver_fields, &msg) with its
+    audio-data callback (hardware/src/network.cpp:406-430, 212-249; nanopb + ip.pb.c compiled in place as oracle/_ref) ->
+    the Opus bytes the transmitter put in."""
+    import ctypes as C
+    import os
+
+    from oracle_binding import REF_LIB
+
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref/libref_nanopb.so not present")
+    R = C.CDLL(REF_LIB)
+    R.ref_decode_to_receiver_from_stream.restype = C.c_long
+    R.ref_decode_to_receiver_from_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    R.ref_encode_to_receiver_audio.restype = C.c_size_t
+    R.ref_encode_to_receiver_audio.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    L = anm.lib()
+    cfg = anm.config_preset("ref4")
+    rng = np.random.default_rng(77)
+    buf = (C.c_uint8 * 2048)()
+    sent, prog = [], [np.full(5, 255, np.uint8)]
+    for i in range(12):
+        opus = rng.integers(0, 256, size=int(rng.integers(1, 900)), dtype=np.uint8).tobytes()
+        n = R.ref_encode_to_receiver_audio(opus, len(opus), buf, 2048)      # the reference's own encoder makes the wire bytes
+        assert n > 0
+        sent.append(opus)
+        prog += [anm.frame_symbols(cfg, bytes(buf[:n])), np.full(int(rng.integers(2, 9)), 255, np.uint8)]
+    prog = np.concatenate(prog)
+    n = (len(prog) + 8) * cfg.sym_len
+    pcm = anm.tx_render(cfg, prog, anm.tx_params(seed=4, amplitude=0.5, snr_db=11.0), 0, n)
+    assert L.demod_initialize(C.byref(cfg)) == 0
+    d = L.demod_create()
+    for pos in range(0, n, 50000):                                             # the firmware idiom: arbitrary buffer sizes
+        part = np.ascontiguousarray(pcm[pos: pos + 50000])
+        assert L.demod_feed(d, part.ctypes.data, C.c_size_t(len(part))) == 0
+
+    class PbStream(C.Structure):
+        _fields_ = [("callback", C.c_void_p), ("state", C.c_void_p), ("bytes_left", C.c_size_t), ("errmsg", C.c_char_p)]
+
+    L.demod_as_pb_istream.restype = PbStream
+    L.demod_as_pb_istream.argtypes = [C.c_void_p]
+    s = L.demod_as_pb_istream(d)
+    out = (C.c_uint8 * 4096)()
+    for want in sent:
+        got = R.ref_decode_to_receiver_from_stream(s.callback, s.state, out, 4096)
+        assert got == len(want) and bytes(out[:got]) == want
+    assert R.ref_decode_to_receiver_from_stream(s.callback, s.state, out, 4096) == -1      # drained: like a closed socket
+    L.demod_destroy(d)
+
+
+def test_collect_upto_after_collect_hands_nothing_out_twice():
+    """feed_async twice, collect(), collect_upto(1), collect() -- the stale snapshot of the older launch
+    must not rewind the read position: no duplicates, no false overflow."""
+    cfg = anm.config_preset("ref4")
+    pcm, _ = make_channels(cfg, 12, 480 * cfg.sym_len, seed=67, snr_db=10.0, offset_max=600, payload_len=(4, 24), gap=(1, 6))
+    half = 240 * cfg.sym_len
+    a, b = np.ascontiguousarray(pcm[:, :half]), np.ascontiguousarray(pcm[:, half:])
+    dm = anm.Demod(cfg, 12, device=0)
+    dm.feed_host_async_ptr(a.ctypes.data, half, half)
+    dm.feed_host_async_ptr(b.ctypes.data, half, half)
+    dm.collect()
+    got = anm.frames_to_list(*dm.read_frames())
+    assert dm.collect_upto(1) == 0 and dm.collect_upto(0) == 0      # older / same launches: nothing new
+    got += anm.frames_to_list(*dm.read_frames())
+    dm.collect()
+    got += anm.frames_to_list(*dm.read_frames())
+    assert not dm.overflowed()
+    dm.close()
+    want = oracle_frames_batch(cfg, pcm)
+    assert sorted(got, key=lambda f: (f[0], f[1])) == want and len(got) == len(set((f[0], f[1]) for f in got))
+
+
+def test_take_frames_and_one_at_a_time_reads():
+    """take_frames moves a whole drain out in arrival order; read_frames(cap=1) pops in (channel, start_sample) order from a
+    cursor (no re-sort per call); mixing feeds between reads keeps the order of what is still unread."""
+    torch = _torch()
+    cfg = anm.config_preset("ref4")
+    pcm, _ = make_channels(cfg, 30, 640 * cfg.sym_len, seed=71, snr_db=10.0, offset_max=700, payload_len=(4, 20), gap=(1, 5))
+    want = oracle_frames_batch(cfg, pcm)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    n = pcm.shape[1]
+    stream = torch.cuda.current_stream().cuda_stream
+    # (1) take_frames
+    dm = anm.Demod(cfg, 30, device=0)
+    dm.feed_device(d_pcm.data_ptr(), n, n, stream)
+    dm.collect()
+    recs = np.zeros(1 << 14, dtype=anm.FRAME_DTYPE)
+    by = np.zeros(1 << 20, dtype=np.uint8)
+    small = np.zeros(3, dtype=anm.FRAME_DTYPE)
+    assert dm.take_frames(small, by) == (0, 0)                       # too small: queue untouched
+    nf, nb = dm.take_frames(recs, by)
+    got = anm.frames_to_list(recs[:nf], by[:nb])
+    assert sorted(got, key=lambda f: (f[0], f[1])) == want and nb == sum(len(f[3]) for f in want)
+    for c in range(30):                                              # per channel still chronological
+        starts = [f[1] for f in got if f[0] == c]
+        assert starts == sorted(starts)
+    assert anm.frames_digest(recs[:nf], by[:nb]) == __import__("oracle_binding").frames_digest(want)
+    assert dm.take_frames(recs, by) == (0, 0)
+    dm.close()
+    # (2) cap=1 reads interleaved with a second feed
+    dm = anm.Demod(cfg, 30, device=0)
+    half = 320 * cfg.sym_len
+    dm.feed_device(d_pcm.data_ptr(), n, half, stream)
+    dm.collect()
+    first = [anm.frames_to_list(*dm.read_frames(cap=1))[0] for _ in range(5)]
+    dm.feed_device(d_pcm.data_ptr() + half * 2, n, n - half, stream)
+    dm.collect()
+    rest = []
+    while True:
+        r = anm.frames_to_list(*dm.read_frames(cap=1))
+        if not r:
+            break
+        rest += r
+    assert sorted(first + rest, key=lambda f: (f[0], f[1])) == want
+    assert rest == sorted(rest, key=lambda f: (f[0], f[1]))          # what was unread comes out fully ordered
+    dm.close()
+
+
+def test_feed_on_two_streams_is_ordered():
+    """A launch on another stream than the handle's previous launch is ordered behind it."""
+    torch = _torch()
+    cfg = anm.config_preset("ref4")
+    pcm, _ = make_channels(cfg, 200, 512 * cfg.sym_len, seed=73, snr_db=10.0, offset_max=500)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    torch.cuda.synchronize()
+    n = pcm.shape[1]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    dm = anm.Demod(cfg, 200, device=0)
+    q = 128 * cfg.sym_len
+    for i in range(4):
+        dm.feed_device(d_pcm.data_ptr() + i * q * 2, n, q, (s1 if i % 2 == 0 else s2).cuda_stream)
+    dm.collect()
+    got = anm.frames_to_list(*dm.read_frames())
+    dm.close()
+    assert got == oracle_frames_batch(cfg, pcm)

@@ -119,3 +119,21 @@ def test_energies_equal_the_sliding_dft(name, S):
         w = (xx[N + n][:, None] * np.exp(-2j * np.pi * bins[None, :] * n[:, None] / N)).sum(axis=0)
         e64 = np.abs(w) ** 2
         assert np.max(np.abs(o.E[h] - e64)) <= 1e-5 * e64.max()
+
+
+def test_spec_revision_and_goldens_are_frozen():
+    """SPEC.md revision 2 is frozen: the committed golden files are the ones generated under it (SHA-256 recorded in
+    tests/golden/SPEC_VERSION.json), SPEC.md and the library name the same revision."""
+    import hashlib
+    import json
+    import re
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    ver = json.load(open(os.path.join(here, "golden", "SPEC_VERSION.json")))
+    for name, digest in ver["sha256"].items():
+        assert hashlib.sha256(open(os.path.join(here, "golden", name), "rb").read()).hexdigest() == digest, \
+            "%s changed: a change of the golden vectors needs a new SPEC revision with the old files kept" % name
+    spec = open(os.path.join(os.path.dirname(here), "SPEC.md")).read()
+    m = re.search(r"\*\*Revision (\d+) . FROZEN", spec)
+    assert m and int(m.group(1)) == ver["spec_revision"]
+    assert ("rev %d" % ver["spec_revision"]).encode() in anm.lib().anm_version()
