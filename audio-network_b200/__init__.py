@@ -168,7 +168,11 @@ EXPORTS = [
     "anm_frame_num_symbols", "anm_frame_symbols", "anm_tx_render", "anm_tx_render_device",
     "anm_tone_energies_device", "anm_demod_create", "anm_demod_destroy", "anm_demod_reset",
     "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_feed_host_async", "anm_demod_wait_input",
-    "anm_demod_collect", "anm_demod_collect_upto", "anm_demod_read_frames", "anm_demod_take_frames", "anm_demod_frame_rings", "demod_create_cfg", "anm_frames_digest",
+    "anm_demod_collect", "anm_demod_collect_upto", "anm_demod_read_frames", "anm_demod_take_frames", "anm_demod_frame_rings", "demod_create_cfg", "anm_frames_digest", "anm_demod_peek_frames", "anm_demod_drop_frames", "anm_frames_summary",
+    "anm_demod_multi_create", "anm_demod_multi_destroy", "anm_demod_multi_reset", "anm_demod_multi_num_devices", "anm_demod_multi_shard",
+    "anm_demod_multi_device_handle", "anm_demod_multi_alloc_pcm", "anm_demod_multi_feed_host", "anm_demod_multi_wait_input",
+    "anm_demod_multi_collect", "anm_demod_multi_collect_upto", "anm_demod_multi_read_frames", "anm_demod_multi_take_frames",
+    "anm_demod_multi_overflowed", "anm_demod_multi_stats",
     "anm_demod_read_symbols", "anm_demod_stats", "anm_demod_launch_count", "anm_demod_overflowed", "anm_demod_last_kernel_ms",
     "anm_last_error", "anm_version", "demod_initialize", "demod_create", "demod_feed",
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
@@ -218,6 +222,24 @@ def lib():
         "anm_demod_take_frames": (C.c_size_t, [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "anm_demod_frame_rings": (C.c_int, [vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
         "demod_create_cfg": (vp, [cfgp]),
+        "anm_demod_peek_frames": (C.c_size_t, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "anm_demod_drop_frames": (None, [vp]),
+        "anm_frames_summary": (None, [vp, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "anm_demod_multi_create": (C.c_int, [cfgp, C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+        "anm_demod_multi_destroy": (None, [vp]),
+        "anm_demod_multi_reset": (C.c_int, [vp]),
+        "anm_demod_multi_num_devices": (C.c_uint32, [vp]),
+        "anm_demod_multi_shard": (C.c_int, [vp, C.c_uint32, C.POINTER(C.c_int), u32p, u32p, C.POINTER(C.c_int)]),
+        "anm_demod_multi_device_handle": (vp, [vp, C.c_uint32]),
+        "anm_demod_multi_alloc_pcm": (C.c_int, [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+        "anm_demod_multi_feed_host": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
+        "anm_demod_multi_wait_input": (C.c_int, [vp]),
+        "anm_demod_multi_collect": (C.c_long, [vp]),
+        "anm_demod_multi_collect_upto": (C.c_long, [vp, C.c_uint32]),
+        "anm_demod_multi_read_frames": (C.c_size_t, [vp, vp, C.c_size_t, vp, C.c_size_t]),
+        "anm_demod_multi_take_frames": (C.c_size_t, [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "anm_demod_multi_overflowed": (C.c_int, [vp]),
+        "anm_demod_multi_stats": (C.c_int, [vp, vp]),
         "anm_frames_digest": (C.c_uint64, [vp, C.c_size_t, vp]),
         "anm_demod_read_symbols": (C.c_size_t, [vp, C.c_uint32, vp, C.c_size_t]),
         "anm_demod_stats": (C.c_int, [vp, vp]),
@@ -481,6 +503,20 @@ class Demod:
         n = lib().anm_demod_take_frames(self._h, _ptr(recs), len(recs), _ptr(by), len(by), C.byref(nb))
         return int(n), int(nb.value)
 
+    def peek_frames(self):
+        """Zero-copy views (FRAME_DTYPE records, uint8 bytes) of everything queued, arrival order; valid until the next
+        collect / feed.  Call drop_frames() when done."""
+        f, b, nb = C.c_void_p(), C.c_void_p(), C.c_size_t(0)
+        n = lib().anm_demod_peek_frames(self._h, C.byref(f), C.byref(b), C.byref(nb))
+        if n == 0:
+            return np.zeros(0, dtype=FRAME_DTYPE), np.zeros(0, dtype=np.uint8)
+        recs = np.ctypeslib.as_array(C.cast(f.value, C.POINTER(C.c_uint8)), shape=(n * FRAME_DTYPE.itemsize,)).view(FRAME_DTYPE)
+        by = np.ctypeslib.as_array(C.cast(b.value, C.POINTER(C.c_uint8)), shape=(max(nb.value, 1),))[: nb.value]
+        return recs, by
+
+    def drop_frames(self):
+        lib().anm_demod_drop_frames(self._h)
+
     def frame_rings(self):
         """(d_frames ptr, frames_mask, d_bytes ptr, bytes_mask) of the device-resident rings."""
         f, b, fm, bm = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint32()
@@ -520,6 +556,86 @@ def frames_digest(recs, by):
     recs = np.ascontiguousarray(recs, dtype=FRAME_DTYPE)
     by = np.ascontiguousarray(by, dtype=np.uint8)
     return int(lib().anm_frames_digest(_ptr(recs) if len(recs) else None, len(recs), _ptr(by) if len(by) else None))
+
+
+class DemodMulti:
+    """Several GPUs behind one handle (anm_demod_multi_*): channels shard over `devices`, one host thread per device."""
+
+    def __init__(self, cfg, n_channels, devices, flags=0):
+        self.cfg, self.n_channels = cfg, n_channels
+        devs = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        _check(lib().anm_demod_multi_create(C.byref(cfg), n_channels, devs, len(devices), flags, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().anm_demod_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shards(self):
+        out = []
+        for d in range(lib().anm_demod_multi_num_devices(self._h)):
+            dev, first, cnt, node = C.c_int(), C.c_uint32(), C.c_uint32(), C.c_int()
+            _check(lib().anm_demod_multi_shard(self._h, d, C.byref(dev), C.byref(first), C.byref(cnt), C.byref(node)))
+            out.append({"device": dev.value, "first_channel": first.value, "n_channels": cnt.value, "numa_node": node.value})
+        return out
+
+    def alloc_pcm(self, n_samples):
+        """Page-locked int16 array [n_channels, n_samples] (a view with the library's row stride), shards placed next to their GPUs."""
+        p, st = C.c_void_p(), C.c_size_t()
+        _check(lib().anm_demod_multi_alloc_pcm(self._h, n_samples, C.byref(p), C.byref(st)))
+        buf = np.ctypeslib.as_array(C.cast(p.value, C.POINTER(C.c_int16)), shape=(self.n_channels, st.value))
+        return buf[:, :n_samples]
+
+    def feed_host(self, pcm):
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n_channels and pcm.strides[1] == 2
+        _check(lib().anm_demod_multi_feed_host(self._h, pcm.ctypes.data, pcm.strides[0] // 2, pcm.shape[1]))
+
+    def wait_input(self):
+        _check(lib().anm_demod_multi_wait_input(self._h))
+
+    def reset(self):
+        _check(lib().anm_demod_multi_reset(self._h))
+
+    def collect(self):
+        return _check(lib().anm_demod_multi_collect(self._h))
+
+    def collect_upto(self, lag):
+        return _check(lib().anm_demod_multi_collect_upto(self._h, lag))
+
+    def read_frames(self, cap=1 << 16, bytes_cap=1 << 24):
+        recs = np.zeros(cap, dtype=FRAME_DTYPE)
+        by = np.zeros(bytes_cap, dtype=np.uint8)
+        n = lib().anm_demod_multi_read_frames(self._h, _ptr(recs), cap, _ptr(by), bytes_cap)
+        recs = recs[:n]
+        return recs, by[: int(recs["len"].sum()) if n else 0]
+
+    def take_frames(self, recs, by):
+        nb = C.c_size_t(0)
+        n = lib().anm_demod_multi_take_frames(self._h, _ptr(recs), len(recs), _ptr(by), len(by), C.byref(nb))
+        return int(n), int(nb.value)
+
+    def overflowed(self):
+        return bool(lib().anm_demod_multi_overflowed(self._h))
+
+    def stats(self):
+        out = np.zeros(self.n_channels, dtype=STATS_DTYPE)
+        _check(lib().anm_demod_multi_stats(self._h, _ptr(out)))
+        return out
+
+
+def frames_summary(recs):
+    """(CRC-valid frames, their payload bytes) of a record array, one pass in C."""
+    recs = np.ascontiguousarray(recs, dtype=FRAME_DTYPE)
+    ok, by = C.c_uint64(0), C.c_uint64(0)
+    lib().anm_frames_summary(_ptr(recs) if len(recs) else None, len(recs), C.byref(ok), C.byref(by))
+    return int(ok.value), int(by.value)
 
 
 def frames_to_list(recs, by):

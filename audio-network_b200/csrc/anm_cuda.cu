@@ -168,19 +168,18 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
 }
 
 /* int8 basis of a dense configuration in the panel order the MMA descriptors of k_demod_tc address:
- * [hop phase q][tone group][16-sample K chunk][column = 2*tone_in_group + (0: cos, 1: sin)][sample in chunk] */
+ * [hop phase q][16-sample K chunk][column = 2 * tone + (0: cos, 1: sin)][sample in chunk] */
 static int upload_basis_panels(const anm_config_t *cfg, uint8_t **d_out, cudaStream_t stream) {
-    const uint32_t N = cfg->sym_len, T = cfg->n_tones, S = cfg->hops_per_sym, H = N / S, KC = H / 16, NG = T / tc::kTG;
+    const uint32_t N = cfg->sym_len, T = cfg->n_tones, S = cfg->hops_per_sym, H = N / S, KC = H / 16;
+    if (2u * T != tc::kNcol) return ANM_ERR_UNSUPPORTED;
     std::vector<int8_t> q7((size_t)N * T * 2);
     if (anm_basis_q7(cfg, q7.data()) != ANM_OK) return ANM_ERR_ARG;
-    std::vector<uint8_t> pan((size_t)S * NG * KC * tc::kBPanel);
+    std::vector<uint8_t> pan((size_t)S * KC * tc::kBPanel);
     for (uint32_t q = 0; q < S; ++q)
-        for (uint32_t g = 0; g < NG; ++g)
-            for (uint32_t kc = 0; kc < KC; ++kc)
-                for (uint32_t n = 0; n < tc::kNcol; ++n)
-                    for (uint32_t kk = 0; kk < 16; ++kk)
-                        pan[((size_t)((q * NG + g) * KC + kc) * tc::kNcol + n) * 16 + kk] =
-                            (uint8_t)q7[((size_t)(q * H + kc * 16 + kk) * T + (g * tc::kTG + n / 2)) * 2 + (n & 1u)];
+        for (uint32_t kc = 0; kc < KC; ++kc)
+            for (uint32_t n = 0; n < tc::kNcol; ++n)
+                for (uint32_t kk = 0; kk < 16; ++kk)
+                    pan[((size_t)(q * KC + kc) * tc::kNcol + n) * 16 + kk] = (uint8_t)q7[((size_t)(q * H + kc * 16 + kk) * T + n / 2) * 2 + (n & 1u)];
     CK(cudaMalloc(d_out, pan.size()));
     /* pageable source: the runtime stages it before the call returns, the copy itself is ordered on `stream` */
     CK(cudaMemcpyAsync(*d_out, pan.data(), pan.size(), cudaMemcpyHostToDevice, stream));
@@ -195,8 +194,10 @@ static int set_device(const anm_demod *h) {
 
 static void choose_launch(anm_demod *h) {
     if (h->var->dense) {
-        h->warps_per_cta = tc::kWorkerWarps + 1; /* two worker warps per TMEM quadrant (four channels per CTA) + the MMA issuer */
-        h->grid = (h->n_ch + 3u) / 4u;
+        /* one persistent CTA per SM (it owns all 512 TMEM columns) walks groups of four channels: 8 epilogue + 1 issuer +
+         * 4 loader + 8 state-machine warps */
+        h->warps_per_cta = tc::kWarps;
+        h->grid = std::min<uint32_t>((uint32_t)h->num_sms, ((h->n_ch + 3u) / 4u + 1u) / 2u); /* two groups in flight per CTA */
         h->smem_bytes = h->var->cta_smem;
         return;
     }
@@ -626,6 +627,28 @@ extern "C" size_t anm_demod_take_frames(anm_demod_t *h, anm_frame_t *out, size_t
     return h->q.take_all(out, cap, bytes, bytes_cap, n_bytes);
 }
 
+extern "C" size_t anm_demod_peek_frames(anm_demod_t *h, const anm_frame_t **frames, const uint8_t **bytes, size_t *n_bytes) {
+    if (!h || !frames || h->q.cursor != 0) return 0;
+    *frames = h->q.frames.p;
+    if (bytes) *bytes = h->q.bytes.p;
+    if (n_bytes) *n_bytes = h->q.bytes.n;
+    return h->q.frames.n;
+}
+
+extern "C" void anm_demod_drop_frames(anm_demod_t *h) {
+    if (h) h->q.clear();
+}
+
+extern "C" void anm_frames_summary(const anm_frame_t *frames, size_t n, uint64_t *n_ok, uint64_t *payload_bytes_ok) {
+    uint64_t ok = 0, by = 0;
+    for (size_t i = 0; i < n; ++i) {
+        ok += frames[i].crc_ok ? 1u : 0u;
+        by += frames[i].crc_ok ? frames[i].len : 0u;
+    }
+    if (n_ok) *n_ok = ok;
+    if (payload_bytes_ok) *payload_bytes_ok = by;
+}
+
 extern "C" int anm_demod_frame_rings(const anm_demod_t *h, const anm_frame_t **d_frames, uint32_t *frames_mask, const uint8_t **d_bytes,
                                      uint32_t *bytes_mask) {
     if (!h) return ANM_ERR_ARG;
@@ -745,8 +768,8 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
         if (var->dense) {
             rc = upload_basis_panels(cfg, &d_basis, s);
             k.tc_basis = d_basis;
-            W = tc::kWorkerWarps + 1;
-            grid = (n_ch + 3u) / 4u;
+            W = tc::kWarps;
+            grid = std::min<uint32_t>((uint32_t)sms, ((n_ch + 3u) / 4u + 1u) / 2u);
             smem = var->cta_smem;
         } else {
             W = std::min<uint32_t>(8u, (227u * 1024u - var->cta_smem) / var->warp_smem);

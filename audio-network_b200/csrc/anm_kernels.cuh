@@ -24,6 +24,11 @@
 
 /* which of the four "before the centre" samples of an 8-sample group are converted on the ALU pipe (PRMT + I2FP, two issue
  * slots) instead of the XU pipe (I2F.S16, one issue slot at a quarter of the rate); the "after" samples always take XU */
+/* 1: the folded loop of a single tone group reads the PCM stage with 16-byte loads (LDS.128, conflict-free with the stage's
+ * odd-chunk row pitch) instead of 8-byte ones (two lanes of every half-warp on the same bank) */
+#ifndef ANM_LDS128
+#define ANM_LDS128 1
+#endif
 #ifndef ANM_CVT_ALU_MASK
 #define ANM_CVT_ALU_MASK 0xF
 #endif
@@ -291,13 +296,28 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                 for (int i = 0; i < S; ++i) {
                     const uint32_t dprev = REC((lane - 32) * S + i).y; /* same lane, previous step */
                     uint32_t mism = 0;
-#pragma unroll
-                    for (int j = 0; j <= B; ++j) {
+                    auto plane = [&](int j) {
                         const uint32_t bc = (j < B) ? ((dc[i] >> j) & 1u) : (dc[i] > (uint32_t)(T - 1));
                         const uint32_t bp = (j < B) ? ((dprev >> j) & 1u) : (dprev > (uint32_t)(T - 1));
                         const unsigned long long hist = ((unsigned long long)__ballot_sync(FULL, bc) << 32) | __ballot_sync(FULL, bp);
                         const uint32_t w = (uint32_t)(hist >> sh);
                         mism |= (j < B) ? (w ^ p.pre_plane[j]) : w;
+                    };
+                    if (B >= 4) {
+                        /* Many bits per symbol: mismatches only accumulate from plane to plane, so when the two lowest planes
+                         * already rule out every alignment of this phase (random symbols agree with the preamble in two bits one
+                         * time in four) the other planes need not be looked at.  Same candidates, fewer ballots. */
+                        plane(0);
+                        plane(1);
+                        if (__ballot_sync(FULL, (uint32_t)__popc(mism & pmask) <= p.tol) == 0u) {
+                            cand[i] = 0u;
+                            continue;
+                        }
+#pragma unroll
+                        for (int j = 2; j <= B; ++j) plane(j);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j <= B; ++j) plane(j);
                     }
                     const uint32_t m = p.P - __popc(mism & pmask);
                     cand[i] = __ballot_sync(FULL, active && m >= p.P - p.tol);
@@ -701,14 +721,33 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                             for (int t = 0; t < TG; ++t) acc[q][t] = make_float2(0.f, 0.f);
                         uint32_t twa = stw + (uint32_t)(g * TG) * 8u;
                         uint32_t fwd = row + (uint32_t)(pass * 2 * H + H), bwd = fwd; /* walk away from the hop centres */
+#if ANM_LDS128
+                        uint4 wf[NQ], wb4[NQ];
+#endif
 #pragma unroll(NG == 1 ? H / 8 : 1) /* one tone group: straight-line loop, every twiddle address an immediate */
                         for (int i = 0; i < H / 8; ++i, twa += 4 * T * 8, fwd += 8u) {
                             bwd -= 8u;
                             uint2 vf[NQ], vb[NQ]; /* four samples after / before the centre of each hop */
+#if ANM_LDS128
+                            /* 16-byte loads (conflict-free with the odd-chunk row pitch): every second iteration fetches the
+                             * eight samples on either side that this and the next iteration consume */
+#endif
 #pragma unroll
                             for (int q = 0; q < NQ; ++q) {
+#if ANM_LDS128
+                                if ((i & 1) == 0) {
+                                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wf[q].x), "=r"(wf[q].y), "=r"(wf[q].z), "=r"(wf[q].w) : "r"(fwd + (uint32_t)(q * GR * 2 * H)));
+                                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wb4[q].x), "=r"(wb4[q].y), "=r"(wb4[q].z), "=r"(wb4[q].w) : "r"(bwd - 8u + (uint32_t)(q * GR * 2 * H)));
+                                    vf[q] = make_uint2(wf[q].x, wf[q].y);
+                                    vb[q] = make_uint2(wb4[q].z, wb4[q].w);
+                                } else {
+                                    vf[q] = make_uint2(wf[q].z, wf[q].w);
+                                    vb[q] = make_uint2(wb4[q].x, wb4[q].y);
+                                }
+#else
                                 asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(vf[q].x), "=r"(vf[q].y) : "r"(fwd + (uint32_t)(q * GR * 2 * H)));
                                 asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(vb[q].x), "=r"(vb[q].y) : "r"(bwd + (uint32_t)(q * GR * 2 * H)));
+#endif
                             }
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {

@@ -389,14 +389,15 @@ def cfg4_leg(anm, torch, dev, local, stream, steps=12, warmup=3, n_ch=4736):
 class FrameTotals:
     """What the consumer of a drain keeps in this bench: counts (frames, CRC-valid frames, payload bits)."""
 
-    def __init__(self):
+    def __init__(self, anm):
+        self.anm = anm
         self.frames = self.ok = self.bits = self.d2h = 0
 
     def add(self, recs, nbytes):
-        ok = recs["crc_ok"] == 1
+        ok, by = self.anm.frames_summary(recs)
         self.frames += len(recs)
-        self.ok += int(ok.sum())
-        self.bits += int(recs["len"][ok].sum()) * 8
+        self.ok += ok
+        self.bits += by * 8
         self.d2h += 16 + recs.nbytes + nbytes
 
 
@@ -435,47 +436,46 @@ def main():
     d_pcm, total = render_resident(anm, torch, cfg, dev, n_ch, rank * n_ch, CPS, chunk, stream)
     dm = anm.Demod(cfg, n_ch, device=local)
     L = anm.lib()
-    rec_buf = np.zeros(1 << 22, dtype=anm.FRAME_DTYPE)       # one step's drain: ~1 M frames
-    by_buf = np.zeros(1 << 28, dtype=np.uint8)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(n_steps, totals, keep_last=False):
-        """n_steps x CPS launches; the frames of step s are drained (device -> pinned host queue -> the consumer's arrays) while
-        the launches of step s+1 are already queued, so the GPU never waits for the host."""
-        kept = None
+    def run_steps(n_steps, totals):
+        """n_steps x CPS launches; the frames of step s are drained (device -> the handle's pinned host queue) and consumed in
+        place while the launches of step s+1 are already queued, so the GPU never waits for the host.  The last drain is left
+        in the queue for the caller (peek_frames)."""
         for s in range(n_steps):
             for c in range(CPS):
                 dm.feed_device(d_pcm.data_ptr() + c * chunk * 2, total, chunk, stream)
             if s > 0:
                 dm.collect_upto(CPS)                        # everything up to the last launch of step s-1
-                nf, nb = dm.take_frames(rec_buf, by_buf)
-                totals.add(rec_buf[:nf], nb)
+                recs, by = dm.peek_frames()
+                totals.add(recs, len(by))
+                dm.drop_frames()
         dm.collect()
-        nf, nb = dm.take_frames(rec_buf, by_buf)
-        totals.add(rec_buf[:nf], nb)
-        if keep_last:
-            kept = (rec_buf[:nf].copy(), by_buf[:nb].copy())
+        recs, by = dm.peek_frames()
+        totals.add(recs, len(by))
         assert not dm.overflowed(), "frame queue overflowed inside the timed region"
-        return kept
 
     sampler = NvmlSampler(local)
     sampler.start()
-    run_steps(args.warmup, FrameTotals())
+    run_steps(args.warmup, FrameTotals(anm))
+    dm.drop_frames()
     dm.kernel_time()
     l0 = dm.launch_count()
     barrier()
     tm0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    tot = FrameTotals()
-    kept = run_steps(args.steps, tot, keep_last=True)
+    tot = FrameTotals(anm)
+    run_steps(args.steps, tot)
     e1.record()
     barrier()
     tm1 = time.perf_counter()
+    kept = tuple(a.copy() for a in dm.peek_frames())        # the last step's frames, for the decode-chain leg (outside the timed region)
+    dm.drop_frames()
     ms = e0.elapsed_time(e1)
     launches = dm.launch_count() - l0
     k_ms, k_n = dm.kernel_time()                             # the first 64 launches of the region, one event pair each
@@ -498,10 +498,11 @@ def main():
         ts0 = time.perf_counter()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        run_steps(n_sus, FrameTotals())
+        run_steps(n_sus, FrameTotals(anm))
         s1.record()
         barrier()
         ts1 = time.perf_counter()
+        dm.drop_frames()
         sms = s0.elapsed_time(s1)
         tt = torch.tensor([sms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -543,16 +544,17 @@ def main():
         dm2.collect()
         dm2.read_frames(cap=1 << 20, bytes_cap=1 << 26)
         dm2.reset()
-        et = FrameTotals()
+        et = FrameTotals(anm)
         gathered = {"frames": 0, "bytes": 0, "digest_ok": None}
         step_recs, step_by = [], []
 
         def consume():
-            nf, nb = dm2.take_frames(rec_buf, by_buf)
-            if nf:
-                et.add(rec_buf[:nf], nb)
-                step_recs.append(rec_buf[:nf].copy())
-                step_by.append(by_buf[:nb].copy())
+            recs, by = dm2.peek_frames()
+            if len(recs):
+                et.add(recs, len(by))
+                step_recs.append(recs.copy())                # out of the handle's queue: these travel to rank 0
+                step_by.append(by.copy())
+            dm2.drop_frames()
 
         def gather_step():
             """host-side gather of the step's frame records on rank 0: binary records over gloo (no pickles, no NCCL)"""

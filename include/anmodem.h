@@ -181,6 +181,12 @@ size_t anm_demod_read_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8
  * payload bytes written.  Returns the number of frames; 0 (queue untouched) when a destination is too small or a sorted
  * read is half way through what it had ordered. */
 size_t anm_demod_take_frames(anm_demod_t *h, anm_frame_t *out, size_t cap, uint8_t *bytes, size_t bytes_cap, size_t *n_bytes);
+/* Zero-copy form of the same: pointers into the handle's (pinned) queue storage, arrival order; valid until the next
+ * collect / feed on this handle.  anm_demod_drop_frames() then empties the queue.  Returns the number of frames. */
+size_t anm_demod_peek_frames(anm_demod_t *h, const anm_frame_t **frames, const uint8_t **bytes, size_t *n_bytes);
+void anm_demod_drop_frames(anm_demod_t *h);
+/* CRC-valid frames and their payload bytes among n records (one pass; what a throughput report needs) */
+void anm_frames_summary(const anm_frame_t *frames, size_t n, uint64_t *n_ok, uint64_t *payload_bytes_ok);
 /* The device-resident frame record / payload rings (powers of two; masks = size - 1) for consumers that stay on the GPU,
  * e.g. anm_pb_deframe_device() directly on the rings (include/anmodem_pb.h). */
 int anm_demod_frame_rings(const anm_demod_t *h, const anm_frame_t **d_frames, uint32_t *frames_mask, const uint8_t **d_bytes,
@@ -208,6 +214,35 @@ int anm_demod_launch_geometry(const anm_demod_t *h, uint32_t *grid, uint32_t *wa
 void anm_tx_params_prepare(anm_tx_params_t *p, size_t n);
 const char *anm_last_error(void);
 const char *anm_version(void);
+
+/* ---- several GPUs behind one handle ------------------------------------------
+ * Channels shard over the listed devices in contiguous ranges (sizes differing by at most one); every device has its own
+ * anm_demod_t and ONE host thread that issues all CUDA work for it (bound to the CPUs of the GPU's NUMA node when sysfs
+ * names one).  No collective and no peer traffic: the only exchange is the host-side gather of frame records, which
+ * come out with global channel ids in (channel, start_sample) order.  A device may be listed more than once. */
+typedef struct anm_demod_multi anm_demod_multi_t;
+int anm_demod_multi_create(const anm_config_t *cfg, uint32_t n_channels, const int *devices, uint32_t n_devices, uint32_t flags,
+                           anm_demod_multi_t **out);
+void anm_demod_multi_destroy(anm_demod_multi_t *m);
+int anm_demod_multi_reset(anm_demod_multi_t *m);
+uint32_t anm_demod_multi_num_devices(const anm_demod_multi_t *m);
+/* shard d: its CUDA device, channel range and the NUMA node its thread is bound to (-1: not bound) */
+int anm_demod_multi_shard(const anm_demod_multi_t *m, uint32_t d, int *device, uint32_t *first_channel, uint32_t *n_channels, int *numa_node);
+anm_demod_t *anm_demod_multi_device_handle(anm_demod_multi_t *m, uint32_t d); /* for stats / timing queries of one shard */
+/* Page-locked PCM buffer [n_channels][*ch_stride] whose shards are first touched next to their GPUs; freed with the handle. */
+int anm_demod_multi_alloc_pcm(anm_demod_multi_t *m, size_t n_samples, int16_t **out, size_t *ch_stride);
+/* h_pcm[ch * ch_stride + i] for ALL channels; every device's thread enqueues the copy + kernel of its shard
+ * (anm_demod_feed_host_async) and the call returns.  The buffer must stay untouched until anm_demod_multi_wait_input()
+ * or a collect returns. */
+int anm_demod_multi_feed_host(anm_demod_multi_t *m, const int16_t *h_pcm, size_t ch_stride, size_t n_samples);
+int anm_demod_multi_wait_input(anm_demod_multi_t *m);
+/* every device drains (in parallel), then the frames are gathered into one queue; return = frames queued or an error */
+long anm_demod_multi_collect(anm_demod_multi_t *m);
+long anm_demod_multi_collect_upto(anm_demod_multi_t *m, uint32_t lag);
+size_t anm_demod_multi_read_frames(anm_demod_multi_t *m, anm_frame_t *out, size_t cap, uint8_t *bytes, size_t bytes_cap);
+size_t anm_demod_multi_take_frames(anm_demod_multi_t *m, anm_frame_t *out, size_t cap, uint8_t *bytes, size_t bytes_cap, size_t *n_bytes);
+int anm_demod_multi_overflowed(const anm_demod_multi_t *m);
+int anm_demod_multi_stats(anm_demod_multi_t *m, anm_chan_stats_t *out /*[n_channels]*/);
 
 /* ---- firmware-idiom single-channel interface ------------ */
 typedef struct demod demod_t;

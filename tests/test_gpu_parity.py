@@ -593,3 +593,48 @@ def test_feed_on_two_streams_is_ordered():
     got = anm.frames_to_list(*dm.read_frames())
     dm.close()
     assert got == oracle_frames_batch(cfg, pcm)
+
+
+def _multi_devices():
+    torch = _torch()
+    n = torch.cuda.device_count()
+    return [0, 1 % n, 0] if n > 1 else [0, 0, 0]     # a device may appear more than once: three shards, three host threads
+
+
+def test_multi_device_handle_gathers_frames_in_order():
+    """anm_demod_multi_*: channels sharded over several device handles (one host thread each), PCM fed from ONE pinned host
+    buffer, frames gathered host-side with global channel ids in (channel, start_sample) order == the oracle; uneven shards
+    (50 channels over 3), streamed in chunks with pipelined collects."""
+    cfg = anm.config_preset("ref4")
+    n_ch, n = 50, 900 * cfg.sym_len
+    pcm, _ = make_channels(cfg, n_ch, n, seed=83, snr_db=9.0, offset_max=800, payload_len=(4, 30), gap=(1, 8))
+    m = anm.DemodMulti(cfg, n_ch, _multi_devices())
+    sh = m.shards()
+    assert [s["n_channels"] for s in sh] == [17, 17, 16] and [s["first_channel"] for s in sh] == [0, 17, 34]
+    step = 300 * cfg.sym_len
+    bufs = [m.alloc_pcm(step) for _ in range(2)]
+    got = []
+    for i, pos in enumerate(range(0, n, step)):
+        b = bufs[i % 2]
+        if i >= 2:
+            m.wait_input()                         # the copy that read this buffer two feeds ago has completed
+        b[:, :] = pcm[:, pos: pos + step]
+        m.feed_host(b)
+        m.collect_upto(1)
+        got += anm.frames_to_list(*m.read_frames())
+    m.collect()
+    got += anm.frames_to_list(*m.read_frames())
+    assert not m.overflowed()
+    st = m.stats()
+    m.close()
+    want = oracle_frames_batch(cfg, pcm)
+    assert sorted(got, key=lambda f: (f[0], f[1])) == want and len(want) > 300
+    assert int(st["frames_ok"].sum()) == sum(f[2] for f in want)
+    # one collect hands out frames globally ordered
+    m = anm.DemodMulti(cfg, n_ch, _multi_devices())
+    b = m.alloc_pcm(n)
+    b[:, :] = pcm
+    m.feed_host(b)
+    m.collect()
+    assert anm.frames_to_list(*m.read_frames()) == want
+    m.close()
