@@ -11,7 +11,14 @@
  * (anm_pb_deframe_*) located the Opus bytes in: per packet the TOC fields, the frame count and every
  * frame's size -- the work list a batched frame decoder consumes.  Integer / byte work, results equal to
  * libopus 1.3.1's (tests/test_opus_parse.py, against the reference's libopus compiled in place).
- * The frame decoder itself (SILK / CELT) is NOT part of this library yet.
+ *
+ * Second stage (anm_celt_entropy_*): the ENTROPY DECODE of CELT frames -- everything celt_decode_with_ec
+ * (celt/celt_decoder.c:946-1095) reads off the range coder: frame flags, post-filter parameters, coarse / fine / final band
+ * energies, time-frequency and spread decisions, dynamic allocation, the bit allocation and, band by band with every split, the
+ * PVQ codeword of each partition.  One GPU thread per stream walks that stream's frames in order (the band energies predict
+ * from frame to frame); streams are the batch.  The check is the reference's own: the range coder's final state of every frame
+ * equals OPUS_GET_FINAL_RANGE of libopus 1.3.1.  The spectrum (PVQ vectors, folding, denormalisation) and the synthesis
+ * (inverse MDCT, post-filter, de-emphasis) are NOT part of this library yet.
  */
 #ifndef ANMODEM_OPUS_H_INCLUDED
 #define ANMODEM_OPUS_H_INCLUDED
@@ -51,6 +58,80 @@ int anm_opus_parse_device(const anm_pb_span_t *d_spans, uint32_t n, const uint8_
 /* host arrays: copies in, runs the kernel, copies out (no CPU fallback: ANM_ERR_CUDA without a device) */
 int anm_opus_parse_host(const anm_pb_span_t *spans, size_t n, const uint8_t *bytes, size_t n_bytes, int32_t Fs,
                         anm_opus_packet_t *out);
+
+
+/* ---- CELT frame entropy decode (row f1, stage 1) -------------------------------------------------------------- */
+#define ANM_CELT_BANDS 21          /* bands of the 48 kHz standard mode (celt/modes.c:42-45) */
+#define ANM_CELT_ALLOC_VECTORS 11  /* rows of the allocation table (celt/modes.c:48-63) */
+#define ANM_CELT_PVQ_ROWS 15       /* U(n, k) is kept for min(n, k) <= 14 ... */
+#define ANM_CELT_PVQ_COLS 180      /* ... and max(n, k) < 180 (largest band 176 coefficients, + 1) */
+
+/* Static data of the decoder, built by anm_celt_tables_build(): the normative constants of RFC 6716 (band edges, allocation
+ * table, Laplace parameters of the coarse energy) and the tables derived from them by the standard's own formulas (logN, the
+ * pulse cache and its caps, the PVQ codebook sizes). */
+typedef struct anm_celt_tables {
+    int16_t ebands[ANM_CELT_BANDS + 1];
+    int16_t logn[ANM_CELT_BANDS];
+    int16_t cache_index[5 * ANM_CELT_BANDS]; /* [LM + 1][band] -> offset into cache_bits */
+    uint16_t cache_size;
+    uint8_t cache_bits[512];
+    uint8_t cache_caps[4 * 2 * ANM_CELT_BANDS]; /* [LM][C - 1][band] */
+    uint8_t alloc[ANM_CELT_ALLOC_VECTORS * ANM_CELT_BANDS];
+    uint8_t e_prob[4 * 2 * 42];               /* [LM][intra][2 * min(band, 20) + {p0, decay}] */
+    uint32_t pvq_u[ANM_CELT_PVQ_ROWS * ANM_CELT_PVQ_COLS];
+} anm_celt_tables_t;
+int anm_celt_tables_build(anm_celt_tables_t *out); /* host; deterministic */
+
+enum { /* anm_celt_frame_t.flags */
+    ANM_CELT_F_SILENCE = 1, ANM_CELT_F_POSTFILTER = 2, ANM_CELT_F_TRANSIENT = 4, ANM_CELT_F_INTRA = 8, ANM_CELT_F_DUAL_STEREO = 16,
+    ANM_CELT_F_ANTI_COLLAPSE = 32,
+    ANM_CELT_F_LOST = 256,     /* frame of <= 1 byte: the reference conceals (celt_decode_lost), nothing is decoded */
+    ANM_CELT_F_EC_ERROR = 512, /* the range decoder flagged an impossible symbol (ec_get_error) */
+    ANM_CELT_F_OVERRUN = 1024  /* more bits consumed than the frame holds: OPUS_INTERNAL_ERROR in the reference */
+};
+
+/* what to decode: one CELT frame of a stream.  Frames of a stream must be listed in stream order, streams back to back. */
+typedef struct anm_celt_job {
+    uint32_t offset;   /* first byte of the frame in the byte arena (after the TOC / length bytes: anm_opus_packet_t.size[]) */
+    uint32_t len;      /* bytes of the frame */
+    uint8_t channels;  /* 1 or 2: the packet's stereo flag (opus_packet_get_nb_channels) */
+    uint8_t lm;        /* log2(frame samples at 48 kHz / 120): 0..3 for 2.5, 5, 10, 20 ms */
+    uint8_t end_band;  /* bands coded at the packet's bandwidth: 13 NB, 17 WB, 19 SWB, 21 FB (opus_decoder.c:462-481) */
+    uint8_t pad;
+} anm_celt_job_t;
+
+typedef struct anm_celt_frame {
+    uint32_t final_range;   /* the range coder's rng after the frame = OPUS_GET_FINAL_RANGE (0 for a lost frame) */
+    int32_t tell_bits;      /* ec_tell at the end of the frame */
+    uint32_t flags;         /* ANM_CELT_F_* */
+    uint16_t pf_pitch;      /* post-filter period (celt_decoder.c:978) */
+    uint8_t pf_gain_q, pf_tapset;
+    uint8_t spread, alloc_trim, intensity, coded_bands, lm, channels, pad[2];
+    uint32_t pvq_codewords; /* partitions that carried a PVQ codeword ... */
+    uint32_t pvq_pulses;    /* ... their pulses in total ... */
+    uint32_t pvq_index_xor; /* ... and a checksum of the codeword indices */
+    int8_t tf_res[ANM_CELT_BANDS];
+    uint8_t fine_quant[ANM_CELT_BANDS];
+    int16_t pulses[ANM_CELT_BANDS];     /* PVQ bit budget per band, 1/8 bit */
+    int16_t band_e[2 * ANM_CELT_BANDS]; /* band log-energies after the frame, Q10 (oldBandE) */
+} anm_celt_frame_t;
+
+/* per-stream state carried between calls: the band energies the next frame predicts from */
+typedef struct anm_celt_stream {
+    int16_t old_e[2 * ANM_CELT_BANDS];
+} anm_celt_stream_t;
+
+/* Opaque device-side context (tables in HBM). */
+typedef struct anm_celt_ctx anm_celt_ctx_t;
+int anm_celt_ctx_create(int device, anm_celt_ctx_t **out);
+void anm_celt_ctx_destroy(anm_celt_ctx_t *c);
+/* stream s decodes jobs[stream_begin[s] .. stream_begin[s + 1]) in order; d_* in device memory; d_streams is read and written
+ * (zero-initialised for a fresh stream); bytes_mask as for anm_pb_deframe_device; stream is a cudaStream_t */
+int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams,
+                            const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, void *stream);
+/* host arrays: copies in, runs the kernel, copies out (no CPU fallback: ANM_ERR_CUDA without a device) */
+int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
+                          anm_celt_stream_t *streams, anm_celt_frame_t *out);
 
 #ifdef __cplusplus
 }

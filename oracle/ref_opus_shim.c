@@ -66,6 +66,23 @@ int ref_opus_encode_stream(const int16_t *pcm, int n_frames, int frame_samples, 
     return n_frames;
 }
 
+/* CELT-only packets at any bitrate (OPUS_APPLICATION_RESTRICTED_LOWDELAY never uses SILK): test corpus for the frame decoder */
+int ref_opus_encode_stream_celt(const int16_t *pcm, int n_frames, int frame_samples, int channels, int bitrate, int max_bandwidth, uint8_t *out,
+                                int32_t *lens, int max_len) {
+    int err = 0;
+    OpusEncoder *e = opus_encoder_create(48000, channels, OPUS_APPLICATION_RESTRICTED_LOWDELAY, &err);
+    if (!e || err != OPUS_OK) return -1;
+    opus_encoder_ctl(e, OPUS_SET_BITRATE(bitrate));
+    opus_encoder_ctl(e, OPUS_SET_COMPLEXITY(10));
+    if (max_bandwidth) opus_encoder_ctl(e, OPUS_SET_MAX_BANDWIDTH(max_bandwidth));
+    for (int i = 0; i < n_frames; ++i) {
+        lens[i] = opus_encode(e, pcm + (size_t)i * frame_samples * channels, frame_samples, out + (size_t)i * max_len, max_len);
+        if (lens[i] < 0) { opus_encoder_destroy(e); return lens[i]; }
+    }
+    opus_encoder_destroy(e);
+    return n_frames;
+}
+
 /* returns the samples per channel decoded in total (negative OPUS_* error of the first failing packet) */
 int ref_opus_decode_stream(const uint8_t *packets, const int32_t *lens, int n, int max_len, int channels, int16_t *pcm, int max_frame_samples) {
     int err = 0, total = 0;
