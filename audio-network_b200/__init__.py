@@ -256,7 +256,7 @@ def lib():
         "anm_celt_tables_build": (C.c_int, [vp]),
         "anm_celt_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
         "anm_celt_ctx_destroy": (None, [vp]),
-        "anm_celt_entropy_device": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp]),
+        "anm_celt_entropy_device": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp]),
         "anm_celt_entropy_host": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp]),
         "anm_pb_encode_broadcast": (C.c_size_t, [C.POINTER(PbBroadcast), vp, C.c_size_t]),
         "anm_pb_encode_to_transmitter": (C.c_size_t, [C.POINTER(PbToTransmitter), vp, C.c_size_t]),

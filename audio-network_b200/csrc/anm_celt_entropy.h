@@ -663,16 +663,17 @@ ANM_CE_FN int ce_compute_allocation(const anm_celt_tables_t *t, int start, int e
 }
 
 /* ---------------------------------------------------------------- one frame */
-/* old_e: the stream's band energies (Q10, [2][21]) carried from frame to frame; end = coded bands of the packet's bandwidth.
- * Returns 0, or a negative ANM_OPUS_* code (nothing is read then). */
-ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
-                                     int end, int16_t *old_e, anm_celt_frame_t *out) {
+/* Everything the frame's bits say, WITHOUT the stream's history: the coarse energy symbols qi[c * 21 + band] and the sum of the fine and
+ * final energy offsets eoff[c * 21 + band] (Q10) are returned instead of being applied -- no symbol of a frame depends on the band energies,
+ * so frames decode independently of each other and only anm_celt_apply_energies() below is sequential per stream.
+ * end = coded bands of the packet's bandwidth.  Returns 0, or a negative ANM_OPUS_* code (nothing is read then). */
+ANM_CE_FN int anm_celt_entropy_symbols(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
+                                       int end, int16_t *qi_out, int16_t *eoff, anm_celt_frame_t *out) {
     const uint8_t trim_icdf[11] = {126, 124, 119, 109, 87, 41, 19, 9, 4, 2, 0};
     const uint8_t spread_icdf[4] = {25, 23, 2, 0};
     const uint8_t tapset_icdf[3] = {2, 1, 0};
     const uint8_t small_energy_icdf[3] = {2, 1, 0};
     const int8_t tf_select_table[4][8] = {{0, -1, 0, -1, 0, -1, 0, -1}, {0, -1, 0, -2, 1, 0, 1, -1}, {0, -2, 0, -3, 2, 0, 1, -1}, {0, -2, 0, -3, 3, 0, 1, -1}};
-    const int16_t pred_coef[4] = {29440, 26112, 21248, 16384}, beta_coef[4] = {30147, 22282, 12124, 6554};
     const int start = 0, M = 1 << LM;
     const int16_t *eb = t->ebands;
     anm_ec_t dec;
@@ -686,8 +687,7 @@ ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *
         return 0;
     }
     ce_init(&dec, bytes, mask, base, len);
-    if (C == 1)
-        for (i = 0; i < ANM_CE_NB; i++) old_e[i] = old_e[i] > old_e[ANM_CE_NB + i] ? old_e[i] : old_e[ANM_CE_NB + i];
+    for (i = 0; i < 2 * ANM_CE_NB; i++) qi_out[i] = eoff[i] = 0;
     int32_t total_bits = (int32_t)len * 8;
     int32_t tell = ce_tell(&dec);
     int silence;
@@ -717,11 +717,9 @@ ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *
     const int short_blocks = transient ? M : 0;
     const int intra = tell + 3 <= total_bits ? ce_bit_logp(&dec, 3) : 0;
 
-    /* ---- coarse energy (unquant_coarse_energy) ---- */
+    /* ---- coarse energy (unquant_coarse_energy): the symbols only ---- */
     {
         const uint8_t *prob = t->e_prob + (LM * 2 + intra) * 42;
-        int32_t prev[2] = {0, 0};
-        const int coef = intra ? 0 : pred_coef[LM], beta = intra ? 4915 : beta_coef[LM];
         const int32_t budget = (int32_t)len * 8;
         for (i = start; i < end; i++) {
             for (c = 0; c < C; ++c) {
@@ -738,13 +736,7 @@ ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *
                 } else {
                     qi = -1;
                 }
-                const int32_t q = (int32_t)qi * 1024; /* SHL32(qi, DB_SHIFT) */
-                int16_t *e = &old_e[i + c * ANM_CE_NB];
-                if (*e < -9216) *e = -9216; /* MAX16(-QCONST16(9, DB_SHIFT), .) */
-                int32_t tmp = ce_pshr32((int32_t)coef * *e, 8) + prev[c] + q * 128;
-                if (tmp < -3670016) tmp = -3670016; /* -QCONST32(28, DB_SHIFT + 7) */
-                *e = (int16_t)ce_pshr32(tmp, 7);
-                prev[c] = prev[c] + q * 128 - (int32_t)beta * (int16_t)ce_pshr32(q, 8);
+                qi_out[i + c * ANM_CE_NB] = (int16_t)qi;
             }
         }
     }
@@ -814,7 +806,7 @@ ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *
         for (c = 0; c < C; ++c) {
             const int q2 = (int)ce_bits(&dec, (uint32_t)fine_quant[i]);
             const int16_t offset = (int16_t)((((int32_t)q2 * 1024 + 512) >> fine_quant[i]) - 512);
-            old_e[i + c * ANM_CE_NB] = (int16_t)(old_e[i + c * ANM_CE_NB] + offset);
+            eoff[i + c * ANM_CE_NB] = (int16_t)(eoff[i + c * ANM_CE_NB] + offset); /* 16-bit wrapping adds commute with the coarse value */
         }
     }
     /* ---- the bands (quant_all_bands): bits only ---- */
@@ -865,19 +857,12 @@ ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *
                 for (c = 0; c < C; ++c) {
                     const int q2 = (int)ce_bits(&dec, 1);
                     const int16_t offset = (int16_t)((int16_t)(q2 * 1024 - 512) >> (fine_quant[i] + 1));
-                    old_e[i + c * ANM_CE_NB] = (int16_t)(old_e[i + c * ANM_CE_NB] + offset);
+                    eoff[i + c * ANM_CE_NB] = (int16_t)(eoff[i + c * ANM_CE_NB] + offset);
                     bits_left--;
                 }
             }
         }
     }
-    if (silence)
-        for (i = 0; i < C * ANM_CE_NB; i++) old_e[i] = -28672; /* -QCONST16(28, DB_SHIFT) */
-    if (C == 1)
-        for (i = 0; i < ANM_CE_NB; i++) old_e[ANM_CE_NB + i] = old_e[i];
-    for (c = 0; c < 2; ++c)
-        for (i = end; i < ANM_CE_NB; i++) old_e[c * ANM_CE_NB + i] = 0;
-
     out->final_range = dec.rng;
     out->tell_bits = ce_tell(&dec);
     out->flags = (uint32_t)(silence ? ANM_CELT_F_SILENCE : 0) | (uint32_t)(pf ? ANM_CELT_F_POSTFILTER : 0) | (uint32_t)(transient ? ANM_CELT_F_TRANSIENT : 0) |
@@ -892,13 +877,56 @@ ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *
     out->coded_bands = (uint8_t)coded_bands;
     out->lm = (uint8_t)LM;
     out->channels = (uint8_t)C;
+    out->pad[0] = (uint8_t)end;
     for (i = 0; i < ANM_CE_NB; i++) {
         out->tf_res[i] = (int8_t)(i < end ? tf_res[i] : 0);
         out->fine_quant[i] = (uint8_t)fine_quant[i];
         out->pulses[i] = (int16_t)pulses[i];
-        out->band_e[i] = old_e[i];
-        out->band_e[ANM_CE_NB + i] = old_e[ANM_CE_NB + i];
     }
+    return 0;
+}
+
+/* The sequential part of a stream: the band energies after a frame from the energies before it (old_e, Q10, [2][21]), the frame's coarse
+ * symbols and offsets -- unquant_coarse_energy's prediction (celt/quant_bands.c:427-490, fixed-point build) followed by the fine and final
+ * offsets, the mono / silence / band-limit rules of celt_decode_with_ec (celt/celt_decoder.c:941-945, 1100-1104, 1137-1166).  `fr` is the
+ * record anm_celt_entropy_symbols() filled; its band_e is written here. */
+ANM_CE_FN void anm_celt_apply_energies(anm_celt_frame_t *fr, const int16_t *qi, const int16_t *eoff, int16_t *old_e) {
+    const int16_t pred_coef[4] = {29440, 26112, 21248, 16384}, beta_coef[4] = {30147, 22282, 12124, 6554};
+    int i, c;
+    if (!(fr->flags & ANM_CELT_F_LOST)) {
+        const int C = fr->channels, LM = fr->lm, end = fr->pad[0], intra = (fr->flags & ANM_CELT_F_INTRA) != 0;
+        const int coef = intra ? 0 : pred_coef[LM], beta = intra ? 4915 : beta_coef[LM];
+        int32_t prev[2] = {0, 0};
+        if (C == 1)
+            for (i = 0; i < ANM_CE_NB; i++) old_e[i] = old_e[i] > old_e[ANM_CE_NB + i] ? old_e[i] : old_e[ANM_CE_NB + i];
+        for (i = 0; i < end; i++) {
+            for (c = 0; c < C; ++c) {
+                const int32_t q = (int32_t)qi[i + c * ANM_CE_NB] * 1024; /* SHL32(qi, DB_SHIFT) */
+                int16_t *e = &old_e[i + c * ANM_CE_NB];
+                if (*e < -9216) *e = -9216; /* MAX16(-QCONST16(9, DB_SHIFT), .) */
+                int32_t tmp = ce_pshr32((int32_t)coef * *e, 8) + prev[c] + q * 128;
+                if (tmp < -3670016) tmp = -3670016; /* -QCONST32(28, DB_SHIFT + 7) */
+                *e = (int16_t)(ce_pshr32(tmp, 7) + eoff[i + c * ANM_CE_NB]);
+                prev[c] = prev[c] + q * 128 - (int32_t)beta * (int16_t)ce_pshr32(q, 8);
+            }
+        }
+        if (fr->flags & ANM_CELT_F_SILENCE)
+            for (i = 0; i < C * ANM_CE_NB; i++) old_e[i] = -28672; /* -QCONST16(28, DB_SHIFT) */
+        if (C == 1)
+            for (i = 0; i < ANM_CE_NB; i++) old_e[ANM_CE_NB + i] = old_e[i];
+        for (c = 0; c < 2; ++c)
+            for (i = end; i < ANM_CE_NB; i++) old_e[c * ANM_CE_NB + i] = 0;
+    }
+    for (i = 0; i < 2 * ANM_CE_NB; i++) fr->band_e[i] = old_e[i];
+}
+
+/* both parts for one frame (the host-side test harness; the kernels run them as two passes) */
+ANM_CE_FN int anm_celt_entropy_frame(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
+                                     int end, int16_t *old_e, anm_celt_frame_t *out) {
+    int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
+    const int rc = anm_celt_entropy_symbols(t, bytes, mask, base, len, C, LM, end, qi, eoff, out);
+    if (rc != 0) return rc;
+    anm_celt_apply_energies(out, qi, eoff, old_e);
     return 0;
 }
 

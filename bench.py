@@ -319,6 +319,41 @@ def decode_chain_leg(anm, torch, dev, recs, by, reps=20):
     spans = d_spans.cpu().numpy().view(anm.PB_SPAN_DTYPE)
     pk = d_pk.cpu().numpy().view(anm.OPUS_PACKET_DTYPE)
     ok = recs["crc_ok"] == 1
+    # row f1 stage 1: the CELT entropy decode of every located packet, one GPU thread per channel (= stream), frames in stream order
+    celt = None
+    sel = np.flatnonzero((pk["count"] == 1) & (pk["mode"] == 1002))
+    if len(sel):
+        order = sel[np.lexsort((recs["start_sample"][sel], recs["channel"][sel]))]
+        jobs = np.zeros(len(order), dtype=anm.CELT_JOB_DTYPE)
+        jobs["offset"] = spans["audio_offset"][order] + pk["payload_offset"][order].astype(np.uint32)
+        jobs["len"] = pk["size"][order, 0]
+        jobs["channels"] = pk["channels"][order]
+        jobs["lm"] = 3
+        jobs["end_band"] = 21
+        chs, first = np.unique(recs["channel"][order], return_index=True)
+        sb = np.concatenate([first, [len(order)]]).astype(np.uint32)
+        ctx = ctypes.c_void_p()
+        assert L.anm_celt_ctx_create(dev.index or 0, ctypes.byref(ctx)) == 0
+        d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).to(dev)
+        d_sb = torch.from_numpy(sb.view(np.uint8).copy()).to(dev)
+        d_st = torch.zeros(len(chs) * anm.CELT_STREAM_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        d_fr = torch.zeros(len(jobs) * anm.CELT_FRAME_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        t_celt = 0.0
+        for r in range(reps // 2 + 2):
+            d_st.zero_()
+            ev[0].record()
+            assert L.anm_celt_entropy_device(ctx, d_jobs.data_ptr(), d_sb.data_ptr(), len(chs), len(jobs), d_by.data_ptr(), 0xFFFFFFFF, d_st.data_ptr(), d_fr.data_ptr(), stream) == 0
+            ev[1].record()
+            torch.cuda.synchronize()
+            if r >= 2:
+                t_celt += ev[0].elapsed_time(ev[1])
+        L.anm_celt_ctx_destroy(ctx)
+        fr = d_fr.cpu().numpy().view(anm.CELT_FRAME_DTYPE)
+        ms = t_celt / (reps // 2)
+        celt = {"k_celt_entropy_plus_energies_ms": round(ms, 4), "streams": int(len(chs)), "frames": int(len(jobs)), "Mframes_per_s": round(len(jobs) / (ms * 1e-3) / 1e6, 2),
+                "packet_bytes": int(jobs["len"].sum()), "frames_within_budget": int(((fr["flags"] & 1024) == 0).sum()),
+                "note": "payloads of the synthetic workload are random bytes behind a CELT TOC: valid range-coder input, worst case for branch divergence; "
+                        "parity of this stage is pinned on real encoder output in tests/test_celt_entropy.py"}
     peak, _src = peaks()
     # algorithmic bytes per frame: k_pb_deframe = 24 (frame record) + 32 (the sector holding the message header) + 16 (span out);
     # k_opus_parse = 16 (span) + 32 (the sector holding the TOC / size bytes) + 128 (packet record out)
@@ -327,7 +362,7 @@ def decode_chain_leg(anm, torch, dev, recs, by, reps=20):
     return {"batch_frames": int(n), "payload_bytes": int(len(by)), "k_pb_deframe_ms": round(t_def / reps, 4), "k_opus_parse_ms": round(t_par / reps, 4),
             "k_pb_deframe_hbm": {"algorithmic_bytes_per_frame": 72, "achieved_gbs": round(gbs_def, 1), "frac": round(gbs_def / peak, 4)},
             "k_opus_parse_hbm": {"algorithmic_bytes_per_frame": 176, "achieved_gbs": round(gbs_par, 1), "frac": round(gbs_par / peak, 4)},
-            "Mframes_per_s": round(n / ((t_def + t_par) / reps * 1e-3) / 1e6, 1), "gpu_launches": 2 * reps,
+            "Mframes_per_s": round(n / ((t_def + t_par) / reps * 1e-3) / 1e6, 1), "gpu_launches": 2 * reps, "celt_entropy": celt,
             "audio_located": int((spans["status"] == anm.ANM_PB_OK).sum()), "crc_ok_frames": int(ok.sum()),
             "opus_packets_parsed": int((pk["count"] == 1).sum()),
             "all_crc_ok_frames_decode": bool(((spans["status"] == anm.ANM_PB_OK) == ok).all() and ((pk["count"] == 1) == ok).all()

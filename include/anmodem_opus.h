@@ -15,8 +15,8 @@
  * Second stage (anm_celt_entropy_*): the ENTROPY DECODE of CELT frames -- everything celt_decode_with_ec
  * (celt/celt_decoder.c:946-1095) reads off the range coder: frame flags, post-filter parameters, coarse / fine / final band
  * energies, time-frequency and spread decisions, dynamic allocation, the bit allocation and, band by band with every split, the
- * PVQ codeword of each partition.  One GPU thread per stream walks that stream's frames in order (the band energies predict
- * from frame to frame); streams are the batch.  The check is the reference's own: the range coder's final state of every frame
+ * PVQ codeword of each partition.  No symbol of a frame depends on another frame, so one GPU thread per FRAME decodes all frames of all
+ * streams at once; only the band energies predict from frame to frame and are chained per stream in a second, short pass.  The check is the reference's own: the range coder's final state of every frame
  * equals OPUS_GET_FINAL_RANGE of libopus 1.3.1.  The spectrum (PVQ vectors, folding, denormalisation) and the synthesis
  * (inverse MDCT, post-filter, de-emphasis) are NOT part of this library yet.
  */
@@ -106,7 +106,7 @@ typedef struct anm_celt_frame {
     uint32_t flags;         /* ANM_CELT_F_* */
     uint16_t pf_pitch;      /* post-filter period (celt_decoder.c:978) */
     uint8_t pf_gain_q, pf_tapset;
-    uint8_t spread, alloc_trim, intensity, coded_bands, lm, channels, pad[2];
+    uint8_t spread, alloc_trim, intensity, coded_bands, lm, channels, pad[2]; /* pad[0]: the frame's end band */
     uint32_t pvq_codewords; /* partitions that carried a PVQ codeword ... */
     uint32_t pvq_pulses;    /* ... their pulses in total ... */
     uint32_t pvq_index_xor; /* ... and a checksum of the codeword indices */
@@ -125,9 +125,10 @@ typedef struct anm_celt_stream {
 typedef struct anm_celt_ctx anm_celt_ctx_t;
 int anm_celt_ctx_create(int device, anm_celt_ctx_t **out);
 void anm_celt_ctx_destroy(anm_celt_ctx_t *c);
-/* stream s decodes jobs[stream_begin[s] .. stream_begin[s + 1]) in order; d_* in device memory; d_streams is read and written
- * (zero-initialised for a fresh stream); bytes_mask as for anm_pb_deframe_device; stream is a cudaStream_t */
-int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams,
+/* stream s owns jobs[stream_begin[s] .. stream_begin[s + 1]) (n_jobs = stream_begin[n_streams]), in stream order; d_* in device memory;
+ * d_streams is read and written (zero-initialised for a fresh stream); bytes_mask as for anm_pb_deframe_device; stream is a cudaStream_t.
+ * Two launches: every frame's symbols in parallel (k_celt_entropy), then the per-stream energy recurrence (k_celt_energies). */
+int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
                             const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, void *stream);
 /* host arrays: copies in, runs the kernel, copies out (no CPU fallback: ANM_ERR_CUDA without a device) */
 int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,

@@ -56,3 +56,39 @@ def test_argument_errors():
     assert L.anm_pacer_init(C.byref(raw), -1, 1000, 0) == anm.ANM_ERR_ARG
     assert L.anm_pacer_init(C.byref(raw), 10, 0, 0) == anm.ANM_ERR_ARG
     assert L.anm_pacer_init(None, 10, 10, 0) == anm.ANM_ERR_ARG
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_paced_feed_through_the_demodulator():
+    """Row f4 on a real feed path: chunks of PCM are submitted to the CUDA demodulator under the transmitter's leaky bucket (1200 ms of receiver
+    buffer, MulticastAudioOutput.kt:85) at 25x real time on a virtual clock -- the schedule is the bucket's (a burst of one buffer, then one chunk
+    per chunk-duration / 25), the frames are the oracle's."""
+    import numpy as np
+
+    import audio_network_b200 as anm
+    from oracle_binding import oracle_frames_batch
+    from sigutil import make_channels
+
+    cfg = anm.config_preset("ref4")
+    chunk = 64 * cfg.sym_len                         # 8,192 samples = 185.76 ms of audio
+    chunk_ms = 186
+    pcm, _ = make_channels(cfg, 6, 20 * chunk, seed=91, snr_db=10.0, offset_max=500)
+    factor = 25
+    pacer = anm.Pacer(1200, 1000 * factor, 0)
+    dm = anm.Demod(cfg, 6, device=0)
+    now, submit_times, got = 0, [], []
+    for k in range(20):
+        now, _waited = pacer.wait_for_capacity(chunk_ms, now)      # virtual clock: returns the time at which the chunk may go
+        submit_times.append(now)
+        dm.feed_host(np.ascontiguousarray(pcm[:, k * chunk: (k + 1) * chunk]))
+        dm.collect()
+        got += anm.frames_to_list(*dm.read_frames())
+    dm.close()
+    assert sorted(got, key=lambda f: (f[0], f[1])) == oracle_frames_batch(cfg, pcm)
+    burst = 1200 // chunk_ms                                        # chunks that fit the empty bucket at once
+    assert all(t == 0 for t in submit_times[:burst]) and submit_times[burst] > 0
+    steady = np.diff(submit_times[burst + 1:])
+    assert np.all(np.abs(steady - chunk_ms * 1e6 / factor) <= 1e5)  # then one chunk per chunk_ms / factor of (virtual) time
