@@ -33,6 +33,13 @@
 #pragma once
 #include "anm_kernels.cuh"
 
+/* 1: two CTAs on the two SMs of a TPC form a pair (cluster of 2, tcgen05 cta_group::2): one MMA covers both CTAs' rows (M = 256) and every
+ * CTA keeps and reads only HALF of the basis (the B operand) -- a quarter less shared-memory operand traffic per SM, which is what bounds
+ * this kernel.  0: every CTA on its own (cta_group::1). */
+#ifndef ANM_TC_PAIR
+#define ANM_TC_PAIR 1
+#endif
+
 namespace anm {
 namespace tc {
 
@@ -40,14 +47,19 @@ constexpr uint32_t kRows = 128;                    /* MMA M: 4 channels x 32 sym
 constexpr uint32_t kCarryRows = 4;                 /* the symbol period before the job, one row per channel */
 constexpr uint32_t kPanel = (kCarryRows + kRows) * 16u + 16u; /* one 16-byte K chunk of all rows; +16: spreads the panels over the banks */
 constexpr uint32_t kNcol = 128;                    /* MMA N: (cos, sin) columns of all 64 tones */
-constexpr uint32_t kBPanel = kNcol * 16u;          /* one 16-byte K chunk of all basis rows */
+constexpr uint32_t kPair = ANM_TC_PAIR ? 2u : 1u;   /* CTAs that share one MMA */
+constexpr uint32_t kBPanel = kNcol / kPair * 16u;  /* one 16-byte K chunk of this CTA's share of the basis rows */
 constexpr uint32_t kAccCols = 2u * kNcol;          /* one accumulator set: 2 byte planes x 128 columns */
 constexpr uint32_t kTmemCols = 2u * kAccCols;      /* two sets = all 512 TMEM columns of the SM */
-constexpr int kEpiWarps = 8;                       /* warps 0..7: quadrant = warp & 3, tone half = warp >> 2 */
-constexpr int kIssuerWarp = 8;
-constexpr int kLoaderWarp0 = 9;                    /* warps 9..12: channel slot = warp - 9 */
-constexpr int kSmWarp0 = 13;                       /* warps 13..20: group slot = (warp - 13) >> 2, channel slot = (warp - 13) & 3 */
-constexpr int kWarps = 21;
+/* Warp roles, lowest priority first: the SM's warp schedulers prefer the highest warp id among the eligible warps, and the epilogue is the
+ * critical path -- polling loops of the other roles must not win issue slots against it. */
+constexpr int kSmWarp0 = 0;                        /* warps 0..7: group slot = warp >> 2, channel slot = warp & 3 */
+constexpr int kLoaderWarp0 = 8;                    /* warps 8..15: channel slot = (warp - 8) & 3, which 16 of the job's 32 symbol periods = (warp - 8) >> 2 */
+constexpr int kLoaderWarps = 8;
+constexpr int kEpiWarp0 = 16;                      /* warps 16..23: TMEM lane quadrant = warp & 3, tone half = (warp - 16) >> 2 */
+constexpr int kEpiWarps = 8;
+constexpr int kIssuerWarp = 24;
+constexpr int kWarps = 25;                         /* 800 threads x 80 registers = 64,000 of the SM's 65,536 */
 
 template <int N, int S>
 __host__ __device__ constexpr uint32_t a_bytes() { return 2u * S * (uint32_t)(N / S / 16) * kPanel; } /* one buffer */
@@ -61,7 +73,7 @@ template <int S>
 __host__ __device__ constexpr uint32_t cand_bytes() { return 2u * 2u * (uint32_t)S * kRows * 8u; } /* [job parity][tone half][hop][row] x {e, d} */
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t smem_bytes() {
-    return 2u * a_bytes<N, S>() + b_bytes<T, N, S>() + 8u * warp_bytes<T, S>() + cand_bytes<S>() + 128u;
+    return 2u * a_bytes<N, S>() + b_bytes<T, N, S>() + 8u * warp_bytes<T, S>() + cand_bytes<S>() + 192u; /* tail: mbarriers, TMEM address, bias words */
 }
 
 /* shared-memory matrix descriptor: K-major, no swizzle; LBO = stride between the two 16-byte K chunks
@@ -69,11 +81,20 @@ __host__ __device__ constexpr uint32_t smem_bytes() {
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-/* instruction descriptor of kind::i8: D = s32, B = s8, A = s8 (a_signed) or u8, both K-major, M = 128, N = ncol */
+/* instruction descriptor of kind::i8: D = s32, B = s8, A = s8 (a_signed) or u8, both K-major, M = 128 rows per CTA of the group, N = ncol */
 __device__ __forceinline__ uint32_t idesc_i8_n(bool a_signed, uint32_t ncol) {
-    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((ncol >> 3) << 17) | ((kRows >> 4) << 24);
+    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | (1u << 10) | ((ncol >> 3) << 17) | (((kRows * kPair) >> 4) << 24);
 }
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#if ANM_TC_PAIR
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -81,9 +102,47 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
+#endif
 }
+/* completion of every MMA issued so far -> one arrival on the barrier at this shared-memory offset (in both CTAs of a pair) */
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
+#if ANM_TC_PAIR
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+#else
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+#if ANM_TC_PAIR
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+#else
+    return 0u;
+#endif
+}
+__device__ __forceinline__ void cluster_sync_all() {
+#if ANM_TC_PAIR
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+    __syncthreads();
+#endif
+}
+/* Arrivals on the barrier at the same shared-memory offset in the pair's LEADER CTA (rank 0): the issuer there waits for both CTAs.
+ * RELEASE = true: the arrival publishes shared-memory writes of this CTA (the loaders' A panels) to the other CTA's issuer: release at
+ * cluster scope.  RELEASE = false: the arrival only says "my TMEM reads are complete" (the epilogue: tcgen05.wait::ld has returned and
+ * tcgen05.fence::before_thread_sync was executed): default semantics, as CUTLASS' ClusterBarrier::arrive(cta_id) -- a cluster-scope
+ * release costs a MEMBAR + ERRBAR per arrival, 11 % of the kernel's stall samples when all 36 arrivals per job had it. */
+template <bool RELEASE>
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+#if ANM_TC_PAIR
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(0u));
+    if (RELEASE) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+    else asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+#else
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -96,6 +155,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
+/* the same word to 8 consecutive columns of this warp's 32 lanes */
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void load_bias8(uint32_t saddr, uint32_t (&v)[8]) {
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(saddr));
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(saddr + 16u));
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -113,7 +183,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 /* the same for a warp that mostly waits (the MMA issuer): it sleeps between polls instead of spinning on the issue slots
- * of the scheduler it shares with two epilogue warps */
+ * of the scheduler it shares with two epilogue warps.  ACQUIRE = true pairs with the loaders' cluster-scope release in a CTA pair. */
+template <int NS, bool ACQUIRE>
+__device__ __forceinline__ void mbar_wait_issuer(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+#if ANM_TC_PAIR
+        if (ACQUIRE)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        else
+#endif
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(NS);
+    }
+}
 template <int NS>
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -123,6 +209,12 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         if (ok) break;
         __nanosleep(NS);
     }
+}
+constexpr uint32_t kAccBias = 0x4B400000u; /* 1.5 * 2^23 as fp32: kAccBias + s reads as 12582912.0f + s for |s| < 2^22 */
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 /* running argmax step: if (E > em) { em = E; dm = t; } as one compare and two predicated moves (ptxas issues predicated
  * moves on the FMA pipe as IMAD.MOV, the ALU pipe -- conversions, compares -- is the busy one in the epilogue) */
@@ -144,16 +236,22 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 } /* namespace tc */
 
-/* MODE 0: streaming demodulator; MODE 1: stateless tone-energy pass (trace outputs). */
-template <int T, int N, int S, int MODE>
-__global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams p) {
+/* MODE 0: streaming demodulator; MODE 1: stateless tone-energy pass (trace outputs).
+ * BIAS: the accumulators start every window at kAccBias instead of 0 (valid when every basis column sums to zero, see
+ * dense_zero_sum in anm_cuda.cu): read as fp32 they are 12582912 + sum exactly, and 256 * hi + lo needs no I2FP. */
+template <int T, int N, int S, int MODE, bool BIAS>
+__global__ void
+#if ANM_TC_PAIR
+__cluster_dims__(2, 1, 1)
+#endif
+__launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams p) {
     using namespace tc;
     constexpr int H = N / S;
     constexpr int KC = H / 16;          /* 16-byte K chunks per hop */
     constexpr int KS = H / 32;          /* MMAs (K = 32) per hop */
     constexpr int CPS = N / 8;          /* 16-byte PCM chunks per symbol period */
     constexpr int TH = T / 2;           /* tones per epilogue warp */
-    constexpr int TN = 8;               /* tones per tcgen05.ld batch (16 columns per byte plane) */
+    constexpr int TN = 4;               /* tones per tcgen05.ld batch (8 columns per byte plane) = one group of the running argmax */
     constexpr uint32_t RM = 64u * S - 1u;
     constexpr uint32_t CUR = kCarryRows * 16u; /* byte offset of the current rows inside a panel */
     static_assert(T == 64 && 2 * T == (int)kNcol, "the dense kernel contracts all 64 tones (128 columns) per MMA");
@@ -164,7 +262,7 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const int w = threadIdx.x >> 5;
+    const int w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); /* through a shuffle: the compiler then treats it (and the TMEM addresses built on it) as warp-uniform */
     const uint32_t sA = (uint32_t)__cvta_generic_to_shared(smem_raw);       /* two A buffers */
     const uint32_t sB = sA + 2u * a_bytes<N, S>();
     unsigned char *chsm = smem_raw + 2u * a_bytes<N, S>() + b_bytes<T, N, S>(); /* per channel slot: HopRec ring [64*S] | ChanScalars */
@@ -180,40 +278,72 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
     const uint32_t n_steps = (p.n_syms + 31u) / 32u;
     const uint32_t n_groups = (p.n_ch + 3u) / 4u;
     const uint32_t n_pairs = (n_groups + 1u) / 2u;
+    /* A pair of CTAs walks the group pairs in lockstep: unit u of the grid's n_units holds kPair group pairs, CTA rank r takes pair kPair * u + r.  A job
+     * exists for the pair when rank 0's group exists; a CTA whose own group does not exist still runs the job's barriers (on no channels). */
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0u;
+    const uint32_t n_units = (n_pairs + kPair - 1u) / kPair, unit0 = blockIdx.x / kPair, unit_step = gridDim.x / kPair;
     /* Two groups are in flight per CTA, group slot g2 of a pair always in A buffer / candidate buffer g2: their jobs alternate
      * (pair, step, slot 0), (pair, step, slot 1), ... so that every channel's state machine -- one warp, latency bound -- has two
      * job times for one job.  A missing second group (odd group count) is skipped by every role alike. */
 
     /* ---- one-time setup: basis panels, mbarriers, TMEM ---- */
     {
+        /* global panels [hop phase][K chunk][128 columns][16]; this CTA keeps columns [rank * 128 / kPair, (rank + 1) * 128 / kPair) of every panel */
         const uint4 *gsrc = reinterpret_cast<const uint4 *>(p.tc_basis);
         uint4 *dst = reinterpret_cast<uint4 *>(smem_raw + 2u * a_bytes<N, S>());
-        for (uint32_t i = threadIdx.x; i < b_bytes<T, N, S>() / 16u; i += blockDim.x) dst[i] = __ldg(&gsrc[i]);
+        constexpr uint32_t CPP = kNcol / kPair; /* 16-byte column entries per local panel */
+        for (uint32_t i = threadIdx.x; i < b_bytes<T, N, S>() / 16u; i += blockDim.x)
+            dst[i] = __ldg(&gsrc[(i / CPP) * kNcol + cta_rank * CPP + (i % CPP)]);
     }
     if (threadIdx.x == 0) {
+        for (uint32_t j = 0; j < 8; ++j) reinterpret_cast<volatile uint32_t *>(tail + 128)[j] = kAccBias;
         for (uint32_t b = 0; b < 2; ++b) {
-            mbar_init(bar_a_full + 8u * b, 4u);                     /* one arrival per loader warp */
+            mbar_init(bar_a_full + 8u * b, (uint32_t)kLoaderWarps * kPair); /* one arrival per loader warp of the pair (the leader's barrier is the one in use) */
             mbar_init(bar_a_empty + 8u * b, 1u);                    /* tcgen05.commit */
             mbar_init(bar_acc_full + 8u * b, 1u);                   /* tcgen05.commit */
-            mbar_init(bar_acc_empty + 8u * b, (uint32_t)kEpiWarps);
+            mbar_init(bar_acc_empty + 8u * b, (uint32_t)kEpiWarps * kPair); /* every epilogue warp of the pair, on the leader's barrier */
             mbar_init(bar_cand_full + 8u * b, (uint32_t)kEpiWarps);
             mbar_init(bar_cand_empty + 8u * b, 4u);                 /* one arrival per state-machine warp */
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (w == 0) {
+    if (w == 0) { /* in a pair, warp 0 of BOTH CTAs issues the allocation */
+#if ANM_TC_PAIR
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+#else
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+#endif
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* basis panels -> visible to the MMA's async proxy */
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all(); /* barriers initialised and basis in place in both CTAs before anything crosses over */
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (BIAS) {
+        /* both accumulator sets start biased; afterwards every epilogue warp re-biases the columns it has read */
+        if (w >= kEpiWarp0 && w < kEpiWarp0 + kEpiWarps) {
+            uint32_t bias8[8];
+            load_bias8(bars + 128u, bias8);
+            const uint32_t t = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(((w - kEpiWarp0) >> 2) * 2 * TH);
+#pragma unroll 1
+            for (uint32_t c = 0; c < 2u * kAccCols; c += kNcol)
+#pragma unroll
+                for (uint32_t cc = 0; cc < (uint32_t)(2 * TH); cc += 8u) tmem_st8(t + c + cc, bias8);
+            tmem_st_wait();
+            tc_fence_before();
+        }
+        __syncthreads();
+        cluster_sync_all(); /* the leader's MMAs write both CTAs' accumulators */
+        tc_fence_after();
+    }
 
-    if (w >= kLoaderWarp0 && w < kSmWarp0) {
+    if (w >= kLoaderWarp0 && w < kLoaderWarp0 + kLoaderWarps) {
         /* =================== loader: PCM of one job of this warp's channel -> byte planes in the A panels =================== */
-        const int c4 = w - kLoaderWarp0;
+        const int c4 = (w - kLoaderWarp0) & 3, rh = (w - kLoaderWarp0) >> 2; /* two warps per channel: symbol periods [16 * rh, 16 * rh + 16) of the job */
         /* Every load instruction of the warp covers ONE symbol period (32 lanes x 16 bytes = 512 bytes = N samples): the lane is the
          * 16-byte chunk, i.e. (hop q, K chunk kc, which half of the 16-sample K chunk) are lane constants. */
         const uint32_t q = (uint32_t)lane / (uint32_t)(H / 8), hc = (uint32_t)lane % (uint32_t)(H / 8);
@@ -221,14 +351,14 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
         const uint32_t plane_lo = (uint32_t)(S * KC) * kPanel;
         const uint32_t st_hi = (q * KC + (hc >> 1)) * 16u + (hc & 1u) * 8u, st_lo = st_hi + (uint32_t)(S * KC) * 16u; /* state carry: [plane][hop][K chunk] x 16 bytes */
         uint32_t use[2] = {0u, 0u};
-        for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step)
             for (uint32_t step = 0; step < n_steps; ++step)
 #pragma unroll
             for (uint32_t b = 0; b < 2; ++b) {
-                const uint32_t grp = 2u * pair + b;
-                if (grp >= n_groups) continue;
+                if (2u * (kPair * unit) + b >= n_groups) continue; /* no such job for the pair */
+                const uint32_t grp = 2u * (kPair * unit + cta_rank) + b;
                 const uint32_t ch = grp * 4u + (uint32_t)c4;
-                const bool have = ch < p.n_ch;
+                const bool have = grp < n_groups && ch < p.n_ch;
                 const char *src = reinterpret_cast<const char *>(p.pcm + (size_t)(have ? ch : 0u) * p.ch_stride) + (size_t)lane * 16u;
                 unsigned char *gst = p.state + (size_t)(have ? ch : 0u) * p.state_stride + state_carry_offset<T, S>();
                 const uint32_t k = use[b]++;
@@ -238,7 +368,8 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                     const uint32_t base = sA + b * a_bytes<N, S>() + lane_off;
                     const char *g = src + (size_t)step * (32u * N * 2u);
                     /* carry row: the symbol period before the job (step 0: the planes saved by the previous chunk) */
-                    if (step == 0) {
+                    if (rh != 0) {
+                    } else if (step == 0) {
                         const uint2 chi = *reinterpret_cast<const uint2 *>(gst + st_hi);
                         const uint2 clo = *reinterpret_cast<const uint2 *>(gst + st_lo);
                         asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(base), "r"(chi.x), "r"(chi.y) : "memory");
@@ -250,7 +381,7 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                     }
                     constexpr int BATCH = 8; /* loads in flight before the first split (21 warps leave 80 registers per thread) */
 #pragma unroll 1
-                    for (int r0 = 0; r0 < 32; r0 += BATCH) {
+                    for (int r0 = 16 * rh; r0 < 16 * rh + 16; r0 += BATCH) {
                         uint4 v[BATCH];
                         if (nv == 32) {
 #pragma unroll
@@ -260,11 +391,12 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
 #pragma unroll
                             for (int j = 0; j < BATCH; ++j) v[j] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)min(r0 + j, nv - 1) * 512u));
                         }
-                        if (r0 == 0 && step + 1 < n_steps) {
+                        if (r0 == 16 * rh && step + 1 < n_steps) {
                             /* next job of this channel: 32 * N * 2 bytes = N / 2 lines of 128 bytes, N / 64 per lane, pulled into L2 */
-                            const char *nx = reinterpret_cast<const char *>(p.pcm + (size_t)ch * p.ch_stride) + (size_t)(step + 1) * (32u * N * 2u) + (size_t)lane * 128u;
+                            const char *nx = reinterpret_cast<const char *>(p.pcm + (size_t)ch * p.ch_stride) + (size_t)(step + 1) * (32u * N * 2u) + (size_t)lane * 128u +
+                                             (size_t)rh * (N / 128) * 4096u; /* each of the channel's two warps its half */
 #pragma unroll
-                            for (int j = 0; j < N / 64; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * 4096u));
+                            for (int j = 0; j < N / 128; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * 4096u));
                         }
 #pragma unroll
                         for (int j = 0; j < BATCH; ++j) {
@@ -275,7 +407,7 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a + plane_lo), "r"(lo0), "r"(lo1) : "memory");
                         }
                     }
-                    if (step + 1 == n_steps) {
+                    if (rh == 0 && step + 1 == n_steps) { /* the warp that read the old carry at step 0 */
                         /* the chunk's last symbol period is the next chunk's carry row (read back from L2: once per chunk) */
                         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)(nv - 1) * 512u));
                         *reinterpret_cast<uint2 *>(gst + st_hi) = make_uint2(prmt(v.x, v.y, 0x7531u), prmt(v.z, v.w, 0x7531u));
@@ -284,26 +416,27 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> the MMA's async proxy */
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a_full + 8u * b);
+                if (lane == 0) mbar_arrive_leader<false>(bar_a_full + 8u * b);
             }
     } else if (w == kIssuerWarp) {
+        if (leader) {
         /* =================== issuer: 4 windows x (2 planes x 4 hops x 2 K steps) MMAs per job =================== */
         uint32_t use[2] = {0u, 0u}, rnd = 0;
         const uint32_t id_hi = idesc_i8_n(true, kNcol), id_lo = idesc_i8_n(false, kNcol);
         const uint64_t b0 = smem_desc(sB, kBPanel, 128u);
-        for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step)
             for (uint32_t step = 0; step < n_steps; ++step)
 #pragma unroll
             for (uint32_t b = 0; b < 2; ++b) {
-                if (2u * pair + b >= n_groups) continue;
+                if (2u * (kPair * unit) + b >= n_groups) continue;
                 const uint32_t k = use[b]++;
-                mbar_wait_relaxed<32>(bar_a_full + 8u * b, k & 1u);
+                mbar_wait_issuer<32, false>(bar_a_full + 8u * b, k & 1u);
                 tc_fence_after();
                 const uint64_t a0 = smem_desc(sA + b * a_bytes<N, S>(), kPanel, 128u);
 #pragma unroll 1 /* rolled: the four roles share the instruction cache, keep every role's loop body small */
                 for (int i = 0; i < S; ++i, ++rnd) {
                     const uint32_t set = rnd & 1u, u = rnd >> 1;
-                    mbar_wait_relaxed<32>(bar_acc_empty + 8u * set, (u & 1u) ^ 1u);
+                    mbar_wait_issuer<32, false>(bar_acc_empty + 8u * set, (u & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d0 = tmem_base + set * kAccCols;
                     if (elect_one()) {
@@ -318,7 +451,7 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                                     const uint32_t aoff = (uint32_t)((pl * S + j) * KC + 2 * ks) * kPanel + ((j <= i) ? CUR : 0u);
                                     const uint32_t boff = (uint32_t)(j * KC + 2 * ks) * kBPanel;
                                     mma_i8(d0 + (uint32_t)pl * kNcol, a0 + (uint64_t)(aoff >> 4), b0 + (uint64_t)(boff >> 4), pl == 0 ? id_hi : id_lo,
-                                           (j > 0 || ks > 0) ? 1u : 0u);
+                                           (BIAS || j > 0 || ks > 0) ? 1u : 0u);
                                 }
                         mma_commit(bar_acc_full + 8u * set);
                         if (i == S - 1) mma_commit(bar_a_empty + 8u * b); /* every contraction that reads this A buffer is complete */
@@ -326,20 +459,23 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                     __syncwarp();
                 }
             }
-    } else if (w < kEpiWarps) {
+        }
+    } else if (w >= kEpiWarp0) {
         /* =================== epilogue: this warp's 32 tones of its TMEM lane quadrant =================== */
-        const int c4 = w & 3, hf = w >> 2;
+        const int c4 = w & 3, hf = (w - kEpiWarp0) >> 2;
         const int esp = 8 * c4 + (lane >> 2), ec4 = lane & 3; /* TMEM lane 32 * c4 + lane = row 4 * esp + ec4 */
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * c4) << 16) + (uint32_t)(hf * 2 * TH);
         const uint32_t row = (uint32_t)(32 * c4 + lane);
         uint32_t use[2] = {0u, 0u}, rnd = 0;
-        for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        uint32_t bias8[8]; /* kAccBias eight times, from shared memory: as immediates ptxas re-creates them (8 moves) before every tcgen05.st */
+        if (BIAS) load_bias8(bars + 128u, bias8);
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step)
             for (uint32_t step = 0; step < n_steps; ++step)
 #pragma unroll
             for (uint32_t b = 0; b < 2; ++b) {
-                const uint32_t grp = 2u * pair + b;
-                if (grp >= n_groups) continue;
-                const uint32_t ech = grp * 4u + (uint32_t)ec4;
+                if (2u * (kPair * unit) + b >= n_groups) continue;
+                const uint32_t grp = 2u * (kPair * unit + cta_rank) + b;
+                const uint32_t ech = grp < n_groups ? grp * 4u + (uint32_t)ec4 : 0xFFFFFFFFu;
                 const uint32_t k = use[b]++;
                 /* candidates of this tone half: [job parity][half][hop][row] x {e, d} */
                 mbar_wait(bar_cand_empty + 8u * b, (k & 1u) ^ 1u); /* the state machines have read what job - 2 left here */
@@ -350,11 +486,11 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                     mbar_wait(bar_acc_full + 8u * set, u & 1u);
                     tc_fence_after();
                     const uint32_t t0 = tmem_lane + set * kAccCols;
-                    float em = -1.0f;
-                    uint32_t dm = 0u;
+                    float em = -1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f; /* running maximum; the first three energies of the group of four it came from */
+                    uint32_t dq = 0u;                                   /* first tone of that group */
                     int32_t vh[2][2 * TN], vl[2][2 * TN];
-                    tmem_ld16(t0, vh[0]);
-                    tmem_ld16(t0 + kNcol, vl[0]);
+                    tmem_ld8(t0, vh[0]);
+                    tmem_ld8(t0 + kNcol, vl[0]);
                     /* two batches per trip (ping-pong registers): a short loop body -- the roles share the instruction cache */
 #pragma unroll 1
                     for (int tb2 = 0; tb2 < TH / TN; tb2 += 2) {
@@ -362,37 +498,74 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
                         for (int h2 = 0; h2 < 2; ++h2) {
                             const int tb = tb2 + h2;
                             tmem_ld_wait();
-                            if (h2 == 0 || tb + 1 < TH / TN) { /* the next batch travels while this one is evaluated */
-                                tmem_ld16(t0 + (uint32_t)(2 * TN * (tb + 1)), vh[h2 ^ 1]);
-                                tmem_ld16(t0 + kNcol + (uint32_t)(2 * TN * (tb + 1)), vl[h2 ^ 1]);
+                            { /* the next batch travels while this one is evaluated; behind the last batch the same one again, rather than a
+                               * branch: the trip stays one basic block and ptxas overlaps the two batches' dependency chains */
+                                const uint32_t nb = (uint32_t)(2 * TN) * (uint32_t)min(tb + 1, TH / TN - 1);
+                                tmem_ld8(t0 + nb, vh[h2 ^ 1]);
+                                tmem_ld8(t0 + kNcol + nb, vl[h2 ^ 1]);
+                            }
+                            if (BIAS) { /* this batch is in registers: its columns go back to the bias for the next window of the set */
+#pragma unroll
+                                for (uint32_t pl = 0; pl < 2; ++pl)
+#pragma unroll
+                                    for (uint32_t cc = 0; cc < (uint32_t)(2 * TN); cc += 8u) tmem_st8(t0 + pl * kNcol + (uint32_t)(2 * TN * tb) + cc, bias8);
                             }
                             const int32_t(&xh)[2 * TN] = vh[h2];
                             const int32_t(&xl)[2 * TN] = vl[h2];
                             const int tone0 = hf * TH + tb * TN;
 #pragma unroll
-                            for (int tt = 0; tt < TN; tt += 2) {
-                                /* two tones per packed fp32 operation; each component sees exactly fma(fI, fI, fQ * fQ) of SPEC 3b */
-                                const float i0 = (float)(xh[2 * tt] * 256 + xl[2 * tt]), q0 = (float)(xh[2 * tt + 1] * 256 + xl[2 * tt + 1]);
-                                const float i1 = (float)(xh[2 * tt + 2] * 256 + xl[2 * tt + 2]), q1 = (float)(xh[2 * tt + 3] * 256 + xl[2 * tt + 3]);
-                                const float2 qq = fmul2(make_float2(q0, q1), make_float2(q0, q1));
-                                const float2 E = ffma2vv(make_float2(i0, i1), make_float2(i0, i1), qq);
+                            for (int tq = 0; tq < TN; tq += 4) {
+                                float E[4];
+#pragma unroll
+                                for (int pr = 0; pr < 2; ++pr) {
+                                    /* columns 4 * (tone / 2) + {I even, I odd, Q even, Q odd}: two tones per packed fp32 operation; each
+                                     * component sees exactly fma(fI, fI, fQ * fQ) of SPEC 3b on fI = RN(256 * hi + lo) */
+                                    const int c = 2 * tq + 4 * pr;
+                                    float2 fi, fq;
+                                    if (BIAS) {
+                                        /* as fp32 the accumulators are 12582912 + hi and 12582912 + lo: 256 * hi by one exact fma, lo by one exact
+                                         * subtraction, their sum rounds once -- the same value as I2FP.RN(256 * hi + lo) */
+                                        const float2 k256 = make_float2(256.0f, 256.0f), kh = make_float2(-256.0f * 12582912.0f, -256.0f * 12582912.0f),
+                                                     kl = make_float2(-12582912.0f, -12582912.0f);
+                                        fi = fadd2(ffma2vv(make_float2(__int_as_float(xh[c]), __int_as_float(xh[c + 1])), k256, kh),
+                                                   fadd2(make_float2(__int_as_float(xl[c]), __int_as_float(xl[c + 1])), kl));
+                                        fq = fadd2(ffma2vv(make_float2(__int_as_float(xh[c + 2]), __int_as_float(xh[c + 3])), k256, kh),
+                                                   fadd2(make_float2(__int_as_float(xl[c + 2]), __int_as_float(xl[c + 3])), kl));
+                                    } else {
+                                        fi = make_float2((float)(xh[c] * 256 + xl[c]), (float)(xh[c + 1] * 256 + xl[c + 1]));
+                                        fq = make_float2((float)(xh[c + 2] * 256 + xl[c + 2]), (float)(xh[c + 3] * 256 + xl[c + 3]));
+                                    }
+                                    const float2 e2 = ffma2vv(fi, fi, fmul2(fq, fq));
+                                    E[2 * pr] = e2.x;
+                                    E[2 * pr + 1] = e2.y;
+                                }
                                 if (MODE == 1) {
                                     if (p.trE && ech < p.n_ch && esp < (int)min(32u, p.n_syms - step * 32u)) {
                                         const size_t hop = ((size_t)step * 32 + esp) * S + i;
-                                        float *o = p.trE + ((size_t)ech * p.tr_hops + hop) * T + tone0 + tt;
-                                        o[0] = E.x;
-                                        o[1] = E.y;
+                                        float *o = p.trE + ((size_t)ech * p.tr_hops + hop) * T + tone0 + tq;
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) o[j] = E[j];
                                     }
                                 }
-                                argmax_step(em, dm, E.x, (uint32_t)(tone0 + tt)); /* the first tone always wins against em = -1: energies are >= 0 */
-                                argmax_step(em, dm, E.y, (uint32_t)(tone0 + tt + 1));
+                                /* the running argmax by groups of four tones: strictly greater replaces (the first group always wins against
+                                 * em = -1: energies are >= 0), so the lowest tone among equal maxima is kept, as tone by tone */
+                                const float m = fmaxf(fmax3(E[0], E[1], E[2]), E[3]);
+                                const bool gt = m > em;
+                                em = gt ? m : em;
+                                w0 = gt ? E[0] : w0;
+                                w1 = gt ? E[1] : w1;
+                                w2 = gt ? E[2] : w2;
+                                dq = gt ? (uint32_t)(tone0 + tq) : dq;
                             }
                         }
                     }
-                    /* this warp's TMEM reads of the set are complete (tcgen05.wait::ld): hand it back */
+                    const uint32_t dm = dq + (w0 == em ? 0u : w1 == em ? 1u : w2 == em ? 2u : 3u);
+                    tmem_ld_wait(); /* the repeated load of the last batch */
+                    if (BIAS) tmem_st_wait();
+                    /* this warp's TMEM reads of the set are complete (tcgen05.wait::ld) and its columns re-biased (wait::st): hand it back */
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acc_empty + 8u * set);
+                    if (lane == 0) mbar_arrive_leader<false>(bar_acc_empty + 8u * set);
                     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(ca + (uint32_t)i * (kRows * 8u)), "r"(__float_as_uint(em)), "r"(dm) : "memory");
                 }
                 __syncwarp();
@@ -407,11 +580,11 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
         const uint32_t crc_k = (MODE == 0) ? (uint32_t)p.crc_pow[lane] : 0u;
         const uint32_t row = (uint32_t)(4 * lane + c4);
         uint32_t k = 0;
-        for (uint32_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-            const uint32_t grp = 2u * pair + b;
-            if (grp >= n_groups) continue;
+        for (uint32_t unit = unit0; unit < n_units; unit += unit_step) {
+            if (2u * (kPair * unit) + b >= n_groups) continue;
+            const uint32_t grp = 2u * (kPair * unit + cta_rank) + b;
             const uint32_t ch = grp * 4u + (uint32_t)c4;
-            const bool have = ch < p.n_ch;
+            const bool have = grp < n_groups && ch < p.n_ch;
             unsigned char *stp = p.state + (size_t)(have ? ch : 0u) * p.state_stride;
             uint2 *grec = reinterpret_cast<uint2 *>(stp + sizeof(ChanScalars));
             if (have) {
@@ -491,7 +664,14 @@ __global__ void __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_co
     if (MODE == 0 && lane == 0) publish_snapshot(p, gridDim.x * (blockDim.x >> 5));
     tc_fence_before();
     __syncthreads();
-    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    cluster_sync_all(); /* the peer's shared memory and barriers stay alive until both CTAs are done */
+    if (w == 0) {
+#if ANM_TC_PAIR
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+#else
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+#endif
+    }
 }
 
 } /* namespace anm */

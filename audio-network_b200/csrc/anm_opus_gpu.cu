@@ -11,7 +11,11 @@
  *       padding chains, the 120 ms and 1275-byte limits, every OPUS_INVALID_PACKET exit
  * on the byte arena in HBM (ring-addressed like the deframer's).  Packets are short (<= 4096 bytes,
  * network.cpp:24) and independent; the work is byte / integer bookkeeping and bit-exact by construction.
- * Written from the behaviour of the code above, not copied; parity against the reference's libopus compiled
+ * TRANSCRIPTION NOTICE: the framing rules are RFC 6716 section 3 and the kernel body follows opus_packet_parse_impl branch for
+ * branch (last_size, framesize, count, the padding loop, every error exit) -- a restatement of that function ((c) Xiph.Org /
+ * Skype, BSD 3-clause) onto one GPU thread per packet, not a new design; what is this repository's is the batching: the ring-
+ * addressed arena, records staged in shared memory and stored one whole record per warp instruction.
+ * Parity against the reference's libopus compiled
  * in place (oracle/_ref/libref_opus.so) on packets of its own encoder, on all 256 TOC bytes x framings, and
  * on truncated / mutated / random packets (tests/test_opus_parse.py).
  */

@@ -638,3 +638,29 @@ def test_multi_device_handle_gathers_frames_in_order():
     m.collect()
     assert anm.frames_to_list(*m.read_frames()) == want
     m.close()
+
+
+def test_gpu_transmitter_equals_cpu_transmitters_far_into_a_stream():
+    """beyond 2^31 samples (13.5 h at 44.1 kHz) and with large |start_offset| the GPU renderer must still equal the CPU renderers
+    (128-bit positions); checked against the product's CPU transmitter and the oracle's own one."""
+    import oracle_binding as ob
+
+    cfg = anm.config_preset("ref4")
+    rng = np.random.default_rng(97)
+    n_ch, n = 6, 4096
+    progs = np.full((n_ch, 64), anm.ANM_SILENCE, dtype=np.uint8)
+    lens = np.zeros(n_ch, dtype=np.int32)
+    plist = []
+    for c in range(n_ch):
+        ln = int(rng.integers(3, 64))
+        progs[c, :ln] = rng.integers(0, 4, size=ln)
+        lens[c] = ln
+        plist.append(dict(seed=1000 + c, start_offset=int(rng.choice([-(1 << 33), -12345, 0, (1 << 34) + 77])), amplitude=0.5, snr_db=9.0,
+                          ppm=float(rng.uniform(-250, 250))))
+    params = anm.tx_params_array([anm.tx_params(**k) for k in plist])
+    for first in (0, (1 << 31) - 100, (1 << 33) + 12345, (1 << 40) + 5):
+        d = _gpu_render(cfg, progs, lens, params, n, first=first).cpu().numpy()
+        for c in range(n_ch):
+            a = anm.tx_render(cfg, progs[c, : lens[c]], anm.tx_params(**plist[c]), first, n)
+            b = ob.tx_render(ob.preset("ref4"), progs[c, : lens[c]], ob.tx_params(**plist[c]), first, n)
+            assert np.array_equal(d[c], a) and np.array_equal(a, b), (first, c)

@@ -100,6 +100,20 @@ def test_deframer_matches_reference_nanopb():
             assert arena[s["audio_offset"]: s["audio_offset"] + n].tobytes() == bytes(out[:n]), (i, m.hex())
         kinds[int(s["status"])] += 1
     assert min(kinds.values()) > 10          # the corpus exercises every verdict
+    # the host scanner is the same walk (anm_pb_wire.h): it accepts exactly what the GPU deframer reports as OK, with the same span
+    L = anm.lib()
+    L.anm_pb_scan_to_receiver_audio.restype = C.c_size_t
+    L.anm_pb_scan_to_receiver_audio.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    for i, m in enumerate(msgs):
+        p, ln = C.c_void_p(), C.c_size_t()
+        buf = C.create_string_buffer(m, max(1, len(m)))
+        used = L.anm_pb_scan_to_receiver_audio(buf, len(m), C.byref(p), C.byref(ln))
+        s = spans[i]
+        if s["status"] == anm.ANM_PB_OK:
+            assert used == s["consumed"] and ln.value == s["audio_len"], (i, m.hex())
+            assert p.value - C.addressof(buf) == int(s["audio_offset"]) - int(recs[i]["offset"]), (i, m.hex())
+        else:
+            assert used == 0, (i, m.hex(), int(s["status"]))
 
 
 def test_crc_failed_frames_are_not_decoded_and_ring_addressing():

@@ -1,8 +1,10 @@
-# gen-2 tensor-core kernel iteration: dense tests, cfg4 timing, ncu summary input
+# gen-2 tensor-core kernel iteration: dense tests (both accumulator modes), cfg4 timing, ncu capture
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_dense.py tests/test_gpu_parity.py -m gpu -x -q -k "dense or wide64 or golden or tone_energies or multi" > gpurun_out/r2_pytest_tc.log 2>&1; echo "dense rc=$?" >> gpurun_out/r2_pytest_tc.log
+timeout 300 python -m pytest tests/test_dense.py tests/test_gpu_parity.py -m gpu -x -q -k "dense or wide64 or golden or tone_energies or multi" > gpurun_out/r2_pytest_tc.log 2>&1; echo "dense rc=$?" >> gpurun_out/r2_pytest_tc.log
 tail -8 gpurun_out/r2_pytest_tc.log
+ANM_TC_NO_BIAS=1 timeout 300 python -m pytest tests/test_dense.py -m gpu -x -q > gpurun_out/r2_pytest_tc_nobias.log 2>&1; echo "dense (unbiased accumulators) rc=$?" >> gpurun_out/r2_pytest_tc_nobias.log
+tail -4 gpurun_out/r2_pytest_tc_nobias.log
 timeout 600 python bench.py --preset wide64 --channels 4736 --steps 5 --warmup 2 --e2e-steps 0 --no-cpu-baseline --no-sustain --no-cfg4 > gpurun_out/r2_bench_tc.json 2> gpurun_out/r2_bench_tc.err; echo "bench rc=$?"
 python - <<'PY'
 import json
