@@ -42,8 +42,7 @@ struct Variant {
     uint32_t T, N, S;
     kern_fn fn;       /* streaming demodulator */
     kern_fn fn_trace; /* stateless tone-energy pass */
-    kern_fn fn_fold, fn_trace_fold; /* the same for foldable configurations (SPEC 3, centre-folded hop partials); dense: the
-                                     * instantiations for a basis whose columns do not all sum to zero (no biased accumulators) */
+    kern_fn fn_fold, fn_trace_fold; /* the same for foldable configurations (SPEC 3, centre-folded hop partials) */
     uint32_t warp_smem, cta_smem, state_bytes;
     bool dense; /* SPEC 3b: tensor-core contraction kernel, 4 channels per CTA */
 };
@@ -53,8 +52,7 @@ struct Variant {
      (kern_fn)k_demod<T_, N_, S_, 0, 1>, (kern_fn)k_demod<T_, N_, S_, 1, 1>, warp_smem_bytes<T_, N_, S_>(), \
      cta_smem_bytes<T_, N_, S_>(), state_bytes<T_, S_>(), false}
 #define VARIANT_TC(T_, N_, S_)                                                                    \
-    {T_, N_, S_, (kern_fn)k_demod_tc<T_, N_, S_, 0, true>, (kern_fn)k_demod_tc<T_, N_, S_, 1, true>,        \
-     (kern_fn)k_demod_tc<T_, N_, S_, 0, false>, (kern_fn)k_demod_tc<T_, N_, S_, 1, false>, 0u, tc::smem_bytes<T_, N_, S_>(), \
+    {T_, N_, S_, (kern_fn)k_demod_tc<T_, N_, S_, 0>, (kern_fn)k_demod_tc<T_, N_, S_, 1>, nullptr, nullptr, 0u, tc::smem_bytes<T_, N_, S_>(), \
      state_bytes<T_, S_>(), true}
 
 const Variant kVariants[] = {
@@ -62,11 +60,10 @@ const Variant kVariants[] = {
     VARIANT_TC(64, 256, 4), VARIANT(4, 128, 8),  VARIANT(4, 128, 2), VARIANT(4, 64, 4),
 };
 
-/* the kernel of a configuration: the folded instantiation when SPEC 3's centre folding applies; for a dense configuration
- * tc_bias (dense_zero_sum) selects the instantiation with biased accumulators */
-kern_fn variant_fn(const Variant *v, const anm_config_t *c, bool trace, bool tc_bias) {
-    const bool alt = v->dense ? !tc_bias : anm_config_foldable(c) != 0;
-    return trace ? (alt ? v->fn_trace_fold : v->fn_trace) : (alt ? v->fn_fold : v->fn);
+/* the kernel of a configuration: the folded instantiation when SPEC 3's centre folding applies */
+kern_fn variant_fn(const Variant *v, const anm_config_t *c, bool trace) {
+    const bool fold = !v->dense && anm_config_foldable(c);
+    return trace ? (fold ? v->fn_trace_fold : v->fn_trace) : (fold ? v->fn_fold : v->fn);
 }
 
 const Variant *find_variant(const anm_config_t *c) {
@@ -109,7 +106,6 @@ struct anm_demod {
     float2 *d_tw;
     std::vector<float> h_tw;
     uint8_t *d_basis; /* dense tone sets: int8 basis panels */
-    bool tc_bias;     /* dense tone sets: every basis column sums to zero -> the kernel with biased accumulators */
     /* host feeds: two staging buffers, so that the copy of chunk k+1 crosses PCIe while the kernel of chunk k runs */
     int16_t *d_stage[2];
     size_t stage_cap;
@@ -169,24 +165,6 @@ static void set_tw_sign(const anm_config_t *cfg, KParams *k) {
         const uint8_t one = (uint8_t)b;
         k->crc8_tab[b] = anm_crc8(&one, 1, 0);
     }
-}
-
-/* Does every column of the int8 basis sum to zero over the symbol period?  True for every tone bin that is not a multiple of N
- * (the rounding of SPEC 3b is odd-symmetric, so opposite phases cancel exactly).  Then sum(lo * b) = sum((lo - 128) * b) is
- * bounded by 128 * 127 * N < 2^22 like the high plane, and k_demod_tc may keep its accumulators biased by 0x4B400000: the
- * int32 in TMEM, read as fp32, IS 12582912 + sum, and the epilogue needs no integer -> float conversion. */
-static bool dense_zero_sum(const anm_config_t *cfg) {
-    const uint32_t N = cfg->sym_len, T = cfg->n_tones;
-    if ((uint64_t)N * 128u * 127u >= (1u << 22)) return false;
-    if (getenv("ANM_TC_NO_BIAS")) return false; /* tests: the other instantiation on the same configuration */
-    std::vector<int8_t> q7((size_t)N * T * 2);
-    if (anm_basis_q7(cfg, q7.data()) != ANM_OK) return false;
-    for (uint32_t c = 0; c < 2 * T; ++c) {
-        int32_t sum = 0;
-        for (uint32_t m = 0; m < N; ++m) sum += q7[(size_t)m * T * 2 + c];
-        if (sum != 0) return false;
-    }
-    return true;
 }
 
 /* int8 basis of a dense configuration in the panel order the MMA descriptors of k_demod_tc address:
@@ -261,8 +239,7 @@ static int create_impl(anm_demod *h, const anm_config_t *cfg, const Variant *var
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     choose_launch(h);
-    h->tc_bias = var->dense && dense_zero_sum(cfg);
-    CK(cudaFuncSetAttribute((const void *)variant_fn(var, cfg, false, h->tc_bias), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CK(cudaFuncSetAttribute((const void *)variant_fn(var, cfg, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     const uint32_t b = anm_bits_per_sym(cfg);
     const uint32_t hdr_syms = (24 + b - 1) / b;
     h->max_frame_syms = hdr_syms + ((cfg->max_payload + 2) * 8 + b - 1) / b;
@@ -452,7 +429,7 @@ static int launch(anm_demod *h, KParams &k, cudaStream_t s, bool timed) {
     k.seq1 = (uint32_t)(seq + 1);
     if (ev) CK(cudaEventRecord(ev->a, s));
     void *args[] = {(void *)&k};
-    CK(cudaLaunchKernel((const void *)variant_fn(h->var, &h->cfg, false, h->tc_bias), dim3(h->grid), dim3(h->warps_per_cta * 32), args, h->smem_bytes, s));
+    CK(cudaLaunchKernel((const void *)variant_fn(h->var, &h->cfg, false), dim3(h->grid), dim3(h->warps_per_cta * 32), args, h->smem_bytes, s));
     if (ev) CK(cudaEventRecord(ev->b, s));
     /* the kernel's last warp writes the queue counters as they stand after this launch into snap[slot] (pinned host
      * memory); the event tells the host when that has happened.  A later drain can therefore stop exactly behind this
@@ -806,10 +783,9 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
             grid = std::min<uint32_t>((n_ch + W - 1) / W, (uint32_t)sms * 4u);
             smem = (size_t)W * var->warp_smem + var->cta_smem;
         }
-        const bool tc_bias = var->dense && dense_zero_sum(cfg);
-        cudaFuncSetAttribute((const void *)variant_fn(var, cfg, true, tc_bias), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        cudaFuncSetAttribute((const void *)variant_fn(var, cfg, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
         void *args[] = {(void *)&k};
-        cudaError_t e = rc == ANM_OK ? cudaLaunchKernel((const void *)variant_fn(var, cfg, true, tc_bias), dim3(grid), dim3(W * 32), args, smem, s) : cudaSuccess;
+        cudaError_t e = rc == ANM_OK ? cudaLaunchKernel((const void *)variant_fn(var, cfg, true), dim3(grid), dim3(W * 32), args, smem, s) : cudaSuccess;
         if (rc == ANM_OK && e == cudaSuccess) {
             const cudaError_t es = cudaStreamSynchronize(s);
             if (es != cudaSuccess) { anm_set_error("tone pass: %s", cudaGetErrorString(es)); rc = ANM_ERR_CUDA; }

@@ -196,6 +196,14 @@ struct Log2 { static constexpr int v = 1 + Log2<T / 2>::v; };
 template <>
 struct Log2<1> { static constexpr int v = 0; };
 
+/* The hop-record ring of a channel in shared memory: HopRec[64 * S], addressed by hop index & (64 * S - 1), laid out PHASE-major --
+ * [hop % S][symbol period % 64] -- because every access of the state machine is one hop phase over the 32 symbol periods of the lanes:
+ * consecutive lanes then read consecutive 8-byte records (2 wavefronts) instead of records S * 8 bytes apart (8 wavefronts for S = 4). */
+template <int S>
+__device__ __forceinline__ uint32_t ring_off(uint32_t idx) { /* idx < 64 * S; byte offset of the record */
+    return (((idx & (uint32_t)(S - 1)) << 6) | (idx >> Log2<S>::v)) << 3;
+}
+
 /* Per-channel state in HBM: ChanScalars | HopRec[32 slots][S] | tree carry */
 template <int T, int S>
 __host__ __device__ constexpr uint32_t state_carry_offset() { return (uint32_t)sizeof(ChanScalars) + 32u * S * 8u; }
@@ -237,7 +245,7 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
     /* hop record by hop index r relative to the step start, r in [-32S, 32S): .x = emax bits, .y = d */
     auto REC = [&](int r) -> uint2 {
         uint2 v;
-        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + (((hic + (uint32_t)r) & RM) << 3)) : "memory");
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + ring_off<S>((hic + (uint32_t)r) & RM)) : "memory");
         return v;
     };
     /* warp-uniform working set: three broadcast LDS.128; everything else of ChanScalars is read / written
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             const uint2 rv = grec[lane * S + i];
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + (uint32_t)((32 + lane) * S + i) * 8u), "r"(rv.x), "r"(rv.y) : "memory");
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>((uint32_t)((32 + lane) * S + i))), "r"(rv.x), "r"(rv.y) : "memory");
         }
         for (int i = lane; i < (S - 1) * T; i += 32) carry[i] = gcarry[i];
         if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = reinterpret_cast<const uint32_t *>(stp)[lane];
@@ -971,17 +979,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
             /* publish this step's hop records in the ring (slots of lanes past a ragged end keep their
              * older content: they are never addressed) */
             if (active) {
-                const uint32_t a0 = sr + (((hic + (uint32_t)(lane * S)) & RM) << 3); /* S consecutive ring entries */
-                if (S % 2 == 0) {
+                const uint32_t i0 = (hic + (uint32_t)(lane * S)) & RM; /* a multiple of S: record i is hop phase i of this lane's symbol period */
 #pragma unroll
-                    for (int i = 0; i < S; i += 2)
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]),
-                                     "r"(__float_as_uint(ec[(i + 1) % S])), "r"(dc[(i + 1) % S]) : "memory");
-                } else {
-#pragma unroll
-                    for (int i = 0; i < S; ++i)
-                        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
-                }
+                for (int i = 0; i < S; ++i)
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>(i0 + (uint32_t)i)), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
             }
             __syncwarp();
             if (MODE == 1) {
@@ -1004,7 +1005,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
         for (int i = 0; i < S; ++i) {
             const uint32_t idx = ((p.n_syms - 32u + (uint32_t)lane) * S + (uint32_t)i) & RM;
             uint2 rv;
-            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + idx * 8u) : "memory");
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + ring_off<S>(idx)) : "memory");
             grec[lane * S + i] = rv;
         }
         for (int i = lane; i < (S - 1) * T; i += 32) gcarry[i] = carry[i];

@@ -54,12 +54,22 @@ constexpr uint32_t kTmemCols = 2u * kAccCols;      /* two sets = all 512 TMEM co
 /* Warp roles, lowest priority first: the SM's warp schedulers prefer the highest warp id among the eligible warps, and the epilogue is the
  * critical path -- polling loops of the other roles must not win issue slots against it. */
 constexpr int kSmWarp0 = 0;                        /* warps 0..7: group slot = warp >> 2, channel slot = warp & 3 */
-constexpr int kLoaderWarp0 = 8;                    /* warps 8..15: channel slot = (warp - 8) & 3, which 16 of the job's 32 symbol periods = (warp - 8) >> 2 */
-constexpr int kLoaderWarps = 8;
-constexpr int kEpiWarp0 = 16;                      /* warps 16..23: TMEM lane quadrant = warp & 3, tone half = (warp - 16) >> 2 */
-constexpr int kEpiWarps = 8;
-constexpr int kIssuerWarp = 24;
-constexpr int kWarps = 25;                         /* 800 threads x 80 registers = 64,000 of the SM's 65,536 */
+#ifndef ANM_TC_LOADERS
+#define ANM_TC_LOADERS 4
+#endif
+#ifndef ANM_TC_EPI_PARTS
+#define ANM_TC_EPI_PARTS 2
+#endif
+constexpr int kLoaderWarp0 = 8;                    /* channel slot = (warp - 8) & 3; with 8 loader warps (warp - 8) >> 2 says which 16 of the job's 32 symbol periods */
+constexpr int kLoaderWarps = ANM_TC_LOADERS;
+constexpr int kLoaderRows = 128 / kLoaderWarps;    /* symbol periods of one channel per loader warp and job */
+constexpr int kEpiParts = ANM_TC_EPI_PARTS;        /* epilogue warps per TMEM lane quadrant (= per warp scheduler): each a range of the tones */
+constexpr int kEpiWarp0 = kLoaderWarp0 + kLoaderWarps; /* TMEM lane quadrant = warp & 3, tone range = (warp - kEpiWarp0) >> 2 */
+constexpr int kEpiWarps = 4 * kEpiParts;
+constexpr int kIssuerWarp = kEpiWarp0 + kEpiWarps;
+constexpr int kWarps = kIssuerWarp + 1;            /* 25: 72 registers per thread (one scheduler holds 7 warps) */
+static_assert(kEpiParts == 2 || kEpiParts == 3, "tone ranges");
+static_assert(kLoaderWarps == 4 || kLoaderWarps == 8, "one or two loader warps per channel slot");                         /* 800 threads x 80 registers = 64,000 of the SM's 65,536 */
 
 template <int N, int S>
 __host__ __device__ constexpr uint32_t a_bytes() { return 2u * S * (uint32_t)(N / S / 16) * kPanel; } /* one buffer */
@@ -69,11 +79,16 @@ template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t b_bytes() { return (uint32_t)S * (uint32_t)(N / S / 16) * kBPanel; }
 template <int T, int S>
 __host__ __device__ constexpr uint32_t warp_bytes() { return 64u * S * 8u + 128u; } /* per channel: HopRec ring | scalars */
+/* candidates [job parity][tone range][hop][channel slot: 36 entries, 32 used][symbol period] x {e, d}: an epilogue warp writes rows
+ * 32 * quadrant + lane (8 symbol periods x 4 channels), a state-machine warp reads one channel's 32 symbol periods; the 36 keeps both
+ * free of bank conflicts (the channels' 8-entry pieces of a store land 32 bytes apart modulo 128) */
+constexpr uint32_t kCandPlane = 4u * 36u * 8u;
+__host__ __device__ constexpr uint32_t cand_pos(uint32_t row) { return ((row & 3u) * 36u + (row >> 2)) * 8u; }
 template <int S>
-__host__ __device__ constexpr uint32_t cand_bytes() { return 2u * 2u * (uint32_t)S * kRows * 8u; } /* [job parity][tone half][hop][row] x {e, d} */
+__host__ __device__ constexpr uint32_t cand_bytes() { return 2u * (uint32_t)kEpiParts * (uint32_t)S * kCandPlane; }
 template <int T, int N, int S>
 __host__ __device__ constexpr uint32_t smem_bytes() {
-    return 2u * a_bytes<N, S>() + b_bytes<T, N, S>() + 8u * warp_bytes<T, S>() + cand_bytes<S>() + 192u; /* tail: mbarriers, TMEM address, bias words */
+    return 2u * a_bytes<N, S>() + b_bytes<T, N, S>() + 8u * warp_bytes<T, S>() + cand_bytes<S>() + 128u; /* tail: mbarriers, TMEM address */
 }
 
 /* shared-memory matrix descriptor: K-major, no swizzle; LBO = stride between the two 16-byte K chunks
@@ -155,17 +170,8 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
-/* the same word to 8 consecutive columns of this warp's 32 lanes */
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void load_bias8(uint32_t saddr, uint32_t (&v)[8]) {
-    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(saddr));
-    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(saddr + 16u));
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, int32_t (&v)[8]) { tmem_ld8(taddr, v); }
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, int32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -210,7 +216,6 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         __nanosleep(NS);
     }
 }
-constexpr uint32_t kAccBias = 0x4B400000u; /* 1.5 * 2^23 as fp32: kAccBias + s reads as 12582912.0f + s for |s| < 2^22 */
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -236,10 +241,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 } /* namespace tc */
 
-/* MODE 0: streaming demodulator; MODE 1: stateless tone-energy pass (trace outputs).
- * BIAS: the accumulators start every window at kAccBias instead of 0 (valid when every basis column sums to zero, see
- * dense_zero_sum in anm_cuda.cu): read as fp32 they are 12582912 + sum exactly, and 256 * hi + lo needs no I2FP. */
-template <int T, int N, int S, int MODE, bool BIAS>
+/* MODE 0: streaming demodulator; MODE 1: stateless tone-energy pass (trace outputs). */
+template <int T, int N, int S, int MODE>
 __global__ void
 #if ANM_TC_PAIR
 __cluster_dims__(2, 1, 1)
@@ -250,15 +253,21 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
     constexpr int KC = H / 16;          /* 16-byte K chunks per hop */
     constexpr int KS = H / 32;          /* MMAs (K = 32) per hop */
     constexpr int CPS = N / 8;          /* 16-byte PCM chunks per symbol period */
-    constexpr int TH = T / 2;           /* tones per epilogue warp */
-    constexpr int TN = 4;               /* tones per tcgen05.ld batch (8 columns per byte plane) = one group of the running argmax */
+    /* Tone ranges of the kEpiParts epilogue warps of a lane quadrant, [kTB[part], kTB[part + 1]).  Three warps: the schedulers' issue slots
+     * were a third idle with two -- each warp alone is bound by its dependency chains -- and the first (lowest warp id = lowest priority
+     * of the three) gets the short range. */
+    constexpr int kTB1 = kEpiParts == 3 ? 16 : T / 2, kTB2 = kEpiParts == 3 ? 40 : T;
+#ifndef ANM_TC_TN
+#define ANM_TC_TN 8
+#endif
+    constexpr int TN = ANM_TC_TN;       /* tones per tcgen05.ld batch (2 * TN columns per byte plane); the running argmax goes by groups of four */
     constexpr uint32_t RM = 64u * S - 1u;
     constexpr uint32_t CUR = kCarryRows * 16u; /* byte offset of the current rows inside a panel */
     static_assert(T == 64 && 2 * T == (int)kNcol, "the dense kernel contracts all 64 tones (128 columns) per MMA");
     static_assert(S == 4 && (H % 32) == 0 && CPS == 32, "unsupported dense geometry");
     static_assert(2 * S * KC == 32, "one (plane, hop, K chunk) panel per lane");
     static_assert(2u * S * KC * 16u <= (uint32_t)(S - 1) * T * 8u, "carry rows must fit the state's carry area");
-    static_assert((TH % TN) == 0, "tone batches");
+    static_assert((kTB1 % (2 * TN)) == 0 && (kTB2 % (2 * TN)) == 0 && (T % (2 * TN)) == 0, "two tone batches per trip of the epilogue loop");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -297,7 +306,6 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
             dst[i] = __ldg(&gsrc[(i / CPP) * kNcol + cta_rank * CPP + (i % CPP)]);
     }
     if (threadIdx.x == 0) {
-        for (uint32_t j = 0; j < 8; ++j) reinterpret_cast<volatile uint32_t *>(tail + 128)[j] = kAccBias;
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(bar_a_full + 8u * b, (uint32_t)kLoaderWarps * kPair); /* one arrival per loader warp of the pair (the leader's barrier is the one in use) */
             mbar_init(bar_a_empty + 8u * b, 1u);                    /* tcgen05.commit */
@@ -323,24 +331,6 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
     cluster_sync_all(); /* barriers initialised and basis in place in both CTAs before anything crosses over */
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (BIAS) {
-        /* both accumulator sets start biased; afterwards every epilogue warp re-biases the columns it has read */
-        if (w >= kEpiWarp0 && w < kEpiWarp0 + kEpiWarps) {
-            uint32_t bias8[8];
-            load_bias8(bars + 128u, bias8);
-            const uint32_t t = tmem_base + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(((w - kEpiWarp0) >> 2) * 2 * TH);
-#pragma unroll 1
-            for (uint32_t c = 0; c < 2u * kAccCols; c += kNcol)
-#pragma unroll
-                for (uint32_t cc = 0; cc < (uint32_t)(2 * TH); cc += 8u) tmem_st8(t + c + cc, bias8);
-            tmem_st_wait();
-            tc_fence_before();
-        }
-        __syncthreads();
-        cluster_sync_all(); /* the leader's MMAs write both CTAs' accumulators */
-        tc_fence_after();
-    }
-
     if (w >= kLoaderWarp0 && w < kLoaderWarp0 + kLoaderWarps) {
         /* =================== loader: PCM of one job of this warp's channel -> byte planes in the A panels =================== */
         const int c4 = (w - kLoaderWarp0) & 3, rh = (w - kLoaderWarp0) >> 2; /* two warps per channel: symbol periods [16 * rh, 16 * rh + 16) of the job */
@@ -381,7 +371,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                     }
                     constexpr int BATCH = 8; /* loads in flight before the first split (21 warps leave 80 registers per thread) */
 #pragma unroll 1
-                    for (int r0 = 16 * rh; r0 < 16 * rh + 16; r0 += BATCH) {
+                    for (int r0 = kLoaderRows * rh; r0 < kLoaderRows * rh + kLoaderRows; r0 += BATCH) {
                         uint4 v[BATCH];
                         if (nv == 32) {
 #pragma unroll
@@ -391,12 +381,12 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
 #pragma unroll
                             for (int j = 0; j < BATCH; ++j) v[j] = __ldg(reinterpret_cast<const uint4 *>(g + (size_t)min(r0 + j, nv - 1) * 512u));
                         }
-                        if (r0 == 16 * rh && step + 1 < n_steps) {
+                        if (r0 == kLoaderRows * rh && step + 1 < n_steps) {
                             /* next job of this channel: 32 * N * 2 bytes = N / 2 lines of 128 bytes, N / 64 per lane, pulled into L2 */
                             const char *nx = reinterpret_cast<const char *>(p.pcm + (size_t)ch * p.ch_stride) + (size_t)(step + 1) * (32u * N * 2u) + (size_t)lane * 128u +
-                                             (size_t)rh * (N / 128) * 4096u; /* each of the channel's two warps its half */
+                                             (size_t)rh * (N * kLoaderRows / 2048) * 4096u; /* each of the channel's warps its share */
 #pragma unroll
-                            for (int j = 0; j < N / 128; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * 4096u));
+                            for (int j = 0; j < N * kLoaderRows / 2048; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)j * 4096u));
                         }
 #pragma unroll
                         for (int j = 0; j < BATCH; ++j) {
@@ -450,8 +440,10 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                                      * previous symbol period of the same channel: four rows (64 bytes) up */
                                     const uint32_t aoff = (uint32_t)((pl * S + j) * KC + 2 * ks) * kPanel + ((j <= i) ? CUR : 0u);
                                     const uint32_t boff = (uint32_t)(j * KC + 2 * ks) * kBPanel;
+#ifndef ANM_TC_DEBUG_SKIP_MMA /* timing experiment only: results are garbage */
                                     mma_i8(d0 + (uint32_t)pl * kNcol, a0 + (uint64_t)(aoff >> 4), b0 + (uint64_t)(boff >> 4), pl == 0 ? id_hi : id_lo,
-                                           (BIAS || j > 0 || ks > 0) ? 1u : 0u);
+                                           (j > 0 || ks > 0) ? 1u : 0u);
+#endif
                                 }
                         mma_commit(bar_acc_full + 8u * set);
                         if (i == S - 1) mma_commit(bar_a_empty + 8u * b); /* every contraction that reads this A buffer is complete */
@@ -464,11 +456,11 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
         /* =================== epilogue: this warp's 32 tones of its TMEM lane quadrant =================== */
         const int c4 = w & 3, hf = (w - kEpiWarp0) >> 2;
         const int esp = 8 * c4 + (lane >> 2), ec4 = lane & 3; /* TMEM lane 32 * c4 + lane = row 4 * esp + ec4 */
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * c4) << 16) + (uint32_t)(hf * 2 * TH);
+        const int tlo = hf == 0 ? 0 : hf == 1 ? kTB1 : kTB2, thi = hf == 0 ? kTB1 : hf == 1 ? kTB2 : T; /* this warp's tones */
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * c4) << 16) + (uint32_t)(2 * tlo);
+        const int n_tb = (thi - tlo) / TN; /* tone batches of this warp per window */
         const uint32_t row = (uint32_t)(32 * c4 + lane);
         uint32_t use[2] = {0u, 0u}, rnd = 0;
-        uint32_t bias8[8]; /* kAccBias eight times, from shared memory: as immediates ptxas re-creates them (8 moves) before every tcgen05.st */
-        if (BIAS) load_bias8(bars + 128u, bias8);
         for (uint32_t unit = unit0; unit < n_units; unit += unit_step)
             for (uint32_t step = 0; step < n_steps; ++step)
 #pragma unroll
@@ -479,7 +471,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                 const uint32_t k = use[b]++;
                 /* candidates of this tone half: [job parity][half][hop][row] x {e, d} */
                 mbar_wait(bar_cand_empty + 8u * b, (k & 1u) ^ 1u); /* the state machines have read what job - 2 left here */
-                const uint32_t ca = sCand + ((b * 2u + (uint32_t)hf) * (uint32_t)S) * (kRows * 8u) + row * 8u;
+                const uint32_t ca = sCand + ((b * (uint32_t)kEpiParts + (uint32_t)hf) * (uint32_t)S) * kCandPlane + cand_pos(row);
 #pragma unroll 1 /* rolled: see the issuer */
                 for (int i = 0; i < S; ++i, ++rnd) {
                     const uint32_t set = rnd & 1u, u = rnd >> 1;
@@ -489,30 +481,28 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                     float em = -1.0f, w0 = 0.0f, w1 = 0.0f, w2 = 0.0f; /* running maximum; the first three energies of the group of four it came from */
                     uint32_t dq = 0u;                                   /* first tone of that group */
                     int32_t vh[2][2 * TN], vl[2][2 * TN];
-                    tmem_ld8(t0, vh[0]);
-                    tmem_ld8(t0 + kNcol, vl[0]);
+                    tmem_ldn(t0, vh[0]);
+                    tmem_ldn(t0 + kNcol, vl[0]);
                     /* two batches per trip (ping-pong registers): a short loop body -- the roles share the instruction cache */
 #pragma unroll 1
-                    for (int tb2 = 0; tb2 < TH / TN; tb2 += 2) {
+#ifdef ANM_TC_DEBUG_SKIP_EPI /* timing experiment only: results are garbage */
+                    for (int tb2 = 0; tb2 < 0; tb2 += 2) {
+#else
+                    for (int tb2 = 0; tb2 < n_tb; tb2 += 2) {
+#endif
 #pragma unroll
                         for (int h2 = 0; h2 < 2; ++h2) {
                             const int tb = tb2 + h2;
                             tmem_ld_wait();
                             { /* the next batch travels while this one is evaluated; behind the last batch the same one again, rather than a
                                * branch: the trip stays one basic block and ptxas overlaps the two batches' dependency chains */
-                                const uint32_t nb = (uint32_t)(2 * TN) * (uint32_t)min(tb + 1, TH / TN - 1);
-                                tmem_ld8(t0 + nb, vh[h2 ^ 1]);
-                                tmem_ld8(t0 + kNcol + nb, vl[h2 ^ 1]);
-                            }
-                            if (BIAS) { /* this batch is in registers: its columns go back to the bias for the next window of the set */
-#pragma unroll
-                                for (uint32_t pl = 0; pl < 2; ++pl)
-#pragma unroll
-                                    for (uint32_t cc = 0; cc < (uint32_t)(2 * TN); cc += 8u) tmem_st8(t0 + pl * kNcol + (uint32_t)(2 * TN * tb) + cc, bias8);
+                                const uint32_t nb = (uint32_t)(2 * TN) * (uint32_t)min(tb + 1, n_tb - 1);
+                                tmem_ldn(t0 + nb, vh[h2 ^ 1]);
+                                tmem_ldn(t0 + kNcol + nb, vl[h2 ^ 1]);
                             }
                             const int32_t(&xh)[2 * TN] = vh[h2];
                             const int32_t(&xl)[2 * TN] = vl[h2];
-                            const int tone0 = hf * TH + tb * TN;
+                            const int tone0 = tlo + tb * TN;
 #pragma unroll
                             for (int tq = 0; tq < TN; tq += 4) {
                                 float E[4];
@@ -522,19 +512,8 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                                      * component sees exactly fma(fI, fI, fQ * fQ) of SPEC 3b on fI = RN(256 * hi + lo) */
                                     const int c = 2 * tq + 4 * pr;
                                     float2 fi, fq;
-                                    if (BIAS) {
-                                        /* as fp32 the accumulators are 12582912 + hi and 12582912 + lo: 256 * hi by one exact fma, lo by one exact
-                                         * subtraction, their sum rounds once -- the same value as I2FP.RN(256 * hi + lo) */
-                                        const float2 k256 = make_float2(256.0f, 256.0f), kh = make_float2(-256.0f * 12582912.0f, -256.0f * 12582912.0f),
-                                                     kl = make_float2(-12582912.0f, -12582912.0f);
-                                        fi = fadd2(ffma2vv(make_float2(__int_as_float(xh[c]), __int_as_float(xh[c + 1])), k256, kh),
-                                                   fadd2(make_float2(__int_as_float(xl[c]), __int_as_float(xl[c + 1])), kl));
-                                        fq = fadd2(ffma2vv(make_float2(__int_as_float(xh[c + 2]), __int_as_float(xh[c + 3])), k256, kh),
-                                                   fadd2(make_float2(__int_as_float(xl[c + 2]), __int_as_float(xl[c + 3])), kl));
-                                    } else {
-                                        fi = make_float2((float)(xh[c] * 256 + xl[c]), (float)(xh[c + 1] * 256 + xl[c + 1]));
-                                        fq = make_float2((float)(xh[c + 2] * 256 + xl[c + 2]), (float)(xh[c + 3] * 256 + xl[c + 3]));
-                                    }
+                                    fi = make_float2((float)(xh[c] * 256 + xl[c]), (float)(xh[c + 1] * 256 + xl[c + 1]));
+                                    fq = make_float2((float)(xh[c + 2] * 256 + xl[c + 2]), (float)(xh[c + 3] * 256 + xl[c + 3]));
                                     const float2 e2 = ffma2vv(fi, fi, fmul2(fq, fq));
                                     E[2 * pr] = e2.x;
                                     E[2 * pr + 1] = e2.y;
@@ -561,12 +540,11 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                     }
                     const uint32_t dm = dq + (w0 == em ? 0u : w1 == em ? 1u : w2 == em ? 2u : 3u);
                     tmem_ld_wait(); /* the repeated load of the last batch */
-                    if (BIAS) tmem_st_wait();
-                    /* this warp's TMEM reads of the set are complete (tcgen05.wait::ld) and its columns re-biased (wait::st): hand it back */
+                    /* this warp's TMEM reads of the set are complete (tcgen05.wait::ld): hand it back */
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader<false>(bar_acc_empty + 8u * set);
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(ca + (uint32_t)i * (kRows * 8u)), "r"(__float_as_uint(em)), "r"(dm) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(ca + (uint32_t)i * kCandPlane), "r"(__float_as_uint(em)), "r"(dm) : "memory");
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_cand_full + 8u * b);
@@ -592,7 +570,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
                     const uint2 rv = grec[lane * S + i];
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + (uint32_t)((32 + lane) * S + i) * 8u), "r"(rv.x), "r"(rv.y) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>((uint32_t)((32 + lane) * S + i))), "r"(rv.x), "r"(rv.y) : "memory");
                 }
                 if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = reinterpret_cast<const uint32_t *>(stp)[lane];
             }
@@ -605,16 +583,22 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                 uint32_t dc[S];
                 float ec[S];
                 {
-                    const uint32_t c0 = sCand + ((b * 2u) * (uint32_t)S) * (kRows * 8u) + row * 8u;
+                    const uint32_t c0 = sCand + ((b * (uint32_t)kEpiParts) * (uint32_t)S) * kCandPlane + cand_pos(row);
 #pragma unroll
                     for (int i = 0; i < S; ++i) {
-                        uint32_t e0, d0, f0, g0;
-                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e0), "=r"(d0) : "r"(c0 + (uint32_t)i * (kRows * 8u)) : "memory");
-                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(f0), "=r"(g0) : "r"(c0 + (uint32_t)(S + i) * (kRows * 8u)) : "memory");
-                        /* lowest tone index wins a tie (SPEC 3): the second half holds the higher tones */
-                        const bool t0 = __uint_as_float(f0) > __uint_as_float(e0);
-                        ec[i] = __uint_as_float(t0 ? f0 : e0);
-                        dc[i] = t0 ? g0 : d0;
+                        uint32_t e0, d0;
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(e0), "=r"(d0) : "r"(c0 + (uint32_t)i * kCandPlane) : "memory");
+#pragma unroll
+                        for (int part = 1; part < kEpiParts; ++part) {
+                            uint32_t f0, g0;
+                            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(f0), "=r"(g0) : "r"(c0 + (uint32_t)(part * S + i) * kCandPlane) : "memory");
+                            /* lowest tone index wins a tie (SPEC 3): later ranges hold the higher tones */
+                            const bool t0 = __uint_as_float(f0) > __uint_as_float(e0);
+                            e0 = t0 ? f0 : e0;
+                            d0 = t0 ? g0 : d0;
+                        }
+                        ec[i] = __uint_as_float(e0);
+                        dc[i] = d0;
                     }
                 }
                 __syncwarp();
@@ -625,11 +609,10 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                 }
                 if (have) {
                     if (active) {
-                        const uint32_t a1 = sr + (((hic + (uint32_t)(lane * S)) & RM) << 3);
+                        const uint32_t i0 = (hic + (uint32_t)(lane * S)) & RM;
 #pragma unroll
-                        for (int i = 0; i < S; i += 2)
-                            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a1 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]),
-                                         "r"(__float_as_uint(ec[i + 1])), "r"(dc[i + 1]) : "memory");
+                        for (int i = 0; i < S; ++i)
+                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>(i0 + (uint32_t)i)), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
                         if (MODE == 1) {
                             if (p.trD) {
 #pragma unroll
@@ -652,7 +635,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                 for (int i = 0; i < S; ++i) {
                     const uint32_t idx = ((p.n_syms - 32u + (uint32_t)lane) * S + (uint32_t)i) & RM;
                     uint2 rv;
-                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + idx * 8u) : "memory");
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + ring_off<S>(idx)) : "memory");
                     grec[lane * S + i] = rv;
                 }
                 if (MODE == 0) reinterpret_cast<uint32_t *>(stp)[lane] = reinterpret_cast<const uint32_t *>(ssc)[lane];
