@@ -178,7 +178,7 @@ EXPORTS = [
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
     "anm_pacer_init", "anm_pacer_level", "anm_pacer_try_put", "anm_pacer_wait_for_capacity",
     "anm_opus_parse_device", "anm_opus_parse_host",
-    "anm_celt_tables_build", "anm_celt_ctx_create", "anm_celt_ctx_destroy", "anm_celt_entropy_device", "anm_celt_entropy_host",
+    "anm_celt_tables_build", "anm_celt_ctx_create", "anm_celt_ctx_destroy", "anm_celt_entropy_device", "anm_celt_entropy_host", "anm_celt_spectrum_device", "anm_celt_spectrum_host",
 ]
 
 _lib = None
@@ -258,6 +258,8 @@ def lib():
         "anm_celt_ctx_destroy": (None, [vp]),
         "anm_celt_entropy_device": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp]),
         "anm_celt_entropy_host": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp]),
+        "anm_celt_spectrum_device": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp]),
+        "anm_celt_spectrum_host": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp, vp, C.c_uint32, vp]),
         "anm_pb_encode_broadcast": (C.c_size_t, [C.POINTER(PbBroadcast), vp, C.c_size_t]),
         "anm_pb_encode_to_transmitter": (C.c_size_t, [C.POINTER(PbToTransmitter), vp, C.c_size_t]),
         "anm_pb_decode_broadcast": (C.c_int, [vp, C.c_size_t, C.POINTER(PbBroadcast), C.POINTER(C.c_size_t)]),
@@ -340,12 +342,15 @@ def opus_parse(spans, payload_bytes, fs=48000):
 
 
 CELT_BANDS = 21
-CELT_JOB_DTYPE = np.dtype([("offset", "<u4"), ("len", "<u4"), ("channels", "u1"), ("lm", "u1"), ("end_band", "u1"), ("pad", "u1")])   # anm_celt_job_t
+CELT_JOB_DTYPE = np.dtype([("offset", "<u4"), ("len", "<u4"), ("channels", "u1"), ("lm", "u1"), ("end_band", "u1"), ("flags", "u1")])   # anm_celt_job_t
 CELT_FRAME_DTYPE = np.dtype([("final_range", "<u4"), ("tell_bits", "<i4"), ("flags", "<u4"), ("pf_pitch", "<u2"), ("pf_gain_q", "u1"), ("pf_tapset", "u1"),
                              ("spread", "u1"), ("alloc_trim", "u1"), ("intensity", "u1"), ("coded_bands", "u1"), ("lm", "u1"), ("channels", "u1"), ("pad", "u1", (2,)),
                              ("pvq_codewords", "<u4"), ("pvq_pulses", "<u4"), ("pvq_index_xor", "<u4"), ("tf_res", "i1", (CELT_BANDS,)),
                              ("fine_quant", "u1", (CELT_BANDS,)), ("pulses", "<i2", (CELT_BANDS,)), ("band_e", "<i2", (2 * CELT_BANDS,))])    # anm_celt_frame_t
-CELT_STREAM_DTYPE = np.dtype([("old_e", "<i2", (2 * CELT_BANDS,))])                                                                              # anm_celt_stream_t
+CELT_STREAM_DTYPE = np.dtype([("old_e", "<i2", (2 * CELT_BANDS,)), ("log_e1", "<i2", (2 * CELT_BANDS,)), ("log_e2", "<i2", (2 * CELT_BANDS,)),
+                              ("rng", "<u4"), ("flags", "<u4")])                                                                                  # anm_celt_stream_t
+CELT_JOB_DISABLE_INV = 1
+CELT_X_STRIDE = 1920            # int16 coefficients per frame in celt_spectrum()'s output: [channels][120 << lm], at most 2 x 960
 
 
 def celt_entropy(jobs, stream_begin, payload_bytes, streams=None):
@@ -360,6 +365,22 @@ def celt_entropy(jobs, stream_begin, payload_bytes, streams=None):
     _check(lib().anm_celt_entropy_host(_ptr(jobs) if len(jobs) else None, _ptr(sb), n_streams, _ptr(by) if len(by) else None, len(by), _ptr(st),
                                        _ptr(out) if len(jobs) else None))
     return out, st
+
+
+def celt_spectrum(jobs, stream_begin, payload_bytes, streams=None):
+    """Batched CELT decode up to the normalised spectrum (stages 1 + 2, include/anmodem_opus.h anm_celt_spectrum_*): as celt_entropy(), plus
+    x[n_jobs, CELT_X_STRIDE] int16 (Q14; frame j's channel c at x[j, c * (120 << lm):][:120 << lm]) and the collapse masks [n_jobs, 42]."""
+    jobs = np.ascontiguousarray(jobs, dtype=CELT_JOB_DTYPE)
+    sb = np.ascontiguousarray(stream_begin, dtype=np.uint32)
+    by = np.ascontiguousarray(payload_bytes, dtype=np.uint8)
+    n_streams = len(sb) - 1
+    st = np.zeros(n_streams, dtype=CELT_STREAM_DTYPE) if streams is None else np.ascontiguousarray(streams, dtype=CELT_STREAM_DTYPE).copy()
+    out = np.zeros(len(jobs), dtype=CELT_FRAME_DTYPE)
+    x = np.zeros((max(len(jobs), 1), CELT_X_STRIDE), dtype=np.int16)
+    cm = np.zeros((max(len(jobs), 1), 2 * CELT_BANDS), dtype=np.uint8)
+    _check(lib().anm_celt_spectrum_host(_ptr(jobs) if len(jobs) else None, _ptr(sb), n_streams, _ptr(by) if len(by) else None, len(by), _ptr(st),
+                                        _ptr(out) if len(jobs) else None, _ptr(x), CELT_X_STRIDE, _ptr(cm)))
+    return out, st, x[:len(jobs)], cm[:len(jobs)]
 
 
 def pb_encode_broadcast(m):

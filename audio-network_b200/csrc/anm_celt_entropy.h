@@ -251,13 +251,25 @@ ANM_CE_FN uint32_t ce_pvq_u(const anm_celt_tables_t *t, int n, int k) {
     return t->pvq_u[r * ANM_CELT_PVQ_COLS + c];
 }
 
-/* ---------------------------------------------------------------- band splitting: bits only */
+#include "anm_celt_vec.h"
+
+/* ---------------------------------------------------------------- band splitting (stage 1: bits only; stage 2: with the spectrum) */
+/* per-frame working storage of stage 2 (NULL in a ce_band_ctx_t = stage 1: no spectrum arithmetic at all) */
+typedef struct ce_spec {
+    int16_t norm[2 * 624]; /* folding source: the decoded bands so far, scaled by sqrt(N) (two channels for dual stereo) */
+    int16_t tmp[176];      /* Hadamard reordering scratch */
+    int iy[176];           /* pulse vector of one partition */
+    uint32_t seed;         /* noise generator (CELTDecoder.rng) */
+    int spread, disable_inv;
+} ce_spec_t;
+
 typedef struct ce_band_ctx {
     const anm_celt_tables_t *t;
     anm_ec_t *ec;
     int i, intensity, tf_change;
     int32_t remaining_bits;
     anm_celt_frame_t *out; /* pulse statistics */
+    ce_spec_t *sp;
 } ce_band_ctx_t;
 
 typedef struct ce_split {
@@ -281,10 +293,9 @@ ANM_CE_FN int ce_compute_qn(int N, int b, int offset, int pulse_cap, int stereo)
     return qn;
 }
 
-ANM_CE_FN void ce_compute_theta(ce_band_ctx_t *ctx, ce_split_t *s, int N, int *b, int B, int B0, int LM, int stereo) {
+ANM_CE_FN void ce_compute_theta(ce_band_ctx_t *ctx, ce_split_t *s, int N, int *b, int B, int B0, int LM, int stereo, int *fill) {
     anm_ec_t *ec = ctx->ec;
     int itheta = 0, inv = 0, imid, iside, delta;
-    (void)B;
     const int pulse_cap = ctx->t->logn[ctx->i] + LM * (1 << ANM_CE_BITRES);
     const int offset = (pulse_cap >> 1) - (stereo && N == 2 ? 16 : 4); /* QTHETA_OFFSET_TWOPHASE : QTHETA_OFFSET */
     int qn = ce_compute_qn(N, *b, offset, pulse_cap, stereo);
@@ -322,6 +333,7 @@ ANM_CE_FN void ce_compute_theta(ce_band_ctx_t *ctx, ce_split_t *s, int N, int *b
     } else if (stereo) {
         if (*b > 2 << ANM_CE_BITRES && ctx->remaining_bits > 2 << ANM_CE_BITRES) inv = ce_bit_logp(ec, 2);
         else inv = 0;
+        if (ctx->sp && ctx->sp->disable_inv) inv = 0; /* a mono decoder never inverts (downmix) */
         itheta = 0;
     }
     const int qalloc = (int)((int32_t)ce_tell_frac(ec) - tell);
@@ -329,10 +341,12 @@ ANM_CE_FN void ce_compute_theta(ce_band_ctx_t *ctx, ce_split_t *s, int N, int *b
     if (itheta == 0) {
         imid = 32767;
         iside = 0;
+        *fill &= (1 << B) - 1;
         delta = -16384;
     } else if (itheta == 16384) {
         imid = 0;
         iside = 32767;
+        *fill &= ((1 << B) - 1) << B;
         delta = 16384;
     } else {
         imid = ce_bitexact_cos((int16_t)itheta);
@@ -347,30 +361,44 @@ ANM_CE_FN void ce_compute_theta(ce_band_ctx_t *ctx, ce_split_t *s, int N, int *b
     s->qalloc = qalloc;
 }
 
-ANM_CE_FN void ce_band_n1(ce_band_ctx_t *ctx, int stereo) {
+/* a band of one coefficient: its sign */
+ANM_CE_FN unsigned ce_band_n1(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, int stereo, int16_t *lowband_out) {
+    int16_t *x = X;
     for (int c = 0; c < 1 + stereo; ++c) {
+        int sign = 0;
         if (ctx->remaining_bits >= 1 << ANM_CE_BITRES) {
-            (void)ce_bits(ctx->ec, 1); /* the sign */
+            sign = (int)ce_bits(ctx->ec, 1);
             ctx->remaining_bits -= 1 << ANM_CE_BITRES;
         }
+        if (ctx->sp) x[0] = sign ? -16384 : 16384; /* NORM_SCALING */
+        x = Y;
     }
+    if (ctx->sp && lowband_out) lowband_out[0] = (int16_t)(X[0] >> 4);
+    return 1;
 }
 
-/* a mono partition: splits in two while the budget exceeds what one codeword can carry, then reads the PVQ codeword */
+/* a mono partition: splits in two while the budget exceeds what one codeword can carry, then reads the PVQ codeword; with a spectrum
+ * (ctx->sp) the codeword becomes the partition's coefficients, an empty partition is folded from `lowband` or filled with noise.
+ * Returns the collapse mask (which of the B interleaved blocks received energy). */
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-static void ce_partition(ce_band_ctx_t *ctx, int N, int b, int B, int LM) {
+static unsigned ce_partition(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int16_t gain, int fill) {
     const uint8_t *cache = ce_cache(ctx->t, ctx->i, LM);
+    ce_spec_t *sp = ctx->sp;
+    unsigned cm = 0;
     if (LM != -1 && b > cache[cache[0]] + 12 && N > 2) {
         ce_split_t s;
         const int B0 = B;
         N >>= 1;
+        int16_t *Y = X ? X + N : X;
         LM -= 1;
+        if (B == 1) fill = (fill & 1) | (fill << 1);
         B = (B + 1) >> 1;
-        ce_compute_theta(ctx, &s, N, &b, B, B0, LM, 0);
+        ce_compute_theta(ctx, &s, N, &b, B, B0, LM, 0, &fill);
         int delta = s.delta;
         const int itheta = s.itheta;
+        const int16_t mid = (int16_t)s.imid, side = (int16_t)s.iside;
         /* more bits to low-energy MDCTs than they would otherwise deserve */
         if (B0 > 1 && (itheta & 0x3fff)) {
             if (itheta > 8192) delta -= delta >> (4 - LM);
@@ -379,17 +407,18 @@ static void ce_partition(ce_band_ctx_t *ctx, int N, int b, int B, int LM) {
         int mbits = ce_imax(0, ce_imin(b, (b - delta) / 2));
         int sbits = b - mbits;
         ctx->remaining_bits -= s.qalloc;
+        int16_t *next_lowband2 = lowband ? lowband + N : lowband;
         int32_t rebalance = ctx->remaining_bits;
         if (mbits >= sbits) {
-            ce_partition(ctx, N, mbits, B, LM);
+            cm = ce_partition(ctx, X, N, mbits, B, lowband, LM, (int16_t)CV_P15(gain, mid), fill);
             rebalance = mbits - (rebalance - ctx->remaining_bits);
             if (rebalance > 3 << ANM_CE_BITRES && itheta != 0) sbits += rebalance - (3 << ANM_CE_BITRES);
-            ce_partition(ctx, N, sbits, B, LM);
+            cm |= ce_partition(ctx, Y, N, sbits, B, next_lowband2, LM, (int16_t)CV_P15(gain, side), fill >> B) << (B0 >> 1);
         } else {
-            ce_partition(ctx, N, sbits, B, LM);
+            cm = ce_partition(ctx, Y, N, sbits, B, next_lowband2, LM, (int16_t)CV_P15(gain, side), fill >> B) << (B0 >> 1);
             rebalance = sbits - (rebalance - ctx->remaining_bits);
             if (rebalance > 3 << ANM_CE_BITRES && itheta != 16384) mbits += rebalance - (3 << ANM_CE_BITRES);
-            ce_partition(ctx, N, mbits, B, LM);
+            cm |= ce_partition(ctx, X, N, mbits, B, lowband, LM, (int16_t)CV_P15(gain, mid), fill);
         }
     } else {
         int q = ce_bits2pulses(ctx->t, ctx->i, LM, b);
@@ -403,70 +432,170 @@ static void ce_partition(ce_band_ctx_t *ctx, int N, int b, int B, int LM) {
         }
         if (q != 0) {
             const int K = ce_get_pulses(q);
-            /* decode_pulses: one uniform symbol over the V(N, K) codewords; the vector itself is stage 2's business */
+            /* decode_pulses: one uniform symbol over the V(N, K) codewords */
             const uint32_t v = ce_pvq_u(ctx->t, N, K) + ce_pvq_u(ctx->t, N, K + 1);
             const uint32_t idx = ce_uint(ctx->ec, v);
             ctx->out->pvq_codewords++;
             ctx->out->pvq_pulses += (uint32_t)K;
             ctx->out->pvq_index_xor ^= idx * 2654435761u + (uint32_t)(N * 131 + K);
+            if (sp) { /* alg_unquant */
+                const int32_t Ryy = cv_cwrsi(ctx->t, N, K, idx, sp->iy);
+                cv_normalise_residual(sp->iy, X, N, Ryy, gain);
+                cv_exp_rotation_dec(X, N, B, K, sp->spread);
+                cm = cv_collapse_mask(sp->iy, N, B);
+            }
+        } else if (sp) {
+            /* no pulse: fill the partition anyway */
+            const unsigned cm_mask = (unsigned)(1UL << B) - 1;
+            fill &= (int)cm_mask;
+            if (!fill) {
+                for (int j = 0; j < N; j++) X[j] = 0;
+            } else {
+                if (lowband == 0) { /* noise */
+                    for (int j = 0; j < N; j++) {
+                        sp->seed = cv_lcg(sp->seed);
+                        X[j] = (int16_t)((int32_t)sp->seed >> 20);
+                    }
+                    cm = cm_mask;
+                } else { /* folded spectrum, plus a little noise about 48 dB below it */
+                    for (int j = 0; j < N; j++) {
+                        sp->seed = cv_lcg(sp->seed);
+                        const int16_t tmp = (sp->seed & 0x8000u) ? 4 : -4; /* QCONST16(1 / 256, 10) */
+                        X[j] = (int16_t)(lowband[j] + tmp);
+                    }
+                    cm = (unsigned)fill;
+                }
+                cv_renormalise(X, N, gain);
+            }
         }
     }
+    return cm;
 }
 
-/* one band of one channel (or the mid / side of a stereo band): time-frequency reshaping only changes B */
-ANM_CE_FN void ce_band(ce_band_ctx_t *ctx, int N, int b, int B, int LM) {
+/* one band of one channel (or the mid / side of a stereo band): the time-frequency reshaping around the partition */
+ANM_CE_FN unsigned ce_band(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int16_t *lowband_out, int16_t gain,
+                           int16_t *lowband_scratch, int fill) {
+    const uint8_t bit_interleave_table[16] = {0, 1, 1, 1, 2, 3, 3, 3, 2, 3, 3, 3, 2, 3, 3, 3};
+    const uint8_t bit_deinterleave_table[16] = {0x00, 0x03, 0x0C, 0x0F, 0x30, 0x33, 0x3C, 0x3F, 0xC0, 0xC3, 0xCC, 0xCF, 0xF0, 0xF3, 0xFC, 0xFF};
+    ce_spec_t *sp = ctx->sp;
+    const int N0 = N;
+    int B0 = B, time_divide = 0, recombine = 0, k;
     int tf_change = ctx->tf_change;
-    if (N == 1) {
-        ce_band_n1(ctx, 0);
-        return;
-    }
-    int N_B = N / B;
-    int recombine = 0;
+    const int long_blocks = B0 == 1;
+    if (N == 1) return ce_band_n1(ctx, X, 0, 0, lowband_out);
+    int N_B = (int)((uint32_t)N / (uint32_t)B);
     if (tf_change > 0) recombine = tf_change;
+    if (sp && lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
+        for (k = 0; k < N; k++) lowband_scratch[k] = lowband[k];
+        lowband = lowband_scratch;
+    }
+    for (k = 0; k < recombine; k++) { /* band recombining: more frequency resolution */
+        if (sp && lowband) cv_haar1(lowband, N >> k, 1 << k);
+        fill = bit_interleave_table[fill & 0xF] | bit_interleave_table[fill >> 4] << 2;
+    }
     B >>= recombine;
     N_B <<= recombine;
-    while ((N_B & 1) == 0 && tf_change < 0) { /* increasing the time resolution */
+    while ((N_B & 1) == 0 && tf_change < 0) { /* more time resolution */
+        if (sp && lowband) cv_haar1(lowband, N_B, B);
+        fill |= fill << B;
         B <<= 1;
         N_B >>= 1;
+        time_divide++;
         tf_change++;
     }
-    ce_partition(ctx, N, b, B, LM);
+    B0 = B;
+    const int N_B0 = N_B;
+    /* time order instead of frequency order */
+    if (sp && B0 > 1 && lowband) cv_deinterleave_hadamard(lowband, sp->tmp, N_B >> recombine, B0 << recombine, long_blocks);
+    unsigned cm = ce_partition(ctx, X, N, b, B, lowband, LM, gain, fill);
+    if (sp) {
+        if (B0 > 1) cv_interleave_hadamard(X, sp->tmp, N_B >> recombine, B0 << recombine, long_blocks);
+        /* undo the time-frequency changes */
+        N_B = N_B0;
+        B = B0;
+        for (k = 0; k < time_divide; k++) {
+            B >>= 1;
+            N_B <<= 1;
+            cm |= cm >> B;
+            cv_haar1(X, N_B, B);
+        }
+        for (k = 0; k < recombine; k++) {
+            cm = bit_deinterleave_table[cm];
+            cv_haar1(X, N0 >> k, 1 << k);
+        }
+        B <<= recombine;
+        if (lowband_out) { /* scaled for later folding */
+            const int16_t n = (int16_t)cv_sqrt((int32_t)((uint32_t)N0 << 22));
+            for (k = 0; k < N0; k++) lowband_out[k] = (int16_t)CV_Q15(n, X[k]);
+        }
+        cm &= (unsigned)(1 << B) - 1;
+    }
+    return cm;
 }
 
-ANM_CE_FN void ce_band_stereo(ce_band_ctx_t *ctx, int N, int b, int B, int LM) {
-    if (N == 1) {
-        ce_band_n1(ctx, 1);
-        return;
-    }
+ANM_CE_FN unsigned ce_band_stereo(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, int N, int b, int B, int16_t *lowband, int LM, int16_t *lowband_out,
+                                  int16_t *lowband_scratch, int fill) {
+    ce_spec_t *sp = ctx->sp;
+    unsigned cm = 0;
+    if (N == 1) return ce_band_n1(ctx, X, Y, 1, lowband_out);
+    const int orig_fill = fill;
     ce_split_t s;
-    ce_compute_theta(ctx, &s, N, &b, B, B, LM, 1);
-    const int itheta = s.itheta;
+    ce_compute_theta(ctx, &s, N, &b, B, B, LM, 1, &fill);
+    const int itheta = s.itheta, inv = s.inv;
+    const int16_t mid = (int16_t)s.imid, side = (int16_t)s.iside;
     int mbits, sbits;
     if (N == 2) {
+        /* mid and side are orthogonal: one bit for the side's sign */
         mbits = b;
         sbits = 0;
-        if (itheta != 0 && itheta != 16384) sbits = 1 << ANM_CE_BITRES; /* one bit for the side */
+        if (itheta != 0 && itheta != 16384) sbits = 1 << ANM_CE_BITRES;
         mbits -= sbits;
+        const int c = itheta > 8192;
         ctx->remaining_bits -= s.qalloc + sbits;
-        if (sbits) (void)ce_bits(ctx->ec, 1);
-        ce_band(ctx, N, mbits, B, LM);
+        int16_t *x2 = c ? Y : X, *y2 = c ? X : Y;
+        int sign = 0;
+        if (sbits) sign = (int)ce_bits(ctx->ec, 1);
+        sign = 1 - 2 * sign;
+        /* orig_fill: the side is folded even when itheta == 16384 cleared the low bits of fill */
+        cm = ce_band(ctx, x2, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, orig_fill);
+        if (sp) {
+            y2[0] = (int16_t)(-sign * x2[1]);
+            y2[1] = (int16_t)(sign * x2[0]);
+            X[0] = (int16_t)CV_Q15(mid, X[0]);
+            X[1] = (int16_t)CV_Q15(mid, X[1]);
+            Y[0] = (int16_t)CV_Q15(side, Y[0]);
+            Y[1] = (int16_t)CV_Q15(side, Y[1]);
+            int16_t tmp = X[0];
+            X[0] = (int16_t)CV_S16(tmp, Y[0]);
+            Y[0] = CV_A16(tmp, Y[0]);
+            tmp = X[1];
+            X[1] = (int16_t)CV_S16(tmp, Y[1]);
+            Y[1] = CV_A16(tmp, Y[1]);
+        }
     } else {
         mbits = ce_imax(0, ce_imin(b, (b - s.delta) / 2));
         sbits = b - mbits;
         ctx->remaining_bits -= s.qalloc;
         int32_t rebalance = ctx->remaining_bits;
+        /* the mid keeps unit norm (it is the folding source of later bands); a stereo split never folds the side */
         if (mbits >= sbits) {
-            ce_band(ctx, N, mbits, B, LM);
+            cm = ce_band(ctx, X, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, fill);
             rebalance = mbits - (rebalance - ctx->remaining_bits);
             if (rebalance > 3 << ANM_CE_BITRES && itheta != 0) sbits += rebalance - (3 << ANM_CE_BITRES);
-            ce_band(ctx, N, sbits, B, LM);
+            cm |= ce_band(ctx, Y, N, sbits, B, 0, LM, 0, side, 0, fill >> B);
         } else {
-            ce_band(ctx, N, sbits, B, LM);
+            cm = ce_band(ctx, Y, N, sbits, B, 0, LM, 0, side, 0, fill >> B);
             rebalance = sbits - (rebalance - ctx->remaining_bits);
             if (rebalance > 3 << ANM_CE_BITRES && itheta != 16384) mbits += rebalance - (3 << ANM_CE_BITRES);
-            ce_band(ctx, N, mbits, B, LM);
+            cm |= ce_band(ctx, X, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, fill);
         }
     }
+    if (sp) {
+        if (N != 2) cv_stereo_merge(X, Y, mid, N);
+        if (inv)
+            for (int j = 0; j < N; j++) Y[j] = (int16_t)-Y[j];
+    }
+    return cm;
 }
 
 /* ---------------------------------------------------------------- bit allocation */
@@ -667,8 +796,11 @@ ANM_CE_FN int ce_compute_allocation(const anm_celt_tables_t *t, int start, int e
  * final energy offsets eoff[c * 21 + band] (Q10) are returned instead of being applied -- no symbol of a frame depends on the band energies,
  * so frames decode independently of each other and only anm_celt_apply_energies() below is sequential per stream.
  * end = coded bands of the packet's bandwidth.  Returns 0, or a negative ANM_OPUS_* code (nothing is read then). */
-ANM_CE_FN int anm_celt_entropy_symbols(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
-                                       int end, int16_t *qi_out, int16_t *eoff, anm_celt_frame_t *out) {
+/* sp != NULL (stage 2): the frame's normalised spectrum as well -- X_: [C][120 << LM] coefficients (celt_norm, Q14: what quant_all_bands leaves in
+ * X, before anti-collapse), collapse_masks: [21 * C]; sp->seed / spread / disable_inv are inputs, sp->seed is updated.  The last band's part of
+ * X_ doubles as scratch while the earlier bands are decoded, as in the reference. */
+ANM_CE_FN int anm_celt_frame_symbols(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
+                                     int end, int16_t *qi_out, int16_t *eoff, anm_celt_frame_t *out, ce_spec_t *sp, int16_t *X_, uint8_t *collapse_masks) {
     const uint8_t trim_icdf[11] = {126, 124, 119, 109, 87, 41, 19, 9, 4, 2, 0};
     const uint8_t spread_icdf[4] = {25, 23, 2, 0};
     const uint8_t tapset_icdf[3] = {2, 1, 0};
@@ -809,19 +941,29 @@ ANM_CE_FN int anm_celt_entropy_symbols(const anm_celt_tables_t *t, const uint8_t
             eoff[i + c * ANM_CE_NB] = (int16_t)(eoff[i + c * ANM_CE_NB] + offset); /* 16-bit wrapping adds commute with the coarse value */
         }
     }
-    /* ---- the bands (quant_all_bands): bits only ---- */
+    /* ---- the bands (quant_all_bands) ---- */
     {
         ce_band_ctx_t ctx;
         ctx.t = t;
         ctx.ec = &dec;
         ctx.intensity = intensity;
         ctx.out = out;
+        ctx.sp = sp;
         const int32_t band_total = (int32_t)len * (8 << ANM_CE_BITRES) - anti_collapse_rsv;
         const int B = short_blocks ? M : 1;
+        const int NF = M * 120; /* coefficients per channel */
         int ds = dual_stereo;
+        /* folding state: norm holds the bands decoded so far (per channel while dual stereo lasts), up to the last band's start */
+        const int norm_offset = M * eb[start], norm_len = M * eb[ANM_CE_NB - 1] - norm_offset;
+        int16_t *norm = sp ? sp->norm : 0, *norm2 = sp ? sp->norm + norm_len : 0;
+        int16_t *lowband_scratch = sp ? X_ + M * eb[ANM_CE_NB - 1] : 0;
+        int lowband_offset = 0, update_lowband = 1;
+        if (sp) sp->spread = spread;
         for (i = start; i < end; i++) {
             ctx.i = i;
+            const int last = i == end - 1;
             const int N = M * eb[i + 1] - M * eb[i];
+            int16_t *X = sp ? X_ + M * eb[i] : 0, *Y = (sp && C == 2) ? X_ + NF + M * eb[i] : 0;
             const int32_t tl = (int32_t)ce_tell_frac(&dec);
             if (i != start) balance -= tl;
             const int32_t remaining = band_total - tl - 1;
@@ -833,17 +975,52 @@ ANM_CE_FN int anm_celt_entropy_symbols(const anm_celt_tables_t *t, const uint8_t
             } else {
                 b = 0;
             }
+            if ((M * eb[i] - N >= M * eb[start] || i == start + 1) && (update_lowband || lowband_offset == 0)) lowband_offset = i;
             ctx.tf_change = tf_res[i];
-            if (ds && i == intensity) ds = 0; /* dual stereo switches off to do intensity */
-            if (ds) {
-                ce_band(&ctx, N, b / 2, B, LM);
-                ce_band(&ctx, N, b / 2, B, LM);
-            } else if (C == 2) {
-                ce_band_stereo(&ctx, N, b, B, LM);
+            if (last) lowband_scratch = 0;
+            /* a conservative estimate of the collapse masks of the bands this one folds from */
+            int effective_lowband = -1;
+            unsigned x_cm, y_cm;
+            if (lowband_offset != 0 && (spread != 3 || B > 1 || tf_res[i] < 0)) { /* SPREAD_AGGRESSIVE */
+                effective_lowband = ce_imax(0, M * eb[lowband_offset] - norm_offset - N); /* never repeat spectral content within one band */
+                int fold_start = lowband_offset;
+                while (M * eb[--fold_start] > effective_lowband + norm_offset) {}
+                int fold_end = lowband_offset - 1;
+                while (++fold_end < i && M * eb[fold_end] < effective_lowband + norm_offset + N) {}
+                x_cm = y_cm = 0;
+                if (sp) {
+                    int fold_i = fold_start;
+                    do {
+                        x_cm |= collapse_masks[fold_i * C + 0];
+                        y_cm |= collapse_masks[fold_i * C + C - 1];
+                    } while (++fold_i < fold_end);
+                }
             } else {
-                ce_band(&ctx, N, b, B, LM);
+                x_cm = y_cm = (1u << B) - 1; /* folding from the noise generator: every block gets energy */
+            }
+            if (ds && i == intensity) { /* dual stereo switches off to do intensity */
+                ds = 0;
+                if (sp)
+                    for (int j = 0; j < M * eb[i] - norm_offset; j++) norm[j] = (int16_t)(((int32_t)norm[j] + norm2[j]) >> 1);
+            }
+            int16_t *lb = (sp && effective_lowband != -1) ? norm + effective_lowband : 0;
+            int16_t *lbo = (sp && !last) ? norm + M * eb[i] - norm_offset : 0;
+            if (ds) {
+                int16_t *lb2 = (sp && effective_lowband != -1) ? norm2 + effective_lowband : 0;
+                int16_t *lbo2 = (sp && !last) ? norm2 + M * eb[i] - norm_offset : 0;
+                x_cm = ce_band(&ctx, X, N, b / 2, B, lb, LM, lbo, 32767, lowband_scratch, (int)x_cm);
+                y_cm = ce_band(&ctx, Y, N, b / 2, B, lb2, LM, lbo2, 32767, lowband_scratch, (int)y_cm);
+            } else {
+                if (C == 2) x_cm = ce_band_stereo(&ctx, X, Y, N, b, B, lb, LM, lbo, lowband_scratch, (int)(x_cm | y_cm));
+                else x_cm = ce_band(&ctx, X, N, b, B, lb, LM, lbo, 32767, lowband_scratch, (int)(x_cm | y_cm));
+                y_cm = x_cm;
+            }
+            if (sp) {
+                collapse_masks[i * C + 0] = (uint8_t)x_cm;
+                collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
             }
             balance += pulses[i] + tl;
+            update_lowband = b > (N << ANM_CE_BITRES); /* the folding position moves only while there is 1 bit / sample of depth */
         }
     }
     int anti_collapse_on = 0;
@@ -886,6 +1063,11 @@ ANM_CE_FN int anm_celt_entropy_symbols(const anm_celt_tables_t *t, const uint8_t
     return 0;
 }
 
+ANM_CE_FN int anm_celt_entropy_symbols(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
+                                       int end, int16_t *qi_out, int16_t *eoff, anm_celt_frame_t *out) {
+    return anm_celt_frame_symbols(t, bytes, mask, base, len, C, LM, end, qi_out, eoff, out, 0, 0, 0);
+}
+
 /* The sequential part of a stream: the band energies after a frame from the energies before it (old_e, Q10, [2][21]), the frame's coarse
  * symbols and offsets -- unquant_coarse_energy's prediction (celt/quant_bands.c:427-490, fixed-point build) followed by the fine and final
  * offsets, the mono / silence / band-limit rules of celt_decode_with_ec (celt/celt_decoder.c:941-945, 1100-1104, 1137-1166).  `fr` is the
@@ -918,6 +1100,62 @@ ANM_CE_FN void anm_celt_apply_energies(anm_celt_frame_t *fr, const int16_t *qi, 
             for (i = end; i < ANM_CE_NB; i++) old_e[c * ANM_CE_NB + i] = 0;
     }
     for (i = 0; i < 2 * ANM_CE_NB; i++) fr->band_e[i] = old_e[i];
+}
+
+/* what stage 2 needs of the stream's history for one frame, as the stream stood BEFORE the frame */
+typedef struct ce_hist {
+    int16_t log_e1[2 * ANM_CE_NB], log_e2[2 * ANM_CE_NB];
+    uint32_t seed;
+} ce_hist_t;
+
+/* One frame's step of the per-stream state: hist (may be NULL) receives the histories before the frame, then the band energies are applied
+ * and the histories updated as celt_decode_with_ec does after synthesis (celt/celt_decoder.c:1134-1166).  Lost frames change nothing here
+ * (the reference's concealment, which does, is not built). */
+ANM_CE_FN void anm_celt_stream_step(anm_celt_frame_t *fr, const int16_t *qi, const int16_t *eoff, anm_celt_stream_t *st, ce_hist_t *hist) {
+    int i;
+    if (!(st->flags & 1u)) {
+        for (i = 0; i < 2 * ANM_CE_NB; i++) st->log_e1[i] = st->log_e2[i] = -28672; /* -QCONST16(28, DB_SHIFT) */
+        st->flags |= 1u;
+    }
+    if (hist) {
+        for (i = 0; i < 2 * ANM_CE_NB; i++) {
+            hist->log_e1[i] = st->log_e1[i];
+            hist->log_e2[i] = st->log_e2[i];
+        }
+        hist->seed = st->rng;
+    }
+    anm_celt_apply_energies(fr, qi, eoff, st->old_e);
+    if (fr->flags & ANM_CELT_F_LOST) return;
+    const int end = fr->pad[0];
+    if (!(fr->flags & ANM_CELT_F_TRANSIENT)) {
+        for (i = 0; i < 2 * ANM_CE_NB; i++) {
+            st->log_e2[i] = st->log_e1[i];
+            st->log_e1[i] = st->old_e[i];
+        }
+    } else {
+        for (i = 0; i < 2 * ANM_CE_NB; i++) st->log_e1[i] = st->log_e1[i] < st->old_e[i] ? st->log_e1[i] : st->old_e[i];
+    }
+    for (int c = 0; c < 2; ++c)
+        for (i = end; i < ANM_CE_NB; i++) st->log_e1[c * ANM_CE_NB + i] = st->log_e2[c * ANM_CE_NB + i] = -28672;
+    st->rng = fr->final_range;
+}
+
+/* Stage 2 for one frame whose stage-1 record `rec` (band energies applied) and history `hist` are known: the frame is decoded again, this time
+ * with its spectrum, and anti-collapse is applied when the frame asks for it.  X: [C][120 << LM]; cm: 42 collapse masks; sp: working storage.
+ * Returns the noise seed after the bands in sp->seed. */
+ANM_CE_FN int anm_celt_frame_spectrum(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM, int end,
+                                      int disable_inv, const ce_hist_t *hist, const anm_celt_frame_t *rec, ce_spec_t *sp, int16_t *X, uint8_t *cm) {
+    int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
+    anm_celt_frame_t again;
+    sp->seed = hist->seed;
+    sp->disable_inv = disable_inv;
+    for (int i = 0; i < 2 * ANM_CE_NB; i++) cm[i] = 0;
+    const int rc = anm_celt_frame_symbols(t, bytes, mask, base, len, C, LM, end, qi, eoff, &again, sp, X, cm);
+    if (rc != 0) return rc;
+    if (again.flags & ANM_CELT_F_LOST) return 0;
+    if (again.flags & ANM_CELT_F_ANTI_COLLAPSE)
+        cv_anti_collapse(t, X, cm, LM, C, 120 << LM, end, rec->band_e, hist->log_e1, hist->log_e2, rec->pulses, sp->seed);
+    return 0;
 }
 
 /* both parts for one frame (the host-side test harness; the kernels run them as two passes) */

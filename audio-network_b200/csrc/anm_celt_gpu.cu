@@ -7,11 +7,18 @@
  * operations per frame over the coarse symbols and offsets pass 1 left in a scratch array (anm_celt_entropy.h holds the decode itself,
  * shared with the host-side test harness).
  *
+ * Stage 2 (anm_celt_spectrum_*) adds k_celt_spectrum, one thread per frame again: the frame is decoded once more, this time with the spectrum
+ * arithmetic switched on (anm_celt_vec.h: PVQ vectors, rotations, folding, reorderings, stereo merge, anti-collapse), seeded and informed by what
+ * the per-stream pass left (the noise seed is the previous frame's final range, anti-collapse reads the stream's two log-energy histories).  A
+ * first, plainly thread-per-frame version: the per-thread working set (3.7 KB) lives in a global scratch slab, throughput is bound by local
+ * latency, not by HBM -- the warp-per-frame form (lanes over the coefficients of a band) is the next step.
+ *
  * Reference path replaced: playback.cpp:115-122 opus_decode() -> opus_decode_frame (opus_decoder.c:214-626, CELT-only branch)
- * -> celt_decode_with_ec (celt/celt_decoder.c:815-1095), up to and including unquant_energy_finalise.
+ * -> celt_decode_with_ec (celt/celt_decoder.c:815-1098), up to the call of celt_synthesis.
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <new>
 
 #include "anm_celt_entropy.h"
@@ -22,6 +29,10 @@ struct anm_celt_ctx {
     anm_celt_tables_t *d_tables;
     int16_t *d_scratch; /* per frame: 42 coarse symbols + 42 energy offsets */
     size_t scratch_frames;
+    ce_hist_t *d_hist;  /* per frame: the stream's histories before the frame (stage 2) */
+    size_t hist_frames;
+    ce_spec_t *d_spec;  /* per resident thread of k_celt_spectrum: working storage */
+    size_t spec_threads;
 };
 
 namespace {
@@ -51,15 +62,32 @@ __global__ void __launch_bounds__(128) k_celt_entropy(const anm_celt_tables_t *_
 /* pass 2, one thread per STREAM: the band energies predict from frame to frame (celt/quant_bands.c:427-490) -- a short recurrence over the
  * stream's frames in order, about a hundred integer operations per frame */
 __global__ void __launch_bounds__(128) k_celt_energies(const uint32_t *__restrict__ stream_begin, uint32_t n_streams, const int16_t *__restrict__ scratch,
-                                                       anm_celt_stream_t *streams, anm_celt_frame_t *out) {
+                                                       anm_celt_stream_t *streams, anm_celt_frame_t *out, ce_hist_t *hist) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streams) return;
     anm_celt_stream_t st = streams[s];
     for (uint32_t j = stream_begin[s]; j < stream_begin[s + 1]; ++j) {
         const int16_t *sc = scratch + (size_t)j * (4 * ANM_CE_NB);
-        anm_celt_apply_energies(&out[j], sc, sc + 2 * ANM_CE_NB, st.old_e);
+        anm_celt_stream_step(&out[j], sc, sc + 2 * ANM_CE_NB, &st, hist ? &hist[j] : nullptr);
     }
     streams[s] = st;
+}
+
+/* stage 2, one thread per FRAME (grid-stride: the working storage is per resident thread) */
+__global__ void __launch_bounds__(64) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
+                                                      const uint8_t *__restrict__ bytes, uint32_t mask, const anm_celt_frame_t *__restrict__ recs,
+                                                      const ce_hist_t *__restrict__ hist, ce_spec_t *spec, int16_t *x, uint32_t x_stride, uint8_t *collapse) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    ce_spec_t *sp = spec + tid;
+    for (uint32_t j = tid; j < n_jobs; j += nthr) {
+        const anm_celt_job_t job = jobs[j];
+        if (recs[j].flags & ANM_CELT_F_LOST) continue;
+        uint8_t cm[2 * ANM_CE_NB];
+        const int rc = anm_celt_frame_spectrum(t, bytes, mask, job.offset, job.len, job.channels, job.lm, job.end_band, job.flags & ANM_CELT_JOB_DISABLE_INV,
+                                               &hist[j], &recs[j], sp, x + (size_t)j * x_stride, cm);
+        if (rc == 0 && collapse)
+            for (int i = 0; i < 2 * ANM_CE_NB; ++i) collapse[(size_t)j * (2 * ANM_CE_NB) + i] = cm[i];
+    }
 }
 
 } /* namespace */
@@ -80,6 +108,10 @@ extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
     c->d_tables = nullptr;
     c->d_scratch = nullptr;
     c->scratch_frames = 0;
+    c->d_hist = nullptr;
+    c->hist_frames = 0;
+    c->d_spec = nullptr;
+    c->spec_threads = 0;
     int rc = anm_celt_tables_build(h);
     if (rc == ANM_OK && (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&c->d_tables, sizeof *h) != cudaSuccess ||
                          cudaMemcpy(c->d_tables, h, sizeof *h, cudaMemcpyHostToDevice) != cudaSuccess)) {
@@ -104,29 +136,34 @@ extern "C" void anm_celt_ctx_destroy(anm_celt_ctx_t *c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_tables);
     cudaFree(c->d_scratch);
+    cudaFree(c->d_hist);
+    cudaFree(c->d_spec);
     delete c;
 }
 
-extern "C" int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
-                                       const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, void *stream) {
-    if (!c || ((!d_jobs || !d_stream_begin || !d_streams || !d_out) && n_streams)) return ANM_ERR_ARG;
-    if (n_streams == 0 || n_jobs == 0) return ANM_OK;
-    if (bytes_mask != 0xFFFFFFFFu && (bytes_mask & (bytes_mask + 1u)) != 0u) return ANM_ERR_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (n_jobs > c->scratch_frames) {
-        if (cudaStreamSynchronize(s) != cudaSuccess) { anm_set_error("anm_celt_entropy_device: %s", cudaGetErrorString(cudaGetLastError())); return ANM_ERR_CUDA; }
-        cudaFree(c->d_scratch);
-        c->d_scratch = nullptr;
-        c->scratch_frames = 0;
-        if (cudaMalloc(&c->d_scratch, (size_t)n_jobs * 4 * ANM_CE_NB * sizeof(int16_t)) != cudaSuccess) {
-            anm_set_error("anm_celt_entropy_device: out of device memory for %u frames", n_jobs);
-            cudaGetLastError();
-            return ANM_ERR_NOMEM;
-        }
-        c->scratch_frames = n_jobs;
+/* grows a per-frame / per-thread device array of the context; the stream is drained first: launches in flight may still use the old one */
+template <typename T>
+static int grow(T **p, size_t *have, size_t want, cudaStream_t s, const char *what) {
+    if (want <= *have) return ANM_OK;
+    if (cudaStreamSynchronize(s) != cudaSuccess) { anm_set_error("%s: %s", what, cudaGetErrorString(cudaGetLastError())); return ANM_ERR_CUDA; }
+    cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    if (cudaMalloc(p, want * sizeof(T)) != cudaSuccess) {
+        anm_set_error("%s: out of device memory (%zu bytes)", what, want * sizeof(T));
+        cudaGetLastError();
+        return ANM_ERR_NOMEM;
     }
+    *have = want;
+    return ANM_OK;
+}
+
+static int entropy_impl(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
+                        const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, ce_hist_t *d_hist, cudaStream_t s) {
+    const int rcg = grow(&c->d_scratch, &c->scratch_frames, (size_t)n_jobs * 4 * ANM_CE_NB, s, "anm_celt_entropy_device");
+    if (rcg != ANM_OK) return rcg;
     k_celt_entropy<<<(n_jobs + 127u) / 128u, 128, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, c->d_scratch, d_out);
-    k_celt_energies<<<(n_streams + 127u) / 128u, 128, 0, s>>>(d_stream_begin, n_streams, c->d_scratch, d_streams, d_out);
+    k_celt_energies<<<(n_streams + 127u) / 128u, 128, 0, s>>>(d_stream_begin, n_streams, c->d_scratch, d_streams, d_out, d_hist);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         anm_set_error("k_celt_entropy launch failed: %s", cudaGetErrorString(e));
@@ -135,9 +172,48 @@ extern "C" int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *
     return ANM_OK;
 }
 
-extern "C" int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
-                                     anm_celt_stream_t *streams, anm_celt_frame_t *out) {
+static int check_args(anm_celt_ctx_t *c, const void *d_jobs, const void *d_stream_begin, const void *d_streams, const void *d_out, uint32_t n_streams,
+                      uint32_t bytes_mask) {
+    if (!c || ((!d_jobs || !d_stream_begin || !d_streams || !d_out) && n_streams)) return ANM_ERR_ARG;
+    if (bytes_mask != 0xFFFFFFFFu && (bytes_mask & (bytes_mask + 1u)) != 0u) return ANM_ERR_ARG;
+    return ANM_OK;
+}
+
+extern "C" int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
+                                       const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, void *stream) {
+    const int rc = check_args(c, d_jobs, d_stream_begin, d_streams, d_out, n_streams, bytes_mask);
+    if (rc != ANM_OK) return rc;
+    if (n_streams == 0 || n_jobs == 0) return ANM_OK;
+    return entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
+                                        const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, int16_t *d_x,
+                                        uint32_t x_stride, uint8_t *d_collapse, void *stream) {
+    int rc = check_args(c, d_jobs, d_stream_begin, d_streams, d_out, n_streams, bytes_mask);
+    if (rc != ANM_OK) return rc;
+    if ((!d_x && n_jobs) || x_stride < 120u) return ANM_ERR_ARG;
+    if (n_streams == 0 || n_jobs == 0) return ANM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * 8u);
+    if ((rc = grow(&c->d_hist, &c->hist_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
+    if ((rc = grow(&c->d_spec, &c->spec_threads, (size_t)blocks * 64u, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
+    if ((rc = entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_hist, s)) != ANM_OK) return rc;
+    k_celt_spectrum<<<blocks, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, c->d_spec, d_x, x_stride, d_collapse);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        anm_set_error("k_celt_spectrum launch failed: %s", cudaGetErrorString(e));
+        return ANM_ERR_CUDA;
+    }
+    return ANM_OK;
+}
+
+static int host_impl(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
+                     anm_celt_stream_t *streams, anm_celt_frame_t *out, int16_t *x, uint32_t x_stride, uint8_t *collapse, bool spectrum) {
     if ((!jobs || !stream_begin || !streams || !out) && n_streams) return ANM_ERR_ARG;
+    if (spectrum && ((!x && n_streams) || x_stride < 120u)) return ANM_ERR_ARG;
     if (n_streams == 0) return ANM_OK;
     const uint32_t n_jobs = stream_begin[n_streams];
     for (uint32_t i = 0; i < n_jobs; ++i)
@@ -145,7 +221,7 @@ extern "C" int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t 
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
         cudaGetLastError();
-        anm_set_error("no CUDA device: the CELT entropy decoder has no CPU fallback");
+        anm_set_error("no CUDA device: the CELT decoder stages have no CPU fallback");
         return ANM_ERR_CUDA;
     }
     anm_celt_ctx_t *c = nullptr;
@@ -153,28 +229,47 @@ extern "C" int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t 
     if (rc != ANM_OK) return rc;
     anm_celt_job_t *d_j = nullptr;
     uint32_t *d_sb = nullptr;
-    uint8_t *d_b = nullptr;
+    uint8_t *d_b = nullptr, *d_cm = nullptr;
     anm_celt_stream_t *d_s = nullptr;
     anm_celt_frame_t *d_o = nullptr;
+    int16_t *d_x = nullptr;
+    const size_t nj = n_jobs ? n_jobs : 1, x_bytes = spectrum ? nj * x_stride * sizeof(int16_t) : 0;
     rc = ANM_ERR_CUDA;
-    if (cudaMalloc(&d_j, (n_jobs ? n_jobs : 1) * sizeof *d_j) == cudaSuccess && cudaMalloc(&d_sb, (n_streams + 1) * sizeof *d_sb) == cudaSuccess &&
+    if (cudaMalloc(&d_j, nj * sizeof *d_j) == cudaSuccess && cudaMalloc(&d_sb, (n_streams + 1) * sizeof *d_sb) == cudaSuccess &&
         cudaMalloc(&d_b, n_bytes ? n_bytes : 1) == cudaSuccess && cudaMalloc(&d_s, n_streams * sizeof *d_s) == cudaSuccess &&
-        cudaMalloc(&d_o, (n_jobs ? n_jobs : 1) * sizeof *d_o) == cudaSuccess &&
+        cudaMalloc(&d_o, nj * sizeof *d_o) == cudaSuccess && (!spectrum || (cudaMalloc(&d_x, x_bytes) == cudaSuccess && cudaMalloc(&d_cm, nj * 42) == cudaSuccess)) &&
         cudaMemcpy(d_j, jobs, n_jobs * sizeof *d_j, cudaMemcpyHostToDevice) == cudaSuccess &&
         cudaMemcpy(d_sb, stream_begin, (n_streams + 1) * sizeof *d_sb, cudaMemcpyHostToDevice) == cudaSuccess &&
         cudaMemcpy(d_b, bytes, n_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
-        cudaMemcpy(d_s, streams, n_streams * sizeof *d_s, cudaMemcpyHostToDevice) == cudaSuccess) {
-        rc = anm_celt_entropy_device(c, d_j, d_sb, n_streams, n_jobs, d_b, 0xFFFFFFFFu, d_s, d_o, nullptr);
+        cudaMemcpy(d_s, streams, n_streams * sizeof *d_s, cudaMemcpyHostToDevice) == cudaSuccess &&
+        (!spectrum || (cudaMemcpy(d_x, x, x_bytes, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemset(d_cm, 0, nj * 42) == cudaSuccess))) {
+        rc = spectrum ? anm_celt_spectrum_device(c, d_j, d_sb, n_streams, n_jobs, d_b, 0xFFFFFFFFu, d_s, d_o, d_x, x_stride, d_cm, nullptr)
+                      : anm_celt_entropy_device(c, d_j, d_sb, n_streams, n_jobs, d_b, 0xFFFFFFFFu, d_s, d_o, nullptr);
         if (rc == ANM_OK && (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(out, d_o, n_jobs * sizeof *d_o, cudaMemcpyDeviceToHost) != cudaSuccess ||
-                             cudaMemcpy(streams, d_s, n_streams * sizeof *d_s, cudaMemcpyDeviceToHost) != cudaSuccess))
+                             cudaMemcpy(streams, d_s, n_streams * sizeof *d_s, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                             (spectrum && (cudaMemcpy(x, d_x, x_bytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                                           (collapse && cudaMemcpy(collapse, d_cm, (size_t)n_jobs * 42, cudaMemcpyDeviceToHost) != cudaSuccess)))))
             rc = ANM_ERR_CUDA;
     }
-    if (rc == ANM_ERR_CUDA) anm_set_error("anm_celt_entropy_host: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == ANM_ERR_CUDA) anm_set_error("anm_celt_*_host: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(d_j);
     cudaFree(d_sb);
     cudaFree(d_b);
     cudaFree(d_s);
     cudaFree(d_o);
+    cudaFree(d_x);
+    cudaFree(d_cm);
     anm_celt_ctx_destroy(c);
     return rc;
+}
+
+extern "C" int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
+                                     anm_celt_stream_t *streams, anm_celt_frame_t *out) {
+    return host_impl(jobs, stream_begin, n_streams, bytes, n_bytes, streams, out, nullptr, 0, nullptr, false);
+}
+
+/* x is read as well as written: coefficients the decode does not touch keep what the caller put there */
+extern "C" int anm_celt_spectrum_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
+                                      anm_celt_stream_t *streams, anm_celt_frame_t *out, int16_t *x, uint32_t x_stride, uint8_t *collapse) {
+    return host_impl(jobs, stream_begin, n_streams, bytes, n_bytes, streams, out, x, x_stride, collapse, true);
 }

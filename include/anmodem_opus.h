@@ -17,8 +17,12 @@
  * energies, time-frequency and spread decisions, dynamic allocation, the bit allocation and, band by band with every split, the
  * PVQ codeword of each partition.  No symbol of a frame depends on another frame, so one GPU thread per FRAME decodes all frames of all
  * streams at once; only the band energies predict from frame to frame and are chained per stream in a second, short pass.  The check is the reference's own: the range coder's final state of every frame
- * equals OPUS_GET_FINAL_RANGE of libopus 1.3.1.  The spectrum (PVQ vectors, folding, denormalisation) and the synthesis
- * (inverse MDCT, post-filter, de-emphasis) are NOT part of this library yet.
+ * equals OPUS_GET_FINAL_RANGE of libopus 1.3.1.
+ *
+ * Third stage (anm_celt_spectrum_*): the frames' normalised spectra -- PVQ codewords to pulse vectors, normalisation, spreading rotations,
+ * folding / noise filling, the Haar and Hadamard reorderings, stereo merge, collapse masks and anti-collapse, in the reference's fixed-point
+ * arithmetic: every coefficient equals what the reference's quant_all_bands() + anti_collapse() hand to celt_synthesis().  The synthesis itself
+ * (denormalisation, inverse MDCT, post-filter, de-emphasis) and packet-loss concealment are NOT part of this library yet.
  */
 #ifndef ANMODEM_OPUS_H_INCLUDED
 #define ANMODEM_OPUS_H_INCLUDED
@@ -97,8 +101,9 @@ typedef struct anm_celt_job {
     uint8_t channels;  /* 1 or 2: the packet's stereo flag (opus_packet_get_nb_channels) */
     uint8_t lm;        /* log2(frame samples at 48 kHz / 120): 0..3 for 2.5, 5, 10, 20 ms */
     uint8_t end_band;  /* bands coded at the packet's bandwidth: 13 NB, 17 WB, 19 SWB, 21 FB (opus_decoder.c:462-481) */
-    uint8_t pad;
+    uint8_t flags;     /* ANM_CELT_JOB_* */
 } anm_celt_job_t;
+enum { ANM_CELT_JOB_DISABLE_INV = 1 }; /* the stream is decoded to ONE output channel: no phase inversion of the side (celt_decoder.c:208, st->disable_inv) */
 
 typedef struct anm_celt_frame {
     uint32_t final_range;   /* the range coder's rng after the frame = OPUS_GET_FINAL_RANGE (0 for a lost frame) */
@@ -116,10 +121,15 @@ typedef struct anm_celt_frame {
     int16_t band_e[2 * ANM_CELT_BANDS]; /* band log-energies after the frame, Q10 (oldBandE) */
 } anm_celt_frame_t;
 
-/* per-stream state carried between calls: the band energies the next frame predicts from */
+/* per-stream state carried between calls (zero-initialised = a fresh decoder): the band energies the next frame predicts from, the two
+ * log-energy histories anti-collapse looks at (oldLogE, oldLogE2 of the reference's CELTDecoder) and the noise seed (its rng = the final
+ * range of the stream's previous frame) */
 typedef struct anm_celt_stream {
     int16_t old_e[2 * ANM_CELT_BANDS];
-} anm_celt_stream_t;
+    int16_t log_e1[2 * ANM_CELT_BANDS], log_e2[2 * ANM_CELT_BANDS];
+    uint32_t rng;
+    uint32_t flags; /* bit 0: log_e1 / log_e2 are valid (clear: both are -28 dB, the decoder's reset value) */
+} anm_celt_stream_t;  /* 260 bytes */
 
 /* Opaque device-side context (tables in HBM). */
 typedef struct anm_celt_ctx anm_celt_ctx_t;
@@ -130,6 +140,19 @@ void anm_celt_ctx_destroy(anm_celt_ctx_t *c);
  * Two launches: every frame's symbols in parallel (k_celt_entropy), then the per-stream energy recurrence (k_celt_energies). */
 int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
                             const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, void *stream);
+/* Stage 2 as well: the frames' normalised spectra, as celt_synthesis() receives them (quant_all_bands + anti_collapse, celt/celt_decoder.c:
+ * 1084-1098).  Three launches: the two of anm_celt_entropy_device (d_out is filled as there), then one thread per frame decodes the frame again
+ * WITH its spectrum -- the noise seed of a frame is the final range of the stream's previous frame, the anti-collapse histories come from the
+ * per-stream pass.  d_x: n_jobs x x_stride int16 (celt_norm, Q14), frame j's channel c at d_x + j * x_stride + c * (120 << lm), x_stride >=
+ * channels * (120 << lm) (1920 always fits); coefficients above the frame's end band are left untouched, and the last band's part of a frame whose
+ * end band is below 21 is scratch.  d_collapse (may be NULL): 42 collapse masks per frame, [band * channels + channel].  Frames of <= 1 byte are
+ * lost frames: the reference conceals them (celt_decode_lost), which is NOT built -- their spectrum is not written and the stream's noise seed
+ * and histories pass through unchanged. */
+int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
+                             const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, int16_t *d_x,
+                             uint32_t x_stride, uint8_t *d_collapse, void *stream);
+int anm_celt_spectrum_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
+                           anm_celt_stream_t *streams, anm_celt_frame_t *out, int16_t *x, uint32_t x_stride, uint8_t *collapse);
 /* host arrays: copies in, runs the kernel, copies out (no CPU fallback: ANM_ERR_CUDA without a device) */
 int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
                           anm_celt_stream_t *streams, anm_celt_frame_t *out);

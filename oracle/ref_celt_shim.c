@@ -57,7 +57,11 @@ static void tf_decode_(int start, int end, int isTransient, int *tf_res, int LM,
 
 #define MARK(k) do { tr->rng[k] = dec.rng; tr->tell[k] = ec_tell(&dec); } while (0)
 
-int ref_celt_entropy_trace(const uint8_t *data, int len, int C, int LM, int end, int16_t *oldBandE /* [42] in/out */, ref_celt_trace_t *tr) {
+/* x_out (may be NULL): the normalised spectrum quant_all_bands leaves, [2][960] celt_norm (Q14), channel c at x_out + 960 c, N = 120 << LM
+ * coefficients each; cm_out: the 42 collapse masks; seed_in / seed_out: the decoder's noise seed (CELTDecoder.rng) before / after the bands */
+static int trace_impl(const uint8_t *data, int len, int C, int LM, int end, int16_t *oldBandE /* [42] in/out */, ref_celt_trace_t *tr, uint32_t seed_in,
+                      int disable_inv, int16_t *x_out, uint8_t *cm_out, uint32_t *seed_out, const int16_t *prev1logE, const int16_t *prev2logE,
+                      int16_t *x_post_out) {
     int err = 0;
     const CELTMode *mode = opus_custom_mode_create(48000, 960, &err);
     if (!mode || len <= 1 || len > 1275) return -1;
@@ -144,15 +148,27 @@ int ref_celt_entropy_trace(const uint8_t *data, int len, int C, int LM, int end,
     MARK(5);
     celt_norm *X = (celt_norm *)calloc((size_t)2 * N + 64, sizeof(celt_norm));
     unsigned char collapse_masks[42];
-    opus_uint32 seed = 0;
+    opus_uint32 seed = seed_in;
     memset(collapse_masks, 0, sizeof collapse_masks);
     quant_all_bands(0, mode, start, end, X, C == 2 ? X + N : NULL, collapse_masks, NULL, pulses, shortBlocks, spread_decision, dual_stereo, intensity, tf_res,
-                    len * (8 << BITRES) - anti_collapse_rsv, balance, &dec, LM, codedBands, &seed, 0, 0, 0);
-    free(X);
+                    len * (8 << BITRES) - anti_collapse_rsv, balance, &dec, LM, codedBands, &seed, 0, 0, disable_inv);
+    if (x_out) {
+        memset(x_out, 0, 2 * 960 * sizeof(int16_t));
+        for (c = 0; c < C; c++) memcpy(x_out + 960 * c, X + N * c, (size_t)(M * eBands[end]) * sizeof(int16_t));
+    }
+    if (cm_out) memcpy(cm_out, collapse_masks, 42);
+    if (seed_out) *seed_out = seed;
     MARK(6);
     if (anti_collapse_rsv > 0) tr->anti_collapse_on = ec_dec_bits(&dec, 1);
     unquant_energy_finalise(mode, start, end, oldBandE, fine_quant, fine_priority, len * 8 - ec_tell(&dec), &dec, C);
     MARK(7);
+    /* celt_decoder.c:1096-1098: the spectrum synthesis starts from */
+    if (x_post_out) {
+        if (tr->anti_collapse_on) anti_collapse(mode, X, collapse_masks, LM, C, N, start, end, oldBandE, prev1logE, prev2logE, pulses, seed, 0);
+        memset(x_post_out, 0, 2 * 960 * sizeof(int16_t));
+        for (c = 0; c < C; c++) memcpy(x_post_out + 960 * c, X + N * c, (size_t)(M * eBands[end]) * sizeof(int16_t));
+    }
+    free(X);
     if (silence)
         for (i = 0; i < C * nbEBands; i++) oldBandE[i] = -QCONST16(28.f, DB_SHIFT);
     if (C == 1) OPUS_COPY(&oldBandE[nbEBands], oldBandE, nbEBands);
@@ -176,6 +192,21 @@ int ref_celt_entropy_trace(const uint8_t *data, int len, int C, int LM, int end,
     }
     memcpy(tr->band_e, oldBandE, 42 * sizeof(int16_t));
     return 0;
+}
+
+int ref_celt_entropy_trace(const uint8_t *data, int len, int C, int LM, int end, int16_t *oldBandE /* [42] in/out */, ref_celt_trace_t *tr) {
+    return trace_impl(data, len, C, LM, end, oldBandE, tr, 0u, 0, NULL, NULL, NULL, NULL, NULL, NULL);
+}
+/* the same with the spectrum kept: what celt_decode_with_ec holds in X after quant_all_bands (celt/celt_decoder.c:1084-1088) */
+int ref_celt_spectrum_trace(const uint8_t *data, int len, int C, int LM, int end, int16_t *oldBandE, ref_celt_trace_t *tr, uint32_t seed_in, int disable_inv,
+                            int16_t *x_out, uint8_t *cm_out, uint32_t *seed_out) {
+    return trace_impl(data, len, C, LM, end, oldBandE, tr, seed_in, disable_inv, x_out, cm_out, seed_out, NULL, NULL, NULL);
+}
+/* ... and with anti_collapse() applied (celt/celt_decoder.c:1096-1098) on the log-energy histories given (oldLogE, oldLogE2 of the decoder before
+ * the frame: ref_celt_stream_states() reads them off the reference decoder itself): the spectrum celt_synthesis() starts from */
+int ref_celt_spectrum_trace2(const uint8_t *data, int len, int C, int LM, int end, int16_t *oldBandE, ref_celt_trace_t *tr, uint32_t seed_in, int disable_inv,
+                             int16_t *x_out, uint8_t *cm_out, uint32_t *seed_out, const int16_t *prev1logE, const int16_t *prev2logE, int16_t *x_post_out) {
+    return trace_impl(data, len, C, LM, end, oldBandE, tr, seed_in, disable_inv, x_out, cm_out, seed_out, prev1logE, prev2logE, x_post_out);
 }
 
 /* static tables of the standard mode: logN[21], cache.index[105], cache.bits[size], cache.caps[168]; returns cache.size */

@@ -16,7 +16,7 @@ FRAME_DTYPE = np.dtype([("final_range", "<u4"), ("tell_bits", "<i4"), ("flags", 
                         ("spread", "u1"), ("alloc_trim", "u1"), ("intensity", "u1"), ("coded_bands", "u1"), ("lm", "u1"), ("channels", "u1"), ("pad", "u1", (2,)),
                         ("pvq_codewords", "<u4"), ("pvq_pulses", "<u4"), ("pvq_index_xor", "<u4"), ("tf_res", "i1", (NB,)), ("fine_quant", "u1", (NB,)),
                         ("pulses", "<i2", (NB,)), ("band_e", "<i2", (2 * NB,))])
-JOB_DTYPE = np.dtype([("offset", "<u4"), ("len", "<u4"), ("channels", "u1"), ("lm", "u1"), ("end_band", "u1"), ("pad", "u1")])
+JOB_DTYPE = np.dtype([("offset", "<u4"), ("len", "<u4"), ("channels", "u1"), ("lm", "u1"), ("end_band", "u1"), ("flags", "u1")])
 TABLES_FIELDS = [("ebands", "<i2", (NB + 1,)), ("logn", "<i2", (NB,)), ("cache_index", "<i2", (5 * NB,)), ("cache_size", "<u2"), ("cache_bits", "u1", (512,)),
                  ("cache_caps", "u1", (4 * 2 * NB,)), ("alloc", "u1", (11 * NB,)), ("e_prob", "u1", (4 * 2 * 42,))]
 

@@ -11,3 +11,52 @@ int harness_celt_frame(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_
 }
 uint32_t harness_sizeof_tables(void) { return (uint32_t)sizeof(anm_celt_tables_t); }
 uint32_t harness_sizeof_frame(void) { return (uint32_t)sizeof(anm_celt_frame_t); }
+
+/* stage 2: the frame's normalised spectrum (X: [2][960], channel c at X + 960 c ... repacked from the product's [C][120 << LM] layout) */
+int harness_celt_spectrum(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t len, int C, int LM, int end, int16_t *old_e, anm_celt_frame_t *out,
+                          uint32_t seed_in, int disable_inv, int16_t *x_out, uint8_t *cm_out, uint32_t *seed_out) {
+    static ce_spec_t sp;
+    static int16_t X[2 * 960];
+    int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
+    uint8_t cm[2 * ANM_CE_NB];
+    const int NF = 120 << LM;
+    for (int i = 0; i < 2 * 960; i++) X[i] = 0;
+    for (int i = 0; i < 2 * ANM_CE_NB; i++) cm[i] = 0;
+    sp.seed = seed_in;
+    sp.disable_inv = disable_inv;
+    const int rc = anm_celt_frame_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out, &sp, X, cm);
+    if (rc != 0) return rc;
+    anm_celt_apply_energies(out, qi, eoff, old_e);
+    const int ncmp = (1 << LM) * t->ebands[end];
+    for (int i = 0; i < 2 * 960; i++) x_out[i] = 0;
+    for (int c = 0; c < C; c++)
+        for (int i = 0; i < ncmp; i++) x_out[960 * c + i] = X[NF * c + i];
+    for (int i = 0; i < 2 * ANM_CE_NB; i++) cm_out[i] = cm[i];
+    *seed_out = sp.seed;
+    return 0;
+}
+
+/* stages 1 + 2 for one frame of a stream, exactly as the kernels chain them: symbols -> per-stream step (histories) -> spectrum + anti-collapse.
+ * x_post: [2][960] repacked like x_out above; hist_out: the histories the frame saw (ce_hist_t). */
+int harness_celt_frame_full(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t len, int C, int LM, int end, int disable_inv, anm_celt_stream_t *st,
+                            anm_celt_frame_t *out, int16_t *x_post, uint8_t *cm_out, ce_hist_t *hist_out) {
+    static ce_spec_t sp;
+    static int16_t X[2 * 960];
+    int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
+    uint8_t cm[2 * ANM_CE_NB];
+    const int NF = 120 << LM;
+    int rc = anm_celt_entropy_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out);
+    if (rc != 0) return rc;
+    anm_celt_stream_step(out, qi, eoff, st, hist_out);
+    for (int i = 0; i < 2 * 960; i++) X[i] = 0;
+    rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, disable_inv, hist_out, out, &sp, X, cm);
+    if (rc != 0) return rc;
+    const int ncmp = (1 << LM) * t->ebands[end];
+    for (int i = 0; i < 2 * 960; i++) x_post[i] = 0;
+    for (int c = 0; c < C; c++)
+        for (int i = 0; i < ncmp; i++) x_post[960 * c + i] = X[NF * c + i];
+    for (int i = 0; i < 2 * ANM_CE_NB; i++) cm_out[i] = cm[i];
+    return 0;
+}
+uint32_t harness_sizeof_stream(void) { return (uint32_t)sizeof(anm_celt_stream_t); }
+uint32_t harness_sizeof_hist(void) { return (uint32_t)sizeof(ce_hist_t); }
