@@ -178,7 +178,7 @@ EXPORTS = [
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
     "anm_pacer_init", "anm_pacer_level", "anm_pacer_try_put", "anm_pacer_wait_for_capacity",
     "anm_opus_parse_device", "anm_opus_parse_host",
-    "anm_celt_tables_build", "anm_celt_ctx_create", "anm_celt_ctx_destroy", "anm_celt_entropy_device", "anm_celt_entropy_host", "anm_celt_spectrum_device", "anm_celt_spectrum_host",
+    "anm_celt_tables_build", "anm_celt_ctx_create", "anm_celt_ctx_destroy", "anm_celt_entropy_device", "anm_celt_entropy_host", "anm_celt_spectrum_device", "anm_celt_spectrum_host", "anm_celt_decode_device", "anm_celt_decode_host", "anm_celt_synth_tables_build",
 ]
 
 _lib = None
@@ -260,6 +260,9 @@ def lib():
         "anm_celt_entropy_host": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp]),
         "anm_celt_spectrum_device": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp]),
         "anm_celt_spectrum_host": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp, vp, C.c_uint32, vp]),
+        "anm_celt_decode_device": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp]),
+        "anm_celt_decode_host": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp, vp, vp, C.c_uint32]),
+        "anm_celt_synth_tables_build": (C.c_int, [vp]),
         "anm_pb_encode_broadcast": (C.c_size_t, [C.POINTER(PbBroadcast), vp, C.c_size_t]),
         "anm_pb_encode_to_transmitter": (C.c_size_t, [C.POINTER(PbToTransmitter), vp, C.c_size_t]),
         "anm_pb_decode_broadcast": (C.c_int, [vp, C.c_size_t, C.POINTER(PbBroadcast), C.POINTER(C.c_size_t)]),
@@ -349,6 +352,10 @@ CELT_FRAME_DTYPE = np.dtype([("final_range", "<u4"), ("tell_bits", "<i4"), ("fla
                              ("fine_quant", "u1", (CELT_BANDS,)), ("pulses", "<i2", (CELT_BANDS,)), ("band_e", "<i2", (2 * CELT_BANDS,))])    # anm_celt_frame_t
 CELT_STREAM_DTYPE = np.dtype([("old_e", "<i2", (2 * CELT_BANDS,)), ("log_e1", "<i2", (2 * CELT_BANDS,)), ("log_e2", "<i2", (2 * CELT_BANDS,)),
                               ("rng", "<u4"), ("flags", "<u4")])                                                                                  # anm_celt_stream_t
+CELT_SYNTH_DTYPE = np.dtype([("mem", "<i4", (2, 2048 + 120)), ("preemph_mem", "<i4", (2,)), ("pf_period", "<i4"), ("pf_period_old", "<i4"), ("pf_tapset", "<i4"),
+                             ("pf_tapset_old", "<i4"), ("pf_gain", "<i2"), ("pf_gain_old", "<i2"), ("out_channels", "<u4")])                        # anm_celt_synth_t
+CELT_SYNTH_TABLES_DTYPE = np.dtype([("window", "<i2", (120,)), ("trig", "<i2", (1800,)), ("fft_tw", "<i2", (960,)), ("bitrev", "<i2", (900,)), ("e_means", "i1", (25,)),
+                                    ("pad", "i1", (3,))])                                                                                           # anm_celt_synth_tables_t
 CELT_JOB_DISABLE_INV = 1
 CELT_X_STRIDE = 1920            # int16 coefficients per frame in celt_spectrum()'s output: [channels][120 << lm], at most 2 x 960
 
@@ -381,6 +388,25 @@ def celt_spectrum(jobs, stream_begin, payload_bytes, streams=None):
     _check(lib().anm_celt_spectrum_host(_ptr(jobs) if len(jobs) else None, _ptr(sb), n_streams, _ptr(by) if len(by) else None, len(by), _ptr(st),
                                         _ptr(out) if len(jobs) else None, _ptr(x), CELT_X_STRIDE, _ptr(cm)))
     return out, st, x[:len(jobs)], cm[:len(jobs)]
+
+
+def celt_decode(jobs, stream_begin, payload_bytes, out_channels=None, streams=None, synth=None):
+    """Batched CELT decode to PCM (all three stages, include/anmodem_opus.h anm_celt_decode_*): as celt_entropy(), plus pcm[n_jobs, CELT_X_STRIDE] int16
+    (frame j: (120 << lm) x out_channels interleaved samples) and the streams' synthesis state.  out_channels: per-stream decoder channels (default: the
+    channel count of the stream's first frame); a mono decoder sets CELT_JOB_DISABLE_INV on its jobs itself."""
+    jobs = np.ascontiguousarray(jobs, dtype=CELT_JOB_DTYPE)
+    sb = np.ascontiguousarray(stream_begin, dtype=np.uint32)
+    by = np.ascontiguousarray(payload_bytes, dtype=np.uint8)
+    n_streams = len(sb) - 1
+    st = np.zeros(n_streams, dtype=CELT_STREAM_DTYPE) if streams is None else np.ascontiguousarray(streams, dtype=CELT_STREAM_DTYPE).copy()
+    sy = np.zeros(n_streams, dtype=CELT_SYNTH_DTYPE) if synth is None else np.ascontiguousarray(synth, dtype=CELT_SYNTH_DTYPE).copy()
+    if out_channels is not None:
+        sy["out_channels"] = np.asarray(out_channels, dtype=np.uint32)
+    out = np.zeros(len(jobs), dtype=CELT_FRAME_DTYPE)
+    pcm = np.zeros((max(len(jobs), 1), CELT_X_STRIDE), dtype=np.int16)
+    _check(lib().anm_celt_decode_host(_ptr(jobs) if len(jobs) else None, _ptr(sb), n_streams, _ptr(by) if len(by) else None, len(by), _ptr(st), _ptr(sy),
+                                      _ptr(out) if len(jobs) else None, _ptr(pcm), CELT_X_STRIDE))
+    return out, st, sy, pcm[:len(jobs)]
 
 
 def pb_encode_broadcast(m):

@@ -15,7 +15,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 CU = ["anm_cuda.cu", "anm_multi.cu", "anm_tx.cu", "anm_pb_gpu.cu", "anm_opus_gpu.cu", "anm_celt_gpu.cu"]
 C = ["anm_config.c", "anm_tx.c", "anm_pb.c", "anm_pb_msgs.c", "anm_pacer.c", "anm_celt_tables.c"]
-DEPS = ["anm_kernels.cuh", "anm_kernels_tc.cuh", "anm_internal.h", "anm_host_queue.h", "anm_pb_wire.h", "anm_celt_entropy.h", "../../include/anmodem.h", "../../include/anmodem_pb.h", "../../include/anmodem_opus.h"]
+DEPS = ["anm_kernels.cuh", "anm_kernels_tc.cuh", "anm_internal.h", "anm_host_queue.h", "anm_pb_wire.h", "anm_celt_entropy.h", "anm_celt_vec.h", "anm_celt_synth.h", "../../include/anmodem.h", "../../include/anmodem_pb.h", "../../include/anmodem_opus.h"]
 
 
 def _newer(target, sources):

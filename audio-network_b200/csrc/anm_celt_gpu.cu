@@ -21,7 +21,7 @@
 #include <algorithm>
 #include <new>
 
-#include "anm_celt_entropy.h"
+#include "anm_celt_synth.h"
 #include "anm_internal.h"
 
 struct anm_celt_ctx {
@@ -33,6 +33,13 @@ struct anm_celt_ctx {
     size_t hist_frames;
     ce_spec_t *d_spec;  /* per resident thread of k_celt_spectrum: working storage */
     size_t spec_threads;
+    anm_celt_synth_tables_t *d_synth_tables; /* stage 3 */
+    int16_t *d_x;       /* per frame: the normalised spectrum (anm_celt_decode_device keeps it to itself) */
+    size_t x_frames;
+    int32_t *d_raw;     /* per frame: the raw inverse-MDCT blocks of both output channels */
+    size_t raw_frames;
+    int32_t *d_freq;    /* per resident thread of k_celt_blocks: denormalised coefficients (two channels for the downmix) */
+    size_t freq_threads;
 };
 
 namespace {
@@ -90,6 +97,59 @@ __global__ void __launch_bounds__(64) k_celt_spectrum(const anm_celt_tables_t *_
     }
 }
 
+/* stage 3, frame-parallel part: one thread per FRAME (grid-stride) -- denormalisation and the raw inverse-MDCT blocks of every output channel */
+__global__ void __launch_bounds__(64) k_celt_blocks(const anm_celt_tables_t *__restrict__ t, const anm_celt_synth_tables_t *__restrict__ stb,
+                                                    const anm_celt_job_t *__restrict__ jobs, const uint32_t *__restrict__ stream_begin, uint32_t n_streams,
+                                                    uint32_t n_jobs, const anm_celt_frame_t *__restrict__ recs, const anm_celt_synth_t *__restrict__ synth,
+                                                    const int16_t *__restrict__ x, int32_t *freq, int32_t *raw) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    int32_t *fq = freq + (size_t)tid * 1920;
+    for (uint32_t j = tid; j < n_jobs; j += nthr) {
+        const anm_celt_frame_t *fr = &recs[j];
+        if (fr->flags & ANM_CELT_F_LOST) continue;
+        /* the frame's stream: the last s with stream_begin[s] <= j */
+        uint32_t lo = 0, hi = n_streams;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (stream_begin[mid] <= j) lo = mid;
+            else hi = mid;
+        }
+        int CC = (int)synth[lo].out_channels;
+        if (CC == 0) CC = jobs[stream_begin[lo]].channels;
+        cs_frame_blocks(t, stb, x + (size_t)j * 1920, fr->band_e, fr->channels, CC, fr->lm, fr->pad[0], (fr->flags & ANM_CELT_F_TRANSIENT) != 0,
+                        (fr->flags & ANM_CELT_F_SILENCE) != 0, fq, raw + (size_t)j * 1920);
+    }
+}
+
+/* stage 3, per-stream part: one thread per (stream, output channel) -- window overlap-add, pitch post-filter, de-emphasis */
+__global__ void __launch_bounds__(64) k_celt_overlap(const anm_celt_synth_tables_t *__restrict__ stb, const anm_celt_job_t *__restrict__ jobs,
+                                                     const uint32_t *__restrict__ stream_begin, uint32_t n_streams, const anm_celt_frame_t *__restrict__ recs,
+                                                     anm_celt_synth_t *synth, const int32_t *__restrict__ raw, int16_t *pcm, uint32_t pcm_stride) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x, s = id >> 1;
+    const int c = (int)(id & 1u);
+    if (s >= n_streams) return;
+    anm_celt_synth_t *sy = &synth[s];
+    int CC = (int)sy->out_channels;
+    if (CC == 0) CC = stream_begin[s + 1] > stream_begin[s] ? jobs[stream_begin[s]].channels : 1;
+    cs_pf_t pf;
+    cs_pf_load(&pf, sy);
+    if (c < CC) {
+        int32_t pm = sy->preemph_mem[c];
+        for (uint32_t j = stream_begin[s]; j < stream_begin[s + 1]; ++j) {
+            const anm_celt_frame_t *fr = &recs[j];
+            if (fr->flags & ANM_CELT_F_LOST) continue;
+            cs_channel_frame(stb, sy->mem[c], &pm, &pf, fr, raw + (size_t)j * 1920 + (size_t)c * (120u << fr->lm), CC, c, pcm + (size_t)j * pcm_stride);
+        }
+        sy->preemph_mem[c] = pm;
+    }
+    /* both channels computed the same post-filter state; the pair meets before one of them writes it back (they read it above) */
+    __syncwarp();
+    if (c == 0) {
+        cs_pf_store(&pf, sy);
+        sy->out_channels = (uint32_t)CC;
+    }
+}
+
 } /* namespace */
 
 extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
@@ -112,6 +172,13 @@ extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
     c->hist_frames = 0;
     c->d_spec = nullptr;
     c->spec_threads = 0;
+    c->d_synth_tables = nullptr;
+    c->d_x = nullptr;
+    c->x_frames = 0;
+    c->d_raw = nullptr;
+    c->raw_frames = 0;
+    c->d_freq = nullptr;
+    c->freq_threads = 0;
     int rc = anm_celt_tables_build(h);
     if (rc == ANM_OK && (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&c->d_tables, sizeof *h) != cudaSuccess ||
                          cudaMemcpy(c->d_tables, h, sizeof *h, cudaMemcpyHostToDevice) != cudaSuccess)) {
@@ -119,8 +186,19 @@ extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
         rc = ANM_ERR_CUDA;
     }
     delete h;
+    if (rc == ANM_OK) {
+        anm_celt_synth_tables_t *hs = new (std::nothrow) anm_celt_synth_tables_t();
+        if (!hs) rc = ANM_ERR_NOMEM;
+        else if ((rc = anm_celt_synth_tables_build(hs)) == ANM_OK &&
+                 (cudaMalloc(&c->d_synth_tables, sizeof *hs) != cudaSuccess || cudaMemcpy(c->d_synth_tables, hs, sizeof *hs, cudaMemcpyHostToDevice) != cudaSuccess)) {
+            anm_set_error("anm_celt_ctx_create: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = ANM_ERR_CUDA;
+        }
+        delete hs;
+    }
     if (rc != ANM_OK) {
         cudaFree(c->d_tables);
+        cudaFree(c->d_synth_tables);
         delete c;
         return rc;
     }
@@ -138,6 +216,10 @@ extern "C" void anm_celt_ctx_destroy(anm_celt_ctx_t *c) {
     cudaFree(c->d_scratch);
     cudaFree(c->d_hist);
     cudaFree(c->d_spec);
+    cudaFree(c->d_synth_tables);
+    cudaFree(c->d_x);
+    cudaFree(c->d_raw);
+    cudaFree(c->d_freq);
     delete c;
 }
 
@@ -210,6 +292,32 @@ extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t 
     return ANM_OK;
 }
 
+extern "C" int anm_celt_decode_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
+                                      const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_synth_t *d_synth, anm_celt_frame_t *d_out,
+                                      int16_t *d_pcm, uint32_t pcm_stride, void *stream) {
+    int rc = check_args(c, d_jobs, d_stream_begin, d_streams, d_out, n_streams, bytes_mask);
+    if (rc != ANM_OK) return rc;
+    if (((!d_pcm || !d_synth) && n_jobs) || pcm_stride < 120u) return ANM_ERR_ARG;
+    if (n_streams == 0 || n_jobs == 0) return ANM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * 8u);
+    if ((rc = grow(&c->d_x, &c->x_frames, (size_t)n_jobs * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
+    if ((rc = grow(&c->d_raw, &c->raw_frames, (size_t)n_jobs * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
+    if ((rc = grow(&c->d_freq, &c->freq_threads, (size_t)blocks * 64u * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
+    if ((rc = anm_celt_spectrum_device(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_x, 1920u, nullptr, stream)) != ANM_OK)
+        return rc;
+    k_celt_blocks<<<blocks, 64, 0, s>>>(c->d_tables, c->d_synth_tables, d_jobs, d_stream_begin, n_streams, n_jobs, d_out, d_synth, c->d_x, c->d_freq, c->d_raw);
+    k_celt_overlap<<<(2u * n_streams + 63u) / 64u, 64, 0, s>>>(c->d_synth_tables, d_jobs, d_stream_begin, n_streams, d_out, d_synth, c->d_raw, d_pcm, pcm_stride);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        anm_set_error("k_celt_blocks / k_celt_overlap launch failed: %s", cudaGetErrorString(e));
+        return ANM_ERR_CUDA;
+    }
+    return ANM_OK;
+}
+
 static int host_impl(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
                      anm_celt_stream_t *streams, anm_celt_frame_t *out, int16_t *x, uint32_t x_stride, uint8_t *collapse, bool spectrum) {
     if ((!jobs || !stream_begin || !streams || !out) && n_streams) return ANM_ERR_ARG;
@@ -272,4 +380,57 @@ extern "C" int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t 
 extern "C" int anm_celt_spectrum_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
                                       anm_celt_stream_t *streams, anm_celt_frame_t *out, int16_t *x, uint32_t x_stride, uint8_t *collapse) {
     return host_impl(jobs, stream_begin, n_streams, bytes, n_bytes, streams, out, x, x_stride, collapse, true);
+}
+
+extern "C" int anm_celt_decode_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
+                                    anm_celt_stream_t *streams, anm_celt_synth_t *synth, anm_celt_frame_t *out, int16_t *pcm, uint32_t pcm_stride) {
+    if ((!jobs || !stream_begin || !streams || !synth || !out || !pcm) && n_streams) return ANM_ERR_ARG;
+    if (pcm_stride < 120u) return ANM_ERR_ARG;
+    if (n_streams == 0) return ANM_OK;
+    const uint32_t n_jobs = stream_begin[n_streams];
+    for (uint32_t i = 0; i < n_jobs; ++i)
+        if ((size_t)jobs[i].offset + jobs[i].len > n_bytes) return ANM_ERR_ARG;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        anm_set_error("no CUDA device: the CELT decoder stages have no CPU fallback");
+        return ANM_ERR_CUDA;
+    }
+    anm_celt_ctx_t *c = nullptr;
+    int rc = anm_celt_ctx_create(dev, &c);
+    if (rc != ANM_OK) return rc;
+    anm_celt_job_t *d_j = nullptr;
+    uint32_t *d_sb = nullptr;
+    uint8_t *d_b = nullptr;
+    anm_celt_stream_t *d_s = nullptr;
+    anm_celt_synth_t *d_y = nullptr;
+    anm_celt_frame_t *d_o = nullptr;
+    int16_t *d_p = nullptr;
+    const size_t nj = n_jobs ? n_jobs : 1, p_bytes = nj * pcm_stride * sizeof(int16_t);
+    rc = ANM_ERR_CUDA;
+    if (cudaMalloc(&d_j, nj * sizeof *d_j) == cudaSuccess && cudaMalloc(&d_sb, (n_streams + 1) * sizeof *d_sb) == cudaSuccess &&
+        cudaMalloc(&d_b, n_bytes ? n_bytes : 1) == cudaSuccess && cudaMalloc(&d_s, n_streams * sizeof *d_s) == cudaSuccess &&
+        cudaMalloc(&d_y, n_streams * sizeof *d_y) == cudaSuccess && cudaMalloc(&d_o, nj * sizeof *d_o) == cudaSuccess && cudaMalloc(&d_p, p_bytes) == cudaSuccess &&
+        cudaMemcpy(d_j, jobs, n_jobs * sizeof *d_j, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(d_sb, stream_begin, (n_streams + 1) * sizeof *d_sb, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(d_b, bytes, n_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(d_s, streams, n_streams * sizeof *d_s, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(d_y, synth, n_streams * sizeof *d_y, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemset(d_p, 0, p_bytes) == cudaSuccess) {
+        rc = anm_celt_decode_device(c, d_j, d_sb, n_streams, n_jobs, d_b, 0xFFFFFFFFu, d_s, d_y, d_o, d_p, pcm_stride, nullptr);
+        if (rc == ANM_OK && (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(out, d_o, n_jobs * sizeof *d_o, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                             cudaMemcpy(streams, d_s, n_streams * sizeof *d_s, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                             cudaMemcpy(synth, d_y, n_streams * sizeof *d_y, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                             cudaMemcpy(pcm, d_p, (size_t)n_jobs * pcm_stride * sizeof(int16_t), cudaMemcpyDeviceToHost) != cudaSuccess))
+            rc = ANM_ERR_CUDA;
+    }
+    if (rc == ANM_ERR_CUDA) anm_set_error("anm_celt_decode_host: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_j);
+    cudaFree(d_sb);
+    cudaFree(d_b);
+    cudaFree(d_s);
+    cudaFree(d_y);
+    cudaFree(d_o);
+    cudaFree(d_p);
+    anm_celt_ctx_destroy(c);
+    return rc;
 }

@@ -13,10 +13,17 @@
  *        pulse cache   = bits needed for K pulses in N samples   (celt/rate.c:73-140 compute_pulse_cache, cwrs.c:46-72 log2_frac)
  *        cache caps    = highest useful rate per band            (celt/rate.c:142-244)
  *        PVQ sizes     U(n, k) = U(n-1, k) + U(n, k-1) + U(n-1, k-1)   (celt/cwrs.c:75-207)
+ *      and, for the synthesis (anm_celt_synth_tables_t; checked against the reference's static tables in tests/test_celt_synth.py):
+ *        window        = sin(pi/2 sin^2(pi/2 (i + 1/2) / 120)), Q15      (celt/modes.c:379)
+ *        MDCT twiddles = round(32768 cos(2 pi (i + 1/8) / N)), clamped      (celt/mdct.c:94, the form the static tables were dumped from)
+ *        FFT twiddles  = (cos_norm(-i / 480), cos_norm(-i / 480 - 1/4))  (celt/kiss_fft.c:431-437 compute_twiddles, kf_cexp2)
+ *        bit reversal  of the mixed-radix FFTs                           (celt/kiss_fft.c:329-359 compute_bitrev_table)
+ *      The band mean energies eMeans (celt/quant_bands.c:44-50) are normative constants of kind (1).
  */
+#include <math.h>
 #include <string.h>
 
-#include "../../include/anmodem_opus.h"
+#include "anm_celt_entropy.h" /* cv_cos_norm for the synthesis twiddles */
 
 #define NB ANM_CELT_BANDS
 #define BITRES 3
@@ -193,5 +200,65 @@ int anm_celt_tables_build(anm_celt_tables_t *t) {
                 max_bits = (4 * max_bits / (C * ((k_ebands[j + 1] - k_ebands[j]) << i))) - 64;
                 *cap++ = (uint8_t)max_bits;
             }
+    return ANM_OK;
+}
+
+
+/* ---------------------------------------------------------------- synthesis tables */
+static void bitrev_fill(int fout, int16_t *f, int fstride, const int8_t *factors) {
+    const int p = *factors++, m = *factors++;
+    if (m == 1) {
+        for (int j = 0; j < p; j++) {
+            *f = (int16_t)(fout + j);
+            f += fstride;
+        }
+    } else {
+        for (int j = 0; j < p; j++) {
+            bitrev_fill(fout, f, fstride * p, factors);
+            f += fstride;
+            fout += m;
+        }
+    }
+}
+
+int anm_celt_synth_tables_build(anm_celt_synth_tables_t *t) {
+    static const int8_t k_emeans[25] = {103, 100, 92, 85, 81, 77, 72, 70, 78, 75, 73, 71, 78, 74, 69, 72, 70, 74, 76, 71, 60, 60, 60, 60, 60};
+    /* radix / remaining length of every stage of the 480, 240, 120 and 60-point transforms (celt/static_modes_fixed.h:432-498; what kf_factor gives) */
+    static const int8_t k_factors[4][10] = {{5, 96, 3, 32, 4, 8, 2, 4, 4, 1}, {5, 48, 3, 16, 4, 4, 4, 1, 0, 0}, {5, 24, 3, 8, 2, 4, 4, 1, 0, 0}, {5, 12, 3, 4, 4, 1, 0, 0, 0, 0}};
+    const double pi = 3.14159265358979323846; /* M_PI */
+    if (!t) return ANM_ERR_ARG;
+    memset(t, 0, sizeof *t);
+    for (int i = 0; i < 120; i++) {
+        const double s = sin(.5 * pi * (i + .5) / 120);
+        const double w = floor(.5 + 32768. * sin(.5 * pi * s * s));
+        t->window[i] = (int16_t)(w > 32767 ? 32767 : w);
+    }
+    {
+        int16_t *trig = t->trig;
+        int N = 1920, N2 = 960;
+        for (int shift = 0; shift <= 3; shift++) {
+            for (int i = 0; i < N2; i++) { /* the static tables of the reference were dumped from the floating-point formula (celt/mdct.c:94) */
+                double v = floor(.5 + 32768 * cos(2 * pi * (i + .125) / N));
+                v = v > 32767 ? 32767 : v < -32767 ? -32767 : v;
+                trig[i] = (int16_t)v;
+            }
+            trig += N2;
+            N2 >>= 1;
+            N >>= 1;
+        }
+    }
+    for (int i = 0; i < 480; i++) {
+        const int32_t phase = (int32_t)((uint32_t)(-i) << 17) / 480; /* DIV32(SHL32(phase, 17), nfft): C division, towards zero */
+        t->fft_tw[2 * i] = cv_cos_norm(phase);
+        t->fft_tw[2 * i + 1] = cv_cos_norm(phase - 32768);
+    }
+    {
+        int16_t *b = t->bitrev;
+        for (int k = 0; k < 4; k++) {
+            bitrev_fill(0, b, 1, k_factors[k]);
+            b += 480 >> k;
+        }
+    }
+    memcpy(t->e_means, k_emeans, sizeof k_emeans);
     return ANM_OK;
 }

@@ -131,6 +131,30 @@ typedef struct anm_celt_stream {
     uint32_t flags; /* bit 0: log_e1 / log_e2 are valid (clear: both are -28 dB, the decoder's reset value) */
 } anm_celt_stream_t;  /* 260 bytes */
 
+/* ---- CELT synthesis (row f1, stage 3): normalised spectrum -> PCM ------------------------------------------------- */
+/* static data of the synthesis, built by anm_celt_synth_tables_build() from the standard's formulas (and checked against the reference's static
+ * tables): the 120-sample window, the MDCT twiddles of the 1920 / 960 / 480 / 240-point transforms back to back, the FFT twiddles of the 480-point
+ * transform (the shorter ones use every 2nd / 4th / 8th), the bit-reversal permutations of the 480 / 240 / 120 / 60-point FFTs, the band mean energies */
+typedef struct anm_celt_synth_tables {
+    int16_t window[120];
+    int16_t trig[1800];
+    int16_t fft_tw[2 * 480]; /* (re, im) */
+    int16_t bitrev[480 + 240 + 120 + 60];
+    int8_t e_means[25];
+    int8_t pad[3];
+} anm_celt_synth_tables_t;
+int anm_celt_synth_tables_build(anm_celt_synth_tables_t *out); /* host; deterministic */
+
+/* per-stream synthesis state carried between calls (zero-initialised = a fresh decoder): the output history of both channels (overlap-add tail and
+ * the post-filter's memory), the de-emphasis memory and the post-filter parameters of the last two frames */
+typedef struct anm_celt_synth {
+    int32_t mem[2][2048 + 120];
+    int32_t preemph_mem[2];
+    int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
+    int16_t pf_gain, pf_gain_old;
+    uint32_t out_channels; /* channels of the decoder (1 or 2); 0: the channel count of the stream's first frame in the call */
+} anm_celt_synth_t;
+
 /* Opaque device-side context (tables in HBM). */
 typedef struct anm_celt_ctx anm_celt_ctx_t;
 int anm_celt_ctx_create(int device, anm_celt_ctx_t **out);
@@ -153,6 +177,16 @@ int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, co
                              uint32_t x_stride, uint8_t *d_collapse, void *stream);
 int anm_celt_spectrum_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
                            anm_celt_stream_t *streams, anm_celt_frame_t *out, int16_t *x, uint32_t x_stride, uint8_t *collapse);
+/* All three stages: CELT frames -> PCM, sample for sample what the reference's celt_decode_with_ec() writes (fixed-point build; no packet-loss
+ * concealment: frames of <= 1 byte produce no PCM and leave the stream's state untouched).  As anm_celt_spectrum_device, then k_celt_blocks (one thread
+ * per frame and output channel: denormalisation and the inverse MDCT blocks) and k_celt_overlap (one thread per stream and output channel: window
+ * overlap-add, pitch post-filter, de-emphasis -- the per-stream recurrence).  d_synth: one anm_celt_synth_t per stream; d_pcm: frame j's
+ * (120 << lm) x out_channels interleaved int16 samples at d_pcm + j * pcm_stride (pcm_stride >= 1920 always fits). */
+int anm_celt_decode_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
+                           const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_synth_t *d_synth, anm_celt_frame_t *d_out,
+                           int16_t *d_pcm, uint32_t pcm_stride, void *stream);
+int anm_celt_decode_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
+                         anm_celt_stream_t *streams, anm_celt_synth_t *synth, anm_celt_frame_t *out, int16_t *pcm, uint32_t pcm_stride);
 /* host arrays: copies in, runs the kernel, copies out (no CPU fallback: ANM_ERR_CUDA without a device) */
 int anm_celt_entropy_host(const anm_celt_job_t *jobs, const uint32_t *stream_begin, uint32_t n_streams, const uint8_t *bytes, size_t n_bytes,
                           anm_celt_stream_t *streams, anm_celt_frame_t *out);

@@ -249,3 +249,21 @@ int ref_opus_frames_final_range(const uint8_t *frames, const int32_t *lens, int 
     opus_decoder_destroy(d);
     return n;
 }
+
+/* static synthesis tables of the standard mode: window[120], mdct trig[1800], fft twiddles[480] (re, im), bitrev of the four transforms back to back */
+int ref_celt_synth_tables(int16_t *window, int16_t *trig, int16_t *fft_tw, int16_t *bitrev) {
+    int err = 0;
+    const CELTMode *m = opus_custom_mode_create(48000, 960, &err);
+    if (!m) return -1;
+    memcpy(window, m->window, 120 * sizeof(int16_t));
+    memcpy(trig, m->mdct.trig, 1800 * sizeof(int16_t));
+    for (int i = 0; i < 480; i++) {
+        fft_tw[2 * i] = m->mdct.kfft[0]->twiddles[i].r;
+        fft_tw[2 * i + 1] = m->mdct.kfft[0]->twiddles[i].i;
+    }
+    for (int k = 0, off = 0; k < 4; k++) {
+        memcpy(bitrev + off, m->mdct.kfft[k]->bitrev, (size_t)(480 >> k) * sizeof(int16_t));
+        off += 480 >> k;
+    }
+    return m->mdct.n;
+}

@@ -40,9 +40,10 @@ def harness():
     os.makedirs(BUILD, exist_ok=True)
     so = os.path.join(BUILD, "libcelt_harness.so")
     srcs = [os.path.join(HERE, "celt_harness.c"), os.path.join(ROOT, "audio-network_b200", "csrc", "anm_celt_tables.c")]
-    deps = srcs + [os.path.join(ROOT, "audio-network_b200", "csrc", "anm_celt_entropy.h"), os.path.join(ROOT, "include", "anmodem_opus.h")]
+    deps = srcs + [os.path.join(ROOT, "audio-network_b200", "csrc", h) for h in ("anm_celt_entropy.h", "anm_celt_vec.h", "anm_celt_synth.h")] + \
+        [os.path.join(ROOT, "include", "anmodem_opus.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu11", "-Wall", "-o", so] + srcs)
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=gnu11", "-Wall", "-o", so] + srcs + ["-lm"])
     L = C.CDLL(so)
     L.harness_celt_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.anm_celt_tables_build.argtypes = [C.c_void_p]

@@ -60,3 +60,29 @@ int harness_celt_frame_full(const anm_celt_tables_t *t, const uint8_t *bytes, ui
 }
 uint32_t harness_sizeof_stream(void) { return (uint32_t)sizeof(anm_celt_stream_t); }
 uint32_t harness_sizeof_hist(void) { return (uint32_t)sizeof(ce_hist_t); }
+
+/* ---- stage 3 ---- */
+#include "../../audio-network_b200/csrc/anm_celt_synth.h"
+uint32_t harness_sizeof_synth(void) { return (uint32_t)sizeof(anm_celt_synth_t); }
+uint32_t harness_sizeof_synth_tables(void) { return (uint32_t)sizeof(anm_celt_synth_tables_t); }
+
+/* all three stages for one frame of a stream, chained as the kernels chain them; pcm: [120 << LM][CC] */
+int harness_celt_decode_frame(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *stb, const uint8_t *bytes, uint32_t len, int C, int CC, int LM, int end,
+                              anm_celt_stream_t *st, anm_celt_synth_t *syn, anm_celt_frame_t *out, int16_t *pcm) {
+    static ce_spec_t sp;
+    static int16_t X[2 * 960];
+    static int32_t freq[2 * 960], raw[2 * 960];
+    int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
+    uint8_t cm[2 * ANM_CE_NB];
+    ce_hist_t hist;
+    int rc = anm_celt_entropy_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out);
+    if (rc != 0) return rc;
+    anm_celt_stream_step(out, qi, eoff, st, &hist);
+    if (out->flags & ANM_CELT_F_LOST) return 0;
+    for (int i = 0; i < 2 * 960; i++) X[i] = 0;
+    rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, CC == 1, &hist, out, &sp, X, cm);
+    if (rc != 0) return rc;
+    cs_frame_blocks(t, stb, X, out->band_e, C, CC, LM, end, (out->flags & ANM_CELT_F_TRANSIENT) != 0, (out->flags & ANM_CELT_F_SILENCE) != 0, freq, raw);
+    cs_stream_frame(stb, syn, out, raw, CC, pcm);
+    return 0;
+}

@@ -1,0 +1,190 @@
+"""Row f1, stage 3: the batched CELT decode down to PCM (include/anmodem_opus.h, anm_celt_decode_*) against the REFERENCE's libopus 1.3.1 in its fixed-point
+build: every int16 sample equals what the reference decoder writes.
+
+Two independent pins: (1) tests/golden/opus_packets.json -- SHA-256 of the PCM the reference's PUBLIC opus_decode() returns for whole streams of the
+transmitter's settings; (2) tests/golden/celt_pcm.npz -- per-frame digests of what the reference's celt_decode_with_ec() writes for the 1,687 frames
+of the entropy goldens, with a native, a mono (downmix) and a stereo (upmix) decoder (tests/golden/make_celt_pcm_golden.py).  `-m "not gpu"` runs the
+product's headers compiled for the host by the test harness (a checker of the logic: the product has no CPU path); `-m gpu` runs the CUDA kernels
+through the C ABI."""
+import base64
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import audio_network_b200 as anm
+import celt_binding as cb
+import celt_spectrum_binding as sbind
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "celt_entropy.npz"))
+PCM = np.load(os.path.join(HERE, "golden", "celt_pcm.npz"))
+PACKETS = json.load(open(os.path.join(HERE, "golden", "opus_packets.json")))
+HAVE_REF = os.path.exists(cb.REF_OPUS)
+
+
+def _digest(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a, dtype="<i2").tobytes()).digest()[:8], dtype="<u8")[0]
+
+
+def _harness():
+    L = sbind.harness()
+    L.anm_celt_synth_tables_build.argtypes = [C.c_void_p]
+    L.harness_celt_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]
+    assert L.harness_sizeof_synth() == anm.CELT_SYNTH_DTYPE.itemsize == 17376 and L.harness_sizeof_synth_tables() == anm.CELT_SYNTH_TABLES_DTYPE.itemsize
+    stb = np.zeros(1, anm.CELT_SYNTH_TABLES_DTYPE)
+    assert L.anm_celt_synth_tables_build(stb.ctypes.data) == 0
+    return L, stb
+
+
+def _packet_bytes(p):
+    return bytes.fromhex(p) if all(c in "0123456789abcdefABCDEF" for c in p) else base64.b64decode(p)
+
+
+def _stream_frames(s):
+    """the CELT frames of one golden opus stream, in order: [(bytes, channels, lm, end)]"""
+    out = []
+    for p, parse in zip(s["packets"], s["parse"]):
+        out += cb.frames_of_packet(_packet_bytes(p), parse)
+    return out
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libref_opus.so not built (reference tree absent)")
+def test_computed_synthesis_tables_equal_the_reference_static_tables():
+    """window, MDCT twiddles, FFT twiddles and bit-reversal tables are COMPUTED by anm_celt_tables.c; they must equal the reference's static tables"""
+    _, stb = _harness()
+    R = sbind.ref()
+    R.ref_celt_synth_tables.argtypes = [C.c_void_p] * 4
+    w, tr, tw, br = np.zeros(120, np.int16), np.zeros(1800, np.int16), np.zeros(960, np.int16), np.zeros(900, np.int16)
+    assert R.ref_celt_synth_tables(w.ctypes.data, tr.ctypes.data, tw.ctypes.data, br.ctypes.data) == 1920
+    for k, a in (("window", w), ("trig", tr), ("fft_tw", tw), ("bitrev", br)):
+        assert np.array_equal(stb[0][k], a), k
+
+
+def _host_decode_stream(L, stb, frames, cc):
+    t = cb.tables()
+    st, syn = np.zeros(1, anm.CELT_STREAM_DTYPE), np.zeros(1, anm.CELT_SYNTH_DTYPE)
+    out = []
+    for f, ch, lm, end in frames:
+        b = np.frombuffer(f, np.uint8).copy() if len(f) else np.zeros(1, np.uint8)
+        rec, pcm = np.zeros(1, cb.FRAME_DTYPE), np.zeros(960 * cc, np.int16)
+        assert L.harness_celt_decode_frame(t.ctypes.data, stb.ctypes.data, b.ctypes.data, len(f), ch, cc, lm, end, st.ctypes.data, syn.ctypes.data, rec.ctypes.data,
+                                           pcm.ctypes.data) == 0
+        out.append(pcm[: (120 << lm) * cc].copy())
+    return out
+
+
+def test_host_harness_pcm_equals_the_public_api_decode_of_the_golden_streams():
+    L, stb = _harness()
+    for s in PACKETS["streams"]:
+        pcm = np.concatenate(_host_decode_stream(L, stb, _stream_frames(s), s["channels"]))
+        assert hashlib.sha256(pcm.tobytes()).hexdigest() == s["decoded_sha256"], s["name"]
+        assert pcm[:16].tolist() == np.array(s["decoded_head"]).reshape(-1)[:16].tolist()
+
+
+def test_host_harness_pcm_equals_the_reference_decoder_frame_by_frame_native_mono_and_stereo_decoders():
+    L, stb = _harness()
+    fr, by, sb = GOLD["frames"], GOLD["bytes"], GOLD["stream_begin"]
+    for s in range(len(sb) - 1):
+        js = range(sb[s], sb[s + 1])
+        frames = [(bytes(by[fr[j]["offset"]: fr[j]["offset"] + fr[j]["len"]]), int(fr[j]["channels"]), int(fr[j]["lm"]), int(fr[j]["end_band"])) for j in js]
+        native = max(f[1] for f in frames)
+        for key, cc in (("cc_native", native), ("cc_mono", 1), ("cc_stereo", 2)):
+            if s % 4 and key != "cc_native":
+                continue                      # every stream natively, every fourth one through the down- and upmixing decoders too
+            for j, pcm in zip(js, _host_decode_stream(L, stb, frames, cc)):
+                assert _digest(pcm) == PCM[key][j], (s, key, j)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _jobs_from_gold(cc_of_stream):
+    fr, sb = GOLD["frames"], GOLD["stream_begin"]
+    jobs = np.zeros(len(fr), dtype=anm.CELT_JOB_DTYPE)
+    for k in ("offset", "len", "channels", "lm", "end_band"):
+        jobs[k] = fr[k]
+    for s in range(len(sb) - 1):
+        if cc_of_stream[s] == 1:
+            jobs["flags"][sb[s]: sb[s + 1]] = anm.CELT_JOB_DISABLE_INV
+    return jobs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["cc_native", "cc_mono", "cc_stereo"])
+def test_gpu_pcm_equals_the_reference_decoder_on_the_golden_frames(key):
+    """k_celt_entropy -> k_celt_energies -> k_celt_spectrum -> k_celt_blocks -> k_celt_overlap through the C ABI: 58 streams / 1,687 frames"""
+    fr, sb = GOLD["frames"], GOLD["stream_begin"]
+    native = np.array([fr["channels"][sb[s]: sb[s + 1]].max() for s in range(len(sb) - 1)])
+    cc = {"cc_native": native, "cc_mono": np.ones_like(native), "cc_stereo": np.full_like(native, 2)}[key]
+    rec, _, sy, pcm = anm.celt_decode(_jobs_from_gold(cc), sb, GOLD["bytes"], out_channels=cc)
+    assert np.array_equal(rec["final_range"], fr["final_range"]) and np.array_equal(sy["out_channels"], cc)
+    for s in range(len(sb) - 1):
+        for j in range(sb[s], sb[s + 1]):
+            ns = (120 << int(fr["lm"][j])) * int(cc[s])
+            assert _digest(pcm[j, :ns]) == PCM[key][j], (key, s, j)
+    if key == "cc_native":
+        for j, want in zip(PCM["head_idx"], PCM["head"]):
+            assert np.array_equal(pcm[j], want)
+
+
+@pytest.mark.gpu
+def test_gpu_pcm_of_the_transmitter_streams_equals_the_public_api_and_state_carries_across_calls():
+    """the five golden streams of the transmitter's settings, each decoded in ONE call and in two calls with the stream state (energies, histories, noise
+    seed) and the synthesis state (overlap, post-filter memory, de-emphasis) carried through: SHA-256 of the PCM == the reference's opus_decode()"""
+    for s in PACKETS["streams"]:
+        frames = _stream_frames(s)
+        by = np.frombuffer(b"".join(f[0] for f in frames), np.uint8)
+        jobs = np.zeros(len(frames), dtype=anm.CELT_JOB_DTYPE)
+        off = 0
+        for k, (f, ch, lm, end) in enumerate(frames):
+            jobs[k] = (off, len(f), ch, lm, end, anm.CELT_JOB_DISABLE_INV if s["channels"] == 1 else 0)
+            off += len(f)
+        cc = s["channels"]
+
+        def flat(pcm, js):
+            return np.concatenate([pcm[k, : (120 << int(js["lm"][k])) * cc] for k in range(len(js))])
+        _, _, _, pcm = anm.celt_decode(jobs, [0, len(jobs)], by, out_channels=[cc])
+        assert hashlib.sha256(flat(pcm, jobs).tobytes()).hexdigest() == s["decoded_sha256"], s["name"]
+        h = len(jobs) // 2
+        _, st, sy, pa = anm.celt_decode(jobs[:h], [0, h], by, out_channels=[cc])
+        _, _, _, pb = anm.celt_decode(jobs[h:], [0, len(jobs) - h], by, streams=st, synth=sy)
+        assert hashlib.sha256(np.concatenate([flat(pa, jobs[:h]), flat(pb, jobs[h:])]).tobytes()).hexdigest() == s["decoded_sha256"], s["name"]
+
+
+@pytest.mark.gpu
+def test_gpu_receive_chain_pcm_in_pcm_out():
+    """The widened hot path end to end on the GPU: ToReceiver{AudioData{CELT packet}} messages -> modem frames -> modem PCM -> k_demod -> k_pb_deframe ->
+    k_opus_parse -> the five CELT kernels: the AUDIO that comes out equals what the reference's opus_decode() returns for the packets that went in."""
+    s = [x for x in PACKETS["streams"] if x["name"] == "stereo_20ms"][0]
+    L = anm.lib()
+    L.anm_pb_encode_to_receiver_audio.restype = C.c_size_t
+    cfg = anm.config_preset("ref4")
+    buf = (C.c_uint8 * 2048)()
+    prog = [np.full(4, 255, np.uint8)]
+    for p in s["packets"]:
+        opus = _packet_bytes(p)
+        n = L.anm_pb_encode_to_receiver_audio(opus, C.c_size_t(len(opus)), buf, C.c_size_t(2048))
+        prog += [anm.frame_symbols(cfg, bytes(buf[:n])), np.full(5, 255, np.uint8)]
+    prog = np.concatenate(prog)
+    n = ((len(prog) + 8 + 31) // 32 * 32) * cfg.sym_len
+    pcm_in = anm.tx_render(cfg, prog, anm.tx_params(seed=8, amplitude=0.5, snr_db=12.0), 0, n).reshape(1, -1)
+    dm = anm.Demod(cfg, 1, device=0)
+    dm.feed_host(np.ascontiguousarray(pcm_in))
+    dm.collect()
+    recs, pay = dm.read_frames(cap=1 << 12, bytes_cap=1 << 22)
+    dm.close()
+    assert len(recs) == len(s["packets"]) and (recs["crc_ok"] == 1).all()
+    spans = anm.pb_deframe(recs, pay)
+    pk = anm.opus_parse(spans, pay)
+    assert (pk["count"] == 1).all() and (pk["mode"] == 1002).all()
+    jobs = np.zeros(len(recs), dtype=anm.CELT_JOB_DTYPE)
+    jobs["offset"] = spans["audio_offset"] + pk["payload_offset"].astype(np.uint32)
+    jobs["len"] = pk["size"][:, 0]
+    jobs["channels"] = pk["channels"]
+    jobs["lm"] = 3
+    jobs["end_band"] = 21
+    _, _, _, audio = anm.celt_decode(jobs, [0, len(jobs)], pay, out_channels=[2])
+    assert hashlib.sha256(audio[:, :1920].tobytes()).hexdigest() == s["decoded_sha256"]
