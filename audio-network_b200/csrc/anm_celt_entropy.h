@@ -256,12 +256,16 @@ ANM_CE_FN uint32_t ce_pvq_u(const anm_celt_tables_t *t, int n, int k) {
 /* ---------------------------------------------------------------- band splitting (stage 1: bits only; stage 2: with the spectrum) */
 /* per-frame working storage of stage 2 (NULL in a ce_band_ctx_t = stage 1: no spectrum arithmetic at all) */
 typedef struct ce_spec {
-    int16_t norm[2 * 624]; /* folding source: the decoded bands so far, scaled by sqrt(N) (two channels for dual stereo) */
-    int16_t tmp[176];      /* Hadamard reordering scratch */
-    int iy[176];           /* pulse vector of one partition */
+    int16_t *norm;         /* [2 * 624] folding source: the decoded bands so far, scaled by sqrt(N) (two channels for dual stereo) */
+    int16_t *tmp;          /* [176] Hadamard reordering scratch */
+    int *iy;               /* [176] pulse vector of one partition */
     uint32_t seed;         /* noise generator (CELTDecoder.rng) */
     int spread, disable_inv;
+    int lane, nl;          /* this thread's share of the loops over coefficients (anm_celt_vec.h); the arrays above are shared by the nl lanes */
 } ce_spec_t;
+#define CE_SPEC_NORM 1248
+#define CE_SPEC_TMP 176
+#define CE_SPEC_IY 176
 
 typedef struct ce_band_ctx {
     const anm_celt_tables_t *t;
@@ -370,10 +374,13 @@ ANM_CE_FN unsigned ce_band_n1(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, int st
             sign = (int)ce_bits(ctx->ec, 1);
             ctx->remaining_bits -= 1 << ANM_CE_BITRES;
         }
-        if (ctx->sp) x[0] = sign ? -16384 : 16384; /* NORM_SCALING */
+        if (ctx->sp && ctx->sp->lane == 0) x[0] = sign ? -16384 : 16384; /* NORM_SCALING */
         x = Y;
     }
-    if (ctx->sp && lowband_out) lowband_out[0] = (int16_t)(X[0] >> 4);
+    if (ctx->sp) {
+        if (ctx->sp->lane == 0 && lowband_out) lowband_out[0] = (int16_t)(X[0] >> 4);
+        CV_SYNC();
+    }
     return 1;
 }
 
@@ -439,33 +446,36 @@ static unsigned ce_partition(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B
             ctx->out->pvq_pulses += (uint32_t)K;
             ctx->out->pvq_index_xor ^= idx * 2654435761u + (uint32_t)(N * 131 + K);
             if (sp) { /* alg_unquant */
-                const int32_t Ryy = cv_cwrsi(ctx->t, N, K, idx, sp->iy);
-                cv_normalise_residual(sp->iy, X, N, Ryy, gain);
-                cv_exp_rotation_dec(X, N, B, K, sp->spread);
-                cm = cv_collapse_mask(sp->iy, N, B);
+                const int32_t Ryy = cv_cwrsi(ctx->t, N, K, idx, sp->iy, sp->lane);
+                cv_normalise_residual(sp->iy, X, N, Ryy, gain, sp->lane, sp->nl);
+                cv_exp_rotation_dec(X, N, B, K, sp->spread, sp->lane, sp->nl);
+                cm = cv_collapse_mask(sp->iy, N, B, sp->lane, sp->nl);
+                CV_SYNC(); /* iy is free for the next partition */
             }
         } else if (sp) {
             /* no pulse: fill the partition anyway */
             const unsigned cm_mask = (unsigned)(1UL << B) - 1;
             fill &= (int)cm_mask;
             if (!fill) {
-                for (int j = 0; j < N; j++) X[j] = 0;
+                for (int j = sp->lane; j < N; j += sp->nl) X[j] = 0;
+                CV_SYNC();
             } else {
-                if (lowband == 0) { /* noise */
+                CV_SYNC();
+                if (lowband == 0) { /* noise: every lane steps the generator, one stores */
                     for (int j = 0; j < N; j++) {
                         sp->seed = cv_lcg(sp->seed);
-                        X[j] = (int16_t)((int32_t)sp->seed >> 20);
+                        if (sp->lane == 0) X[j] = (int16_t)((int32_t)sp->seed >> 20);
                     }
                     cm = cm_mask;
                 } else { /* folded spectrum, plus a little noise about 48 dB below it */
                     for (int j = 0; j < N; j++) {
                         sp->seed = cv_lcg(sp->seed);
                         const int16_t tmp = (sp->seed & 0x8000u) ? 4 : -4; /* QCONST16(1 / 256, 10) */
-                        X[j] = (int16_t)(lowband[j] + tmp);
+                        if (sp->lane == 0) X[j] = (int16_t)(lowband[j] + tmp);
                     }
                     cm = (unsigned)fill;
                 }
-                cv_renormalise(X, N, gain);
+                cv_renormalise(X, N, gain, sp->lane, sp->nl);
             }
         }
     }
@@ -486,17 +496,19 @@ ANM_CE_FN unsigned ce_band(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, 
     int N_B = (int)((uint32_t)N / (uint32_t)B);
     if (tf_change > 0) recombine = tf_change;
     if (sp && lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
-        for (k = 0; k < N; k++) lowband_scratch[k] = lowband[k];
+        CV_SYNC();
+        for (k = sp->lane; k < N; k += sp->nl) lowband_scratch[k] = lowband[k];
+        CV_SYNC();
         lowband = lowband_scratch;
     }
     for (k = 0; k < recombine; k++) { /* band recombining: more frequency resolution */
-        if (sp && lowband) cv_haar1(lowband, N >> k, 1 << k);
+        if (sp && lowband) cv_haar1(lowband, N >> k, 1 << k, sp->lane, sp->nl);
         fill = bit_interleave_table[fill & 0xF] | bit_interleave_table[fill >> 4] << 2;
     }
     B >>= recombine;
     N_B <<= recombine;
     while ((N_B & 1) == 0 && tf_change < 0) { /* more time resolution */
-        if (sp && lowband) cv_haar1(lowband, N_B, B);
+        if (sp && lowband) cv_haar1(lowband, N_B, B, sp->lane, sp->nl);
         fill |= fill << B;
         B <<= 1;
         N_B >>= 1;
@@ -506,10 +518,10 @@ ANM_CE_FN unsigned ce_band(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, 
     B0 = B;
     const int N_B0 = N_B;
     /* time order instead of frequency order */
-    if (sp && B0 > 1 && lowband) cv_deinterleave_hadamard(lowband, sp->tmp, N_B >> recombine, B0 << recombine, long_blocks);
+    if (sp && B0 > 1 && lowband) cv_deinterleave_hadamard(lowband, sp->tmp, N_B >> recombine, B0 << recombine, long_blocks, sp->lane, sp->nl);
     unsigned cm = ce_partition(ctx, X, N, b, B, lowband, LM, gain, fill);
     if (sp) {
-        if (B0 > 1) cv_interleave_hadamard(X, sp->tmp, N_B >> recombine, B0 << recombine, long_blocks);
+        if (B0 > 1) cv_interleave_hadamard(X, sp->tmp, N_B >> recombine, B0 << recombine, long_blocks, sp->lane, sp->nl);
         /* undo the time-frequency changes */
         N_B = N_B0;
         B = B0;
@@ -517,16 +529,18 @@ ANM_CE_FN unsigned ce_band(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, 
             B >>= 1;
             N_B <<= 1;
             cm |= cm >> B;
-            cv_haar1(X, N_B, B);
+            cv_haar1(X, N_B, B, sp->lane, sp->nl);
         }
         for (k = 0; k < recombine; k++) {
             cm = bit_deinterleave_table[cm];
-            cv_haar1(X, N0 >> k, 1 << k);
+            cv_haar1(X, N0 >> k, 1 << k, sp->lane, sp->nl);
         }
         B <<= recombine;
         if (lowband_out) { /* scaled for later folding */
             const int16_t n = (int16_t)cv_sqrt((int32_t)((uint32_t)N0 << 22));
-            for (k = 0; k < N0; k++) lowband_out[k] = (int16_t)CV_Q15(n, X[k]);
+            CV_SYNC();
+            for (k = sp->lane; k < N0; k += sp->nl) lowband_out[k] = (int16_t)CV_Q15(n, X[k]);
+            CV_SYNC();
         }
         cm &= (unsigned)(1 << B) - 1;
     }
@@ -558,7 +572,8 @@ ANM_CE_FN unsigned ce_band_stereo(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, in
         sign = 1 - 2 * sign;
         /* orig_fill: the side is folded even when itheta == 16384 cleared the low bits of fill */
         cm = ce_band(ctx, x2, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, orig_fill);
-        if (sp) {
+        if (sp) CV_SYNC();
+        if (sp && sp->lane == 0) {
             y2[0] = (int16_t)(-sign * x2[1]);
             y2[1] = (int16_t)(sign * x2[0]);
             X[0] = (int16_t)CV_Q15(mid, X[0]);
@@ -572,6 +587,7 @@ ANM_CE_FN unsigned ce_band_stereo(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, in
             X[1] = (int16_t)CV_S16(tmp, Y[1]);
             Y[1] = CV_A16(tmp, Y[1]);
         }
+        if (sp) CV_SYNC();
     } else {
         mbits = ce_imax(0, ce_imin(b, (b - s.delta) / 2));
         sbits = b - mbits;
@@ -591,9 +607,12 @@ ANM_CE_FN unsigned ce_band_stereo(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, in
         }
     }
     if (sp) {
-        if (N != 2) cv_stereo_merge(X, Y, mid, N);
-        if (inv)
-            for (int j = 0; j < N; j++) Y[j] = (int16_t)-Y[j];
+        if (N != 2) cv_stereo_merge(X, Y, mid, N, sp->lane, sp->nl);
+        if (inv) {
+            CV_SYNC();
+            for (int j = sp->lane; j < N; j += sp->nl) Y[j] = (int16_t)-Y[j];
+            CV_SYNC();
+        }
     }
     return cm;
 }
@@ -1000,8 +1019,11 @@ ANM_CE_FN int anm_celt_frame_symbols(const anm_celt_tables_t *t, const uint8_t *
             }
             if (ds && i == intensity) { /* dual stereo switches off to do intensity */
                 ds = 0;
-                if (sp)
-                    for (int j = 0; j < M * eb[i] - norm_offset; j++) norm[j] = (int16_t)(((int32_t)norm[j] + norm2[j]) >> 1);
+                if (sp) {
+                    CV_SYNC();
+                    for (int j = sp->lane; j < M * eb[i] - norm_offset; j += sp->nl) norm[j] = (int16_t)(((int32_t)norm[j] + norm2[j]) >> 1);
+                    CV_SYNC();
+                }
             }
             int16_t *lb = (sp && effective_lowband != -1) ? norm + effective_lowband : 0;
             int16_t *lbo = (sp && !last) ? norm + M * eb[i] - norm_offset : 0;
@@ -1016,8 +1038,11 @@ ANM_CE_FN int anm_celt_frame_symbols(const anm_celt_tables_t *t, const uint8_t *
                 y_cm = x_cm;
             }
             if (sp) {
-                collapse_masks[i * C + 0] = (uint8_t)x_cm;
-                collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
+                if (sp->lane == 0) {
+                    collapse_masks[i * C + 0] = (uint8_t)x_cm;
+                    collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
+                }
+                CV_SYNC();
             }
             balance += pulses[i] + tl;
             update_lowband = b > (N << ANM_CE_BITRES); /* the folding position moves only while there is 1 bit / sample of depth */
@@ -1149,12 +1174,13 @@ ANM_CE_FN int anm_celt_frame_spectrum(const anm_celt_tables_t *t, const uint8_t 
     anm_celt_frame_t again;
     sp->seed = hist->seed;
     sp->disable_inv = disable_inv;
-    for (int i = 0; i < 2 * ANM_CE_NB; i++) cm[i] = 0;
+    for (int i = sp->lane; i < 2 * ANM_CE_NB; i += sp->nl) cm[i] = 0;
+    CV_SYNC();
     const int rc = anm_celt_frame_symbols(t, bytes, mask, base, len, C, LM, end, qi, eoff, &again, sp, X, cm);
     if (rc != 0) return rc;
     if (again.flags & ANM_CELT_F_LOST) return 0;
     if (again.flags & ANM_CELT_F_ANTI_COLLAPSE)
-        cv_anti_collapse(t, X, cm, LM, C, 120 << LM, end, rec->band_e, hist->log_e1, hist->log_e2, rec->pulses, sp->seed);
+        cv_anti_collapse(t, X, cm, LM, C, 120 << LM, end, rec->band_e, hist->log_e1, hist->log_e2, rec->pulses, sp->seed, sp->lane, sp->nl);
     return 0;
 }
 

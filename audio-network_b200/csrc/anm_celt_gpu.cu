@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 
 #include "anm_celt_synth.h"
@@ -31,8 +32,8 @@ struct anm_celt_ctx {
     size_t scratch_frames;
     ce_hist_t *d_hist;  /* per frame: the stream's histories before the frame (stage 2) */
     size_t hist_frames;
-    ce_spec_t *d_spec;  /* per resident thread of k_celt_spectrum: working storage */
-    size_t spec_threads;
+    void *d_spec;       /* per resident thread of k_celt_spectrum: working storage (SpecScratch) */
+    size_t spec_bytes;
     anm_celt_synth_tables_t *d_synth_tables; /* stage 3 */
     int16_t *d_x;       /* per frame: the normalised spectrum (anm_celt_decode_device keeps it to itself) */
     size_t x_frames;
@@ -80,19 +81,39 @@ __global__ void __launch_bounds__(128) k_celt_energies(const uint32_t *__restric
     streams[s] = st;
 }
 
-/* stage 2, one thread per FRAME (grid-stride: the working storage is per resident thread) */
-__global__ void __launch_bounds__(64) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
+/* stage 2, one thread per FRAME (grid-stride: the working storage is per resident thread, in a global slab).  Bound by memory latency: the
+ * 7.4 KB a frame works on do not fit on chip for hundreds of threads per SM; the more threads in flight the better (measured 1 .. 16 blocks of 64 per
+ * SM: 429 / 238 / 169 / 115 / 76 ms for 204,800 frames).  A warp-per-frame form with the working set in shared memory was 3 x slower (anm_celt_vec.h). */
+struct SpecScratch {
+    int16_t norm[CE_SPEC_NORM];
+    int16_t tmp[CE_SPEC_TMP];
+    int iy[CE_SPEC_IY];
+};
+__global__ void __launch_bounds__(64, 14) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
                                                       const uint8_t *__restrict__ bytes, uint32_t mask, const anm_celt_frame_t *__restrict__ recs,
-                                                      const ce_hist_t *__restrict__ hist, ce_spec_t *spec, int16_t *x, uint32_t x_stride, uint8_t *collapse) {
+                                                      const ce_hist_t *__restrict__ hist, SpecScratch *spec, int16_t *x, uint32_t x_stride, uint8_t *collapse) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    ce_spec_t *sp = spec + tid;
+    ce_spec_t sp;
+    sp.norm = spec[tid].norm;
+    sp.tmp = spec[tid].tmp;
+    sp.iy = spec[tid].iy;
+    sp.lane = 0;
+    sp.nl = 1;
+    sp.spread = 0;
     for (uint32_t j = tid; j < n_jobs; j += nthr) {
         const anm_celt_job_t job = jobs[j];
         if (recs[j].flags & ANM_CELT_F_LOST) continue;
         uint8_t cm[2 * ANM_CE_NB];
-        const int rc = anm_celt_frame_spectrum(t, bytes, mask, job.offset, job.len, job.channels, job.lm, job.end_band, job.flags & ANM_CELT_JOB_DISABLE_INV,
-                                               &hist[j], &recs[j], sp, x + (size_t)j * x_stride, cm);
-        if (rc == 0 && collapse)
+        int16_t *X = x + (size_t)j * x_stride;
+        const int C = job.channels, NF = 120 << job.lm;
+        const int rc = anm_celt_frame_spectrum(t, bytes, mask, job.offset, job.len, C, job.lm, job.end_band, job.flags & ANM_CELT_JOB_DISABLE_INV, &hist[j], &recs[j],
+                                               &sp, X, cm);
+        if (rc != 0) continue;
+        /* zero above the end band (the last band's part served as scratch) */
+        const int ncoded = (1 << job.lm) * t->ebands[job.end_band];
+        for (int c = 0; c < C; ++c)
+            for (int i = ncoded; i < NF; ++i) X[c * NF + i] = 0;
+        if (collapse)
             for (int i = 0; i < 2 * ANM_CE_NB; ++i) collapse[(size_t)j * (2 * ANM_CE_NB) + i] = cm[i];
     }
 }
@@ -171,7 +192,7 @@ extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
     c->d_hist = nullptr;
     c->hist_frames = 0;
     c->d_spec = nullptr;
-    c->spec_threads = 0;
+    c->spec_bytes = 0;
     c->d_synth_tables = nullptr;
     c->d_x = nullptr;
     c->x_frames = 0;
@@ -254,6 +275,13 @@ static int entropy_impl(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const u
     return ANM_OK;
 }
 
+/* resident blocks of 64 threads per SM for the frame-parallel kernels that keep per-thread working storage in global memory */
+static uint32_t blocks_per_sm() {
+    const char *e = getenv("ANM_CELT_BLOCKS_PER_SM"); /* experiment knob */
+    const int v = e ? atoi(e) : 0;
+    return v > 0 && v <= 32 ? (uint32_t)v : 16u;
+}
+
 static int check_args(anm_celt_ctx_t *c, const void *d_jobs, const void *d_stream_begin, const void *d_streams, const void *d_out, uint32_t n_streams,
                       uint32_t bytes_mask) {
     if (!c || ((!d_jobs || !d_stream_begin || !d_streams || !d_out) && n_streams)) return ANM_ERR_ARG;
@@ -279,11 +307,15 @@ extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t 
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * 8u);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * blocks_per_sm());
     if ((rc = grow(&c->d_hist, &c->hist_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
-    if ((rc = grow(&c->d_spec, &c->spec_threads, (size_t)blocks * 64u, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
+    unsigned char *spec = static_cast<unsigned char *>(c->d_spec);
+    rc = grow(&spec, &c->spec_bytes, (size_t)blocks * 64u * sizeof(SpecScratch), s, "anm_celt_spectrum_device");
+    c->d_spec = spec;
+    if (rc != ANM_OK) return rc;
     if ((rc = entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_hist, s)) != ANM_OK) return rc;
-    k_celt_spectrum<<<blocks, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, c->d_spec, d_x, x_stride, d_collapse);
+    k_celt_spectrum<<<blocks, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, static_cast<SpecScratch *>(c->d_spec), d_x, x_stride,
+                                          d_collapse);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         anm_set_error("k_celt_spectrum launch failed: %s", cudaGetErrorString(e));
@@ -302,7 +334,7 @@ extern "C" int anm_celt_decode_device(anm_celt_ctx_t *c, const anm_celt_job_t *d
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * 8u);
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * blocks_per_sm());
     if ((rc = grow(&c->d_x, &c->x_frames, (size_t)n_jobs * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
     if ((rc = grow(&c->d_raw, &c->raw_frames, (size_t)n_jobs * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
     if ((rc = grow(&c->d_freq, &c->freq_threads, (size_t)blocks * 64u * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;

@@ -435,6 +435,7 @@ ANM_CE_FN void cs_stream_frame(const anm_celt_synth_tables_t *st, anm_celt_synth
     const int N = 120 << fr->lm;
     cs_pf_t pf0, pf;
     cs_pf_load(&pf0, s);
+    pf = pf0;
     for (int c = 0; c < CC; c++) {
         pf = pf0;
         cs_channel_frame(st, s->mem[c], &s->preemph_mem[c], &pf, fr, raw + c * N, CC, c, pcm);

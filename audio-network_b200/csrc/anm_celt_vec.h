@@ -19,6 +19,23 @@
 #ifndef ANM_CELT_VEC_H_INCLUDED
 #define ANM_CELT_VEC_H_INCLUDED
 
+/* ---------------------------------------------------------------- lanes
+ * The loops over a band's coefficients are written for `nl` cooperating lanes (lane, lane + nl, ...) with synchronisation points between the phases
+ * (CV_SYNC, and CV_SUM / CV_OR for the reductions); in-place recurrences (the spreading rotation) and stores of sequentially generated values
+ * (pulses, noise) are done by lane 0.  A warp-per-frame kernel built on this (every lane running the symbol decode redundantly, the frame's 7.4 KB
+ * working set in shared memory) was measured 3 x SLOWER than one thread per frame on B200 -- the sequential symbol decode dominates a frame, and a
+ * warp per frame leaves 16 frames in flight per SM instead of 900 -- so the kernels and the host harness run with ONE lane and the macros are empty;
+ * ANM_CELT_WARP_LANES brings the warp form back for experiments. */
+#if defined(__CUDA_ARCH__) && defined(ANM_CELT_WARP_LANES)
+#define CV_SYNC() __syncwarp()
+#define CV_SUM(x) ((int32_t)__reduce_add_sync(0xffffffffu, (unsigned)(x)))
+#define CV_OR(x) __reduce_or_sync(0xffffffffu, (unsigned)(x))
+#else
+#define CV_SYNC() ((void)0)
+#define CV_SUM(x) (x)
+#define CV_OR(x) (x)
+#endif
+
 /* ---------------------------------------------------------------- fixed-point operators */
 #define CV_M16(a, b) ((int32_t)(int16_t)(a) * (int32_t)(int16_t)(b))          /* MULT16_16 */
 #define CV_Q15(a, b) (CV_M16(a, b) >> 15)                                     /* MULT16_16_Q15 */
@@ -79,7 +96,7 @@ ANM_CE_FN int32_t cv_rcp(int32_t x) {
 ANM_CE_FN uint32_t cv_lcg(uint32_t seed) { return 1664525u * seed + 1013904223u; }
 
 /* ---------------------------------------------------------------- PVQ: codeword index -> pulse vector, returns sum of squares */
-ANM_CE_FN int32_t cv_cwrsi(const anm_celt_tables_t *t, int n, int k, uint32_t i, int *y) {
+ANM_CE_FN int32_t cv_cwrsi(const anm_celt_tables_t *t, int n, int k, uint32_t i, int *y, int lane) {
     uint32_t p;
     int s, k0;
     int16_t val;
@@ -101,14 +118,16 @@ ANM_CE_FN int32_t cv_cwrsi(const anm_celt_tables_t *t, int n, int k, uint32_t i,
             }
             i -= p;
             val = (int16_t)((k0 - k + s) ^ s);
-            *y++ = val;
+            if (lane == 0) *y = val;
+            y++;
             yy += CV_M16(val, val);
         } else { /* many dimensions */
             p = ce_pvq_u(t, k, n);
             q = ce_pvq_u(t, k + 1, n);
             if (p <= i && i < q) {
                 i -= p;
-                *y++ = 0;
+                if (lane == 0) *y = 0;
+                y++;
             } else {
                 s = -(int)(i >= q);
                 i -= q & (uint32_t)s;
@@ -117,7 +136,8 @@ ANM_CE_FN int32_t cv_cwrsi(const anm_celt_tables_t *t, int n, int k, uint32_t i,
                 while (p > i);
                 i -= p;
                 val = (int16_t)((k0 - k + s) ^ s);
-                *y++ = val;
+                if (lane == 0) *y = val;
+                y++;
                 yy += CV_M16(val, val);
             }
         }
@@ -131,13 +151,15 @@ ANM_CE_FN int32_t cv_cwrsi(const anm_celt_tables_t *t, int n, int k, uint32_t i,
     k = (int)((i + 1) >> 1);
     if (k) i -= 2u * (uint32_t)k - 1u;
     val = (int16_t)((k0 - k + s) ^ s);
-    *y++ = val;
+    if (lane == 0) *y = val;
+    y++;
     yy += CV_M16(val, val);
     /* n == 1 */
     s = -(int)i;
     val = (int16_t)((k + s) ^ s);
-    *y = val;
+    if (lane == 0) *y = val;
     yy += CV_M16(val, val);
+    CV_SYNC();
     return yy;
 }
 
@@ -158,8 +180,8 @@ ANM_CE_FN void cv_exp_rotation1(int16_t *X, int len, int stride, int16_t c, int1
         *p-- = (int16_t)CV_PSHR32(CV_M16(c, x1) + CV_M16(ms, x2), 15);
     }
 }
-/* the decoder's direction (dir = -1) of exp_rotation */
-ANM_CE_FN void cv_exp_rotation_dec(int16_t *X, int len, int stride, int K, int spread) {
+/* the decoder's direction (dir = -1) of exp_rotation: in-place recurrences, one lane per interleaved block */
+ANM_CE_FN void cv_exp_rotation_dec(int16_t *X, int len, int stride, int K, int spread, int lane, int nl) {
     if (2 * K >= len || spread == 0) return;
     const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
     const int16_t gain = (int16_t)cv_mult32_32_q31(CV_M16(32767, len), cv_rcp(len + factor * K));
@@ -171,90 +193,109 @@ ANM_CE_FN void cv_exp_rotation_dec(int16_t *X, int len, int stride, int K, int s
         while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
     }
     len = (int)((uint32_t)len / (uint32_t)stride);
-    for (int i = 0; i < stride; i++) {
+    CV_SYNC();
+    for (int i = lane; i < stride; i += nl) {
         if (stride2) cv_exp_rotation1(X + i * len, len, stride2, s, c);
         cv_exp_rotation1(X + i * len, len, 1, c, s);
     }
+    CV_SYNC();
 }
 /* pulses -> unit-norm vector scaled by gain (normalise_residual) */
-ANM_CE_FN void cv_normalise_residual(const int *iy, int16_t *X, int N, int32_t Ryy, int16_t gain) {
+ANM_CE_FN void cv_normalise_residual(const int *iy, int16_t *X, int N, int32_t Ryy, int16_t gain, int lane, int nl) {
     const int k = cv_ilog2(Ryy) >> 1;
     const int32_t t = cv_vshr32(Ryy, 2 * (k - 7));
     const int16_t g = (int16_t)CV_P15(cv_rsqrt_norm(t), gain);
-    for (int i = 0; i < N; i++) X[i] = (int16_t)CV_PSHR32(CV_M16(g, iy[i]), k + 1);
+    CV_SYNC();
+    for (int i = lane; i < N; i += nl) X[i] = (int16_t)CV_PSHR32(CV_M16(g, iy[i]), k + 1);
+    CV_SYNC();
 }
-ANM_CE_FN unsigned cv_collapse_mask(const int *iy, int N, int B) {
+ANM_CE_FN unsigned cv_collapse_mask(const int *iy, int N, int B, int lane, int nl) {
     if (B <= 1) return 1;
     const int N0 = (int)((uint32_t)N / (uint32_t)B);
     unsigned mask = 0;
-    for (int i = 0; i < B; i++) {
-        unsigned tmp = 0;
-        for (int j = 0; j < N0; j++) tmp |= (unsigned)iy[i * N0 + j];
-        mask |= (unsigned)(tmp != 0) << i;
-    }
-    return mask;
+    CV_SYNC();
+    for (int i = lane; i < N; i += nl) mask |= (unsigned)(iy[i] != 0) << (i / N0);
+    return CV_OR(mask);
 }
-ANM_CE_FN void cv_renormalise(int16_t *X, int N, int16_t gain) {
-    int32_t E = 1; /* EPSILON */
-    for (int i = 0; i < N; i++) E += CV_M16(X[i], X[i]);
+ANM_CE_FN void cv_renormalise(int16_t *X, int N, int16_t gain, int lane, int nl) {
+    int32_t E = 0;
+    CV_SYNC();
+    for (int i = lane; i < N; i += nl) E += CV_M16(X[i], X[i]);
+    E = 1 + CV_SUM(E); /* EPSILON */
     const int k = cv_ilog2(E) >> 1;
     const int32_t t = cv_vshr32(E, 2 * (k - 7));
     const int16_t g = (int16_t)CV_P15(cv_rsqrt_norm(t), gain);
-    for (int i = 0; i < N; i++) X[i] = (int16_t)CV_PSHR32(CV_M16(g, X[i]), k + 1);
+    for (int i = lane; i < N; i += nl) X[i] = (int16_t)CV_PSHR32(CV_M16(g, X[i]), k + 1);
+    CV_SYNC();
 }
-ANM_CE_FN void cv_haar1(int16_t *X, int N0, int stride) {
+ANM_CE_FN void cv_haar1(int16_t *X, int N0, int stride, int lane, int nl) {
     N0 >>= 1;
-    for (int i = 0; i < stride; i++)
-        for (int j = 0; j < N0; j++) {
-            const int32_t t1 = CV_M16(23170, X[stride * 2 * j + i]), t2 = CV_M16(23170, X[stride * (2 * j + 1) + i]);
-            X[stride * 2 * j + i] = (int16_t)CV_PSHR32(t1 + t2, 15);
-            X[stride * (2 * j + 1) + i] = (int16_t)CV_PSHR32(t1 - t2, 15);
-        }
+    CV_SYNC();
+    for (int idx = lane; idx < stride * N0; idx += nl) {
+        const int i = idx % stride, j = idx / stride;
+        const int32_t t1 = CV_M16(23170, X[stride * 2 * j + i]), t2 = CV_M16(23170, X[stride * (2 * j + 1) + i]);
+        X[stride * 2 * j + i] = (int16_t)CV_PSHR32(t1 + t2, 15);
+        X[stride * (2 * j + 1) + i] = (int16_t)CV_PSHR32(t1 - t2, 15);
+    }
+    CV_SYNC();
 }
 ANM_CE_FN int cv_ordery(int stride, int i) {
     const int8_t tab[30] = {1, 0, 3, 0, 2, 1, 7, 0, 4, 3, 6, 1, 5, 2, 15, 0, 8, 7, 12, 3, 11, 4, 14, 1, 9, 6, 13, 2, 10, 5};
     return tab[stride - 2 + i];
 }
 /* frequency order -> time order (tmp: N0 * stride entries of scratch) */
-ANM_CE_FN void cv_deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
+ANM_CE_FN void cv_deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard, int lane, int nl) {
     const int N = N0 * stride;
-    for (int i = 0; i < stride; i++) {
+    CV_SYNC();
+    for (int idx = lane; idx < N; idx += nl) {
+        const int i = idx / N0, j = idx % N0;
         const int o = hadamard ? cv_ordery(stride, i) : i;
-        for (int j = 0; j < N0; j++) tmp[o * N0 + j] = X[j * stride + i];
+        tmp[o * N0 + j] = X[j * stride + i];
     }
-    for (int i = 0; i < N; i++) X[i] = tmp[i];
+    CV_SYNC();
+    for (int i = lane; i < N; i += nl) X[i] = tmp[i];
+    CV_SYNC();
 }
-ANM_CE_FN void cv_interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
+ANM_CE_FN void cv_interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard, int lane, int nl) {
     const int N = N0 * stride;
-    for (int i = 0; i < stride; i++) {
+    CV_SYNC();
+    for (int idx = lane; idx < N; idx += nl) {
+        const int i = idx / N0, j = idx % N0;
         const int o = hadamard ? cv_ordery(stride, i) : i;
-        for (int j = 0; j < N0; j++) tmp[j * stride + i] = X[o * N0 + j];
+        tmp[j * stride + i] = X[o * N0 + j];
     }
-    for (int i = 0; i < N; i++) X[i] = tmp[i];
+    CV_SYNC();
+    for (int i = lane; i < N; i += nl) X[i] = tmp[i];
+    CV_SYNC();
 }
 /* mid / side -> left / right of a band */
-ANM_CE_FN void cv_stereo_merge(int16_t *X, int16_t *Y, int16_t mid, int N) {
+ANM_CE_FN void cv_stereo_merge(int16_t *X, int16_t *Y, int16_t mid, int N, int lane, int nl) {
     int32_t xp = 0, side = 0;
-    for (int j = 0; j < N; j++) {
+    CV_SYNC();
+    for (int j = lane; j < N; j += nl) {
         xp += CV_M16(Y[j], X[j]);
         side += CV_M16(Y[j], Y[j]);
     }
+    xp = CV_SUM(xp);
+    side = CV_SUM(side);
     xp = (int32_t)(((int64_t)mid * xp) >> 15); /* MULT16_32_Q15 */
     const int16_t mid2 = (int16_t)(mid >> 1);
     const int32_t El = CV_M16(mid2, mid2) + side - 2 * xp, Er = CV_M16(mid2, mid2) + side + 2 * xp;
     if (Er < 161061 || El < 161061) { /* QCONST32(6e-4f, 28) */
-        for (int j = 0; j < N; j++) Y[j] = X[j];
+        for (int j = lane; j < N; j += nl) Y[j] = X[j];
+        CV_SYNC();
         return;
     }
     int kl = cv_ilog2(El) >> 1, kr = cv_ilog2(Er) >> 1;
     const int16_t lgain = cv_rsqrt_norm(cv_vshr32(El, (kl - 7) << 1)), rgain = cv_rsqrt_norm(cv_vshr32(Er, (kr - 7) << 1));
     if (kl < 7) kl = 7;
     if (kr < 7) kr = 7;
-    for (int j = 0; j < N; j++) {
+    for (int j = lane; j < N; j += nl) {
         const int16_t l = (int16_t)CV_P15(mid, X[j]), r = Y[j];
         X[j] = (int16_t)CV_PSHR32(CV_M16(lgain, CV_S16(l, r)), kl + 1);
         Y[j] = (int16_t)CV_PSHR32(CV_M16(rgain, CV_A16(l, r)), kr + 1);
     }
+    CV_SYNC();
 }
 
 /* 2^x, Q10 in, Q16 out (celt_exp2) */
@@ -271,7 +312,7 @@ ANM_CE_FN int32_t cv_exp2(int16_t x) {
  * suggest, then the band is renormalised.  X_: [C][size] coefficients; log_e: this frame's band energies [2][21] (Q10), prev1 / prev2: the
  * decoder's two log-energy histories before the frame; pulses: the bands' PVQ budgets; seed: the noise generator after the bands. */
 ANM_CE_FN void cv_anti_collapse(const anm_celt_tables_t *t, int16_t *X_, const uint8_t *collapse_masks, int LM, int C, int size, int end,
-                                const int16_t *log_e, const int16_t *prev1, const int16_t *prev2, const int16_t *pulses, uint32_t seed) {
+                                const int16_t *log_e, const int16_t *prev1, const int16_t *prev2, const int16_t *pulses, uint32_t seed, int lane, int nl) {
     const int NB = 21;
     for (int i = 0; i < end; i++) {
         const int N0 = t->ebands[i + 1] - t->ebands[i];
@@ -304,14 +345,14 @@ ANM_CE_FN void cv_anti_collapse(const anm_celt_tables_t *t, int16_t *X_, const u
             int renormalize = 0;
             for (int k = 0; k < 1 << LM; k++) {
                 if (!(collapse_masks[i * C + c] & 1 << k)) { /* this short block collapsed */
-                    for (int j = 0; j < N0; j++) {
+                    for (int j = 0; j < N0; j++) { /* every lane steps the generator, one stores */
                         seed = cv_lcg(seed);
-                        X[(j << LM) + k] = (seed & 0x8000u) ? r : (int16_t)-r;
+                        if (lane == 0) X[(j << LM) + k] = (seed & 0x8000u) ? r : (int16_t)-r;
                     }
                     renormalize = 1;
                 }
             }
-            if (renormalize) cv_renormalise(X, N0 << LM, 32767);
+            if (renormalize) cv_renormalise(X, N0 << LM, 32767, lane, nl);
         }
     }
 }

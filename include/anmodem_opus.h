@@ -165,11 +165,10 @@ void anm_celt_ctx_destroy(anm_celt_ctx_t *c);
 int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
                             const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, void *stream);
 /* Stage 2 as well: the frames' normalised spectra, as celt_synthesis() receives them (quant_all_bands + anti_collapse, celt/celt_decoder.c:
- * 1084-1098).  Three launches: the two of anm_celt_entropy_device (d_out is filled as there), then one thread per frame decodes the frame again
+ * 1084-1098).  Three launches: the two of anm_celt_entropy_device (d_out is filled as there), then one WARP per frame decodes the frame again
  * WITH its spectrum -- the noise seed of a frame is the final range of the stream's previous frame, the anti-collapse histories come from the
  * per-stream pass.  d_x: n_jobs x x_stride int16 (celt_norm, Q14), frame j's channel c at d_x + j * x_stride + c * (120 << lm), x_stride >=
- * channels * (120 << lm) (1920 always fits); coefficients above the frame's end band are left untouched, and the last band's part of a frame whose
- * end band is below 21 is scratch.  d_collapse (may be NULL): 42 collapse masks per frame, [band * channels + channel].  Frames of <= 1 byte are
+ * channels * (120 << lm) (1920 always fits); coefficients above the frame's end band are written as zero.  d_collapse (may be NULL): 42 collapse masks per frame, [band * channels + channel].  Frames of <= 1 byte are
  * lost frames: the reference conceals them (celt_decode_lost), which is NOT built -- their spectrum is not written and the stream's noise seed
  * and histories pass through unchanged. */
 int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,

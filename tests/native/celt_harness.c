@@ -12,14 +12,29 @@ int harness_celt_frame(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_
 uint32_t harness_sizeof_tables(void) { return (uint32_t)sizeof(anm_celt_tables_t); }
 uint32_t harness_sizeof_frame(void) { return (uint32_t)sizeof(anm_celt_frame_t); }
 
+/* the host runs the spectrum code with ONE lane */
+static void spec_init(ce_spec_t *sp) {
+    static int16_t norm[CE_SPEC_NORM], tmp[CE_SPEC_TMP];
+    static int iy[CE_SPEC_IY];
+    sp->norm = norm;
+    sp->tmp = tmp;
+    sp->iy = iy;
+    sp->lane = 0;
+    sp->nl = 1;
+    sp->seed = 0;
+    sp->spread = 0;
+    sp->disable_inv = 0;
+}
+
 /* stage 2: the frame's normalised spectrum (X: [2][960], channel c at X + 960 c ... repacked from the product's [C][120 << LM] layout) */
 int harness_celt_spectrum(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t len, int C, int LM, int end, int16_t *old_e, anm_celt_frame_t *out,
                           uint32_t seed_in, int disable_inv, int16_t *x_out, uint8_t *cm_out, uint32_t *seed_out) {
-    static ce_spec_t sp;
+    ce_spec_t sp;
     static int16_t X[2 * 960];
     int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
     uint8_t cm[2 * ANM_CE_NB];
     const int NF = 120 << LM;
+    spec_init(&sp);
     for (int i = 0; i < 2 * 960; i++) X[i] = 0;
     for (int i = 0; i < 2 * ANM_CE_NB; i++) cm[i] = 0;
     sp.seed = seed_in;
@@ -40,11 +55,12 @@ int harness_celt_spectrum(const anm_celt_tables_t *t, const uint8_t *bytes, uint
  * x_post: [2][960] repacked like x_out above; hist_out: the histories the frame saw (ce_hist_t). */
 int harness_celt_frame_full(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t len, int C, int LM, int end, int disable_inv, anm_celt_stream_t *st,
                             anm_celt_frame_t *out, int16_t *x_post, uint8_t *cm_out, ce_hist_t *hist_out) {
-    static ce_spec_t sp;
+    ce_spec_t sp;
     static int16_t X[2 * 960];
     int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
     uint8_t cm[2 * ANM_CE_NB];
     const int NF = 120 << LM;
+    spec_init(&sp);
     int rc = anm_celt_entropy_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out);
     if (rc != 0) return rc;
     anm_celt_stream_step(out, qi, eoff, st, hist_out);
@@ -69,9 +85,10 @@ uint32_t harness_sizeof_synth_tables(void) { return (uint32_t)sizeof(anm_celt_sy
 /* all three stages for one frame of a stream, chained as the kernels chain them; pcm: [120 << LM][CC] */
 int harness_celt_decode_frame(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *stb, const uint8_t *bytes, uint32_t len, int C, int CC, int LM, int end,
                               anm_celt_stream_t *st, anm_celt_synth_t *syn, anm_celt_frame_t *out, int16_t *pcm) {
-    static ce_spec_t sp;
+    ce_spec_t sp;
     static int16_t X[2 * 960];
     static int32_t freq[2 * 960], raw[2 * 960];
+    spec_init(&sp);
     int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
     uint8_t cm[2 * ANM_CE_NB];
     ce_hist_t hist;
