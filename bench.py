@@ -347,11 +347,38 @@ def decode_chain_leg(anm, torch, dev, recs, by, reps=20):
             torch.cuda.synchronize()
             if r >= 2:
                 t_celt += ev[0].elapsed_time(ev[1])
+        # rows f1 stages 2 + 3 on a bounded sample of whole streams (15 KB of intermediate data per frame): spectrum, inverse MDCT, overlap / post-filter / de-emphasis
+        ns_dec = int(np.searchsorted(sb, 65536, side="right")) - 1 if len(jobs) > 65536 else len(chs)
+        ns_dec = max(ns_dec, 1)
+        nj_dec = int(sb[ns_dec])
+        d_sy = torch.zeros(ns_dec * anm.CELT_SYNTH_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        d_pcm = torch.zeros(nj_dec * 1920, dtype=torch.int16, device=dev)
+        t_dec = 0.0
+        for r in range(3):
+            d_st.zero_()
+            d_sy.zero_()
+            ev[0].record()
+            assert L.anm_celt_decode_device(ctx, d_jobs.data_ptr(), d_sb.data_ptr(), ns_dec, nj_dec, d_by.data_ptr(), 0xFFFFFFFF, d_st.data_ptr(), d_sy.data_ptr(),
+                                            d_fr.data_ptr(), d_pcm.data_ptr(), 1920, stream) == 0
+            ev[1].record()
+            torch.cuda.synchronize()
+            if r >= 1:
+                t_dec += ev[0].elapsed_time(ev[1]) / 2
+        pcm_nonzero = bool((d_pcm != 0).any().item())
+        del d_pcm, d_sy
+        d_st.zero_()
+        assert L.anm_celt_entropy_device(ctx, d_jobs.data_ptr(), d_sb.data_ptr(), len(chs), len(jobs), d_by.data_ptr(), 0xFFFFFFFF, d_st.data_ptr(), d_fr.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
         L.anm_celt_ctx_destroy(ctx)
         fr = d_fr.cpu().numpy().view(anm.CELT_FRAME_DTYPE)
         ms = t_celt / (reps // 2)
         celt = {"k_celt_entropy_plus_energies_ms": round(ms, 4), "streams": int(len(chs)), "frames": int(len(jobs)), "Mframes_per_s": round(len(jobs) / (ms * 1e-3) / 1e6, 2),
                 "packet_bytes": int(jobs["len"].sum()), "frames_within_budget": int(((fr["flags"] & 1024) == 0).sum()),
+                "full_decode": {"kernels": "k_celt_entropy, k_celt_energies, k_celt_spectrum, k_celt_blocks, k_celt_overlap", "streams": ns_dec, "frames": nj_dec,
+                                "ms": round(t_dec, 3), "Mframes_per_s": round(nj_dec / (t_dec * 1e-3) / 1e6, 3), "audio_x_realtime": round(nj_dec * 0.02 / (t_dec * 1e-3), 1),
+                                "pcm_nonzero": pcm_nonzero,
+                                "note": "bounded sample of whole streams; PCM parity of these kernels is pinned on real encoder output in tests/test_celt_synth.py, "
+                                        "throughput on real frames: tools/celt_bench.py"},
                 "note": "payloads of the synthetic workload are random bytes behind a CELT TOC: valid range-coder input, worst case for branch divergence; "
                         "parity of this stage is pinned on real encoder output in tests/test_celt_entropy.py"}
     peak, _src = peaks()

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--name", default="gold_stereo_20ms")
+    ap.add_argument("--cpu-baseline", action="store_true", help="also time the REFERENCE decoder (oracle/_ref/libref_opus.so, one core) on the same stream")
     a = ap.parse_args()
     G = np.load(os.path.join(ROOT, "tests", "golden", "celt_entropy.npz"))
     P = np.load(os.path.join(ROOT, "tests", "golden", "celt_pcm.npz"))
@@ -77,6 +78,25 @@ def main():
             d = np.frombuffer(hashlib.sha256(np.ascontiguousarray(got[k, :ns]).tobytes()).digest()[:8], dtype="<u8")[0]
             ok = ok and d == P["cc_native"][lo + k]
     L.anm_celt_ctx_destroy(ctx)
+    cpu = None
+    if a.cpu_baseline:
+        # the reference's own celt_decode_with_ec() (a copy of celt/celt_decoder.c compiled in place, oracle/ref_celt_state_shim.c), one host core
+        import time
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import celt_spectrum_binding as sbind
+        R = sbind.ref()
+        maxlen = int(fr["len"].max())
+        buf, lens = np.zeros((nf, maxlen), np.uint8), fr["len"].astype(np.int32)
+        for k in range(nf):
+            buf[k, :lens[k]] = G["bytes"][fr["offset"][k]: fr["offset"][k] + lens[k]]
+        params = np.ascontiguousarray(np.stack([fr["channels"], fr["lm"], fr["end_band"]], axis=1).astype(np.int32))
+        states, out = np.zeros(nf, sbind.STATE), np.zeros((nf, 960 * cc), np.int16)
+        reps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < 3.0:
+            assert R.ref_celt_stream_states(buf.ctypes.data, lens.ctypes.data, nf, maxlen, params.ctypes.data, cc, states.ctypes.data, out.ctypes.data) == nf
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"kind": "reference", "cores": 1, "frames_per_s": round(reps * nf / dt, 1), "sample": "%d x the %d-frame stream in %.1f s" % (reps, nf, dt)}
     nfr = len(jobs)
     audio_s = nfr * (120 << int(fr["lm"][0])) / 48000.0
     pk_bytes = int(jobs["len"].astype(np.int64).sum())
@@ -84,7 +104,8 @@ def main():
     print(json.dumps({"tool": "celt_bench", "stream": a.name, "streams": a.streams, "frames": nfr, "packet_bytes": pk_bytes, "pcm_bytes": out_bytes,
                       "entropy_ms": round(t_ent, 3), "entropy_plus_spectrum_ms": round(t_spec, 3), "full_decode_ms": round(t_dec, 3),
                       "Mframes_per_s_full": round(nfr / t_dec / 1e3, 3), "audio_seconds_per_second": round(audio_s / (t_dec * 1e-3), 1),
-                      "algorithmic_GBps_full": round((pk_bytes + out_bytes) / (t_dec * 1e-3) / 1e9, 2), "pcm_digests_equal_reference": bool(ok)}))
+                      "algorithmic_GBps_full": round((pk_bytes + out_bytes) / (t_dec * 1e-3) / 1e9, 2), "pcm_digests_equal_reference": bool(ok), "cpu_baseline": cpu,
+                      "kernels": "k_celt_entropy, k_celt_energies, k_celt_spectrum, k_celt_blocks, k_celt_overlap"}))
 
 
 if __name__ == "__main__":
