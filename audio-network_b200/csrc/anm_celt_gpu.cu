@@ -39,8 +39,6 @@ struct anm_celt_ctx {
     size_t x_frames;
     int32_t *d_raw;     /* per frame: the raw inverse-MDCT blocks of both output channels */
     size_t raw_frames;
-    int32_t *d_freq;    /* per resident thread of k_celt_blocks: denormalised coefficients (two channels for the downmix) */
-    size_t freq_threads;
 };
 
 namespace {
@@ -118,14 +116,19 @@ __global__ void __launch_bounds__(64, 14) k_celt_spectrum(const anm_celt_tables_
     }
 }
 
-/* stage 3, frame-parallel part: one thread per FRAME (grid-stride) -- denormalisation and the raw inverse-MDCT blocks of every output channel */
-__global__ void __launch_bounds__(64) k_celt_blocks(const anm_celt_tables_t *__restrict__ t, const anm_celt_synth_tables_t *__restrict__ stb,
-                                                    const anm_celt_job_t *__restrict__ jobs, const uint32_t *__restrict__ stream_begin, uint32_t n_streams,
-                                                    uint32_t n_jobs, const anm_celt_frame_t *__restrict__ recs, const anm_celt_synth_t *__restrict__ synth,
-                                                    const int16_t *__restrict__ x, int32_t *freq, int32_t *raw) {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-    int32_t *fq = freq + (size_t)tid * 1920;
-    for (uint32_t j = tid; j < n_jobs; j += nthr) {
+/* stage 3, frame-parallel part: one WARP per frame -- denormalisation and the raw inverse-MDCT blocks of every output channel; the butterflies of an
+ * FFT stage, the rotations and the band loops go over the lanes, the coefficients sit in shared memory (anm_celt_synth.h) */
+constexpr uint32_t kBlkWarps = 4;
+constexpr uint32_t kBlkWarpBytes = 4u * 960u * 4u; /* freq [2][960] | raw [2][960], int32 */
+__global__ void __launch_bounds__(kBlkWarps * 32) k_celt_blocks(const anm_celt_tables_t *__restrict__ t, const anm_celt_synth_tables_t *__restrict__ stb,
+                                                                const anm_celt_job_t *__restrict__ jobs, const uint32_t *__restrict__ stream_begin,
+                                                                uint32_t n_streams, uint32_t n_jobs, const anm_celt_frame_t *__restrict__ recs,
+                                                                const anm_celt_synth_t *__restrict__ synth, const int16_t *__restrict__ x, int32_t *raw) {
+    extern __shared__ __align__(16) unsigned char blk_smem[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = threadIdx.x >> 5;
+    int32_t *fq = reinterpret_cast<int32_t *>(blk_smem + w * kBlkWarpBytes), *rw = fq + 2 * 960;
+    for (uint32_t j = blockIdx.x * kBlkWarps + w; j < n_jobs; j += gridDim.x * kBlkWarps) {
         const anm_celt_frame_t *fr = &recs[j];
         if (fr->flags & ANM_CELT_F_LOST) continue;
         /* the frame's stream: the last s with stream_begin[s] <= j */
@@ -138,34 +141,56 @@ __global__ void __launch_bounds__(64) k_celt_blocks(const anm_celt_tables_t *__r
         int CC = (int)synth[lo].out_channels;
         if (CC == 0) CC = jobs[stream_begin[lo]].channels;
         cs_frame_blocks(t, stb, x + (size_t)j * 1920, fr->band_e, fr->channels, CC, fr->lm, fr->pad[0], (fr->flags & ANM_CELT_F_TRANSIENT) != 0,
-                        (fr->flags & ANM_CELT_F_SILENCE) != 0, fq, raw + (size_t)j * 1920);
+                        (fr->flags & ANM_CELT_F_SILENCE) != 0, fq, rw, lane, 32);
+        int32_t *ro = raw + (size_t)j * 1920;
+        const int n = CC * (120 << fr->lm);
+        for (int i = lane; i < n; i += 32) ro[i] = rw[i];
+        __syncwarp();
     }
 }
 
-/* stage 3, per-stream part: one thread per (stream, output channel) -- window overlap-add, pitch post-filter, de-emphasis */
-__global__ void __launch_bounds__(64) k_celt_overlap(const anm_celt_synth_tables_t *__restrict__ stb, const anm_celt_job_t *__restrict__ jobs,
-                                                     const uint32_t *__restrict__ stream_begin, uint32_t n_streams, const anm_celt_frame_t *__restrict__ recs,
-                                                     anm_celt_synth_t *synth, const int32_t *__restrict__ raw, int16_t *pcm, uint32_t pcm_stride) {
-    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x, s = id >> 1;
+/* stage 3, per-stream part: one WARP per (stream, output channel) -- window overlap-add, pitch post-filter, de-emphasis, with the channel's output history
+ * (8.7 KB) in shared memory for the whole call; copies, window mix and saturation go over the lanes, the two recurrences run on lane 0 */
+constexpr uint32_t kOvlWarps = 8;
+constexpr uint32_t kOvlWarpBytes = (2048u + 120u) * 4u + 960u * 2u; /* history | one frame of this channel's PCM */
+__global__ void __launch_bounds__(kOvlWarps * 32) k_celt_overlap(const anm_celt_synth_tables_t *__restrict__ stb, const anm_celt_job_t *__restrict__ jobs,
+                                                                 const uint32_t *__restrict__ stream_begin, uint32_t n_streams,
+                                                                 const anm_celt_frame_t *__restrict__ recs, anm_celt_synth_t *synth, const int32_t *__restrict__ raw,
+                                                                 int16_t *pcm, uint32_t pcm_stride) {
+    extern __shared__ __align__(16) unsigned char ovl_smem[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = threadIdx.x >> 5, id = blockIdx.x * kOvlWarps + w, s = id >> 1;
     const int c = (int)(id & 1u);
-    if (s >= n_streams) return;
-    anm_celt_synth_t *sy = &synth[s];
-    int CC = (int)sy->out_channels;
-    if (CC == 0) CC = stream_begin[s + 1] > stream_begin[s] ? jobs[stream_begin[s]].channels : 1;
-    cs_pf_t pf;
-    cs_pf_load(&pf, sy);
+    int32_t *mem = reinterpret_cast<int32_t *>(ovl_smem + w * kOvlWarpBytes);
+    int16_t *pcm_s = reinterpret_cast<int16_t *>(mem + 2048 + 120);
+    const bool live = s < n_streams;
+    anm_celt_synth_t *sy = live ? &synth[s] : nullptr;
+    int CC = 0;
+    cs_pf_t pf = {};
+    if (live) {
+        CC = (int)sy->out_channels;
+        if (CC == 0) CC = stream_begin[s + 1] > stream_begin[s] ? jobs[stream_begin[s]].channels : 1;
+        cs_pf_load(&pf, sy);
+    }
+    __syncthreads(); /* both channels of a stream (neighbouring warps of this block) have read the stream's state before either writes it */
+    if (!live) return;
     if (c < CC) {
+        for (int i = lane; i < 2048 + 120; i += 32) mem[i] = sy->mem[c][i];
         int32_t pm = sy->preemph_mem[c];
+        __syncwarp();
         for (uint32_t j = stream_begin[s]; j < stream_begin[s + 1]; ++j) {
             const anm_celt_frame_t *fr = &recs[j];
             if (fr->flags & ANM_CELT_F_LOST) continue;
-            cs_channel_frame(stb, sy->mem[c], &pm, &pf, fr, raw + (size_t)j * 1920 + (size_t)c * (120u << fr->lm), CC, c, pcm + (size_t)j * pcm_stride);
+            const int N = 120 << fr->lm;
+            cs_channel_frame(stb, mem, &pm, &pf, fr, raw + (size_t)j * 1920 + (size_t)c * N, 1, 0, pcm_s, lane, 32);
+            int16_t *po = pcm + (size_t)j * pcm_stride;
+            for (int i = lane; i < N; i += 32) po[i * CC + c] = pcm_s[i];
+            __syncwarp();
         }
-        sy->preemph_mem[c] = pm;
+        for (int i = lane; i < 2048 + 120; i += 32) sy->mem[c][i] = mem[i];
+        if (lane == 0) sy->preemph_mem[c] = pm;
     }
-    /* both channels computed the same post-filter state; the pair meets before one of them writes it back (they read it above) */
-    __syncwarp();
-    if (c == 0) {
+    if (c == 0 && lane == 0) {
         cs_pf_store(&pf, sy);
         sy->out_channels = (uint32_t)CC;
     }
@@ -198,8 +223,6 @@ extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
     c->x_frames = 0;
     c->d_raw = nullptr;
     c->raw_frames = 0;
-    c->d_freq = nullptr;
-    c->freq_threads = 0;
     int rc = anm_celt_tables_build(h);
     if (rc == ANM_OK && (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&c->d_tables, sizeof *h) != cudaSuccess ||
                          cudaMemcpy(c->d_tables, h, sizeof *h, cudaMemcpyHostToDevice) != cudaSuccess)) {
@@ -240,7 +263,6 @@ extern "C" void anm_celt_ctx_destroy(anm_celt_ctx_t *c) {
     cudaFree(c->d_synth_tables);
     cudaFree(c->d_x);
     cudaFree(c->d_raw);
-    cudaFree(c->d_freq);
     delete c;
 }
 
@@ -334,14 +356,17 @@ extern "C" int anm_celt_decode_device(anm_celt_ctx_t *c, const anm_celt_job_t *d
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * blocks_per_sm());
     if ((rc = grow(&c->d_x, &c->x_frames, (size_t)n_jobs * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
     if ((rc = grow(&c->d_raw, &c->raw_frames, (size_t)n_jobs * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
-    if ((rc = grow(&c->d_freq, &c->freq_threads, (size_t)blocks * 64u * 1920u, s, "anm_celt_decode_device")) != ANM_OK) return rc;
     if ((rc = anm_celt_spectrum_device(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_x, 1920u, nullptr, stream)) != ANM_OK)
         return rc;
-    k_celt_blocks<<<blocks, 64, 0, s>>>(c->d_tables, c->d_synth_tables, d_jobs, d_stream_begin, n_streams, n_jobs, d_out, d_synth, c->d_x, c->d_freq, c->d_raw);
-    k_celt_overlap<<<(2u * n_streams + 63u) / 64u, 64, 0, s>>>(c->d_synth_tables, d_jobs, d_stream_begin, n_streams, d_out, d_synth, c->d_raw, d_pcm, pcm_stride);
+    cudaFuncSetAttribute((const void *)k_celt_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBlkWarps * kBlkWarpBytes)); /* per device */
+    cudaFuncSetAttribute((const void *)k_celt_overlap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kOvlWarps * kOvlWarpBytes));
+    const uint32_t blk_blocks = (uint32_t)std::min<uint64_t>((n_jobs + kBlkWarps - 1u) / kBlkWarps, (uint64_t)sms * 3u);
+    k_celt_blocks<<<blk_blocks, kBlkWarps * 32, kBlkWarps * kBlkWarpBytes, s>>>(c->d_tables, c->d_synth_tables, d_jobs, d_stream_begin, n_streams, n_jobs, d_out, d_synth,
+                                                                                 c->d_x, c->d_raw);
+    k_celt_overlap<<<(2u * n_streams + kOvlWarps - 1u) / kOvlWarps, kOvlWarps * 32, kOvlWarps * kOvlWarpBytes, s>>>(c->d_synth_tables, d_jobs, d_stream_begin, n_streams,
+                                                                                                                       d_out, d_synth, c->d_raw, d_pcm, pcm_stride);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         anm_set_error("k_celt_blocks / k_celt_overlap launch failed: %s", cudaGetErrorString(e));

@@ -23,6 +23,15 @@
 
 #include "anm_celt_entropy.h"
 
+/* On the GPU a WARP works on a frame (k_celt_blocks) or on a channel of a stream (k_celt_overlap): the loops over coefficients / samples are split
+ * over the lanes (lane, lane + nl, ...) with the data in shared memory and CS_SYNC between the phases; what is a recurrence (post-filter, de-emphasis)
+ * runs on lane 0.  The host harness runs the same code with one lane. */
+#ifdef __CUDA_ARCH__
+#define CS_SYNC() __syncwarp()
+#else
+#define CS_SYNC() ((void)0)
+#endif
+
 #define CS_OVERLAP 120
 #define CS_BUF 2048 /* DECODE_BUFFER_SIZE */
 #define CS_SIG_SAT 300000000
@@ -39,18 +48,16 @@ ANM_CE_FN int32_t cs_sat(int32_t x) { return x > CS_SIG_SAT ? CS_SIG_SAT : x < -
 
 /* ---------------------------------------------------------------- denormalise_bands (downsample = 1) */
 ANM_CE_FN void cs_denormalise(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *st, const int16_t *X, int32_t *freq, const int16_t *band_log_e,
-                              int end, int M, int silence) {
+                              int end, int M, int silence, int lane, int nl) {
     const int N = M * 120;
-    int bound = M * t->ebands[end], start = 0;
+    int bound = M * t->ebands[end];
     if (silence) {
         bound = 0;
         end = 0;
     }
-    int32_t *f = freq;
-    const int16_t *x = X + M * t->ebands[start];
-    for (int i = start; i < end; i++) {
-        int j = M * t->ebands[i];
-        const int band_end = M * t->ebands[i + 1];
+    CS_SYNC();
+    for (int i = 0; i < end; i++) {
+        const int j0 = M * t->ebands[i], band_end = M * t->ebands[i + 1];
         int32_t lg32 = (int32_t)band_log_e[i] + (int32_t)((uint32_t)(int32_t)st->e_means[i] << 6);
         const int16_t lg = (int16_t)(lg32 > 32767 ? 32767 : lg32 < -32768 ? -32768 : lg32); /* SATURATE16 */
         int shift = 16 - (lg >> 10);
@@ -67,14 +74,13 @@ ANM_CE_FN void cs_denormalise(const anm_celt_tables_t *t, const anm_celt_synth_t
                 g = 16384;
                 shift = -2;
             }
-            do *f++ = (int32_t)((uint32_t)CV_M16(*x++, g) << -shift);
-            while (++j < band_end);
+            for (int j = j0 + lane; j < band_end; j += nl) freq[j] = (int32_t)((uint32_t)CV_M16(X[j], g) << -shift);
         } else {
-            do *f++ = CV_M16(*x++, g) >> shift;
-            while (++j < band_end);
+            for (int j = j0 + lane; j < band_end; j += nl) freq[j] = CV_M16(X[j], g) >> shift;
         }
     }
-    for (int i = bound; i < N; i++) freq[i] = 0;
+    for (int i = bound + lane; i < N; i += nl) freq[i] = 0;
+    CS_SYNC();
 }
 
 /* ---------------------------------------------------------------- the FFT of the inverse MDCT (opus_fft_impl) */
@@ -84,11 +90,11 @@ ANM_CE_FN void cs_denormalise(const anm_celt_tables_t *t, const anm_celt_synth_t
         (m).i = cs_add(cs_smul((a).r, ti), cs_smul((a).i, tr)); \
     } while (0)
 
-ANM_CE_FN void cs_bfly2(cs_cpx_t *F, int m, int N) {
+ANM_CE_FN void cs_bfly2(cs_cpx_t *Fbeg, int m, int N, int lane, int nl) {
     const int16_t tw = 23170; /* QCONST16(0.7071067812f, 15) */
     (void)m;                  /* m == 4: the radix 2 always follows a radix 4 in these transforms */
-    for (int i = 0; i < N; i++) {
-        cs_cpx_t *F2 = F + 4, t;
+    for (int i = lane; i < N; i += nl) {
+        cs_cpx_t *F = Fbeg + 8 * i, *F2 = F + 4, t;
         t = F2[0];
         F2[0].r = cs_sub(F[0].r, t.r); F2[0].i = cs_sub(F[0].i, t.i);
         F[0].r = cs_add(F[0].r, t.r); F[0].i = cs_add(F[0].i, t.i);
@@ -104,12 +110,12 @@ ANM_CE_FN void cs_bfly2(cs_cpx_t *F, int m, int N) {
         t.i = cs_smul(cs_neg(cs_add(F2[3].i, F2[3].r)), tw);
         F2[3].r = cs_sub(F[3].r, t.r); F2[3].i = cs_sub(F[3].i, t.i);
         F[3].r = cs_add(F[3].r, t.r); F[3].i = cs_add(F[3].i, t.i);
-        F += 8;
     }
 }
-ANM_CE_FN void cs_bfly4(cs_cpx_t *Fout, int fstride, const int16_t *tw, int m, int N, int mm) {
+ANM_CE_FN void cs_bfly4(cs_cpx_t *beg, int fstride, const int16_t *tw, int m, int N, int mm, int lane, int nl) {
     if (m == 1) {
-        for (int i = 0; i < N; i++) {
+        for (int i = lane; i < N; i += nl) {
+            cs_cpx_t *Fout = beg + 4 * i;
             cs_cpx_t s0, s1;
             s0.r = cs_sub(Fout[0].r, Fout[2].r); s0.i = cs_sub(Fout[0].i, Fout[2].i);
             Fout[0].r = cs_add(Fout[0].r, Fout[2].r); Fout[0].i = cs_add(Fout[0].i, Fout[2].i);
@@ -121,102 +127,87 @@ ANM_CE_FN void cs_bfly4(cs_cpx_t *Fout, int fstride, const int16_t *tw, int m, i
             Fout[1].i = cs_sub(s0.i, s1.r);
             Fout[3].r = cs_sub(s0.r, s1.i);
             Fout[3].i = cs_add(s0.i, s1.r);
-            Fout += 4;
         }
         return;
     }
     const int m2 = 2 * m, m3 = 3 * m;
-    cs_cpx_t *beg = Fout;
-    for (int i = 0; i < N; i++) {
-        cs_cpx_t *F = beg + i * mm;
-        const int16_t *tw1 = tw, *tw2 = tw, *tw3 = tw;
-        for (int j = 0; j < m; j++) {
-            cs_cpx_t s0, s1, s2, s3, s4, s5;
-            CS_CMUL(s0, F[m], tw1[0], tw1[1]);
-            CS_CMUL(s1, F[m2], tw2[0], tw2[1]);
-            CS_CMUL(s2, F[m3], tw3[0], tw3[1]);
-            s5.r = cs_sub(F->r, s1.r); s5.i = cs_sub(F->i, s1.i);
-            F->r = cs_add(F->r, s1.r); F->i = cs_add(F->i, s1.i);
-            s3.r = cs_add(s0.r, s2.r); s3.i = cs_add(s0.i, s2.i);
-            s4.r = cs_sub(s0.r, s2.r); s4.i = cs_sub(s0.i, s2.i);
-            F[m2].r = cs_sub(F->r, s3.r); F[m2].i = cs_sub(F->i, s3.i);
-            tw1 += 2 * fstride;
-            tw2 += 2 * fstride * 2;
-            tw3 += 2 * fstride * 3;
-            F->r = cs_add(F->r, s3.r); F->i = cs_add(F->i, s3.i);
-            F[m].r = cs_add(s5.r, s4.i);
-            F[m].i = cs_sub(s5.i, s4.r);
-            F[m3].r = cs_sub(s5.r, s4.i);
-            F[m3].i = cs_add(s5.i, s4.r);
-            ++F;
-        }
+    for (int idx = lane; idx < N * m; idx += nl) {
+        const int i = idx / m, j = idx % m;
+        cs_cpx_t *F = beg + i * mm + j;
+        const int16_t *tw1 = tw + 2 * fstride * j, *tw2 = tw + 2 * fstride * 2 * j, *tw3 = tw + 2 * fstride * 3 * j;
+        cs_cpx_t s0, s1, s2, s3, s4, s5;
+        CS_CMUL(s0, F[m], tw1[0], tw1[1]);
+        CS_CMUL(s1, F[m2], tw2[0], tw2[1]);
+        CS_CMUL(s2, F[m3], tw3[0], tw3[1]);
+        s5.r = cs_sub(F->r, s1.r); s5.i = cs_sub(F->i, s1.i);
+        F->r = cs_add(F->r, s1.r); F->i = cs_add(F->i, s1.i);
+        s3.r = cs_add(s0.r, s2.r); s3.i = cs_add(s0.i, s2.i);
+        s4.r = cs_sub(s0.r, s2.r); s4.i = cs_sub(s0.i, s2.i);
+        F[m2].r = cs_sub(F->r, s3.r); F[m2].i = cs_sub(F->i, s3.i);
+        F->r = cs_add(F->r, s3.r); F->i = cs_add(F->i, s3.i);
+        F[m].r = cs_add(s5.r, s4.i);
+        F[m].i = cs_sub(s5.i, s4.r);
+        F[m3].r = cs_sub(s5.r, s4.i);
+        F[m3].i = cs_add(s5.i, s4.r);
     }
 }
-ANM_CE_FN void cs_bfly3(cs_cpx_t *Fout, int fstride, const int16_t *tw, int m, int N, int mm) {
+ANM_CE_FN void cs_bfly3(cs_cpx_t *beg, int fstride, const int16_t *tw, int m, int N, int mm, int lane, int nl) {
     const int m2 = 2 * m;
     const int16_t epi3_i = -28378;
-    cs_cpx_t *beg = Fout;
-    for (int i = 0; i < N; i++) {
-        cs_cpx_t *F = beg + i * mm;
-        const int16_t *tw1 = tw, *tw2 = tw;
-        int k = m;
-        do {
-            cs_cpx_t s0, s1, s2, s3;
-            CS_CMUL(s1, F[m], tw1[0], tw1[1]);
-            CS_CMUL(s2, F[m2], tw2[0], tw2[1]);
-            s3.r = cs_add(s1.r, s2.r); s3.i = cs_add(s1.i, s2.i);
-            s0.r = cs_sub(s1.r, s2.r); s0.i = cs_sub(s1.i, s2.i);
-            tw1 += 2 * fstride;
-            tw2 += 2 * fstride * 2;
-            F[m].r = cs_sub(F->r, s3.r >> 1);
-            F[m].i = cs_sub(F->i, s3.i >> 1);
-            s0.r = cs_smul(s0.r, epi3_i);
-            s0.i = cs_smul(s0.i, epi3_i);
-            F->r = cs_add(F->r, s3.r); F->i = cs_add(F->i, s3.i);
-            F[m2].r = cs_add(F[m].r, s0.i);
-            F[m2].i = cs_sub(F[m].i, s0.r);
-            F[m].r = cs_sub(F[m].r, s0.i);
-            F[m].i = cs_add(F[m].i, s0.r);
-            ++F;
-        } while (--k);
+    for (int idx = lane; idx < N * m; idx += nl) {
+        const int i = idx / m, j = idx % m;
+        cs_cpx_t *F = beg + i * mm + j;
+        const int16_t *tw1 = tw + 2 * fstride * j, *tw2 = tw + 2 * fstride * 2 * j;
+        cs_cpx_t s0, s1, s2, s3;
+        CS_CMUL(s1, F[m], tw1[0], tw1[1]);
+        CS_CMUL(s2, F[m2], tw2[0], tw2[1]);
+        s3.r = cs_add(s1.r, s2.r); s3.i = cs_add(s1.i, s2.i);
+        s0.r = cs_sub(s1.r, s2.r); s0.i = cs_sub(s1.i, s2.i);
+        F[m].r = cs_sub(F->r, s3.r >> 1);
+        F[m].i = cs_sub(F->i, s3.i >> 1);
+        s0.r = cs_smul(s0.r, epi3_i);
+        s0.i = cs_smul(s0.i, epi3_i);
+        F->r = cs_add(F->r, s3.r); F->i = cs_add(F->i, s3.i);
+        F[m2].r = cs_add(F[m].r, s0.i);
+        F[m2].i = cs_sub(F[m].i, s0.r);
+        F[m].r = cs_sub(F[m].r, s0.i);
+        F[m].i = cs_add(F[m].i, s0.r);
     }
 }
-ANM_CE_FN void cs_bfly5(cs_cpx_t *Fout, int fstride, const int16_t *tw, int m, int N, int mm) {
+ANM_CE_FN void cs_bfly5(cs_cpx_t *beg, int fstride, const int16_t *tw, int m, int N, int mm, int lane, int nl) {
     const int16_t ya_r = 10126, ya_i = -31164, yb_r = -26510, yb_i = -19261;
-    cs_cpx_t *beg = Fout;
-    for (int i = 0; i < N; i++) {
-        cs_cpx_t *F0 = beg + i * mm, *F1 = F0 + m, *F2 = F0 + 2 * m, *F3 = F0 + 3 * m, *F4 = F0 + 4 * m;
-        for (int u = 0; u < m; ++u) {
-            cs_cpx_t s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12;
-            s0 = *F0;
-            CS_CMUL(s1, *F1, tw[2 * u * fstride], tw[2 * u * fstride + 1]);
-            CS_CMUL(s2, *F2, tw[2 * 2 * u * fstride], tw[2 * 2 * u * fstride + 1]);
-            CS_CMUL(s3, *F3, tw[2 * 3 * u * fstride], tw[2 * 3 * u * fstride + 1]);
-            CS_CMUL(s4, *F4, tw[2 * 4 * u * fstride], tw[2 * 4 * u * fstride + 1]);
-            s7.r = cs_add(s1.r, s4.r); s7.i = cs_add(s1.i, s4.i);
-            s10.r = cs_sub(s1.r, s4.r); s10.i = cs_sub(s1.i, s4.i);
-            s8.r = cs_add(s2.r, s3.r); s8.i = cs_add(s2.i, s3.i);
-            s9.r = cs_sub(s2.r, s3.r); s9.i = cs_sub(s2.i, s3.i);
-            F0->r = cs_add(F0->r, cs_add(s7.r, s8.r));
-            F0->i = cs_add(F0->i, cs_add(s7.i, s8.i));
-            s5.r = cs_add(s0.r, cs_add(cs_smul(s7.r, ya_r), cs_smul(s8.r, yb_r)));
-            s5.i = cs_add(s0.i, cs_add(cs_smul(s7.i, ya_r), cs_smul(s8.i, yb_r)));
-            s6.r = cs_add(cs_smul(s10.i, ya_i), cs_smul(s9.i, yb_i));
-            s6.i = cs_neg(cs_add(cs_smul(s10.r, ya_i), cs_smul(s9.r, yb_i)));
-            F1->r = cs_sub(s5.r, s6.r); F1->i = cs_sub(s5.i, s6.i);
-            F4->r = cs_add(s5.r, s6.r); F4->i = cs_add(s5.i, s6.i);
-            s11.r = cs_add(s0.r, cs_add(cs_smul(s7.r, yb_r), cs_smul(s8.r, ya_r)));
-            s11.i = cs_add(s0.i, cs_add(cs_smul(s7.i, yb_r), cs_smul(s8.i, ya_r)));
-            s12.r = cs_sub(cs_smul(s9.i, ya_i), cs_smul(s10.i, yb_i));
-            s12.i = cs_sub(cs_smul(s10.r, yb_i), cs_smul(s9.r, ya_i));
-            F2->r = cs_add(s11.r, s12.r); F2->i = cs_add(s11.i, s12.i);
-            F3->r = cs_sub(s11.r, s12.r); F3->i = cs_sub(s11.i, s12.i);
-            ++F0; ++F1; ++F2; ++F3; ++F4;
-        }
+    for (int idx = lane; idx < N * m; idx += nl) {
+        const int i = idx / m, u = idx % m;
+        cs_cpx_t *F0 = beg + i * mm + u, *F1 = F0 + m, *F2 = F0 + 2 * m, *F3 = F0 + 3 * m, *F4 = F0 + 4 * m;
+        cs_cpx_t s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12;
+        s0 = *F0;
+        CS_CMUL(s1, *F1, tw[2 * u * fstride], tw[2 * u * fstride + 1]);
+        CS_CMUL(s2, *F2, tw[2 * 2 * u * fstride], tw[2 * 2 * u * fstride + 1]);
+        CS_CMUL(s3, *F3, tw[2 * 3 * u * fstride], tw[2 * 3 * u * fstride + 1]);
+        CS_CMUL(s4, *F4, tw[2 * 4 * u * fstride], tw[2 * 4 * u * fstride + 1]);
+        s7.r = cs_add(s1.r, s4.r); s7.i = cs_add(s1.i, s4.i);
+        s10.r = cs_sub(s1.r, s4.r); s10.i = cs_sub(s1.i, s4.i);
+        s8.r = cs_add(s2.r, s3.r); s8.i = cs_add(s2.i, s3.i);
+        s9.r = cs_sub(s2.r, s3.r); s9.i = cs_sub(s2.i, s3.i);
+        F0->r = cs_add(F0->r, cs_add(s7.r, s8.r));
+        F0->i = cs_add(F0->i, cs_add(s7.i, s8.i));
+        s5.r = cs_add(s0.r, cs_add(cs_smul(s7.r, ya_r), cs_smul(s8.r, yb_r)));
+        s5.i = cs_add(s0.i, cs_add(cs_smul(s7.i, ya_r), cs_smul(s8.i, yb_r)));
+        s6.r = cs_add(cs_smul(s10.i, ya_i), cs_smul(s9.i, yb_i));
+        s6.i = cs_neg(cs_add(cs_smul(s10.r, ya_i), cs_smul(s9.r, yb_i)));
+        F1->r = cs_sub(s5.r, s6.r); F1->i = cs_sub(s5.i, s6.i);
+        F4->r = cs_add(s5.r, s6.r); F4->i = cs_add(s5.i, s6.i);
+        s11.r = cs_add(s0.r, cs_add(cs_smul(s7.r, yb_r), cs_smul(s8.r, ya_r)));
+        s11.i = cs_add(s0.i, cs_add(cs_smul(s7.i, yb_r), cs_smul(s8.i, ya_r)));
+        s12.r = cs_sub(cs_smul(s9.i, ya_i), cs_smul(s10.i, yb_i));
+        s12.i = cs_sub(cs_smul(s10.r, yb_i), cs_smul(s9.r, ya_i));
+        F2->r = cs_add(s11.r, s12.r); F2->i = cs_add(s11.i, s12.i);
+        F3->r = cs_sub(s11.r, s12.r); F3->i = cs_sub(s11.i, s12.i);
     }
 }
-/* the transform of 480 >> k complex points, k = 0..3 (the four kiss_fft states of the 48 kHz mode, celt/static_modes_fixed.h:432-498) */
-ANM_CE_FN void cs_fft(const anm_celt_synth_tables_t *st, int k, cs_cpx_t *fout) {
+/* the transform of 480 >> k complex points, k = 0..3 (the four kiss_fft states of the 48 kHz mode, celt/static_modes_fixed.h:432-498); the butterflies of a
+ * stage are independent of each other and go over the lanes */
+ANM_CE_FN void cs_fft(const anm_celt_synth_tables_t *st, int k, cs_cpx_t *fout, int lane, int nl) {
     const int8_t factors[4][10] = {{5, 96, 3, 32, 4, 8, 2, 4, 4, 1}, {5, 48, 3, 16, 4, 4, 4, 1, 0, 0}, {5, 24, 3, 8, 2, 4, 4, 1, 0, 0}, {5, 12, 3, 4, 4, 1, 0, 0, 0, 0}};
     const int8_t *fac = factors[k];
     const int shift = k; /* st->shift: -1 (taken as 0), 1, 2, 3 */
@@ -231,20 +222,22 @@ ANM_CE_FN void cs_fft(const anm_celt_synth_tables_t *st, int k, cs_cpx_t *fout) 
     m = fac[2 * L - 1];
     for (int i = L - 1; i >= 0; i--) {
         const int m2 = i != 0 ? fac[2 * i - 1] : 1;
+        CS_SYNC();
         switch (fac[2 * i]) {
-            case 2: cs_bfly2(fout, m, fstride[i]); break;
-            case 4: cs_bfly4(fout, fstride[i] << shift, st->fft_tw, m, fstride[i], m2); break;
-            case 3: cs_bfly3(fout, fstride[i] << shift, st->fft_tw, m, fstride[i], m2); break;
-            case 5: cs_bfly5(fout, fstride[i] << shift, st->fft_tw, m, fstride[i], m2); break;
+            case 2: cs_bfly2(fout, m, fstride[i], lane, nl); break;
+            case 4: cs_bfly4(fout, fstride[i] << shift, st->fft_tw, m, fstride[i], m2, lane, nl); break;
+            case 3: cs_bfly3(fout, fstride[i] << shift, st->fft_tw, m, fstride[i], m2, lane, nl); break;
+            case 5: cs_bfly5(fout, fstride[i] << shift, st->fft_tw, m, fstride[i], m2, lane, nl); break;
         }
         m = m2;
     }
+    CS_SYNC();
 }
 
 /* ---------------------------------------------------------------- inverse MDCT of one block, up to (not including) the window mix */
 /* in: the block's N2 = 960 >> shift coefficients, `stride` apart; raw: N2 values -- what clt_mdct_backward holds in out[overlap / 2 .. overlap / 2 + N2)
  * before it mirrors the block's ends against the previous block's tail */
-ANM_CE_FN void cs_imdct_raw(const anm_celt_synth_tables_t *st, const int32_t *in, int stride, int shift, int32_t *raw) {
+ANM_CE_FN void cs_imdct_raw(const anm_celt_synth_tables_t *st, const int32_t *in, int stride, int shift, int32_t *raw, int lane, int nl) {
     int N = 1920;
     const int16_t *trig = st->trig;
     const int16_t *bitrev = st->bitrev;
@@ -254,51 +247,43 @@ ANM_CE_FN void cs_imdct_raw(const anm_celt_synth_tables_t *st, const int32_t *in
         bitrev += N >> 1; /* 480, 240, 120 entries */
     }
     const int N2 = N >> 1, N4 = N >> 2;
-    {
-        const int32_t *xp1 = in, *xp2 = in + stride * (N2 - 1);
-        for (int i = 0; i < N4; i++) {
-            const int rev = bitrev[i];
-            const int32_t yr = cs_add(cs_smul(*xp2, trig[i]), cs_smul(*xp1, trig[N4 + i]));
-            const int32_t yi = cs_sub(cs_smul(*xp1, trig[i]), cs_smul(*xp2, trig[N4 + i]));
-            raw[2 * rev + 1] = yr; /* real and imaginary swapped: an FFT instead of an IFFT */
-            raw[2 * rev] = yi;
-            xp1 += 2 * stride;
-            xp2 -= 2 * stride;
-        }
+    CS_SYNC();
+    for (int i = lane; i < N4; i += nl) {
+        const int32_t xp1 = in[2 * stride * i], xp2 = in[stride * (N2 - 1) - 2 * stride * i];
+        const int rev = bitrev[i];
+        const int32_t yr = cs_add(cs_smul(xp2, trig[i]), cs_smul(xp1, trig[N4 + i]));
+        const int32_t yi = cs_sub(cs_smul(xp1, trig[i]), cs_smul(xp2, trig[N4 + i]));
+        raw[2 * rev + 1] = yr; /* real and imaginary swapped: an FFT instead of an IFFT */
+        raw[2 * rev] = yi;
     }
-    cs_fft(st, shift, (cs_cpx_t *)raw);
-    {
-        int32_t *yp0 = raw, *yp1 = raw + N2 - 2;
-        for (int i = 0; i < (N4 + 1) >> 1; i++) {
-            int32_t re = yp0[1], im = yp0[0];
-            int16_t t0 = trig[i], t1 = trig[N4 + i];
-            int32_t yr = cs_add(cs_smul(re, t0), cs_smul(im, t1));
-            int32_t yi = cs_sub(cs_smul(re, t1), cs_smul(im, t0));
-            re = yp1[1];
-            im = yp1[0];
-            yp0[0] = yr;
-            yp1[1] = yi;
-            t0 = trig[N4 - i - 1];
-            t1 = trig[N2 - i - 1];
-            yr = cs_add(cs_smul(re, t0), cs_smul(im, t1));
-            yi = cs_sub(cs_smul(re, t1), cs_smul(im, t0));
-            yp1[0] = yr;
-            yp0[1] = yi;
-            yp0 += 2;
-            yp1 -= 2;
-        }
+    cs_fft(st, shift, (cs_cpx_t *)raw, lane, nl);
+    /* post-rotation from both ends at once: pair i touches words 2i, 2i + 1, N2 - 2 - 2i, N2 - 1 - 2i only (N4 is even in all four transforms) */
+    for (int i = lane; i < (N4 + 1) >> 1; i += nl) {
+        int32_t *yp0 = raw + 2 * i, *yp1 = raw + N2 - 2 - 2 * i;
+        int32_t re = yp0[1], im = yp0[0];
+        int16_t t0 = trig[i], t1 = trig[N4 + i];
+        int32_t yr = cs_add(cs_smul(re, t0), cs_smul(im, t1));
+        int32_t yi = cs_sub(cs_smul(re, t1), cs_smul(im, t0));
+        re = yp1[1];
+        im = yp1[0];
+        yp0[0] = yr;
+        yp1[1] = yi;
+        t0 = trig[N4 - i - 1];
+        t1 = trig[N2 - i - 1];
+        yr = cs_add(cs_smul(re, t0), cs_smul(im, t1));
+        yi = cs_sub(cs_smul(re, t1), cs_smul(im, t0));
+        yp1[0] = yr;
+        yp0[1] = yi;
     }
+    CS_SYNC();
 }
 /* the window mix of a block whose raw output sits at out + overlap / 2: out[0 .. overlap / 2) still holds the previous block's tail */
-ANM_CE_FN void cs_mirror(const anm_celt_synth_tables_t *st, int32_t *out) {
-    int32_t *xp1 = out + CS_OVERLAP - 1, *yp1 = out;
-    const int16_t *wp1 = st->window, *wp2 = st->window + CS_OVERLAP - 1;
-    for (int i = 0; i < CS_OVERLAP / 2; i++) {
-        const int32_t x1 = *xp1, x2 = *yp1;
-        *yp1++ = cs_sub(cs_smul(x2, *wp2), cs_smul(x1, *wp1));
-        *xp1-- = cs_add(cs_smul(x2, *wp1), cs_smul(x1, *wp2));
-        wp1++;
-        wp2--;
+ANM_CE_FN void cs_mirror(const anm_celt_synth_tables_t *st, int32_t *out, int lane, int nl) {
+    for (int i = lane; i < CS_OVERLAP / 2; i += nl) {
+        const int32_t x1 = out[CS_OVERLAP - 1 - i], x2 = out[i];
+        const int16_t w1 = st->window[i], w2 = st->window[CS_OVERLAP - 1 - i];
+        out[i] = cs_sub(cs_smul(x2, w2), cs_smul(x1, w1));
+        out[CS_OVERLAP - 1 - i] = cs_add(cs_smul(x2, w1), cs_smul(x1, w2));
     }
 }
 
@@ -306,67 +291,65 @@ ANM_CE_FN void cs_mirror(const anm_celt_synth_tables_t *st, int32_t *out) {
 /* X: [C][N] normalised spectrum (stage 2), band_e: the frame's band energies [2][21]; raw: [CC][N] -- block b of channel c at raw + c * N + b * (N / B);
  * freq: N words of scratch (two N for the mono downmix of a stereo frame) */
 ANM_CE_FN void cs_frame_blocks(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *st, const int16_t *X, const int16_t *band_e, int C, int CC, int LM,
-                               int end, int transient, int silence, int32_t *freq, int32_t *raw) {
+                               int end, int transient, int silence, int32_t *freq, int32_t *raw, int lane, int nl) {
     const int M = 1 << LM, N = 120 << LM;
     const int B = transient ? M : 1, NB = transient ? 120 : N, shift = transient ? 3 : 3 - LM;
     if (CC == 2 && C == 1) {
-        cs_denormalise(t, st, X, freq, band_e, end, M, silence);
-        for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + NB * b);
-        for (int i = 0; i < N; i++) raw[N + i] = raw[i];
+        cs_denormalise(t, st, X, freq, band_e, end, M, silence, lane, nl);
+        for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + NB * b, lane, nl);
+        for (int i = lane; i < N; i += nl) raw[N + i] = raw[i];
     } else if (CC == 1 && C == 2) {
         int32_t *freq2 = freq + N;
-        cs_denormalise(t, st, X, freq, band_e, end, M, silence);
-        cs_denormalise(t, st, X + N, freq2, band_e + ANM_CE_NB, end, M, silence);
-        for (int i = 0; i < N; i++) freq[i] = (freq[i] >> 1) + (freq2[i] >> 1);
-        for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + NB * b);
+        cs_denormalise(t, st, X, freq, band_e, end, M, silence, lane, nl);
+        cs_denormalise(t, st, X + N, freq2, band_e + ANM_CE_NB, end, M, silence, lane, nl);
+        for (int i = lane; i < N; i += nl) freq[i] = (freq[i] >> 1) + (freq2[i] >> 1);
+        for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + NB * b, lane, nl);
     } else {
         for (int c = 0; c < CC; c++) {
-            cs_denormalise(t, st, X + c * N, freq, band_e + c * ANM_CE_NB, end, M, silence);
-            for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + c * N + NB * b);
+            cs_denormalise(t, st, X + c * N, freq, band_e + c * ANM_CE_NB, end, M, silence, lane, nl);
+            for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + c * N + NB * b, lane, nl);
         }
     }
+    CS_SYNC();
 }
 
 /* ---------------------------------------------------------------- per-stream part */
-ANM_CE_FN void cs_comb_filter(const anm_celt_synth_tables_t *st, int32_t *y, int T0, int T1, int N, int16_t g0, int16_t g1, int tapset0, int tapset1, int overlap) {
+/* The pitch post-filter, in place.  y[i] takes y[i - T .. i - T +- 2] with T >= 15: a recurrence, but one that reaches back at least 13 samples, so
+ * runs of min(T0, T1) - 2 outputs are independent of each other and go over the lanes (the reference's sliding registers x0..x4 hold exactly
+ * y[i - T1 + 2 .. i - T1 - 2] as they stand when y[i] is computed). */
+ANM_CE_FN void cs_comb_filter(const anm_celt_synth_tables_t *st, int32_t *y, int T0, int T1, int N, int16_t g0, int16_t g1, int tapset0, int tapset1, int overlap,
+                              int lane, int nl) {
     const int16_t gains[3][3] = {{10048, 7112, 4248}, {15200, 8784, 0}, {26208, 3280, 0}};
     if (g0 == 0 && g1 == 0) return; /* in place: nothing to move */
     T0 = ce_imax(T0, 15);
     T1 = ce_imax(T1, 15);
     const int16_t g00 = (int16_t)CV_P15(g0, gains[tapset0][0]), g01 = (int16_t)CV_P15(g0, gains[tapset0][1]), g02 = (int16_t)CV_P15(g0, gains[tapset0][2]);
     const int16_t g10 = (int16_t)CV_P15(g1, gains[tapset1][0]), g11 = (int16_t)CV_P15(g1, gains[tapset1][1]), g12 = (int16_t)CV_P15(g1, gains[tapset1][2]);
-    int32_t x1 = y[-T1 + 1], x2 = y[-T1], x3 = y[-T1 - 1], x4 = y[-T1 - 2], x0;
     if (g0 == g1 && T0 == T1 && tapset0 == tapset1) overlap = 0;
-    int i;
-    for (i = 0; i < overlap; i++) {
-        x0 = y[i - T1 + 2];
-        const int16_t f = (int16_t)CV_Q15(st->window[i], st->window[i]);
-        const int16_t nf = (int16_t)(32767 - f);
-        int32_t v = y[i] + cs_smul(y[i - T0], (int16_t)CV_Q15(nf, g00)) + cs_smul(y[i - T0 + 1] + y[i - T0 - 1], (int16_t)CV_Q15(nf, g01)) +
-                    cs_smul(y[i - T0 + 2] + y[i - T0 - 2], (int16_t)CV_Q15(nf, g02)) + cs_smul(x2, (int16_t)CV_Q15(f, g10)) +
-                    cs_smul(x1 + x3, (int16_t)CV_Q15(f, g11)) + cs_smul(x0 + x4, (int16_t)CV_Q15(f, g12));
-        y[i] = cs_sat(v);
-        x4 = x3;
-        x3 = x2;
-        x2 = x1;
-        x1 = x0;
+    const int run = (T0 < T1 ? T0 : T1) - 2; /* >= 13 */
+    CS_SYNC();
+    for (int base = 0; base < overlap; base += run) {
+        const int lim = base + run < overlap ? base + run : overlap;
+        for (int i = base + lane; i < lim; i += nl) {
+            const int16_t f = (int16_t)CV_Q15(st->window[i], st->window[i]);
+            const int16_t nf = (int16_t)(32767 - f);
+            const int32_t v = y[i] + cs_smul(y[i - T0], (int16_t)CV_Q15(nf, g00)) + cs_smul(y[i - T0 + 1] + y[i - T0 - 1], (int16_t)CV_Q15(nf, g01)) +
+                              cs_smul(y[i - T0 + 2] + y[i - T0 - 2], (int16_t)CV_Q15(nf, g02)) + cs_smul(y[i - T1], (int16_t)CV_Q15(f, g10)) +
+                              cs_smul(y[i - T1 + 1] + y[i - T1 - 1], (int16_t)CV_Q15(f, g11)) + cs_smul(y[i - T1 + 2] + y[i - T1 - 2], (int16_t)CV_Q15(f, g12));
+            y[i] = cs_sat(v);
+        }
+        CS_SYNC();
     }
     if (g1 == 0) return;
     /* the part with the constant filter */
-    y += i;
-    N -= i;
-    x4 = y[-T1 - 2];
-    x3 = y[-T1 - 1];
-    x2 = y[-T1];
-    x1 = y[-T1 + 1];
-    for (i = 0; i < N; i++) {
-        x0 = y[i - T1 + 2];
-        const int32_t v = y[i] + cs_smul(x2, g10) + cs_smul(x1 + x3, g11) + cs_smul(x0 + x4, g12);
-        y[i] = cs_sat(v);
-        x4 = x3;
-        x3 = x2;
-        x2 = x1;
-        x1 = x0;
+    const int run1 = T1 - 2;
+    for (int base = overlap; base < N; base += run1) {
+        const int lim = base + run1 < N ? base + run1 : N;
+        for (int i = base + lane; i < lim; i += nl) {
+            const int32_t v = y[i] + cs_smul(y[i - T1], g10) + cs_smul(y[i - T1 + 1] + y[i - T1 - 1], g11) + cs_smul(y[i - T1 + 2] + y[i - T1 - 2], g12);
+            y[i] = cs_sat(v);
+        }
+        CS_SYNC();
     }
 }
 
@@ -377,29 +360,41 @@ typedef struct cs_pf {
 } cs_pf_t;
 
 /* One frame of ONE output channel c of a stream: raw blocks (cs_frame_blocks) -> PCM.  mem: the channel's output history (anm_celt_synth_t.mem[c]);
- * pf: the stream's post-filter state, updated for the next frame (every channel of a stream sees and makes the same updates); pcm: [N][CC] */
+ * pf: the stream's post-filter state, updated for the next frame (every channel of a stream sees and makes the same updates); pcm: [N][CC].
+ * The copies, the window mix, the saturation and (in runs shorter than its period) the post-filter go over the lanes; the de-emphasis is a one-pole
+ * recurrence and runs on lane 0. */
 ANM_CE_FN void cs_channel_frame(const anm_celt_synth_tables_t *st, int32_t *mem, int32_t *preemph_mem, cs_pf_t *pf, const anm_celt_frame_t *fr, const int32_t *raw_c,
-                                int CC, int c, int16_t *pcm) {
+                                int CC, int c, int16_t *pcm, int lane, int nl) {
     const int LM = fr->lm, N = 120 << LM, transient = (fr->flags & ANM_CELT_F_TRANSIENT) != 0;
     const int B = transient ? 1 << LM : 1, NB = transient ? 120 : N;
     const int pf_on = (fr->flags & ANM_CELT_F_POSTFILTER) != 0;
     const int pf_pitch = pf_on ? fr->pf_pitch : 0, pf_tapset = pf_on ? fr->pf_tapset : 0;
     const int16_t pf_gain = pf_on ? (int16_t)(3072 * (fr->pf_gain_q + 1)) : 0; /* QCONST16(.09375f, 15) * (qg + 1) */
-    /* the history moves up by one frame (half of the overlap is still to be mixed) */
-    for (int i = 0; i < CS_BUF - N + CS_OVERLAP / 2; i++) mem[i] = mem[i + N];
+    /* the history moves up by one frame (half of the overlap is still to be mixed): in chunks of nl, every chunk read before it is written */
+    CS_SYNC();
+    for (int i0 = 0; i0 < CS_BUF - N + CS_OVERLAP / 2; i0 += nl) {
+        const int i = i0 + lane;
+        const int32_t v = i < CS_BUF - N + CS_OVERLAP / 2 ? mem[i + N] : 0;
+        CS_SYNC();
+        if (i < CS_BUF - N + CS_OVERLAP / 2) mem[i] = v;
+        CS_SYNC();
+    }
     int32_t *out = mem + CS_BUF - N;
     for (int b = 0; b < B; b++) {
         int32_t *ob = out + NB * b;
         const int32_t *rb = raw_c + NB * b;
-        for (int i = 0; i < NB; i++) ob[CS_OVERLAP / 2 + i] = rb[i];
-        cs_mirror(st, ob);
+        for (int i = lane; i < NB; i += nl) ob[CS_OVERLAP / 2 + i] = rb[i];
+        CS_SYNC();
+        cs_mirror(st, ob, lane, nl);
+        CS_SYNC();
     }
-    for (int i = 0; i < N; i++) out[i] = cs_sat(out[i]);
+    for (int i = lane; i < N; i += nl) out[i] = cs_sat(out[i]);
+    CS_SYNC();
     /* pitch post-filter: the first 120 samples fade from the filter before the previous frame's to the previous frame's, the rest to this frame's */
     pf->period = ce_imax(pf->period, 15);
     pf->period_old = ce_imax(pf->period_old, 15);
-    cs_comb_filter(st, out, pf->period_old, pf->period, 120, pf->gain_old, pf->gain, pf->tapset_old, pf->tapset, CS_OVERLAP);
-    if (LM != 0) cs_comb_filter(st, out + 120, pf->period, pf_pitch, N - 120, pf->gain, pf_gain, pf->tapset, pf_tapset, CS_OVERLAP);
+    cs_comb_filter(st, out, pf->period_old, pf->period, 120, pf->gain_old, pf->gain, pf->tapset_old, pf->tapset, CS_OVERLAP, lane, nl);
+    if (LM != 0) cs_comb_filter(st, out + 120, pf->period, pf_pitch, N - 120, pf->gain, pf_gain, pf->tapset, pf_tapset, CS_OVERLAP, lane, nl);
     pf->period_old = pf->period;
     pf->gain_old = pf->gain;
     pf->tapset_old = pf->tapset;
@@ -412,15 +407,18 @@ ANM_CE_FN void cs_channel_frame(const anm_celt_synth_tables_t *st, int32_t *mem,
         pf->tapset_old = pf->tapset;
     }
     /* de-emphasis to 16 bits */
-    int32_t m = *preemph_mem;
-    for (int j = 0; j < N; j++) {
-        const int32_t tmp = out[j] + m;   /* VERY_SMALL = 0 */
-        m = cs_smul(tmp, 27853);          /* mode->preemph[0] */
-        int32_t v = CV_PSHR32(tmp, 12);   /* SIG2WORD16 */
-        v = v < -32768 ? -32768 : v > 32767 ? 32767 : v;
-        pcm[j * CC + c] = (int16_t)v;
+    if (lane == 0) {
+        int32_t m = *preemph_mem;
+        for (int j = 0; j < N; j++) {
+            const int32_t tmp = out[j] + m;   /* VERY_SMALL = 0 */
+            m = cs_smul(tmp, 27853);          /* mode->preemph[0] */
+            int32_t v = CV_PSHR32(tmp, 12);   /* SIG2WORD16 */
+            v = v < -32768 ? -32768 : v > 32767 ? 32767 : v;
+            pcm[j * CC + c] = (int16_t)v;
+        }
+        *preemph_mem = m;
     }
-    *preemph_mem = m;
+    CS_SYNC();
 }
 ANM_CE_FN void cs_pf_load(cs_pf_t *pf, const anm_celt_synth_t *s) {
     pf->period = s->pf_period; pf->period_old = s->pf_period_old; pf->tapset = s->pf_tapset; pf->tapset_old = s->pf_tapset_old;
@@ -438,7 +436,7 @@ ANM_CE_FN void cs_stream_frame(const anm_celt_synth_tables_t *st, anm_celt_synth
     pf = pf0;
     for (int c = 0; c < CC; c++) {
         pf = pf0;
-        cs_channel_frame(st, s->mem[c], &s->preemph_mem[c], &pf, fr, raw + c * N, CC, c, pcm);
+        cs_channel_frame(st, s->mem[c], &s->preemph_mem[c], &pf, fr, raw + c * N, CC, c, pcm, 0, 1);
     }
     cs_pf_store(&pf, s);
 }

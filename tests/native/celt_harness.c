@@ -99,7 +99,7 @@ int harness_celt_decode_frame(const anm_celt_tables_t *t, const anm_celt_synth_t
     for (int i = 0; i < 2 * 960; i++) X[i] = 0;
     rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, CC == 1, &hist, out, &sp, X, cm);
     if (rc != 0) return rc;
-    cs_frame_blocks(t, stb, X, out->band_e, C, CC, LM, end, (out->flags & ANM_CELT_F_TRANSIENT) != 0, (out->flags & ANM_CELT_F_SILENCE) != 0, freq, raw);
+    cs_frame_blocks(t, stb, X, out->band_e, C, CC, LM, end, (out->flags & ANM_CELT_F_TRANSIENT) != 0, (out->flags & ANM_CELT_F_SILENCE) != 0, freq, raw, 0, 1);
     cs_stream_frame(stb, syn, out, raw, CC, pcm);
     return 0;
 }
