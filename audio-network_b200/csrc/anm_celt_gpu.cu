@@ -1,6 +1,6 @@
 /*
- * anm_celt_gpu.cu -- batched CELT entropy decode on the GPU (include/anmodem_opus.h, anm_celt_entropy_*; SURVEY.md 8(f) row f1,
- * stage 1).  Two passes.  k_celt_entropy, one thread per FRAME: the range decoder is sequential inside a frame, but no symbol of a
+ * anm_celt_gpu.cu -- the batched CELT decoder on the GPU (include/anmodem_opus.h, anm_celt_entropy_* / _spectrum_* / _decode_*).
+ * Stage 1, two passes.  k_celt_entropy, one thread per FRAME: the range decoder is sequential inside a frame, but no symbol of a
  * frame depends on any other frame, so every frame of every stream decodes at once (integer / byte work on a few hundred bytes of
  * packet, latency bound per thread: the batch of frames is what fills the machine).  k_celt_energies, one thread per STREAM: the band
  * energies predict from the previous frame of the same stream (celt/quant_bands.c:427-490) -- a recurrence of about a hundred integer
@@ -10,11 +10,13 @@
  * Stage 2 (anm_celt_spectrum_*) adds k_celt_spectrum, one thread per frame again: the frame is decoded once more, this time with the spectrum
  * arithmetic switched on (anm_celt_vec.h: PVQ vectors, rotations, folding, reorderings, stereo merge, anti-collapse), seeded and informed by what
  * the per-stream pass left (the noise seed is the previous frame's final range, anti-collapse reads the stream's two log-energy histories).  A
- * first, plainly thread-per-frame version: the per-thread working set (3.7 KB) lives in a global scratch slab, throughput is bound by local
- * latency, not by HBM -- the warp-per-frame form (lanes over the coefficients of a band) is the next step.
+ * thread-per-frame kernel: the per-thread working set (3.7 KB + the frame's spectrum) lives in global memory, threads of a warp diverge (3.3 of 32
+ * lanes active per instruction); a warp-per-frame form was measured 3 x slower (anm_celt_vec.h).  Stage 3 (anm_celt_decode_*) adds
+ * k_celt_blocks (a warp per frame: denormalisation, the fixed-point FFT of the inverse MDCT in shared memory) and k_celt_overlap (a warp per stream and
+ * output channel: overlap-add, pitch post-filter, de-emphasis with the output history in shared memory).
  *
  * Reference path replaced: playback.cpp:115-122 opus_decode() -> opus_decode_frame (opus_decoder.c:214-626, CELT-only branch)
- * -> celt_decode_with_ec (celt/celt_decoder.c:815-1098), up to the call of celt_synthesis.
+ * -> celt_decode_with_ec (celt/celt_decoder.c:815-1180), without the concealment of lost frames.
  */
 #include <cuda_runtime.h>
 
@@ -329,7 +331,8 @@ extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t 
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, (uint64_t)sms * blocks_per_sm());
+    /* one frame per thread while the working storage stays below 2 GB (the hardware then balances the very uneven frames block by block), grid-stride beyond */
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, std::max<uint64_t>((uint64_t)sms * blocks_per_sm(), (2ull << 30) / (64u * sizeof(SpecScratch))));
     if ((rc = grow(&c->d_hist, &c->hist_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
     unsigned char *spec = static_cast<unsigned char *>(c->d_spec);
     rc = grow(&spec, &c->spec_bytes, (size_t)blocks * 64u * sizeof(SpecScratch), s, "anm_celt_spectrum_device");
