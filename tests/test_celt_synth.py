@@ -100,6 +100,45 @@ def test_host_harness_pcm_equals_the_reference_decoder_frame_by_frame_native_mon
                 assert _digest(pcm) == PCM[key][j], (s, key, j)
 
 
+def _random_streams(rng, n_streams):
+    """random bytes as frames in streams whose channel count, frame size and bandwidth may change from frame to frame, decoded by a mono or a stereo
+    decoder: [(frames [(bytes, C, lm, end)], cc, reference PCM per frame, reference return codes)]"""
+    R = sbind.ref()
+    out = []
+    for _ in range(n_streams):
+        cc, nfr = int(rng.integers(1, 3)), int(rng.integers(2, 7))
+        params = np.array([[int(rng.integers(1, 3)), int(rng.integers(0, 4)), int(rng.choice([13, 17, 19, 21]))] for _ in range(nfr)], np.int32)
+        if rng.random() < 0.6:
+            params[:] = params[0]
+        frames = [rng.integers(0, 256, int(rng.choice([rng.integers(2, 12), rng.integers(12, 120), rng.integers(120, 500), rng.integers(500, 1276)])), dtype=np.uint8)
+                  for _ in range(nfr)]
+        for f in frames:
+            if rng.random() < 0.7:
+                f[0] &= 0x7F
+        maxlen = max(len(f) for f in frames)
+        buf, lens = np.zeros((nfr, maxlen), np.uint8), np.array([len(f) for f in frames], np.int32)
+        for k, f in enumerate(frames):
+            buf[k, :len(f)] = f
+        states, pcm = np.zeros(nfr, sbind.STATE), np.zeros((nfr, 960 * cc), np.int16)
+        assert R.ref_celt_stream_states(buf.ctypes.data, lens.ctypes.data, nfr, maxlen, params.ctypes.data, cc, states.ctypes.data, pcm.ctypes.data) == nfr
+        out.append(([(frames[k].tobytes(), int(params[k, 0]), int(params[k, 1]), int(params[k, 2])) for k in range(nfr)], cc, pcm, states["ret"].copy()))
+    return out
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libref_opus.so not built (reference tree absent)")
+def test_host_harness_random_streams_pcm_vs_reference_live():
+    """garbage in, the same garbage out: random frames (extreme gains, saturation, every post-filter setting, layout changes inside a stream)"""
+    L, stb = _harness()
+    rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
+    n = 0
+    for frames, cc, want, ret in _random_streams(rng, 120):
+        for k, pcm in enumerate(_host_decode_stream(L, stb, frames, cc)):
+            if ret[k] >= 0:
+                assert np.array_equal(pcm, want[k, : len(pcm)]), (k, frames[k][1:], cc, len(frames[k][0]))
+                n += 1
+    assert n > 300
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _jobs_from_gold(cc_of_stream):
     fr, sb = GOLD["frames"], GOLD["stream_begin"]
@@ -152,6 +191,31 @@ def test_gpu_pcm_of_the_transmitter_streams_equals_the_public_api_and_state_carr
         _, st, sy, pa = anm.celt_decode(jobs[:h], [0, h], by, out_channels=[cc])
         _, _, _, pb = anm.celt_decode(jobs[h:], [0, len(jobs) - h], by, streams=st, synth=sy)
         assert hashlib.sha256(np.concatenate([flat(pa, jobs[:h]), flat(pb, jobs[h:])]).tobytes()).hexdigest() == s["decoded_sha256"], s["name"]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libref_opus.so not built (reference tree absent)")
+def test_gpu_random_streams_pcm_vs_reference_live():
+    """150 streams of random frames with changing layouts in ONE call: every sample the GPU returns equals the reference decoder's"""
+    rng = np.random.default_rng(int.from_bytes(os.urandom(4), "little"))
+    streams = _random_streams(rng, 150)
+    jobs, by, sbeg, ccs = [], bytearray(), [0], []
+    for frames, cc, _, _ in streams:
+        for f, ch, lm, end in frames:
+            jobs.append((len(by), len(f), ch, lm, end, anm.CELT_JOB_DISABLE_INV if cc == 1 else 0))
+            by += f
+        sbeg.append(len(jobs))
+        ccs.append(cc)
+    jobs = np.array(jobs, dtype=anm.CELT_JOB_DTYPE)
+    _, _, _, pcm = anm.celt_decode(jobs, np.array(sbeg, np.uint32), np.frombuffer(bytes(by), np.uint8), out_channels=ccs)
+    n = 0
+    for s, (frames, cc, want, ret) in enumerate(streams):
+        for k in range(len(frames)):
+            if ret[k] >= 0:
+                ns = (120 << frames[k][2]) * cc
+                assert np.array_equal(pcm[sbeg[s] + k, :ns], want[k, :ns]), (s, k, frames[k][1:], cc)
+                n += 1
+    assert n > 400
 
 
 @pytest.mark.gpu
