@@ -167,7 +167,7 @@ EXPORTS = [
     "anm_config_preset", "anm_config_validate", "anm_twiddles", "anm_config_dense", "anm_basis_q7", "anm_config_foldable", "anm_fold_twiddles", "anm_crc16", "anm_crc8",
     "anm_frame_num_symbols", "anm_frame_symbols", "anm_tx_render", "anm_tx_render_device",
     "anm_tone_energies_device", "anm_demod_create", "anm_demod_destroy", "anm_demod_reset",
-    "anm_demod_feed_device", "anm_demod_feed_host", "anm_demod_feed_host_async", "anm_demod_wait_input",
+    "anm_demod_feed_device", "anm_demod_feed_device_chunks", "anm_demod_feed_host", "anm_demod_feed_host_async", "anm_demod_wait_input",
     "anm_demod_collect", "anm_demod_collect_upto", "anm_demod_read_frames", "anm_demod_take_frames", "anm_demod_frame_rings", "demod_create_cfg", "anm_frames_digest", "anm_demod_peek_frames", "anm_demod_drop_frames", "anm_frames_summary",
     "anm_demod_multi_create", "anm_demod_multi_destroy", "anm_demod_multi_reset", "anm_demod_multi_num_devices", "anm_demod_multi_shard",
     "anm_demod_multi_device_handle", "anm_demod_multi_alloc_pcm", "anm_demod_multi_feed_host", "anm_demod_multi_wait_input",
@@ -214,6 +214,7 @@ def lib():
         "anm_demod_destroy": (None, [vp]),
         "anm_demod_reset": (C.c_int, [vp]),
         "anm_demod_feed_device": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp]),
+        "anm_demod_feed_device_chunks": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, vp]),
         "anm_demod_feed_host": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
         "anm_demod_feed_host_async": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t]),
         "anm_demod_wait_input": (C.c_int, [vp]),
@@ -541,6 +542,10 @@ class Demod:
 
     def feed_device(self, d_pcm, ch_stride, n_samples, stream=0):
         _check(lib().anm_demod_feed_device(self._h, d_pcm, ch_stride, n_samples, stream))
+
+    def feed_device_chunks(self, d_pcm, ch_stride, chunk_stride, n_samples, n_chunks, stream=0):
+        """n_chunks resident chunks per channel in one launch (include/anmodem.h anm_demod_feed_device_chunks)"""
+        _check(lib().anm_demod_feed_device_chunks(self._h, d_pcm, ch_stride, chunk_stride, n_samples, n_chunks, stream))
 
     def feed_host(self, pcm):
         """pcm: int16 array [n_channels, n_samples] (C-contiguous rows)."""

@@ -100,6 +100,9 @@ struct anm_demod {
     anm_frame_t *d_frames;
     uint8_t *d_bytes;
     uint32_t *d_counters;
+    uint32_t *d_progress;  /* [n_ch] chunks completed per channel: orders a channel's chunks inside a multi-chunk launch */
+    uint64_t tickets;      /* work-queue tickets handed out since reset (counters[4]) */
+    uint32_t chunks_done;  /* progress[] of every channel between launches */
     uint32_t frames_cap, bytes_cap;
     uint8_t *d_osyms;
     uint32_t osym_cap;
@@ -258,6 +261,7 @@ static int create_impl(anm_demod *h, const anm_config_t *cfg, const Variant *var
     CK(cudaMalloc(&h->d_frames, (size_t)h->frames_cap * sizeof(anm_frame_t)));
     CK(cudaMalloc(&h->d_bytes, h->bytes_cap));
     CK(cudaMalloc(&h->d_counters, 32));
+    CK(cudaMalloc(&h->d_progress, (size_t)n_channels * sizeof(uint32_t)));
     if (h->osym_cap) CK(cudaMalloc(&h->d_osyms, (size_t)n_channels * h->osym_cap));
     h->h_tw.resize((size_t)cfg->sym_len * cfg->n_tones * 2);
     if (anm_config_foldable(cfg)) anm_fold_twiddles(cfg, h->h_tw.data()); /* [H/2][T][2], a prefix of the buffer */
@@ -290,6 +294,8 @@ static int create_impl(anm_demod *h, const anm_config_t *cfg, const Variant *var
     k.frames = h->d_frames;
     k.bytes = h->d_bytes;
     k.counters = h->d_counters;
+    k.progress = h->d_progress;
+    k.n_chunks = 1;
     k.frames_cap = h->frames_cap;
     k.bytes_cap = h->bytes_cap;
     k.osyms = h->d_osyms;
@@ -360,7 +366,10 @@ extern "C" int anm_demod_reset(anm_demod_t *h) {
     int rc = init_state(h->var, h->d_state, h->n_ch, h->own_stream);
     if (rc) return rc;
     CK(cudaMemsetAsync(h->d_counters, 0, 32, h->own_stream));
+    CK(cudaMemsetAsync(h->d_progress, 0, (size_t)h->n_ch * sizeof(uint32_t), h->own_stream));
     CK(cudaStreamSynchronize(h->own_stream));
+    h->tickets = 0;
+    h->chunks_done = 0;
     h->last_stream = h->own_stream;
     h->samples_fed = 0;
     h->syms_since_collect = 0;
@@ -384,6 +393,7 @@ extern "C" void anm_demod_destroy(anm_demod_t *h) {
     cudaFree(h->d_frames);
     cudaFree(h->d_bytes);
     cudaFree(h->d_counters);
+    cudaFree(h->d_progress);
     cudaFree(h->d_osyms);
     cudaFree(h->d_tw);
     cudaFree(h->d_basis);
@@ -423,7 +433,11 @@ static int launch(anm_demod *h, KParams &k, cudaStream_t s, bool timed) {
     k.base_b = h->read_b;
     const uint64_t seq = h->launches_since_reset;
     const size_t slot = (size_t)(seq % kSnapSlots);
-    k.q_base = (uint32_t)(seq * h->n_ch);
+    k.q_base = (uint32_t)h->tickets;
+    k.prog_base = h->chunks_done;
+    const bool multi = k.n_chunks > 1u;
+    h->tickets += (uint64_t)h->n_ch * k.n_chunks + (multi ? (uint64_t)h->grid * h->warps_per_cta : 0u);
+    if (multi) h->chunks_done += k.n_chunks;
     k.done_base = (uint32_t)(seq * (uint64_t)h->grid * h->warps_per_cta);
     k.snap = h->snap + slot * 4;
     k.seq1 = (uint32_t)(seq + 1);
@@ -492,18 +506,28 @@ static int drain_frames(anm_demod *h, uint64_t seq) {
     return ANM_OK;
 }
 
-extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride, size_t n_samples,
-                                     void *stream) {
-    if (!h || (!d_pcm && n_samples)) return ANM_ERR_ARG;
-    if (n_samples == 0) return ANM_OK;
+/* n_chunks consecutive chunks of n_samples per channel, chunk c of a channel chunk_stride samples behind chunk c - 1, in ONE launch of k_demod
+ * (work items = (chunk, channel): no idle tail between the chunks); configurations on the tensor-core kernel and handles that record decided symbols
+ * take the chunks one launch at a time */
+extern "C" int anm_demod_feed_device_chunks(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride, size_t chunk_stride, size_t n_samples, uint32_t n_chunks,
+                                            void *stream) {
+    if (!h || (!d_pcm && n_samples && n_chunks)) return ANM_ERR_ARG;
+    if (n_samples == 0 || n_chunks == 0) return ANM_OK;
     const uint32_t N = h->cfg.sym_len;
     if (n_samples % N) { anm_set_error("n_samples must be a multiple of sym_len=%u", N); return ANM_ERR_ALIGN; }
-    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15u) || ((ch_stride * 2) & 15u) || ch_stride < n_samples) {
-        anm_set_error("pcm base and channel stride must be 16-byte aligned, stride >= n_samples");
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15u) || ((ch_stride * 2) & 15u) || ch_stride < n_samples || (n_chunks > 1 && ((chunk_stride * 2) & 15u))) {
+        anm_set_error("pcm base, channel stride and chunk stride must be 16-byte aligned, channel stride >= n_samples");
         return ANM_ERR_ALIGN;
     }
     if (set_device(h)) return ANM_ERR_CUDA;
     const uint64_t nsyms = n_samples / N;
+    if (n_chunks > 1 && (h->var->dense || h->osym_cap || (uint64_t)h->n_ch * n_chunks >= (1ull << 31))) {
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const int rc = anm_demod_feed_device_chunks(h, d_pcm + (size_t)c * chunk_stride, ch_stride, 0, n_samples, 1, stream);
+            if (rc) return rc;
+        }
+        return ANM_OK;
+    }
     if (h->osym_cap && h->syms_since_collect + nsyms + 8 > h->osym_cap) {
         long rc = anm_demod_collect(h);
         if (rc < 0) return (int)rc;
@@ -513,13 +537,19 @@ extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_
     KParams k = h->kp;
     k.pcm = d_pcm;
     k.ch_stride = ch_stride;
+    k.chunk_stride = chunk_stride;
+    k.n_chunks = n_chunks;
     k.n_syms = (uint32_t)nsyms;
     k.hop_base = h->samples_fed / (N / h->cfg.hops_per_sym);
     int rc = launch(h, k, s, true);
     if (rc) return rc;
-    h->samples_fed += n_samples;
-    h->syms_since_collect += nsyms;
+    h->samples_fed += n_samples * (uint64_t)n_chunks;
+    h->syms_since_collect += nsyms * n_chunks;
     return ANM_OK;
+}
+
+extern "C" int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride, size_t n_samples, void *stream) {
+    return anm_demod_feed_device_chunks(h, d_pcm, ch_stride, 0, n_samples, 1, stream);
 }
 
 static int feed_host_impl(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples, bool async) {
@@ -754,6 +784,7 @@ extern "C" int anm_tone_energies_device(const anm_config_t *cfg, const int16_t *
     if (rc == ANM_OK) {
         KParams k;
         memset(&k, 0, sizeof k);
+        k.n_chunks = 1;
         k.pcm = d_pcm;
         k.ch_stride = ch_stride;
         k.n_ch = n_ch;

@@ -57,6 +57,10 @@ struct ChanScalars {
 };
 static_assert(sizeof(ChanScalars) == 128, "ChanScalars layout");
 
+/* loads that bypass L1: per-channel data another SM may have written earlier in the SAME launch (multi-chunk launches) */
+__device__ __forceinline__ uint32_t ld_cg_u8(const uint8_t *p) { return (uint32_t)__ldcg(p); }
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) { return __ldcg(p); }
+
 /* hop record: energy of the strongest tone and its index (0xFF before the stream) */
 struct HopRec {
     float e;
@@ -86,6 +90,10 @@ struct KParams {
     uint32_t frames_cap, bytes_cap; /* powers of two: the queues are rings */
     uint32_t base_f, base_b;        /* counters as of what the host has consumed (mod 2^32) */
     uint32_t q_base, done_base;     /* values of counters[4] / counters[5] when this launch starts (launch index x n_ch / x warps) */
+    uint32_t n_chunks;              /* k_demod: chunks of n_syms symbol periods per channel in this launch (>= 1), chunk c of a channel chunk_stride samples behind c - 1 */
+    uint32_t prog_base;             /* progress[] of every channel when this launch starts */
+    unsigned long long chunk_stride;
+    uint32_t *progress;             /* [n_ch] chunks completed per channel (free-running): orders the chunks of a channel inside a multi-chunk launch */
     uint32_t *snap;                 /* pinned host memory: {n_frames, n_bytes, dropped, launch seq + 1} as they stand when this launch
                                      * ends, written by the last warp to leave (a stream-ordered snapshot without a copy) */
     uint32_t seq1;
@@ -235,13 +243,13 @@ __host__ __device__ constexpr uint32_t cta_smem_bytes() { return (uint32_t)(N / 
 template <int T, int N, int S>
 __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, const int lane, const uint32_t sr,
                                         const uint32_t hic, const int nvalid, const bool active,
-                                        const uint32_t (&dc)[S], const uint32_t ssa, const uint32_t crc_k) {
+                                        const uint32_t (&dc)[S], const uint32_t ssa, const uint32_t crc_k, const unsigned long long hop_base) {
     constexpr int H = N / S;
     constexpr int B = Log2<T>::v;
     constexpr int LV = Log2<S>::v;
     constexpr uint32_t RM = 64u * S - 1u;
     constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t hb = (uint32_t)p.hop_base + hic; /* wrapping index of the step's first hop */
+    const uint32_t hb = (uint32_t)hop_base + hic; /* wrapping index of the step's first hop */
     /* hop record by hop index r relative to the step start, r in [-32S, 32S): .x = emax bits, .y = d */
     auto REC = [&](int r) -> uint2 {
         uint2 v;
@@ -360,7 +368,7 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                 cold_st(O_BEST_Q, __float_as_uint(best_q));
                 cold_st(O_BEST_H, best_h);
                 if (cur > pend) {
-                    const unsigned long long t0 = p.hop_base + (unsigned long long)hic + (long long)(int)(best_h - hb);
+                    const unsigned long long t0 = hop_base + (unsigned long long)hic + (long long)(int)(best_h - hb);
                     cold_st(O_T0, (uint32_t)t0);
                     cold_st(O_T0 + 4u, (uint32_t)(t0 >> 32));
                     sc.next = best_h + S;
@@ -453,7 +461,7 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                 /* 24 header bits from hdr_syms symbols, one symbol per lane, OR-reduced */
                 uint32_t contrib = 0;
                 if (lane < (int)p.hdr_syms) {
-                    const uint32_t v = gray_inv(fs[lane]);
+                    const uint32_t v = gray_inv(ld_cg_u8(fs + lane));
                     const int pos = 24 - B * (lane + 1);
                     contrib = (pos >= 0) ? (v << pos) : (v >> (-pos));
                 }
@@ -486,18 +494,18 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
                     uint32_t v8 = 0;
                     if (B == 2 && (p.hdr_syms & 3u) == 0u) {
                         /* four 2-bit symbols in one aligned word: Gray-decode all four at once */
-                        const uint32_t wv = *reinterpret_cast<const uint32_t *>(bs + byi * 4u);
+                        const uint32_t wv = ld_cg_u32(reinterpret_cast<const uint32_t *>(bs + byi * 4u));
                         const uint32_t v = wv ^ ((wv >> 1) & 0x01010101u);
                         v8 = ((v & 3u) << 6) | (((v >> 8) & 3u) << 4) | (((v >> 16) & 3u) << 2) | ((v >> 24) & 3u);
                     } else if (8 % B == 0) {
                         constexpr int SPB = (8 % B == 0) ? 8 / B : 1;
 #pragma unroll
-                        for (int j = 0; j < SPB; ++j) v8 |= gray_inv(bs[byi * SPB + j]) << (B * (SPB - 1 - j));
+                        for (int j = 0; j < SPB; ++j) v8 |= gray_inv(ld_cg_u8(bs + byi * SPB + j)) << (B * (SPB - 1 - j));
                     } else {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const uint32_t bit = byi * 8 + k;
-                            const uint32_t v = gray_inv(bs[bit / B]);
+                            const uint32_t v = gray_inv(ld_cg_u8(bs + bit / B));
                             v8 = (v8 << 1) | ((v >> (B - 1 - (bit % B))) & 1u);
                         }
                     }
@@ -651,24 +659,49 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
     const uint32_t n_steps = (p.n_syms + 31u) / 32u;
     const uint32_t total_warps = gridDim.x * wpb;
 
-    uint32_t ch = blockIdx.x * wpb + wib; /* first channel static, further ones from the work queue */
-    while (ch < p.n_ch) {
+    /* Work items = (chunk, channel), chunk-major: the first one static, further ones from the work queue.  With several chunks in one launch
+     * (anm_demod_feed_device_chunks) a warp that finishes a channel's chunk goes on with whatever comes next instead of idling through the
+     * tail of a wave; chunk c of a channel waits for its chunk c - 1 -- handed out n_ch tickets earlier, so almost always long finished. */
+    const uint32_t n_items = p.n_ch * p.n_chunks;
+    const bool multi = MODE == 0 && p.n_chunks > 1u;
+    uint32_t item = blockIdx.x * wpb + wib;
+    if (multi) {
+        /* every item from the queue, the first one too: a warp then only ever waits for items that RUNNING warps hold (tickets go out in
+         * order), whatever part of the grid is resident */
+        uint32_t nx = 0;
+        if (lane == 0) nx = atomicAdd(&p.counters[4], 1u);
+        item = __shfl_sync(0xffffffffu, nx, 0) - p.q_base;
+    }
+    while (item < n_items) {
+        const uint32_t chunk = multi ? item / p.n_ch : 0u, ch = item - chunk * p.n_ch;
+        const unsigned long long hop_base = p.hop_base + (unsigned long long)chunk * p.n_syms * S;
         unsigned char *stp = p.state + (size_t)ch * p.state_stride;
         uint2 *grec = reinterpret_cast<uint2 *>(stp + sizeof(ChanScalars));
         float2 *gcarry = reinterpret_cast<float2 *>(stp + state_carry_offset<T, S>());
+        if constexpr (MODE == 0) if (multi && chunk > 0u) {
+            if (lane == 0) {
+                uint32_t done;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(p.progress + ch) : "memory");
+                    if (done - p.prog_base >= chunk) break;
+                    __nanosleep(200);
+                }
+            }
+            __syncwarp();
+        }
 
-        /* ---- restore carried state: the last 32 symbol slots go to ring slots 32..63 ---- */
+        /* ---- restore carried state: the last 32 symbol slots go to ring slots 32..63 (L1 bypassed: see ld_cg_u8) ---- */
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-            const uint2 rv = grec[lane * S + i];
+            const uint2 rv = __ldcg(&grec[lane * S + i]);
             asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>((uint32_t)((32 + lane) * S + i))), "r"(rv.x), "r"(rv.y) : "memory");
         }
-        for (int i = lane; i < (S - 1) * T; i += 32) carry[i] = gcarry[i];
-        if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = reinterpret_cast<const uint32_t *>(stp)[lane];
+        for (int i = lane; i < (S - 1) * T; i += 32) carry[i] = __ldcg(&gcarry[i]);
+        if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = __ldcg(&reinterpret_cast<const uint32_t *>(stp)[lane]);
         __syncwarp();
 
-        const char *src = reinterpret_cast<const char *>(p.pcm + (size_t)ch * p.ch_stride);
+        const char *src = reinterpret_cast<const char *>(p.pcm + (size_t)ch * p.ch_stride + (size_t)chunk * p.chunk_stride);
         auto issue = [&](uint32_t step) {
             const uint32_t nv = min(32u, p.n_syms - step * 32u);
             const char *g = src + (size_t)step * (32u * N * 2u) + (size_t)lane * 16u;
@@ -996,7 +1029,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                 }
             }
 
-            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k);
+            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k, hop_base);
         }
 
         /* ---- save carried state: the last 32 symbol slots of the chunk ---- */
@@ -1012,13 +1045,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
         if (MODE == 0) reinterpret_cast<uint32_t *>(stp)[lane] = reinterpret_cast<const uint32_t *>(ssc)[lane];
         __syncwarp();
         if (MODE == 0) {
-            /* every processed channel takes one ticket, so a launch advances the counter by exactly n_ch: the host knows the
-             * value it starts from (q_base) and nothing has to be reset between launches */
+            if (multi) { /* this channel's next chunk may start (the state above is visible before the counter) */
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.progress + ch), "r"(p.prog_base + chunk + 1u) : "memory");
+            }
+            /* every processed item takes one ticket (and, in a multi-chunk launch, every warp one more at the start), so a launch advances the
+             * counter by exactly n_ch (n_ch * n_chunks + warps): the host knows the value it starts from (q_base) and nothing is reset between launches */
             uint32_t nx = 0;
             if (lane == 0) nx = atomicAdd(&p.counters[4], 1u);
-            ch = total_warps + (__shfl_sync(FULL, nx, 0) - p.q_base);
+            item = (multi ? 0u : total_warps) + (__shfl_sync(FULL, nx, 0) - p.q_base);
         } else {
-            ch += total_warps;
+            item += total_warps;
         }
     }
     if (MODE == 0 && lane == 0) publish_snapshot(p, total_warps);

@@ -627,7 +627,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                         }
                     }
                     __syncwarp();
-                    if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k);
+                    if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k, p.hop_base);
                 }
             }
             /* ---- save carried state: the last 32 symbol slots of the chunk ---- */

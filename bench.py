@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the dense-tone-set (tensor-core) leg")
     ap.add_argument("--no-sustain", action="store_true", help="skip the >= 2.5 s sustained-clock region")
+    ap.add_argument("--launch-chunks", type=int, default=0, help="resident chunks per launch of k_demod (anm_demod_feed_device_chunks); 0 = the whole step, "
+                                                                 "1 = one launch per chunk as in round 1")
     return ap.parse_args()
 
 
@@ -492,6 +494,9 @@ def main():
     chunk = CHUNK_SYMS * N
     CPS = CHUNKS_PER_STEP
     assert 1 <= CPS <= 62, "a step's launches must fit the handle's snapshot window (collect_upto lag < 63)"
+    LC = max(1, min(CPS, args.launch_chunks if args.launch_chunks > 0 else CPS))
+    if anm.config_dense(cfg):
+        LC = 1                                              # the tensor-core kernel takes its chunks one launch at a time
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- synthesize this rank's shard in HBM (not timed): all CPS chunks of the step are distinct and resident ----
@@ -509,10 +514,11 @@ def main():
         place while the launches of step s+1 are already queued, so the GPU never waits for the host.  The last drain is left
         in the queue for the caller (peek_frames)."""
         for s in range(n_steps):
-            for c in range(CPS):
-                dm.feed_device(d_pcm.data_ptr() + c * chunk * 2, total, chunk, stream)
+            l_step = dm.launch_count()
+            for c in range(0, CPS, LC):                     # LC resident chunks per launch: work items (chunk, channel) from one queue
+                dm.feed_device_chunks(d_pcm.data_ptr() + c * chunk * 2, total, chunk, chunk, min(LC, CPS - c), stream)
             if s > 0:
-                dm.collect_upto(CPS)                        # everything up to the last launch of step s-1
+                dm.collect_upto(dm.launch_count() - l_step)  # everything up to the last launch of step s-1
                 recs, by = dm.peek_frames()
                 totals.add(recs, len(by))
                 dm.drop_frames()
@@ -711,7 +717,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        per_launch_bytes = n_ch * chunk * 2
+        per_launch_bytes = n_ch * chunk * 2 * LC
         avg_ms = (k_ms / k_n) if k_n else ms / max(1, launches)
         achieved = per_launch_bytes / (avg_ms * 1e-3) / 1e9
         grid, wpc, smem = dm.launch_geometry()
@@ -726,13 +732,15 @@ def main():
             "gpu_launches": int(agg[2].item()),
             "launch": {"grid": grid, "warps_per_cta": wpc, "smem_bytes": smem},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": measured_traffic() if (n_ch == CH_PER_GPU and args.preset == "ref4") else None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": (measured_traffic() * LC) if (n_ch == CH_PER_GPU and args.preset == "ref4" and measured_traffic()) else None, "peak_source": peak_src,
                          "kernel": kernel_name(cfg, anm),
                          "avg_kernel_ms": round(avg_ms, 4), "launches_timed": k_n,
                          "algorithmic_bytes_per_launch": per_launch_bytes,
-                         "frac_of_step_time": round(per_launch_bytes * CPS / (ms / args.steps * 1e-3) / 1e9 / peak, 4),
-                         "note": "achieved = bytes / per-launch CUDA-event time of the first %d launches of the timed region; frac_of_step_time divides by "
-                                 "the whole step instead (launch gaps and the per-step drain included)" % k_n},
+                         "chunks_per_launch": LC,
+                         "frac_of_step_time": round(n_ch * chunk * 2 * CPS / (ms / args.steps * 1e-3) / 1e9 / peak, 4),
+                         "note": "achieved = bytes / per-launch CUDA-event time of the first %d launches of the timed region (a launch covers chunks_per_launch "
+                                 "resident chunks; traffic = the ncu DRAM bytes of a one-chunk launch x chunks_per_launch); frac_of_step_time divides by the whole "
+                                 "step instead (launch gaps and the per-step drain included)" % k_n},
             "clocks": clocks,
         }
         if sustained:

@@ -156,6 +156,13 @@ int anm_demod_reset(anm_demod_t *h);
  * works in steps of 32 symbol periods; a ragged last step costs a whole one). */
 int anm_demod_feed_device(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride,
                           size_t n_samples, void *stream);
+/* Several chunks that are already resident, in ONE launch: chunk c of channel ch at d_pcm[ch * ch_stride + c * chunk_stride + i], i < n_samples
+ * (chunk_stride * 2 a multiple of 16 bytes; chunk_stride = n_samples for one contiguous run per channel).  Same result as n_chunks calls of
+ * anm_demod_feed_device; the kernel's work items are then (chunk, channel) pairs handed out from one queue, so no SM idles through the tail of a
+ * chunk while the next one has not been launched (8,192 channels on 2,960 resident warps: 2.77 waves per chunk, 3 are paid).  Configurations on
+ * the tensor-core kernel and handles with ANM_FLAG_SYMBOLS take the chunks one launch at a time. */
+int anm_demod_feed_device_chunks(anm_demod_t *h, const int16_t *d_pcm, size_t ch_stride, size_t chunk_stride, size_t n_samples, uint32_t n_chunks,
+                                 void *stream);
 /* PCM in host memory (pinned for full speed): copies to an internal HBM staging
  * buffer, demodulates, and waits for completion. */
 int anm_demod_feed_host(anm_demod_t *h, const int16_t *h_pcm, size_t ch_stride, size_t n_samples);

@@ -595,6 +595,37 @@ def test_feed_on_two_streams_is_ordered():
     assert got == oracle_frames_batch(cfg, pcm)
 
 
+@pytest.mark.parametrize("preset,n_ch,n_chunks,syms", [("ref4", 3500, 6, 96), ("ref4", 700, 9, 45), ("bfsk2", 300, 4, 64), ("mfsk16", 200, 5, 64)])
+def test_several_chunks_in_one_launch_equal_chunk_by_chunk(preset, n_ch, n_chunks, syms):
+    """anm_demod_feed_device_chunks: (chunk, channel) work items from one queue, a channel's chunks ordered by its progress counter -- the frames equal
+    those of n_chunks single launches (more channels than resident warps, ragged 45-symbol chunks, noisy drifting signals), twice in a row on one handle
+    and mixed with single launches; 40 of the channels against the oracle."""
+    torch = _torch()
+    cfg = anm.config_preset(preset)
+    q = syms * cfg.sym_len
+    pcm, _ = make_channels(cfg, n_ch, 2 * n_chunks * q + q, seed=91, snr_db=9.0, offset_max=700, payload_len=(4, 40), gap=(2, 10), ppm_max=150.0)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    torch.cuda.synchronize()
+    n = pcm.shape[1]
+    st = torch.cuda.current_stream().cuda_stream
+    a = anm.Demod(cfg, n_ch, device=0)
+    for c in range(2 * n_chunks + 1):
+        a.feed_device(d_pcm.data_ptr() + c * q * 2, n, q, st)
+    a.collect()
+    want = anm.frames_to_list(*a.read_frames())
+    a.close()
+    b = anm.Demod(cfg, n_ch, device=0)
+    b.feed_device_chunks(d_pcm.data_ptr(), n, q, q, n_chunks, st)                       # chunks 0 .. n_chunks - 1 in one launch
+    b.feed_device(d_pcm.data_ptr() + n_chunks * q * 2, n, q, st)                        # one single launch in between
+    b.feed_device_chunks(d_pcm.data_ptr() + (n_chunks + 1) * q * 2, n, q, q, n_chunks, st)
+    b.collect()
+    got = anm.frames_to_list(*b.read_frames())
+    assert not b.overflowed()
+    b.close()
+    assert got == want and len(got) > n_ch
+    assert [f for f in got if f[0] < 40] == oracle_frames_batch(cfg, pcm[:40])
+
+
 def _multi_devices():
     torch = _torch()
     n = torch.cuda.device_count()
