@@ -566,7 +566,9 @@ def main():
         ts0 = time.perf_counter()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
+        l_sus = dm.launch_count()
         run_steps(n_sus, FrameTotals(anm))
+        l_sus = dm.launch_count() - l_sus
         s1.record()
         barrier()
         ts1 = time.perf_counter()
@@ -578,7 +580,7 @@ def main():
         sus_clk = sampler.window(ts0, ts1)
         peak, _ = peaks()
         sustained = {"value": round(float(world) * samples_step * n_sus / (float(tt.item()) * 1e-3) / 1e6, 2), "unit": "Msamples/s",
-                     "steps": n_sus, "launches": n_sus * CPS, "seconds": round(float(tt.item()) * 1e-3, 3),
+                     "steps": n_sus, "launches": int(l_sus), "chunks": n_sus * CPS, "seconds": round(float(tt.item()) * 1e-3, 3),
                      "hbm_frac_of_step_time": round(samples_step * 2 * n_sus / (float(tt.item()) * 1e-3) / 1e9 / peak, 4),
                      "clocks": sus_clk}
     sampler.stop()
