@@ -204,12 +204,15 @@ struct Log2 { static constexpr int v = 1 + Log2<T / 2>::v; };
 template <>
 struct Log2<1> { static constexpr int v = 0; };
 
-/* The hop-record ring of a channel in shared memory: HopRec[64 * S], addressed by hop index & (64 * S - 1), laid out PHASE-major --
- * [hop % S][symbol period % 64] -- because every access of the state machine is one hop phase over the 32 symbol periods of the lanes:
- * consecutive lanes then read consecutive 8-byte records (2 wavefronts) instead of records S * 8 bytes apart (8 wavefronts for S = 4). */
-template <int S>
+/* The hop-record ring of a channel in shared memory: HopRec[64 * S], addressed by hop index & (64 * S - 1).  Two layouts.  PM (phase-major,
+ * [hop % S][symbol period % 64]): every access of the state machine is one hop phase over the 32 symbol periods of the lanes, so consecutive
+ * lanes read consecutive 8-byte records (2 wavefronts) instead of records S * 8 bytes apart (8 wavefronts for S = 4) -- used by k_demod_tc, whose
+ * tensor-core operand reads compete for shared-memory bandwidth.  Linear ([hop]): three instructions less per access -- used by k_demod, which is
+ * bound by instruction issue and does not notice the bank conflicts (measured both ways: conflicts 8.6 M -> 1.9 M wavefronts per launch, time
+ * unchanged, +2.4 % instructions). */
+template <int S, bool PM>
 __device__ __forceinline__ uint32_t ring_off(uint32_t idx) { /* idx < 64 * S; byte offset of the record */
-    return (((idx & (uint32_t)(S - 1)) << 6) | (idx >> Log2<S>::v)) << 3;
+    return PM ? ((((idx & (uint32_t)(S - 1)) << 6) | (idx >> Log2<S>::v)) << 3) : (idx << 3);
 }
 
 /* Per-channel state in HBM: ChanScalars | HopRec[32 slots][S] | tree carry */
@@ -240,7 +243,7 @@ __host__ __device__ constexpr uint32_t cta_smem_bytes() { return (uint32_t)(N / 
  * One call per step (32 symbol periods) and channel, by the whole warp.  The step's hop records are
  * already in the ring `sr` (HopRec[64*S], indexed by hop-in-chunk & RM); dc[] are this lane's own
  * decisions of the step (lane = symbol period). */
-template <int T, int N, int S>
+template <int T, int N, int S, bool PM>
 __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, const int lane, const uint32_t sr,
                                         const uint32_t hic, const int nvalid, const bool active,
                                         const uint32_t (&dc)[S], const uint32_t ssa, const uint32_t crc_k, const unsigned long long hop_base) {
@@ -253,7 +256,7 @@ __device__ __forceinline__ void sm_step(const KParams &p, const uint32_t ch, con
     /* hop record by hop index r relative to the step start, r in [-32S, 32S): .x = emax bits, .y = d */
     auto REC = [&](int r) -> uint2 {
         uint2 v;
-        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + ring_off<S>((hic + (uint32_t)r) & RM)) : "memory");
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sr + ring_off<S, PM>((hic + (uint32_t)r) & RM)) : "memory");
         return v;
     };
     /* warp-uniform working set: three broadcast LDS.128; everything else of ChanScalars is read / written
@@ -695,7 +698,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < S; ++i) {
             const uint2 rv = __ldcg(&grec[lane * S + i]);
-            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>((uint32_t)((32 + lane) * S + i))), "r"(rv.x), "r"(rv.y) : "memory");
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S, false>((uint32_t)((32 + lane) * S + i))), "r"(rv.x), "r"(rv.y) : "memory");
         }
         for (int i = lane; i < (S - 1) * T; i += 32) carry[i] = __ldcg(&gcarry[i]);
         if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = __ldcg(&reinterpret_cast<const uint32_t *>(stp)[lane]);
@@ -1012,10 +1015,17 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
             /* publish this step's hop records in the ring (slots of lanes past a ragged end keep their
              * older content: they are never addressed) */
             if (active) {
-                const uint32_t i0 = (hic + (uint32_t)(lane * S)) & RM; /* a multiple of S: record i is hop phase i of this lane's symbol period */
+                const uint32_t a0 = sr + (((hic + (uint32_t)(lane * S)) & RM) << 3); /* S consecutive ring entries (linear layout, ring_off<S, false>) */
+                if (S % 2 == 0) {
 #pragma unroll
-                for (int i = 0; i < S; ++i)
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>(i0 + (uint32_t)i)), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
+                    for (int i = 0; i < S; i += 2)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]),
+                                     "r"(__float_as_uint(ec[(i + 1) % S])), "r"(dc[(i + 1) % S]) : "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < S; ++i)
+                        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a0 + (uint32_t)i * 8u), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
+                }
             }
             __syncwarp();
             if (MODE == 1) {
@@ -1029,7 +1039,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
                 }
             }
 
-            if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k, hop_base);
+            if (MODE == 0) sm_step<T, N, S, false>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k, hop_base);
         }
 
         /* ---- save carried state: the last 32 symbol slots of the chunk ---- */
@@ -1038,7 +1048,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) k_demod(const __grid_constant_
         for (int i = 0; i < S; ++i) {
             const uint32_t idx = ((p.n_syms - 32u + (uint32_t)lane) * S + (uint32_t)i) & RM;
             uint2 rv;
-            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + ring_off<S>(idx)) : "memory");
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + ring_off<S, false>(idx)) : "memory");
             grec[lane * S + i] = rv;
         }
         for (int i = lane; i < (S - 1) * T; i += 32) gcarry[i] = carry[i];

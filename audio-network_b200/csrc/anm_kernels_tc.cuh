@@ -572,7 +572,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
                     const uint2 rv = grec[lane * S + i];
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>((uint32_t)((32 + lane) * S + i))), "r"(rv.x), "r"(rv.y) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S, true>((uint32_t)((32 + lane) * S + i))), "r"(rv.x), "r"(rv.y) : "memory");
                 }
                 if (MODE == 0) reinterpret_cast<uint32_t *>(ssc)[lane] = reinterpret_cast<const uint32_t *>(stp)[lane];
             }
@@ -614,7 +614,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                         const uint32_t i0 = (hic + (uint32_t)(lane * S)) & RM;
 #pragma unroll
                         for (int i = 0; i < S; ++i)
-                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S>(i0 + (uint32_t)i)), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
+                            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(sr + ring_off<S, true>(i0 + (uint32_t)i)), "r"(__float_as_uint(ec[i])), "r"(dc[i]) : "memory");
                         if (MODE == 1) {
                             if (p.trD) {
 #pragma unroll
@@ -627,7 +627,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                         }
                     }
                     __syncwarp();
-                    if (MODE == 0) sm_step<T, N, S>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k, p.hop_base);
+                    if (MODE == 0) sm_step<T, N, S, true>(p, ch, lane, sr, hic, nvalid, active, dc, (uint32_t)__cvta_generic_to_shared(ssc), crc_k, p.hop_base);
                 }
             }
             /* ---- save carried state: the last 32 symbol slots of the chunk ---- */
@@ -637,7 +637,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                 for (int i = 0; i < S; ++i) {
                     const uint32_t idx = ((p.n_syms - 32u + (uint32_t)lane) * S + (uint32_t)i) & RM;
                     uint2 rv;
-                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + ring_off<S>(idx)) : "memory");
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(rv.x), "=r"(rv.y) : "r"(sr + ring_off<S, true>(idx)) : "memory");
                     grec[lane * S + i] = rv;
                 }
                 if (MODE == 0) reinterpret_cast<uint32_t *>(stp)[lane] = reinterpret_cast<const uint32_t *>(ssc)[lane];
