@@ -155,7 +155,8 @@ typedef struct anm_celt_synth {
     uint32_t out_channels; /* channels of the decoder (1 or 2); 0: the channel count of the stream's first frame in the call */
 } anm_celt_synth_t;
 
-/* Opaque device-side context (tables in HBM). */
+/* Opaque device-side context: the tables in HBM and the per-call scratch arrays of the stages (grown on demand).  A context serves ONE call at a
+ * time (one stream, one host thread); use one context per concurrent stream. */
 typedef struct anm_celt_ctx anm_celt_ctx_t;
 int anm_celt_ctx_create(int device, anm_celt_ctx_t **out);
 void anm_celt_ctx_destroy(anm_celt_ctx_t *c);

@@ -626,6 +626,27 @@ def test_several_chunks_in_one_launch_equal_chunk_by_chunk(preset, n_ch, n_chunk
     assert [f for f in got if f[0] < 40] == oracle_frames_batch(cfg, pcm[:40])
 
 
+def test_chunks_call_on_the_dense_kernel_and_with_symbol_recording_takes_one_launch_per_chunk():
+    """anm_demod_feed_device_chunks on a configuration of the tensor-core kernel, and on a handle that records decided symbols: same frames (and
+    symbols) as chunk-by-chunk feeding; the call falls back to one launch per chunk there"""
+    torch = _torch()
+    st = torch.cuda.current_stream().cuda_stream
+    for preset, flags in (("wide64", 0), ("ref4", anm.ANM_FLAG_SYMBOLS)):
+        cfg = anm.config_preset(preset)
+        q, n_chunks, n_ch = 64 * cfg.sym_len, 4, 24
+        pcm, _ = make_channels(cfg, n_ch, n_chunks * q, seed=95, snr_db=12.0, offset_max=300, payload_len=(4, 30), gap=(2, 8))
+        d_pcm = torch.from_numpy(pcm).cuda()
+        torch.cuda.synchronize()
+        a = anm.Demod(cfg, n_ch, device=0, flags=flags)
+        l0 = a.launch_count()
+        a.feed_device_chunks(d_pcm.data_ptr(), pcm.shape[1], q, q, n_chunks, st)
+        assert a.launch_count() - l0 == n_chunks
+        a.collect()
+        got = anm.frames_to_list(*a.read_frames())
+        a.close()
+        assert got == oracle_frames_batch(cfg, pcm) and len(got) > n_ch
+
+
 def _multi_devices():
     torch = _torch()
     n = torch.cuda.device_count()
