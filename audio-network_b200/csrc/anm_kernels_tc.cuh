@@ -42,6 +42,17 @@
 #define ANM_TC_PAIR 1
 #endif
 
+/* nanoseconds a waiting warp sleeps between two polls of its barrier (the roles share the warp schedulers) */
+#ifndef ANM_TC_ISSUER_NS
+#define ANM_TC_ISSUER_NS 32
+#endif
+#ifndef ANM_TC_LOADER_NS
+#define ANM_TC_LOADER_NS 128
+#endif
+#ifndef ANM_TC_SM_NS
+#define ANM_TC_SM_NS 256
+#endif
+
 namespace anm {
 namespace tc {
 
@@ -355,7 +366,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                 unsigned char *gst = p.state + (size_t)(have ? ch : 0u) * p.state_stride + state_carry_offset<T, S>();
                 const uint32_t k = use[b]++;
                 const int nv = (int)min(32u, p.n_syms - step * 32u);
-                mbar_wait_relaxed<128>(bar_a_empty + 8u * b, (k & 1u) ^ 1u); /* the contraction that read this buffer two jobs ago is complete */
+                mbar_wait_relaxed<ANM_TC_LOADER_NS>(bar_a_empty + 8u * b, (k & 1u) ^ 1u); /* the contraction that read this buffer two jobs ago is complete */
                 if (have) {
                     const uint32_t base = sA + b * a_bytes<N, S>() + lane_off;
                     const char *g = src + (size_t)step * (32u * N * 2u);
@@ -422,13 +433,13 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
             for (uint32_t b = 0; b < 2; ++b) {
                 if (2u * (kPair * unit) + b >= n_groups) continue;
                 const uint32_t k = use[b]++;
-                mbar_wait_issuer<32, false>(bar_a_full + 8u * b, k & 1u);
+                mbar_wait_issuer<ANM_TC_ISSUER_NS, false>(bar_a_full + 8u * b, k & 1u);
                 tc_fence_after();
                 const uint64_t a0 = smem_desc(sA + b * a_bytes<N, S>(), kPanel, 128u);
 #pragma unroll 1 /* rolled: the four roles share the instruction cache, keep every role's loop body small */
                 for (int i = 0; i < S; ++i, ++rnd) {
                     const uint32_t set = rnd & 1u, u = rnd >> 1;
-                    mbar_wait_issuer<32, false>(bar_acc_empty + 8u * set, (u & 1u) ^ 1u);
+                    mbar_wait_issuer<ANM_TC_ISSUER_NS, false>(bar_acc_empty + 8u * set, (u & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d0 = tmem_base + set * kAccCols;
                     if (elect_one()) {
@@ -581,7 +592,7 @@ __launch_bounds__(tc::kWarps * 32, 1) k_demod_tc(const __grid_constant__ KParams
                 const int nvalid = (int)min(32u, p.n_syms - step * 32u);
                 const bool active = lane < nvalid;
                 const uint32_t hic = step * 32u * S;
-                mbar_wait_relaxed<256>(bar_cand_full + 8u * b, k & 1u);
+                mbar_wait_relaxed<ANM_TC_SM_NS>(bar_cand_full + 8u * b, k & 1u);
                 uint32_t dc[S];
                 float ec[S];
                 {
