@@ -214,11 +214,7 @@ ANM_CE_FN unsigned cv_collapse_mask(const int *iy, int N, int B, int lane, int n
     const int N0 = (int)((uint32_t)N / (uint32_t)B);
     unsigned mask = 0;
     CV_SYNC();
-    for (int i = 0; i < B; i++) {
-        unsigned tmp = 0;
-        for (int j = lane; j < N0; j += nl) tmp |= (unsigned)iy[i * N0 + j];
-        mask |= (unsigned)(tmp != 0) << i;
-    }
+    for (int i = lane; i < N; i += nl) mask |= (unsigned)(iy[i] != 0) << (i / N0);
     return CV_OR(mask);
 }
 ANM_CE_FN void cv_renormalise(int16_t *X, int N, int16_t gain, int lane, int nl) {
@@ -235,26 +231,26 @@ ANM_CE_FN void cv_renormalise(int16_t *X, int N, int16_t gain, int lane, int nl)
 ANM_CE_FN void cv_haar1(int16_t *X, int N0, int stride, int lane, int nl) {
     N0 >>= 1;
     CV_SYNC();
-    for (int i = 0; i < stride; i++)
-        for (int j = lane; j < N0; j += nl) {
-            const int32_t t1 = CV_M16(23170, X[stride * 2 * j + i]), t2 = CV_M16(23170, X[stride * (2 * j + 1) + i]);
-            X[stride * 2 * j + i] = (int16_t)CV_PSHR32(t1 + t2, 15);
-            X[stride * (2 * j + 1) + i] = (int16_t)CV_PSHR32(t1 - t2, 15);
-        }
+    for (int idx = lane; idx < stride * N0; idx += nl) {
+        const int i = idx % stride, j = idx / stride;
+        const int32_t t1 = CV_M16(23170, X[stride * 2 * j + i]), t2 = CV_M16(23170, X[stride * (2 * j + 1) + i]);
+        X[stride * 2 * j + i] = (int16_t)CV_PSHR32(t1 + t2, 15);
+        X[stride * (2 * j + 1) + i] = (int16_t)CV_PSHR32(t1 - t2, 15);
+    }
     CV_SYNC();
 }
-/* ordery_table of celt/bands.c:576-581 (the natural-to-Hadamard order of 2, 4, 8, 16 interleaved blocks), four bits per entry */
 ANM_CE_FN int cv_ordery(int stride, int i) {
-    const uint64_t tab = stride == 2 ? 0x01ull : stride == 4 ? 0x1203ull : stride == 8 ? 0x25163407ull : 0x5a2d691e4b3c780full;
-    return (int)((tab >> (4 * i)) & 15u);
+    const int8_t tab[30] = {1, 0, 3, 0, 2, 1, 7, 0, 4, 3, 6, 1, 5, 2, 15, 0, 8, 7, 12, 3, 11, 4, 14, 1, 9, 6, 13, 2, 10, 5};
+    return tab[stride - 2 + i];
 }
 /* frequency order -> time order (tmp: N0 * stride entries of scratch) */
 ANM_CE_FN void cv_deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard, int lane, int nl) {
     const int N = N0 * stride;
     CV_SYNC();
-    for (int i = 0; i < stride; i++) {
+    for (int idx = lane; idx < N; idx += nl) {
+        const int i = idx / N0, j = idx % N0;
         const int o = hadamard ? cv_ordery(stride, i) : i;
-        for (int j = lane; j < N0; j += nl) tmp[o * N0 + j] = X[j * stride + i];
+        tmp[o * N0 + j] = X[j * stride + i];
     }
     CV_SYNC();
     for (int i = lane; i < N; i += nl) X[i] = tmp[i];
@@ -263,9 +259,10 @@ ANM_CE_FN void cv_deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int st
 ANM_CE_FN void cv_interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard, int lane, int nl) {
     const int N = N0 * stride;
     CV_SYNC();
-    for (int i = 0; i < stride; i++) {
+    for (int idx = lane; idx < N; idx += nl) {
+        const int i = idx / N0, j = idx % N0;
         const int o = hadamard ? cv_ordery(stride, i) : i;
-        for (int j = lane; j < N0; j += nl) tmp[j * stride + i] = X[o * N0 + j];
+        tmp[j * stride + i] = X[o * N0 + j];
     }
     CV_SYNC();
     for (int i = lane; i < N; i += nl) X[i] = tmp[i];
