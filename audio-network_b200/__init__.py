@@ -178,7 +178,7 @@ EXPORTS = [
     "demod_read_symbols", "demod_read_frames", "demod_destroy",
     "anm_pacer_init", "anm_pacer_level", "anm_pacer_try_put", "anm_pacer_wait_for_capacity",
     "anm_opus_parse_device", "anm_opus_parse_host",
-    "anm_celt_tables_build", "anm_celt_ctx_create", "anm_celt_ctx_destroy", "anm_celt_entropy_device", "anm_celt_entropy_host", "anm_celt_spectrum_device", "anm_celt_spectrum_host", "anm_celt_decode_device", "anm_celt_decode_host", "anm_celt_synth_tables_build",
+    "anm_celt_tables_build", "anm_celt_ctx_create", "anm_celt_ctx_destroy", "anm_celt_entropy_device", "anm_celt_entropy_host", "anm_celt_spectrum_device", "anm_celt_spectrum_host", "anm_celt_decode_device", "anm_celt_decode_host", "anm_celt_synth_tables_build", "anm_celt_jobs_from_packets",
 ]
 
 _lib = None
@@ -264,6 +264,7 @@ def lib():
         "anm_celt_decode_device": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp, C.c_uint32, vp]),
         "anm_celt_decode_host": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_size_t, vp, vp, vp, vp, C.c_uint32]),
         "anm_celt_synth_tables_build": (C.c_int, [vp]),
+        "anm_celt_jobs_from_packets": (C.c_long, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, vp]),
         "anm_pb_encode_broadcast": (C.c_size_t, [C.POINTER(PbBroadcast), vp, C.c_size_t]),
         "anm_pb_encode_to_transmitter": (C.c_size_t, [C.POINTER(PbToTransmitter), vp, C.c_size_t]),
         "anm_pb_decode_broadcast": (C.c_int, [vp, C.c_size_t, C.POINTER(PbBroadcast), C.POINTER(C.c_size_t)]),
@@ -389,6 +390,21 @@ def celt_spectrum(jobs, stream_begin, payload_bytes, streams=None):
     _check(lib().anm_celt_spectrum_host(_ptr(jobs) if len(jobs) else None, _ptr(sb), n_streams, _ptr(by) if len(by) else None, len(by), _ptr(st),
                                         _ptr(out) if len(jobs) else None, _ptr(x), CELT_X_STRIDE, _ptr(cm)))
     return out, st, x[:len(jobs)], cm[:len(jobs)]
+
+
+def celt_jobs_from_packets(spans, packets, flags=0):
+    """parse records -> CELT frame jobs (include/anmodem_opus.h anm_celt_jobs_from_packets): (jobs, first_job per packet)"""
+    spans = np.ascontiguousarray(spans, dtype=PB_SPAN_DTYPE)
+    packets = np.ascontiguousarray(packets, dtype=OPUS_PACKET_DTYPE)
+    n = len(packets)
+    first = np.zeros(max(n, 1), dtype=np.uint32)
+    need = lib().anm_celt_jobs_from_packets(_ptr(spans) if n else None, _ptr(packets) if n else None, n, None, 0, flags, _ptr(first))
+    if need < 0:
+        _check(int(need))
+    jobs = np.zeros(max(need, 1), dtype=CELT_JOB_DTYPE)
+    got = lib().anm_celt_jobs_from_packets(_ptr(spans) if n else None, _ptr(packets) if n else None, n, _ptr(jobs), need, flags, _ptr(first))
+    assert got == need
+    return jobs[:need], first[:n]
 
 
 def celt_decode(jobs, stream_begin, payload_bytes, out_channels=None, streams=None, synth=None):

@@ -262,3 +262,50 @@ int anm_celt_synth_tables_build(anm_celt_synth_tables_t *t) {
     memcpy(t->e_means, k_emeans, sizeof k_emeans);
     return ANM_OK;
 }
+
+
+/* ---------------------------------------------------------------- parse records -> frame jobs (host glue of the receive chain) */
+long anm_celt_jobs_from_packets(const anm_pb_span_t *spans, const anm_opus_packet_t *packets, size_t n, anm_celt_job_t *jobs, size_t cap, uint32_t flags,
+                                uint32_t *first_job) {
+    if ((!spans || !packets) && n) return ANM_ERR_ARG;
+    if (!jobs && cap) return ANM_ERR_ARG;
+    size_t nj = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const anm_opus_packet_t *pk = &packets[i];
+        if (first_job) first_job[i] = 0xFFFFFFFFu;
+        if (pk->count <= 0 || pk->count > 48 || pk->mode != ANM_OPUS_MODE_CELT_ONLY) continue;
+        int lm;
+        switch (pk->samples_per_frame) { /* at 48 kHz */
+            case 120: lm = 0; break;
+            case 240: lm = 1; break;
+            case 480: lm = 2; break;
+            case 960: lm = 3; break;
+            default: continue;
+        }
+        int end;
+        switch (pk->bandwidth) { /* opus_decoder.c:473-488 */
+            case 1101: end = 13; break;
+            case 1102:
+            case 1103: end = 17; break;
+            case 1104: end = 19; break;
+            case 1105: end = 21; break;
+            default: continue;
+        }
+        if (first_job) first_job[i] = (uint32_t)nj;
+        uint32_t off = spans[i].audio_offset + (uint32_t)pk->payload_offset;
+        for (int f = 0; f < pk->count; ++f) {
+            if (nj < cap) {
+                anm_celt_job_t *j = &jobs[nj];
+                j->offset = off;
+                j->len = (uint32_t)pk->size[f];
+                j->channels = pk->channels;
+                j->lm = (uint8_t)lm;
+                j->end_band = (uint8_t)end;
+                j->flags = (uint8_t)flags;
+            }
+            off += (uint32_t)pk->size[f];
+            nj++;
+        }
+    }
+    return (long)nj;
+}

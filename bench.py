@@ -326,12 +326,8 @@ def decode_chain_leg(anm, torch, dev, recs, by, reps=20):
     sel = np.flatnonzero((pk["count"] == 1) & (pk["mode"] == 1002))
     if len(sel):
         order = sel[np.lexsort((recs["start_sample"][sel], recs["channel"][sel]))]
-        jobs = np.zeros(len(order), dtype=anm.CELT_JOB_DTYPE)
-        jobs["offset"] = spans["audio_offset"][order] + pk["payload_offset"][order].astype(np.uint32)
-        jobs["len"] = pk["size"][order, 0]
-        jobs["channels"] = pk["channels"][order]
-        jobs["lm"] = 3
-        jobs["end_band"] = 21
+        jobs, _ = anm.celt_jobs_from_packets(spans[order], pk[order])   # one 20 ms fullband frame per packet in this workload
+        assert len(jobs) == len(order)
         chs, first = np.unique(recs["channel"][order], return_index=True)
         sb = np.concatenate([first, [len(order)]]).astype(np.uint32)
         ctx = ctypes.c_void_p()

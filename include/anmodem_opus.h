@@ -105,6 +105,14 @@ typedef struct anm_celt_job {
 } anm_celt_job_t;
 enum { ANM_CELT_JOB_DISABLE_INV = 1 }; /* the stream is decoded to ONE output channel: no phase inversion of the side (celt_decoder.c:208, st->disable_inv) */
 
+/* Host: expands the parse records of n packets (record i of anm_pb_deframe_* / anm_opus_parse_*, Fs = 48000) into CELT frame jobs -- the frames of a
+ * packet back to back, offset = audio_offset + payload_offset + the sizes of the packet's earlier frames, lm from samples_per_frame, end_band from the
+ * bandwidth (opus_decoder.c:473-488), `flags` copied into every job.  Packets that are not CELT-only, or that the parse rejected (count <= 0), produce no
+ * job.  first_job (optional, [n]): index of packet i's first job, UINT32_MAX for a skipped packet.  Returns the number of jobs (never more than cap are
+ * written; a return value above cap says how many were needed), or ANM_ERR_ARG. */
+long anm_celt_jobs_from_packets(const anm_pb_span_t *spans, const anm_opus_packet_t *packets, size_t n, anm_celt_job_t *jobs, size_t cap, uint32_t flags,
+                                uint32_t *first_job);
+
 typedef struct anm_celt_frame {
     uint32_t final_range;   /* the range coder's rng after the frame = OPUS_GET_FINAL_RANGE (0 for a lost frame) */
     int32_t tell_bits;      /* ec_tell at the end of the frame */

@@ -139,6 +139,33 @@ def test_host_harness_random_streams_pcm_vs_reference_live():
     assert n > 300
 
 
+def test_jobs_from_packets_equals_the_reference_packet_framing():
+    """anm_celt_jobs_from_packets (host glue): frame offsets, sizes, lm, end band and channels of every frame of the golden packets (1-frame and
+    3-frame packets, code 0 and code 3) from the REFERENCE's parse records; non-CELT and rejected packets give no job"""
+    for s in PACKETS["streams"]:
+        spans = np.zeros(len(s["packets"]), dtype=anm.PB_SPAN_DTYPE)
+        pks = np.zeros(len(s["packets"]), dtype=anm.OPUS_PACKET_DTYPE)
+        arena, want = bytearray(), []
+        for i, (p, parse) in enumerate(zip(s["packets"], s["parse"])):
+            b = _packet_bytes(p)
+            spans[i]["audio_offset"], spans[i]["audio_len"] = len(arena), len(b)
+            for k in ("count", "toc", "channels", "mode", "bandwidth", "samples_per_frame", "payload_offset", "nb_frames", "nb_samples"):
+                pks[i][k] = parse[k]
+            pks[i]["size"] = parse["size"]
+            off = len(arena) + parse["payload_offset"]
+            for f, ch, lm, end in cb.frames_of_packet(b, parse):
+                want.append((off, len(f), ch, lm, end, 0))
+                off += len(f)
+            arena += b
+        jobs, first = anm.celt_jobs_from_packets(spans, pks)
+        assert [tuple(int(v) for v in j) for j in jobs] == want, s["name"]
+        assert first[0] == 0 and (np.diff(first.astype(np.int64)) == [p["count"] for p in s["parse"]][:-1]).all()
+    bad = np.zeros(3, dtype=anm.OPUS_PACKET_DTYPE)
+    bad["count"], bad["mode"], bad["bandwidth"], bad["samples_per_frame"] = [1, -4, 1], [1000, 1002, 1002], [1103, 1105, 1105], [960, 960, 1920]
+    jobs, first = anm.celt_jobs_from_packets(np.zeros(3, dtype=anm.PB_SPAN_DTYPE), bad)
+    assert len(jobs) == 0 and (first == 0xFFFFFFFF).all()
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _jobs_from_gold(cc_of_stream):
     fr, sb = GOLD["frames"], GOLD["stream_begin"]
@@ -244,11 +271,7 @@ def test_gpu_receive_chain_pcm_in_pcm_out():
     spans = anm.pb_deframe(recs, pay)
     pk = anm.opus_parse(spans, pay)
     assert (pk["count"] == 1).all() and (pk["mode"] == 1002).all()
-    jobs = np.zeros(len(recs), dtype=anm.CELT_JOB_DTYPE)
-    jobs["offset"] = spans["audio_offset"] + pk["payload_offset"].astype(np.uint32)
-    jobs["len"] = pk["size"][:, 0]
-    jobs["channels"] = pk["channels"]
-    jobs["lm"] = 3
-    jobs["end_band"] = 21
+    jobs, first = anm.celt_jobs_from_packets(spans, pk)                      # the product's own glue from parse records to frame jobs
+    assert len(jobs) == len(recs) and np.array_equal(first, np.arange(len(recs))) and (jobs["lm"] == 3).all() and (jobs["end_band"] == 21).all()
     _, _, _, audio = anm.celt_decode(jobs, [0, len(jobs)], pay, out_channels=[2])
     assert hashlib.sha256(audio[:, :1920].tobytes()).hexdigest() == s["decoded_sha256"]
