@@ -3,6 +3,12 @@
 reference decoder itself (oracle/_ref/libref_opus.so, its own celt_decode_with_ec through oracle/ref_celt_state_shim.c): random bytes as frames, in streams
 whose channel count, frame size and bandwidth may change from frame to frame, decoded by a mono or a stereo decoder; every int16 sample must be equal.
 Test infrastructure (needs /root/reference to have been present when oracle/_ref was built).  Usage: python tools/celt_fuzz.py [seed] [streams]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
 import celt_binding as cb, celt_spectrum_binding as sbind
 import audio_network_b200 as anm
