@@ -34,6 +34,12 @@
 #define ANM_CE_FN static inline
 #endif
 
+#ifdef __CUDACC__
+#define ANM_CE_NOUNROLL _Pragma("unroll 1")
+#else
+#define ANM_CE_NOUNROLL
+#endif
+
 #define ANM_CE_BITRES 3
 #define ANM_CE_NB 21 /* bands of the 48 kHz standard mode */
 
@@ -386,48 +392,83 @@ ANM_CE_FN unsigned ce_band_n1(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, int st
 
 /* a mono partition: splits in two while the budget exceeds what one codeword can carry, then reads the PVQ codeword; with a spectrum
  * (ctx->sp) the codeword becomes the partition's coefficients, an empty partition is folded from `lowband` or filled with noise.
- * Returns the collapse mask (which of the B interleaved blocks received energy). */
-#ifdef __CUDACC__
-__host__ __device__
-#endif
-static unsigned ce_partition(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int16_t gain, int fill) {
-    const uint8_t *cache = ce_cache(ctx->t, ctx->i, LM);
+ * Returns the collapse mask (which of the B interleaved blocks received energy).
+ * The reference recurses (quant_partition, bands.c:915-1078); here the tree is walked depth first with the pending second halves on a
+ * small stack (a partition splits at most four times: LM 3 -> -1), so that the work at the leaves -- codeword to coefficients, the
+ * expensive part -- sits at ONE place in the code: the threads of a warp, each on its own frame, go through it together whatever the
+ * shape of their trees, where a recursion runs them one call path after the other. */
+typedef struct ce_pending { /* the half of a split partition that waits for the other half's subtree */
+    int16_t *X, *lowband;
+    int N, b, B, LM, fill, shift;
+    int first_bits, adj_ok; /* what the first half was given; whether its leftovers may move over (itheta not at its end) */
+    int32_t rebalance0;     /* the budget when the first half started */
+    int16_t gain;
+} ce_pending_t;
+
+ANM_CE_FN unsigned ce_partition(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int16_t gain, int fill) {
     ce_spec_t *sp = ctx->sp;
-    unsigned cm = 0;
-    if (LM != -1 && b > cache[cache[0]] + 12 && N > 2) {
-        ce_split_t s;
-        const int B0 = B;
-        N >>= 1;
-        int16_t *Y = X ? X + N : X;
-        LM -= 1;
-        if (B == 1) fill = (fill & 1) | (fill << 1);
-        B = (B + 1) >> 1;
-        ce_compute_theta(ctx, &s, N, &b, B, B0, LM, 0, &fill);
-        int delta = s.delta;
-        const int itheta = s.itheta;
-        const int16_t mid = (int16_t)s.imid, side = (int16_t)s.iside;
-        /* more bits to low-energy MDCTs than they would otherwise deserve */
-        if (B0 > 1 && (itheta & 0x3fff)) {
-            if (itheta > 8192) delta -= delta >> (4 - LM);
-            else delta = ce_imin(0, delta + (N << ANM_CE_BITRES >> (5 - LM)));
+    ce_pending_t stack[4];
+    int depth = 0, shift = 0; /* shift: where this partition's blocks sit in the mask of the whole */
+    unsigned cm_all = 0;
+    for (;;) {
+        for (;;) { /* down to a leaf, first halves first */
+            const uint8_t *cache = ce_cache(ctx->t, ctx->i, LM);
+            if (!(LM != -1 && b > cache[cache[0]] + 12 && N > 2)) break;
+            ce_split_t s;
+            const int B0 = B;
+            N >>= 1;
+            int16_t *Y = X ? X + N : X;
+            LM -= 1;
+            if (B == 1) fill = (fill & 1) | (fill << 1);
+            B = (B + 1) >> 1;
+            ce_compute_theta(ctx, &s, N, &b, B, B0, LM, 0, &fill);
+            int delta = s.delta;
+            const int itheta = s.itheta;
+            const int16_t mid = (int16_t)s.imid, side = (int16_t)s.iside;
+            /* more bits to low-energy MDCTs than they would otherwise deserve */
+            if (B0 > 1 && (itheta & 0x3fff)) {
+                if (itheta > 8192) delta -= delta >> (4 - LM);
+                else delta = ce_imin(0, delta + (N << ANM_CE_BITRES >> (5 - LM)));
+            }
+            const int mbits = ce_imax(0, ce_imin(b, (b - delta) / 2));
+            const int sbits = b - mbits;
+            ctx->remaining_bits -= s.qalloc;
+            int16_t *next_lowband2 = lowband ? lowband + N : lowband;
+            const int16_t gm = (int16_t)CV_P15(gain, mid), gs = (int16_t)CV_P15(gain, side);
+            ce_pending_t *p = &stack[depth++];
+            p->N = N;
+            p->B = B;
+            p->LM = LM;
+            p->rebalance0 = ctx->remaining_bits;
+            if (mbits >= sbits) { /* the mid first; the side's blocks are the upper ones of the mask */
+                p->X = Y;
+                p->lowband = next_lowband2;
+                p->b = sbits;
+                p->gain = gs;
+                p->fill = fill >> B;
+                p->shift = shift + (B0 >> 1);
+                p->first_bits = mbits;
+                p->adj_ok = itheta != 0;
+                b = mbits;
+                gain = gm;
+            } else {
+                p->X = X;
+                p->lowband = lowband;
+                p->b = mbits;
+                p->gain = gm;
+                p->fill = fill;
+                p->shift = shift;
+                p->first_bits = sbits;
+                p->adj_ok = itheta != 16384;
+                X = Y;
+                lowband = next_lowband2;
+                b = sbits;
+                gain = gs;
+                fill >>= B;
+                shift += B0 >> 1;
+            }
         }
-        int mbits = ce_imax(0, ce_imin(b, (b - delta) / 2));
-        int sbits = b - mbits;
-        ctx->remaining_bits -= s.qalloc;
-        int16_t *next_lowband2 = lowband ? lowband + N : lowband;
-        int32_t rebalance = ctx->remaining_bits;
-        if (mbits >= sbits) {
-            cm = ce_partition(ctx, X, N, mbits, B, lowband, LM, (int16_t)CV_P15(gain, mid), fill);
-            rebalance = mbits - (rebalance - ctx->remaining_bits);
-            if (rebalance > 3 << ANM_CE_BITRES && itheta != 0) sbits += rebalance - (3 << ANM_CE_BITRES);
-            cm |= ce_partition(ctx, Y, N, sbits, B, next_lowband2, LM, (int16_t)CV_P15(gain, side), fill >> B) << (B0 >> 1);
-        } else {
-            cm = ce_partition(ctx, Y, N, sbits, B, next_lowband2, LM, (int16_t)CV_P15(gain, side), fill >> B) << (B0 >> 1);
-            rebalance = sbits - (rebalance - ctx->remaining_bits);
-            if (rebalance > 3 << ANM_CE_BITRES && itheta != 16384) mbits += rebalance - (3 << ANM_CE_BITRES);
-            cm |= ce_partition(ctx, X, N, mbits, B, lowband, LM, (int16_t)CV_P15(gain, mid), fill);
-        }
-    } else {
+        unsigned cm = 0;
         int q = ce_bits2pulses(ctx->t, ctx->i, LM, b);
         int curr_bits = ce_pulses2bits(ctx->t, ctx->i, LM, q);
         ctx->remaining_bits -= curr_bits;
@@ -442,9 +483,11 @@ static unsigned ce_partition(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B
             /* decode_pulses: one uniform symbol over the V(N, K) codewords */
             const uint32_t v = ce_pvq_u(ctx->t, N, K) + ce_pvq_u(ctx->t, N, K + 1);
             const uint32_t idx = ce_uint(ctx->ec, v);
-            ctx->out->pvq_codewords++;
-            ctx->out->pvq_pulses += (uint32_t)K;
-            ctx->out->pvq_index_xor ^= idx * 2654435761u + (uint32_t)(N * 131 + K);
+            if (ctx->out) {
+                ctx->out->pvq_codewords++;
+                ctx->out->pvq_pulses += (uint32_t)K;
+                ctx->out->pvq_index_xor ^= idx * 2654435761u + (uint32_t)(N * 131 + K);
+            }
             if (sp) { /* alg_unquant */
                 const int32_t Ryy = cv_cwrsi(ctx->t, N, K, idx, sp->iy, sp->lane);
                 cv_normalise_residual(sp->iy, X, N, Ryy, gain, sp->lane, sp->nl);
@@ -478,8 +521,23 @@ static unsigned ce_partition(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B
                 cv_renormalise(X, N, gain, sp->lane, sp->nl);
             }
         }
+        cm_all |= cm << shift;
+        if (depth == 0) break;
+        /* on to the half that waited: what its sibling's subtree left over moves to it */
+        const ce_pending_t *p = &stack[--depth];
+        const int32_t rebalance = p->first_bits - (p->rebalance0 - ctx->remaining_bits);
+        b = p->b;
+        if (rebalance > 3 << ANM_CE_BITRES && p->adj_ok) b += rebalance - (3 << ANM_CE_BITRES);
+        X = p->X;
+        lowband = p->lowband;
+        N = p->N;
+        B = p->B;
+        LM = p->LM;
+        gain = p->gain;
+        fill = p->fill;
+        shift = p->shift;
     }
-    return cm;
+    return cm_all;
 }
 
 /* one band of one channel (or the mid / side of a stereo band): the time-frequency reshaping around the partition */
@@ -547,74 +605,130 @@ ANM_CE_FN unsigned ce_band(ce_band_ctx_t *ctx, int16_t *X, int N, int b, int B, 
     return cm;
 }
 
-ANM_CE_FN unsigned ce_band_stereo(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, int N, int b, int B, int16_t *lowband, int LM, int16_t *lowband_out,
-                                  int16_t *lowband_scratch, int fill) {
+/* the channels of one band: mono (C == 1), the two channels of a dual-stereo band coded one after the other (dual), or a mid / side pair
+ * (quant_band_stereo, bands.c:1371-1489).  Whatever the case, it comes down to at most two mono codings -- and they all go through the ONE
+ * ce_band below, in a loop that must not be unrolled: the threads of a warp, each on its own frame, then meet inside it whichever case their
+ * band is (see ce_partition).  lb / lb2, lbo / lbo2: folding source and folding output per channel; x_cm / y_cm: in, the masks of the folding
+ * source; out, the band's. */
+typedef struct ce_mono {
+    int16_t *X, *lowband, *lowband_out, *scratch;
+    int b, fill;
+    int16_t gain;
+} ce_mono_t;
+
+ANM_CE_FN void ce_band_channels(ce_band_ctx_t *ctx, int16_t *X, int16_t *Y, int C, int dual, int N, int b, int B, int16_t *lb, int16_t *lb2, int LM, int16_t *lbo,
+                                int16_t *lbo2, int16_t *lowband_scratch, unsigned *x_cm, unsigned *y_cm) {
     ce_spec_t *sp = ctx->sp;
-    unsigned cm = 0;
-    if (N == 1) return ce_band_n1(ctx, X, Y, 1, lowband_out);
-    const int orig_fill = fill;
+    ce_mono_t cur, nxt;
+    int n = 0;       /* mono codings to do */
+    int first_bits = 0, adj_ok = 0, rebalancing = 0;
+    int32_t rebalance0 = 0;
+    int stereo = 0, sign = 1, c = 0;
     ce_split_t s;
-    ce_compute_theta(ctx, &s, N, &b, B, B, LM, 1, &fill);
-    const int itheta = s.itheta, inv = s.inv;
-    const int16_t mid = (int16_t)s.imid, side = (int16_t)s.iside;
-    int mbits, sbits;
-    if (N == 2) {
-        /* mid and side are orthogonal: one bit for the side's sign */
-        mbits = b;
-        sbits = 0;
-        if (itheta != 0 && itheta != 16384) sbits = 1 << ANM_CE_BITRES;
-        mbits -= sbits;
-        const int c = itheta > 8192;
-        ctx->remaining_bits -= s.qalloc + sbits;
-        int16_t *x2 = c ? Y : X, *y2 = c ? X : Y;
-        int sign = 0;
-        if (sbits) sign = (int)ce_bits(ctx->ec, 1);
-        sign = 1 - 2 * sign;
-        /* orig_fill: the side is folded even when itheta == 16384 cleared the low bits of fill */
-        cm = ce_band(ctx, x2, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, orig_fill);
-        if (sp) CV_SYNC();
-        if (sp && sp->lane == 0) {
-            y2[0] = (int16_t)(-sign * x2[1]);
-            y2[1] = (int16_t)(sign * x2[0]);
-            X[0] = (int16_t)CV_Q15(mid, X[0]);
-            X[1] = (int16_t)CV_Q15(mid, X[1]);
-            Y[0] = (int16_t)CV_Q15(side, Y[0]);
-            Y[1] = (int16_t)CV_Q15(side, Y[1]);
-            int16_t tmp = X[0];
-            X[0] = (int16_t)CV_S16(tmp, Y[0]);
-            Y[0] = CV_A16(tmp, Y[0]);
-            tmp = X[1];
-            X[1] = (int16_t)CV_S16(tmp, Y[1]);
-            Y[1] = CV_A16(tmp, Y[1]);
-        }
-        if (sp) CV_SYNC();
+    s.inv = 0;
+    s.imid = 0;
+    s.iside = 0;
+    s.itheta = 0;
+    cur.X = X; cur.lowband = lb; cur.lowband_out = lbo; cur.scratch = lowband_scratch; cur.b = b; cur.fill = 0; cur.gain = 32767;
+    nxt = cur;
+    if (C == 1) {
+        cur.fill = (int)(*x_cm | *y_cm);
+        n = 1;
+    } else if (dual) {
+        cur.b = b / 2;
+        cur.fill = (int)*x_cm;
+        nxt.X = Y; nxt.lowband = lb2; nxt.lowband_out = lbo2; nxt.b = b / 2; nxt.fill = (int)*y_cm;
+        n = 2;
+    } else if (N == 1) {
+        *x_cm = *y_cm = ce_band_n1(ctx, X, Y, 1, lbo);
+        return;
     } else {
-        mbits = ce_imax(0, ce_imin(b, (b - s.delta) / 2));
-        sbits = b - mbits;
-        ctx->remaining_bits -= s.qalloc;
-        int32_t rebalance = ctx->remaining_bits;
-        /* the mid keeps unit norm (it is the folding source of later bands); a stereo split never folds the side */
-        if (mbits >= sbits) {
-            cm = ce_band(ctx, X, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, fill);
-            rebalance = mbits - (rebalance - ctx->remaining_bits);
-            if (rebalance > 3 << ANM_CE_BITRES && itheta != 0) sbits += rebalance - (3 << ANM_CE_BITRES);
-            cm |= ce_band(ctx, Y, N, sbits, B, 0, LM, 0, side, 0, fill >> B);
+        stereo = 1;
+        int fill = (int)(*x_cm | *y_cm);
+        const int orig_fill = fill;
+        ce_compute_theta(ctx, &s, N, &b, B, B, LM, 1, &fill);
+        const int itheta = s.itheta;
+        if (N == 2) {
+            /* mid and side are orthogonal: one bit for the side's sign */
+            int sbits = 0;
+            if (itheta != 0 && itheta != 16384) sbits = 1 << ANM_CE_BITRES;
+            c = itheta > 8192;
+            ctx->remaining_bits -= s.qalloc + sbits;
+            if (sbits) sign = 1 - 2 * (int)ce_bits(ctx->ec, 1);
+            /* orig_fill: the side is folded even when itheta == 16384 cleared the low bits of fill */
+            cur.X = c ? Y : X;
+            cur.b = b - sbits;
+            cur.fill = orig_fill;
+            n = 1;
         } else {
-            cm = ce_band(ctx, Y, N, sbits, B, 0, LM, 0, side, 0, fill >> B);
-            rebalance = sbits - (rebalance - ctx->remaining_bits);
-            if (rebalance > 3 << ANM_CE_BITRES && itheta != 16384) mbits += rebalance - (3 << ANM_CE_BITRES);
-            cm |= ce_band(ctx, X, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, fill);
+            const int mbits = ce_imax(0, ce_imin(b, (b - s.delta) / 2));
+            const int sbits = b - mbits;
+            ctx->remaining_bits -= s.qalloc;
+            rebalance0 = ctx->remaining_bits;
+            rebalancing = 1;
+            /* the mid keeps unit norm (it is the folding source of later bands); a stereo split never folds the side */
+            ce_mono_t m = cur, sd = cur;
+            m.b = mbits; m.fill = fill;
+            sd.X = Y; sd.lowband = 0; sd.lowband_out = 0; sd.scratch = 0; sd.b = sbits; sd.fill = fill >> B; sd.gain = (int16_t)s.iside;
+            if (mbits >= sbits) {
+                cur = m; nxt = sd;
+                first_bits = mbits;
+                adj_ok = itheta != 0;
+            } else {
+                cur = sd; nxt = m;
+                first_bits = sbits;
+                adj_ok = itheta != 16384;
+            }
+            n = 2;
         }
     }
+    unsigned cm0 = 0, cm1 = 0;
+    ANM_CE_NOUNROLL
+    for (int k = 0; k < n; k++) {
+        if (k == 1 && rebalancing) { /* what the first coding left over goes to the second */
+            const int32_t rebalance = first_bits - (rebalance0 - ctx->remaining_bits);
+            if (rebalance > 3 << ANM_CE_BITRES && adj_ok) cur.b += rebalance - (3 << ANM_CE_BITRES);
+        }
+        const unsigned cm = ce_band(ctx, cur.X, N, cur.b, B, cur.lowband, LM, cur.lowband_out, cur.gain, cur.scratch, cur.fill);
+        if (k == 0) cm0 = cm;
+        else cm1 = cm;
+        cur = nxt;
+    }
+    if (!stereo) {
+        *x_cm = cm0;
+        *y_cm = dual ? cm1 : cm0;
+        return;
+    }
     if (sp) {
-        if (N != 2) cv_stereo_merge(X, Y, mid, N, sp->lane, sp->nl);
-        if (inv) {
+        const int16_t mid = (int16_t)s.imid, side = (int16_t)s.iside;
+        if (N == 2) {
+            int16_t *x2 = c ? Y : X, *y2 = c ? X : Y;
+            CV_SYNC();
+            if (sp->lane == 0) {
+                y2[0] = (int16_t)(-sign * x2[1]);
+                y2[1] = (int16_t)(sign * x2[0]);
+                X[0] = (int16_t)CV_Q15(mid, X[0]);
+                X[1] = (int16_t)CV_Q15(mid, X[1]);
+                Y[0] = (int16_t)CV_Q15(side, Y[0]);
+                Y[1] = (int16_t)CV_Q15(side, Y[1]);
+                int16_t tmp = X[0];
+                X[0] = (int16_t)CV_S16(tmp, Y[0]);
+                Y[0] = CV_A16(tmp, Y[0]);
+                tmp = X[1];
+                X[1] = (int16_t)CV_S16(tmp, Y[1]);
+                Y[1] = CV_A16(tmp, Y[1]);
+            }
+            CV_SYNC();
+        } else {
+            cv_stereo_merge(X, Y, mid, N, sp->lane, sp->nl);
+        }
+        if (s.inv) {
             CV_SYNC();
             for (int j = sp->lane; j < N; j += sp->nl) Y[j] = (int16_t)-Y[j];
             CV_SYNC();
         }
     }
-    return cm;
+    *x_cm = *y_cm = cm0 | cm1;
 }
 
 /* ---------------------------------------------------------------- bit allocation */
@@ -810,6 +924,100 @@ ANM_CE_FN int ce_compute_allocation(const anm_celt_tables_t *t, int start, int e
                                  dual_stereo_rsv, pulses, ebits, fine_priority, C, LM, ec);
 }
 
+/* the range decoder and the allocation's balance as they stand in front of the band loop: stage 1 records them, stage 2 resumes there */
+typedef struct ce_resume {
+    anm_ec_t dec; /* .bytes is not carried (the caller passes the arena again) */
+    int32_t balance, band_total;
+} ce_resume_t;
+
+/* ---------------------------------------------------------------- the band loop (quant_all_bands) */
+/* band_total: the frame's bits in 1/8 bit minus the anti-collapse reserve; balance: what clt_compute_allocation left; pulses / tf_res: per band.
+ * sp == NULL: bits only (stage 1); otherwise the spectrum as well (see anm_celt_frame_symbols). */
+ANM_CE_FN void ce_all_bands(const anm_celt_tables_t *t, anm_ec_t *dec, int C, int LM, int end, const int *pulses, const int *tf_res, int32_t balance,
+                            int32_t band_total, int short_blocks, int spread, int intensity, int dual_stereo, int coded_bands, anm_celt_frame_t *out,
+                            ce_spec_t *sp, int16_t *X_, uint8_t *collapse_masks) {
+    ce_band_ctx_t ctx;
+    ctx.t = t;
+    ctx.ec = dec;
+    ctx.intensity = intensity;
+    ctx.out = out;
+    ctx.sp = sp;
+    const int M = 1 << LM, start = 0;
+    const int16_t *eb = t->ebands;
+    const int B = short_blocks ? M : 1;
+    int i;
+    const int NF = M * 120; /* coefficients per channel */
+    int ds = dual_stereo;
+    /* folding state: norm holds the bands decoded so far (per channel while dual stereo lasts), up to the last band's start */
+    const int norm_offset = M * eb[start], norm_len = M * eb[ANM_CE_NB - 1] - norm_offset;
+    int16_t *norm = sp ? sp->norm : 0, *norm2 = sp ? sp->norm + norm_len : 0;
+    int16_t *lowband_scratch = sp ? X_ + M * eb[ANM_CE_NB - 1] : 0;
+    int lowband_offset = 0, update_lowband = 1;
+    if (sp) sp->spread = spread;
+    for (i = start; i < end; i++) {
+        ctx.i = i;
+        const int last = i == end - 1;
+        const int N = M * eb[i + 1] - M * eb[i];
+        int16_t *X = sp ? X_ + M * eb[i] : 0, *Y = (sp && C == 2) ? X_ + NF + M * eb[i] : 0;
+        const int32_t tl = (int32_t)ce_tell_frac(dec);
+        if (i != start) balance -= tl;
+        const int32_t remaining = band_total - tl - 1;
+        ctx.remaining_bits = remaining;
+        int b;
+        if (i <= coded_bands - 1) {
+            const int32_t curr_balance = balance / ce_imin(3, coded_bands - i); /* celt_sudiv */
+            b = ce_imax(0, ce_imin(16383, ce_imin((int)remaining + 1, pulses[i] + (int)curr_balance)));
+        } else {
+            b = 0;
+        }
+        if ((M * eb[i] - N >= M * eb[start] || i == start + 1) && (update_lowband || lowband_offset == 0)) lowband_offset = i;
+        ctx.tf_change = tf_res[i];
+        if (last) lowband_scratch = 0;
+        /* a conservative estimate of the collapse masks of the bands this one folds from */
+        int effective_lowband = -1;
+        unsigned x_cm, y_cm;
+        if (lowband_offset != 0 && (spread != 3 || B > 1 || tf_res[i] < 0)) { /* SPREAD_AGGRESSIVE */
+            effective_lowband = ce_imax(0, M * eb[lowband_offset] - norm_offset - N); /* never repeat spectral content within one band */
+            int fold_start = lowband_offset;
+            while (M * eb[--fold_start] > effective_lowband + norm_offset) {}
+            int fold_end = lowband_offset - 1;
+            while (++fold_end < i && M * eb[fold_end] < effective_lowband + norm_offset + N) {}
+            x_cm = y_cm = 0;
+            if (sp) {
+                int fold_i = fold_start;
+                do {
+                    x_cm |= collapse_masks[fold_i * C + 0];
+                    y_cm |= collapse_masks[fold_i * C + C - 1];
+                } while (++fold_i < fold_end);
+            }
+        } else {
+            x_cm = y_cm = (1u << B) - 1; /* folding from the noise generator: every block gets energy */
+        }
+        if (ds && i == intensity) { /* dual stereo switches off to do intensity */
+            ds = 0;
+            if (sp) {
+                CV_SYNC();
+                for (int j = sp->lane; j < M * eb[i] - norm_offset; j += sp->nl) norm[j] = (int16_t)(((int32_t)norm[j] + norm2[j]) >> 1);
+                CV_SYNC();
+            }
+        }
+        int16_t *lb = (sp && effective_lowband != -1) ? norm + effective_lowband : 0;
+        int16_t *lbo = (sp && !last) ? norm + M * eb[i] - norm_offset : 0;
+        int16_t *lb2 = (sp && ds && effective_lowband != -1) ? norm2 + effective_lowband : 0;
+        int16_t *lbo2 = (sp && ds && !last) ? norm2 + M * eb[i] - norm_offset : 0;
+        ce_band_channels(&ctx, X, Y, C, ds, N, b, B, lb, lb2, LM, lbo, lbo2, lowband_scratch, &x_cm, &y_cm);
+        if (sp) {
+            if (sp->lane == 0) {
+                collapse_masks[i * C + 0] = (uint8_t)x_cm;
+                collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
+            }
+            CV_SYNC();
+        }
+        balance += pulses[i] + tl;
+        update_lowband = b > (N << ANM_CE_BITRES); /* the folding position moves only while there is 1 bit / sample of depth */
+    }
+}
+
 /* ---------------------------------------------------------------- one frame */
 /* Everything the frame's bits say, WITHOUT the stream's history: the coarse energy symbols qi[c * 21 + band] and the sum of the fine and
  * final energy offsets eoff[c * 21 + band] (Q10) are returned instead of being applied -- no symbol of a frame depends on the band energies,
@@ -819,7 +1027,8 @@ ANM_CE_FN int ce_compute_allocation(const anm_celt_tables_t *t, int start, int e
  * X, before anti-collapse), collapse_masks: [21 * C]; sp->seed / spread / disable_inv are inputs, sp->seed is updated.  The last band's part of
  * X_ doubles as scratch while the earlier bands are decoded, as in the reference. */
 ANM_CE_FN int anm_celt_frame_symbols(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
-                                     int end, int16_t *qi_out, int16_t *eoff, anm_celt_frame_t *out, ce_spec_t *sp, int16_t *X_, uint8_t *collapse_masks) {
+                                     int end, int16_t *qi_out, int16_t *eoff, anm_celt_frame_t *out, ce_spec_t *sp, int16_t *X_, uint8_t *collapse_masks,
+                                     ce_resume_t *resume) {
     const uint8_t trim_icdf[11] = {126, 124, 119, 109, 87, 41, 19, 9, 4, 2, 0};
     const uint8_t spread_icdf[4] = {25, 23, 2, 0};
     const uint8_t tapset_icdf[3] = {2, 1, 0};
@@ -961,93 +1170,13 @@ ANM_CE_FN int anm_celt_frame_symbols(const anm_celt_tables_t *t, const uint8_t *
         }
     }
     /* ---- the bands (quant_all_bands) ---- */
-    {
-        ce_band_ctx_t ctx;
-        ctx.t = t;
-        ctx.ec = &dec;
-        ctx.intensity = intensity;
-        ctx.out = out;
-        ctx.sp = sp;
-        const int32_t band_total = (int32_t)len * (8 << ANM_CE_BITRES) - anti_collapse_rsv;
-        const int B = short_blocks ? M : 1;
-        const int NF = M * 120; /* coefficients per channel */
-        int ds = dual_stereo;
-        /* folding state: norm holds the bands decoded so far (per channel while dual stereo lasts), up to the last band's start */
-        const int norm_offset = M * eb[start], norm_len = M * eb[ANM_CE_NB - 1] - norm_offset;
-        int16_t *norm = sp ? sp->norm : 0, *norm2 = sp ? sp->norm + norm_len : 0;
-        int16_t *lowband_scratch = sp ? X_ + M * eb[ANM_CE_NB - 1] : 0;
-        int lowband_offset = 0, update_lowband = 1;
-        if (sp) sp->spread = spread;
-        for (i = start; i < end; i++) {
-            ctx.i = i;
-            const int last = i == end - 1;
-            const int N = M * eb[i + 1] - M * eb[i];
-            int16_t *X = sp ? X_ + M * eb[i] : 0, *Y = (sp && C == 2) ? X_ + NF + M * eb[i] : 0;
-            const int32_t tl = (int32_t)ce_tell_frac(&dec);
-            if (i != start) balance -= tl;
-            const int32_t remaining = band_total - tl - 1;
-            ctx.remaining_bits = remaining;
-            int b;
-            if (i <= coded_bands - 1) {
-                const int32_t curr_balance = balance / ce_imin(3, coded_bands - i); /* celt_sudiv */
-                b = ce_imax(0, ce_imin(16383, ce_imin((int)remaining + 1, pulses[i] + (int)curr_balance)));
-            } else {
-                b = 0;
-            }
-            if ((M * eb[i] - N >= M * eb[start] || i == start + 1) && (update_lowband || lowband_offset == 0)) lowband_offset = i;
-            ctx.tf_change = tf_res[i];
-            if (last) lowband_scratch = 0;
-            /* a conservative estimate of the collapse masks of the bands this one folds from */
-            int effective_lowband = -1;
-            unsigned x_cm, y_cm;
-            if (lowband_offset != 0 && (spread != 3 || B > 1 || tf_res[i] < 0)) { /* SPREAD_AGGRESSIVE */
-                effective_lowband = ce_imax(0, M * eb[lowband_offset] - norm_offset - N); /* never repeat spectral content within one band */
-                int fold_start = lowband_offset;
-                while (M * eb[--fold_start] > effective_lowband + norm_offset) {}
-                int fold_end = lowband_offset - 1;
-                while (++fold_end < i && M * eb[fold_end] < effective_lowband + norm_offset + N) {}
-                x_cm = y_cm = 0;
-                if (sp) {
-                    int fold_i = fold_start;
-                    do {
-                        x_cm |= collapse_masks[fold_i * C + 0];
-                        y_cm |= collapse_masks[fold_i * C + C - 1];
-                    } while (++fold_i < fold_end);
-                }
-            } else {
-                x_cm = y_cm = (1u << B) - 1; /* folding from the noise generator: every block gets energy */
-            }
-            if (ds && i == intensity) { /* dual stereo switches off to do intensity */
-                ds = 0;
-                if (sp) {
-                    CV_SYNC();
-                    for (int j = sp->lane; j < M * eb[i] - norm_offset; j += sp->nl) norm[j] = (int16_t)(((int32_t)norm[j] + norm2[j]) >> 1);
-                    CV_SYNC();
-                }
-            }
-            int16_t *lb = (sp && effective_lowband != -1) ? norm + effective_lowband : 0;
-            int16_t *lbo = (sp && !last) ? norm + M * eb[i] - norm_offset : 0;
-            if (ds) {
-                int16_t *lb2 = (sp && effective_lowband != -1) ? norm2 + effective_lowband : 0;
-                int16_t *lbo2 = (sp && !last) ? norm2 + M * eb[i] - norm_offset : 0;
-                x_cm = ce_band(&ctx, X, N, b / 2, B, lb, LM, lbo, 32767, lowband_scratch, (int)x_cm);
-                y_cm = ce_band(&ctx, Y, N, b / 2, B, lb2, LM, lbo2, 32767, lowband_scratch, (int)y_cm);
-            } else {
-                if (C == 2) x_cm = ce_band_stereo(&ctx, X, Y, N, b, B, lb, LM, lbo, lowband_scratch, (int)(x_cm | y_cm));
-                else x_cm = ce_band(&ctx, X, N, b, B, lb, LM, lbo, 32767, lowband_scratch, (int)(x_cm | y_cm));
-                y_cm = x_cm;
-            }
-            if (sp) {
-                if (sp->lane == 0) {
-                    collapse_masks[i * C + 0] = (uint8_t)x_cm;
-                    collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
-                }
-                CV_SYNC();
-            }
-            balance += pulses[i] + tl;
-            update_lowband = b > (N << ANM_CE_BITRES); /* the folding position moves only while there is 1 bit / sample of depth */
-        }
+    const int32_t band_total = (int32_t)len * (8 << ANM_CE_BITRES) - anti_collapse_rsv;
+    if (resume && !sp) { /* stage 1 leaves what stage 2 needs to start right here */
+        resume->dec = dec;
+        resume->balance = balance;
+        resume->band_total = band_total;
     }
+    ce_all_bands(t, &dec, C, LM, end, pulses, tf_res, balance, band_total, short_blocks, spread, intensity, dual_stereo, coded_bands, out, sp, X_, collapse_masks);
     int anti_collapse_on = 0;
     if (anti_collapse_rsv > 0) anti_collapse_on = (int)ce_bits(&dec, 1);
     /* ---- unquant_energy_finalise ---- */
@@ -1090,7 +1219,7 @@ ANM_CE_FN int anm_celt_frame_symbols(const anm_celt_tables_t *t, const uint8_t *
 
 ANM_CE_FN int anm_celt_entropy_symbols(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM,
                                        int end, int16_t *qi_out, int16_t *eoff, anm_celt_frame_t *out) {
-    return anm_celt_frame_symbols(t, bytes, mask, base, len, C, LM, end, qi_out, eoff, out, 0, 0, 0);
+    return anm_celt_frame_symbols(t, bytes, mask, base, len, C, LM, end, qi_out, eoff, out, 0, 0, 0, 0);
 }
 
 /* The sequential part of a stream: the band energies after a frame from the energies before it (old_e, Q10, [2][21]), the frame's coarse
@@ -1168,18 +1297,42 @@ ANM_CE_FN void anm_celt_stream_step(anm_celt_frame_t *fr, const int16_t *qi, con
 /* Stage 2 for one frame whose stage-1 record `rec` (band energies applied) and history `hist` are known: the frame is decoded again, this time
  * with its spectrum, and anti-collapse is applied when the frame asks for it.  X: [C][120 << LM]; cm: 42 collapse masks; sp: working storage.
  * Returns the noise seed after the bands in sp->seed. */
+/* resume == NULL: the frame is decoded from its first bit once more (the stand-alone form; tests hold it against the resumed one) */
 ANM_CE_FN int anm_celt_frame_spectrum(const anm_celt_tables_t *t, const uint8_t *bytes, uint32_t mask, uint32_t base, uint32_t len, int C, int LM, int end,
-                                      int disable_inv, const ce_hist_t *hist, const anm_celt_frame_t *rec, ce_spec_t *sp, int16_t *X, uint8_t *cm) {
-    int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
-    anm_celt_frame_t again;
+                                      int disable_inv, const ce_hist_t *hist, const anm_celt_frame_t *rec, const ce_resume_t *resume, ce_spec_t *sp,
+                                      int16_t *X, uint8_t *cm) {
     sp->seed = hist->seed;
     sp->disable_inv = disable_inv;
     for (int i = sp->lane; i < 2 * ANM_CE_NB; i += sp->nl) cm[i] = 0;
     CV_SYNC();
-    const int rc = anm_celt_frame_symbols(t, bytes, mask, base, len, C, LM, end, qi, eoff, &again, sp, X, cm);
-    if (rc != 0) return rc;
-    if (again.flags & ANM_CELT_F_LOST) return 0;
-    if (again.flags & ANM_CELT_F_ANTI_COLLAPSE)
+    uint32_t flags;
+#ifndef __CUDA_ARCH__
+    if (!resume) {
+        int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
+        anm_celt_frame_t again;
+        const int rc = anm_celt_frame_symbols(t, bytes, mask, base, len, C, LM, end, qi, eoff, &again, sp, X, cm, 0);
+        if (rc != 0) return rc;
+        flags = again.flags;
+        if (flags & ANM_CELT_F_LOST) return 0;
+    } else
+#endif
+    {
+        /* everything in front of the band loop was decoded by stage 1: its symbols are in the record, the decoder's state in *resume */
+        flags = rec->flags;
+        if (flags & ANM_CELT_F_LOST) return 0;
+        anm_ec_t dec = resume->dec;
+        dec.bytes = bytes;
+        dec.mask = mask;
+        dec.base = base;
+        int pulses[ANM_CE_NB], tf_res[ANM_CE_NB];
+        for (int i = 0; i < ANM_CE_NB; i++) {
+            pulses[i] = rec->pulses[i];
+            tf_res[i] = rec->tf_res[i];
+        }
+        ce_all_bands(t, &dec, C, LM, end, pulses, tf_res, resume->balance, resume->band_total, (flags & ANM_CELT_F_TRANSIENT) != 0, rec->spread, rec->intensity,
+                     (flags & ANM_CELT_F_DUAL_STEREO) != 0, rec->coded_bands, 0, sp, X, cm);
+    }
+    if (flags & ANM_CELT_F_ANTI_COLLAPSE)
         cv_anti_collapse(t, X, cm, LM, C, 120 << LM, end, rec->band_e, hist->log_e1, hist->log_e2, rec->pulses, sp->seed, sp->lane, sp->nl);
     return 0;
 }

@@ -34,6 +34,8 @@ struct anm_celt_ctx {
     size_t scratch_frames;
     ce_hist_t *d_hist;  /* per frame: the stream's histories before the frame (stage 2) */
     size_t hist_frames;
+    ce_resume_t *d_resume; /* per frame: the range decoder in front of the band loop, where stage 2 picks the frame up */
+    size_t resume_frames;
     void *d_spec;       /* per resident thread of k_celt_spectrum: working storage (SpecScratch) */
     size_t spec_bytes;
     anm_celt_synth_tables_t *d_synth_tables; /* stage 3 */
@@ -48,13 +50,14 @@ namespace {
 /* pass 1, one thread per FRAME: everything the frame's bits say.  No symbol depends on the stream's history, so all frames of all streams
  * decode at once; what the history needs (coarse symbols, energy offsets) goes to the scratch array. */
 __global__ void __launch_bounds__(128) k_celt_entropy(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
-                                                      const uint8_t *__restrict__ bytes, uint32_t mask, int16_t *__restrict__ scratch, anm_celt_frame_t *out) {
+                                                      const uint8_t *__restrict__ bytes, uint32_t mask, int16_t *__restrict__ scratch, anm_celt_frame_t *out,
+                                                      ce_resume_t *resume) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     const anm_celt_job_t job = jobs[j];
     anm_celt_frame_t fr;
     int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
-    const int rc = anm_celt_entropy_symbols(t, bytes, mask, job.offset, job.len, job.channels, job.lm, job.end_band, qi, eoff, &fr);
+    const int rc = anm_celt_frame_symbols(t, bytes, mask, job.offset, job.len, job.channels, job.lm, job.end_band, qi, eoff, &fr, 0, 0, 0, resume ? resume + j : 0);
     if (rc != 0) { /* impossible job description: treated like a lost frame, flagged */
         fr.final_range = 0;
         fr.flags = ANM_CELT_F_LOST | ANM_CELT_F_EC_ERROR;
@@ -89,9 +92,13 @@ struct SpecScratch {
     int16_t tmp[CE_SPEC_TMP];
     int iy[CE_SPEC_IY];
 };
-__global__ void __launch_bounds__(64, 14) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
+#ifndef ANM_CELT_SPEC_MINB
+#define ANM_CELT_SPEC_MINB 8 /* resident blocks of 64 threads the register budget is set for */
+#endif
+__global__ void __launch_bounds__(64, ANM_CELT_SPEC_MINB) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
                                                       const uint8_t *__restrict__ bytes, uint32_t mask, const anm_celt_frame_t *__restrict__ recs,
-                                                      const ce_hist_t *__restrict__ hist, SpecScratch *spec, int16_t *x, uint32_t x_stride, uint8_t *collapse) {
+                                                      const ce_hist_t *__restrict__ hist, const ce_resume_t *__restrict__ resume, SpecScratch *spec, int16_t *x,
+                                                      uint32_t x_stride, uint8_t *collapse) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     ce_spec_t sp;
     sp.norm = spec[tid].norm;
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(64, 14) k_celt_spectrum(const anm_celt_tables_
         int16_t *X = x + (size_t)j * x_stride;
         const int C = job.channels, NF = 120 << job.lm;
         const int rc = anm_celt_frame_spectrum(t, bytes, mask, job.offset, job.len, C, job.lm, job.end_band, job.flags & ANM_CELT_JOB_DISABLE_INV, &hist[j], &recs[j],
-                                               &sp, X, cm);
+                                               &resume[j], &sp, X, cm);
         if (rc != 0) continue;
         /* zero above the end band (the last band's part served as scratch) */
         const int ncoded = (1 << job.lm) * t->ebands[job.end_band];
@@ -261,6 +268,7 @@ extern "C" void anm_celt_ctx_destroy(anm_celt_ctx_t *c) {
     cudaFree(c->d_tables);
     cudaFree(c->d_scratch);
     cudaFree(c->d_hist);
+    cudaFree(c->d_resume);
     cudaFree(c->d_spec);
     cudaFree(c->d_synth_tables);
     cudaFree(c->d_x);
@@ -286,10 +294,11 @@ static int grow(T **p, size_t *have, size_t want, cudaStream_t s, const char *wh
 }
 
 static int entropy_impl(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
-                        const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, ce_hist_t *d_hist, cudaStream_t s) {
+                        const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_frame_t *d_out, ce_hist_t *d_hist, ce_resume_t *d_resume,
+                        cudaStream_t s) {
     const int rcg = grow(&c->d_scratch, &c->scratch_frames, (size_t)n_jobs * 4 * ANM_CE_NB, s, "anm_celt_entropy_device");
     if (rcg != ANM_OK) return rcg;
-    k_celt_entropy<<<(n_jobs + 127u) / 128u, 128, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, c->d_scratch, d_out);
+    k_celt_entropy<<<(n_jobs + 127u) / 128u, 128, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, c->d_scratch, d_out, d_resume);
     k_celt_energies<<<(n_streams + 127u) / 128u, 128, 0, s>>>(d_stream_begin, n_streams, c->d_scratch, d_streams, d_out, d_hist);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -318,7 +327,7 @@ extern "C" int anm_celt_entropy_device(anm_celt_ctx_t *c, const anm_celt_job_t *
     const int rc = check_args(c, d_jobs, d_stream_begin, d_streams, d_out, n_streams, bytes_mask);
     if (rc != ANM_OK) return rc;
     if (n_streams == 0 || n_jobs == 0) return ANM_OK;
-    return entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, nullptr, (cudaStream_t)stream);
+    return entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
@@ -338,8 +347,10 @@ extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t 
     rc = grow(&spec, &c->spec_bytes, (size_t)blocks * 64u * sizeof(SpecScratch), s, "anm_celt_spectrum_device");
     c->d_spec = spec;
     if (rc != ANM_OK) return rc;
-    if ((rc = entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_hist, s)) != ANM_OK) return rc;
-    k_celt_spectrum<<<blocks, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, static_cast<SpecScratch *>(c->d_spec), d_x, x_stride,
+    if ((rc = grow(&c->d_resume, &c->resume_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
+    if ((rc = entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_hist, c->d_resume, s)) != ANM_OK) return rc;
+    k_celt_spectrum<<<blocks, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, c->d_resume, static_cast<SpecScratch *>(c->d_spec), d_x,
+                                          x_stride,
                                           d_collapse);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -39,7 +39,7 @@ int harness_celt_spectrum(const anm_celt_tables_t *t, const uint8_t *bytes, uint
     for (int i = 0; i < 2 * ANM_CE_NB; i++) cm[i] = 0;
     sp.seed = seed_in;
     sp.disable_inv = disable_inv;
-    const int rc = anm_celt_frame_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out, &sp, X, cm);
+    const int rc = anm_celt_frame_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out, &sp, X, cm, 0);
     if (rc != 0) return rc;
     anm_celt_apply_energies(out, qi, eoff, old_e);
     const int ncmp = (1 << LM) * t->ebands[end];
@@ -61,12 +61,28 @@ int harness_celt_frame_full(const anm_celt_tables_t *t, const uint8_t *bytes, ui
     uint8_t cm[2 * ANM_CE_NB];
     const int NF = 120 << LM;
     spec_init(&sp);
-    int rc = anm_celt_entropy_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out);
+    ce_resume_t resume;
+    int rc = anm_celt_frame_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out, 0, 0, 0, &resume);
     if (rc != 0) return rc;
     anm_celt_stream_step(out, qi, eoff, st, hist_out);
     for (int i = 0; i < 2 * 960; i++) X[i] = 0;
-    rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, disable_inv, hist_out, out, &sp, X, cm);
+    rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, disable_inv, hist_out, out, &resume, &sp, X, cm);
     if (rc != 0) return rc;
+    { /* the same frame decoded from its first bit instead of from the resume point: must not differ */
+        static int16_t X2[2 * 960];
+        uint8_t cm2[2 * ANM_CE_NB];
+        for (int i = 0; i < 2 * 960; i++) X2[i] = 0;
+        rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, disable_inv, hist_out, out, 0, &sp, X2, cm2);
+        if (rc != 0) return rc;
+        if (!(out->flags & ANM_CELT_F_LOST)) {
+            const int ncmp2 = (1 << LM) * t->ebands[end];
+            for (int c = 0; c < C; c++)
+                for (int i = 0; i < ncmp2; i++)
+                    if (X2[NF * c + i] != X[NF * c + i]) return -99;
+            for (int i = 0; i < C * end; i++)
+                if (cm2[i] != cm[i]) return -98;
+        }
+    }
     const int ncmp = (1 << LM) * t->ebands[end];
     for (int i = 0; i < 2 * 960; i++) x_post[i] = 0;
     for (int c = 0; c < C; c++)
@@ -92,12 +108,13 @@ int harness_celt_decode_frame(const anm_celt_tables_t *t, const anm_celt_synth_t
     int16_t qi[2 * ANM_CE_NB], eoff[2 * ANM_CE_NB];
     uint8_t cm[2 * ANM_CE_NB];
     ce_hist_t hist;
-    int rc = anm_celt_entropy_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out);
+    ce_resume_t resume;
+    int rc = anm_celt_frame_symbols(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, qi, eoff, out, 0, 0, 0, &resume);
     if (rc != 0) return rc;
     anm_celt_stream_step(out, qi, eoff, st, &hist);
     if (out->flags & ANM_CELT_F_LOST) return 0;
     for (int i = 0; i < 2 * 960; i++) X[i] = 0;
-    rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, CC == 1, &hist, out, &sp, X, cm);
+    rc = anm_celt_frame_spectrum(t, bytes, 0xFFFFFFFFu, 0u, len, C, LM, end, CC == 1, &hist, out, &resume, &sp, X, cm);
     if (rc != 0) return rc;
     cs_frame_blocks(t, stb, X, out->band_e, C, CC, LM, end, (out->flags & ANM_CELT_F_TRANSIENT) != 0, (out->flags & ANM_CELT_F_SILENCE) != 0, freq, raw, 0, 1);
     cs_stream_frame(stb, syn, out, raw, CC, pcm);
