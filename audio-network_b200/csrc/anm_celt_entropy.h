@@ -265,6 +265,8 @@ typedef struct ce_spec {
     int16_t *norm;         /* [2 * 624] folding source: the decoded bands so far, scaled by sqrt(N) (two channels for dual stereo) */
     int16_t *tmp;          /* [176] Hadamard reordering scratch */
     int *iy;               /* [176] pulse vector of one partition */
+    int16_t *band;         /* [3 * 176] or NULL: the band being decoded (two channels) and the folding scratch, when they are to live apart from the
+                              output (thread-local on the GPU); the finished band is then copied out */
     uint32_t seed;         /* noise generator (CELTDecoder.rng) */
     int spread, disable_inv;
     int lane, nl;          /* this thread's share of the loops over coefficients (anm_celt_vec.h); the arrays above are shared by the nl lanes */
@@ -272,6 +274,7 @@ typedef struct ce_spec {
 #define CE_SPEC_NORM 1248
 #define CE_SPEC_TMP 176
 #define CE_SPEC_IY 176
+#define CE_SPEC_BAND (3 * 176)
 
 typedef struct ce_band_ctx {
     const anm_celt_tables_t *t;
@@ -951,14 +954,14 @@ ANM_CE_FN void ce_all_bands(const anm_celt_tables_t *t, anm_ec_t *dec, int C, in
     /* folding state: norm holds the bands decoded so far (per channel while dual stereo lasts), up to the last band's start */
     const int norm_offset = M * eb[start], norm_len = M * eb[ANM_CE_NB - 1] - norm_offset;
     int16_t *norm = sp ? sp->norm : 0, *norm2 = sp ? sp->norm + norm_len : 0;
-    int16_t *lowband_scratch = sp ? X_ + M * eb[ANM_CE_NB - 1] : 0;
+    int16_t *lowband_scratch = sp ? (sp->band ? sp->band + 2 * 176 : X_ + M * eb[ANM_CE_NB - 1]) : 0;
     int lowband_offset = 0, update_lowband = 1;
     if (sp) sp->spread = spread;
     for (i = start; i < end; i++) {
         ctx.i = i;
         const int last = i == end - 1;
         const int N = M * eb[i + 1] - M * eb[i];
-        int16_t *X = sp ? X_ + M * eb[i] : 0, *Y = (sp && C == 2) ? X_ + NF + M * eb[i] : 0;
+        int16_t *X = sp ? (sp->band ? sp->band : X_ + M * eb[i]) : 0, *Y = (sp && C == 2) ? (sp->band ? sp->band + 176 : X_ + NF + M * eb[i]) : 0;
         const int32_t tl = (int32_t)ce_tell_frac(dec);
         if (i != start) balance -= tl;
         const int32_t remaining = band_total - tl - 1;
@@ -1006,6 +1009,13 @@ ANM_CE_FN void ce_all_bands(const anm_celt_tables_t *t, anm_ec_t *dec, int C, in
         int16_t *lb2 = (sp && ds && effective_lowband != -1) ? norm2 + effective_lowband : 0;
         int16_t *lbo2 = (sp && ds && !last) ? norm2 + M * eb[i] - norm_offset : 0;
         ce_band_channels(&ctx, X, Y, C, ds, N, b, B, lb, lb2, LM, lbo, lbo2, lowband_scratch, &x_cm, &y_cm);
+        if (sp && sp->band) { /* the finished band goes to the output */
+            for (int c = 0; c < C; c++) {
+                int16_t *dst = X_ + c * NF + M * eb[i];
+                const int16_t *src = sp->band + 176 * c;
+                for (int k = sp->lane; k < N; k += sp->nl) dst[k] = src[k];
+            }
+        }
         if (sp) {
             if (sp->lane == 0) {
                 collapse_masks[i * C + 0] = (uint8_t)x_cm;

@@ -7,11 +7,13 @@
  * operations per frame over the coarse symbols and offsets pass 1 left in a scratch array (anm_celt_entropy.h holds the decode itself,
  * shared with the host-side test harness).
  *
- * Stage 2 (anm_celt_spectrum_*) adds k_celt_spectrum, one thread per frame again: the frame is decoded once more, this time with the spectrum
- * arithmetic switched on (anm_celt_vec.h: PVQ vectors, rotations, folding, reorderings, stereo merge, anti-collapse), seeded and informed by what
- * the per-stream pass left (the noise seed is the previous frame's final range, anti-collapse reads the stream's two log-energy histories).  A
- * thread-per-frame kernel: the per-thread working set (3.7 KB + the frame's spectrum) lives in global memory, threads of a warp diverge (3.3 of 32
- * lanes active per instruction); a warp-per-frame form was measured 3 x slower (anm_celt_vec.h).  Stage 3 (anm_celt_decode_*) adds
+ * Stage 2 (anm_celt_spectrum_*) adds k_celt_spectrum, one thread per frame again: the frame is picked up where pass 1 left its range decoder in
+ * front of the band loop, and the bands are decoded with the spectrum arithmetic switched on (anm_celt_vec.h: PVQ vectors, rotations, folding,
+ * reorderings, stereo merge, anti-collapse), seeded and informed by what the per-stream pass left (the noise seed is the previous frame's final range,
+ * anti-collapse reads the stream's two log-energy histories).  The threads of a warp work on frames of their own, so what they do differs from band
+ * to band; the band and partition walks are written so that the expensive steps sit at one place in the code each and the lanes meet there
+ * (anm_celt_entropy.h: ce_partition, ce_band_channels) -- 7.9 of 32 lanes active per instruction against 3.3 for the straight transcription of the
+ * reference's recursion.  A warp-per-frame form was measured 3 x slower (anm_celt_vec.h).  Stage 3 (anm_celt_decode_*) adds
  * k_celt_blocks (a warp per frame: denormalisation, the fixed-point FFT of the inverse MDCT in shared memory) and k_celt_overlap (a warp per stream and
  * output channel: overlap-add, pitch post-filter, de-emphasis with the output history in shared memory).
  *
@@ -36,8 +38,6 @@ struct anm_celt_ctx {
     size_t hist_frames;
     ce_resume_t *d_resume; /* per frame: the range decoder in front of the band loop, where stage 2 picks the frame up */
     size_t resume_frames;
-    void *d_spec;       /* per resident thread of k_celt_spectrum: working storage (SpecScratch) */
-    size_t spec_bytes;
     anm_celt_synth_tables_t *d_synth_tables; /* stage 3 */
     int16_t *d_x;       /* per frame: the normalised spectrum (anm_celt_decode_device keeps it to itself) */
     size_t x_frames;
@@ -84,26 +84,28 @@ __global__ void __launch_bounds__(128) k_celt_energies(const uint32_t *__restric
     streams[s] = st;
 }
 
-/* stage 2, one thread per FRAME (grid-stride: the working storage is per resident thread, in a global slab).  Bound by memory latency: the
- * 7.4 KB a frame works on do not fit on chip for hundreds of threads per SM; the more threads in flight the better (measured 1 .. 16 blocks of 64 per
- * SM: 429 / 238 / 169 / 115 / 76 ms for 204,800 frames).  A warp-per-frame form with the working set in shared memory was 3 x slower (anm_celt_vec.h). */
-struct SpecScratch {
-    int16_t norm[CE_SPEC_NORM];
-    int16_t tmp[CE_SPEC_TMP];
-    int iy[CE_SPEC_IY];
-};
+/* stage 2, one thread per FRAME.  What a frame works on -- the folding source, the band being decoded, the pulse vector and the reordering scratch,
+ * 5.1 KB -- sits in thread-local memory: its layout puts the same element of the 32 lanes of a warp side by side, and since the band and partition
+ * walks of anm_celt_entropy.h keep the lanes in step, their accesses fall into the same lines.  A finished band is copied to the output once, where
+ * working in the output in place wrote every coefficient half a dozen times through the write-through L1 (204,800 frames: 32.5 ms with the working
+ * storage in a global slab, 30.7 ms thread-local without the band, 26.5 ms with it; register budget for 14 / 12 / 8 resident blocks of 64 threads:
+ * 26.5 / 26.8 / 31.0 ms).  Bound by memory latency along the dependent chains of a frame, not by bandwidth: the more warps in flight the better.  A
+ * warp-per-frame form with the working set in shared memory was 3 x slower (anm_celt_vec.h). */
 #ifndef ANM_CELT_SPEC_MINB
-#define ANM_CELT_SPEC_MINB 8 /* resident blocks of 64 threads the register budget is set for */
+#define ANM_CELT_SPEC_MINB 14 /* resident blocks of 64 threads the register budget is set for */
 #endif
 __global__ void __launch_bounds__(64, ANM_CELT_SPEC_MINB) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
                                                       const uint8_t *__restrict__ bytes, uint32_t mask, const anm_celt_frame_t *__restrict__ recs,
-                                                      const ce_hist_t *__restrict__ hist, const ce_resume_t *__restrict__ resume, SpecScratch *spec, int16_t *x,
-                                                      uint32_t x_stride, uint8_t *collapse) {
+                                                      const ce_hist_t *__restrict__ hist, const ce_resume_t *__restrict__ resume, int16_t *x, uint32_t x_stride,
+                                                      uint8_t *collapse) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    int16_t l_norm[CE_SPEC_NORM], l_tmp[CE_SPEC_TMP], l_band[CE_SPEC_BAND];
+    int l_iy[CE_SPEC_IY];
     ce_spec_t sp;
-    sp.norm = spec[tid].norm;
-    sp.tmp = spec[tid].tmp;
-    sp.iy = spec[tid].iy;
+    sp.norm = l_norm;
+    sp.tmp = l_tmp;
+    sp.iy = l_iy;
+    sp.band = l_band;
     sp.lane = 0;
     sp.nl = 1;
     sp.spread = 0;
@@ -225,8 +227,8 @@ extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
     c->scratch_frames = 0;
     c->d_hist = nullptr;
     c->hist_frames = 0;
-    c->d_spec = nullptr;
-    c->spec_bytes = 0;
+    c->d_resume = nullptr;
+    c->resume_frames = 0;
     c->d_synth_tables = nullptr;
     c->d_x = nullptr;
     c->x_frames = 0;
@@ -269,7 +271,6 @@ extern "C" void anm_celt_ctx_destroy(anm_celt_ctx_t *c) {
     cudaFree(c->d_scratch);
     cudaFree(c->d_hist);
     cudaFree(c->d_resume);
-    cudaFree(c->d_spec);
     cudaFree(c->d_synth_tables);
     cudaFree(c->d_x);
     cudaFree(c->d_raw);
@@ -308,13 +309,6 @@ static int entropy_impl(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const u
     return ANM_OK;
 }
 
-/* resident blocks of 64 threads per SM for the frame-parallel kernels that keep per-thread working storage in global memory */
-static uint32_t blocks_per_sm() {
-    const char *e = getenv("ANM_CELT_BLOCKS_PER_SM"); /* experiment knob */
-    const int v = e ? atoi(e) : 0;
-    return v > 0 && v <= 32 ? (uint32_t)v : 16u;
-}
-
 static int check_args(anm_celt_ctx_t *c, const void *d_jobs, const void *d_stream_begin, const void *d_streams, const void *d_out, uint32_t n_streams,
                       uint32_t bytes_mask) {
     if (!c || ((!d_jobs || !d_stream_begin || !d_streams || !d_out) && n_streams)) return ANM_ERR_ARG;
@@ -338,20 +332,11 @@ extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t 
     if ((!d_x && n_jobs) || x_stride < 120u) return ANM_ERR_ARG;
     if (n_streams == 0 || n_jobs == 0) return ANM_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    /* one frame per thread while the working storage stays below 2 GB (the hardware then balances the very uneven frames block by block), grid-stride beyond */
-    const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_jobs + 63u) / 64u, std::max<uint64_t>((uint64_t)sms * blocks_per_sm(), (2ull << 30) / (64u * sizeof(SpecScratch))));
     if ((rc = grow(&c->d_hist, &c->hist_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
-    unsigned char *spec = static_cast<unsigned char *>(c->d_spec);
-    rc = grow(&spec, &c->spec_bytes, (size_t)blocks * 64u * sizeof(SpecScratch), s, "anm_celt_spectrum_device");
-    c->d_spec = spec;
-    if (rc != ANM_OK) return rc;
     if ((rc = grow(&c->d_resume, &c->resume_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
     if ((rc = entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_hist, c->d_resume, s)) != ANM_OK) return rc;
-    k_celt_spectrum<<<blocks, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, c->d_resume, static_cast<SpecScratch *>(c->d_spec), d_x,
-                                          x_stride,
-                                          d_collapse);
+    /* one frame per thread: the hardware balances the very uneven frames block by block */
+    k_celt_spectrum<<<(n_jobs + 63u) / 64u, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, c->d_resume, d_x, x_stride, d_collapse);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         anm_set_error("k_celt_spectrum launch failed: %s", cudaGetErrorString(e));

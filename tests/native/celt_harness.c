@@ -16,6 +16,8 @@ uint32_t harness_sizeof_frame(void) { return (uint32_t)sizeof(anm_celt_frame_t);
 static void spec_init(ce_spec_t *sp) {
     static int16_t norm[CE_SPEC_NORM], tmp[CE_SPEC_TMP];
     static int iy[CE_SPEC_IY];
+    static int16_t band[CE_SPEC_BAND];
+    sp->band = band; /* as the kernel runs it */
     sp->norm = norm;
     sp->tmp = tmp;
     sp->iy = iy;
