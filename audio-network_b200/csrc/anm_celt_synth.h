@@ -359,12 +359,13 @@ typedef struct cs_pf {
     int16_t gain, gain_old;
 } cs_pf_t;
 
-/* One frame of ONE output channel c of a stream: raw blocks (cs_frame_blocks) -> PCM.  mem: the channel's output history (anm_celt_synth_t.mem[c]);
- * pf: the stream's post-filter state, updated for the next frame (every channel of a stream sees and makes the same updates); pcm: [N][CC].
- * The copies, the window mix, the saturation and (in runs shorter than its period) the post-filter go over the lanes; the de-emphasis is a one-pole
- * recurrence and runs on lane 0. */
-ANM_CE_FN void cs_channel_frame(const anm_celt_synth_tables_t *st, int32_t *mem, int32_t *preemph_mem, cs_pf_t *pf, const anm_celt_frame_t *fr, const int32_t *raw_c,
-                                int CC, int c, int16_t *pcm, int lane, int nl) {
+/* One frame of ONE output channel c of a stream: raw blocks (cs_frame_blocks) -> PCM (cs_channel_frame below), in two parts.  mem: the channel's
+ * output history (anm_celt_synth_t.mem[c]); pf: the stream's post-filter state, updated for the next frame (every channel of a stream sees and makes
+ * the same updates).  cs_channel_signal, the part in front of the de-emphasis, leaves the frame's N filtered samples at mem + CS_BUF - N (where the
+ * next frame's history move picks them up): the copies, the window mix, the saturation and (in runs shorter than its period) the post-filter go over
+ * the lanes.  cs_deemphasis is a one-pole recurrence over the samples in order: one lane (the GPU runs it in a kernel of its own, a thread per
+ * channel, instead of holding 31 lanes of a warp idle for it). */
+ANM_CE_FN void cs_channel_signal(const anm_celt_synth_tables_t *st, int32_t *mem, cs_pf_t *pf, const anm_celt_frame_t *fr, const int32_t *raw_c, int lane, int nl) {
     const int LM = fr->lm, N = 120 << LM, transient = (fr->flags & ANM_CELT_F_TRANSIENT) != 0;
     const int B = transient ? 1 << LM : 1, NB = transient ? 120 : N;
     const int pf_on = (fr->flags & ANM_CELT_F_POSTFILTER) != 0;
@@ -406,18 +407,27 @@ ANM_CE_FN void cs_channel_frame(const anm_celt_synth_tables_t *st, int32_t *mem,
         pf->gain_old = pf->gain;
         pf->tapset_old = pf->tapset;
     }
-    /* de-emphasis to 16 bits */
-    if (lane == 0) {
-        int32_t m = *preemph_mem;
-        for (int j = 0; j < N; j++) {
-            const int32_t tmp = out[j] + m;   /* VERY_SMALL = 0 */
-            m = cs_smul(tmp, 27853);          /* mode->preemph[0] */
-            int32_t v = CV_PSHR32(tmp, 12);   /* SIG2WORD16 */
-            v = v < -32768 ? -32768 : v > 32767 ? 32767 : v;
-            pcm[j * CC + c] = (int16_t)v;
-        }
-        *preemph_mem = m;
-    }
+    CS_SYNC();
+}
+/* de-emphasis to 16 bits (celt_decoder.c:266-339, the path without downsampling): a one-pole recurrence over the samples of a channel, in order.
+ * sig: the N filtered samples; pcm: [N][CC]. */
+ANM_CE_FN int16_t cs_deemphasis_step(int32_t x, int32_t *m) {
+    const int32_t tmp = x + *m;       /* VERY_SMALL = 0 */
+    *m = cs_smul(tmp, 27853);         /* mode->preemph[0] */
+    int32_t v = CV_PSHR32(tmp, 12);   /* SIG2WORD16 */
+    v = v < -32768 ? -32768 : v > 32767 ? 32767 : v;
+    return (int16_t)v;
+}
+ANM_CE_FN void cs_deemphasis(const int32_t *sig, int N, int32_t *preemph_mem, int16_t *pcm, int CC, int c) {
+    int32_t m = *preemph_mem;
+    for (int j = 0; j < N; j++) pcm[j * CC + c] = cs_deemphasis_step(sig[j], &m);
+    *preemph_mem = m;
+}
+ANM_CE_FN void cs_channel_frame(const anm_celt_synth_tables_t *st, int32_t *mem, int32_t *preemph_mem, cs_pf_t *pf, const anm_celt_frame_t *fr, const int32_t *raw_c,
+                                int CC, int c, int16_t *pcm, int lane, int nl) {
+    const int N = 120 << fr->lm;
+    cs_channel_signal(st, mem, pf, fr, raw_c, lane, nl);
+    if (lane == 0) cs_deemphasis(mem + CS_BUF - N, N, preemph_mem, pcm, CC, c);
     CS_SYNC();
 }
 ANM_CE_FN void cs_pf_load(cs_pf_t *pf, const anm_celt_synth_t *s) {

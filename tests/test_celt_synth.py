@@ -246,6 +246,46 @@ def test_gpu_random_streams_pcm_vs_reference_live():
 
 
 @pytest.mark.gpu
+def test_gpu_device_call_with_pcm_rows_of_any_stride_and_alignment():
+    """anm_celt_decode_device writes 16 bytes of PCM at a time when the rows allow it and sample by sample when they do not (a stride that is no multiple of
+    8 samples, a buffer that starts off a 16-byte boundary): both equal the public API's result, mono and stereo"""
+    import torch
+    L = anm.lib()
+    dev = torch.device("cuda:0")
+    for s in [x for x in PACKETS["streams"] if x["name"] in ("stereo_20ms", "mono_20ms")] or PACKETS["streams"][:2]:
+        frames = _stream_frames(s)
+        by = np.frombuffer(b"".join(f[0] for f in frames), np.uint8)
+        jobs = np.zeros(len(frames), dtype=anm.CELT_JOB_DTYPE)
+        off = 0
+        for k, (f, ch, lm, end) in enumerate(frames):
+            jobs[k] = (off, len(f), ch, lm, end, anm.CELT_JOB_DISABLE_INV if s["channels"] == 1 else 0)
+            off += len(f)
+        cc = s["channels"]
+        _, _, _, want = anm.celt_decode(jobs, [0, len(jobs)], by, out_channels=[cc])
+        ctx = C.c_void_p()
+        assert L.anm_celt_ctx_create(0, C.byref(ctx)) == 0
+        d_by = torch.from_numpy(by.copy()).to(dev)
+        d_jobs = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).to(dev)
+        d_sb = torch.tensor([0, len(jobs)], dtype=torch.int32, device=dev)
+        d_fr = torch.zeros(len(jobs) * anm.CELT_FRAME_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        for stride, shift in ((1920, 0), (1924, 0), (1921, 0), (1920, 3), (1928, 8)):
+            d_st = torch.zeros(anm.CELT_STREAM_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            sy = np.zeros(1, dtype=anm.CELT_SYNTH_DTYPE)
+            sy["out_channels"] = cc
+            d_sy = torch.from_numpy(sy.view(np.uint8).reshape(-1).copy()).to(dev)
+            d_pcm = torch.zeros(len(jobs) * stride + 16, dtype=torch.int16, device=dev)
+            rc = L.anm_celt_decode_device(ctx, d_jobs.data_ptr(), d_sb.data_ptr(), 1, len(jobs), d_by.data_ptr(), 0xFFFFFFFF, d_st.data_ptr(), d_sy.data_ptr(),
+                                          d_fr.data_ptr(), d_pcm.data_ptr() + 2 * shift, stride, None)
+            assert rc == 0, L.anm_last_error()
+            torch.cuda.synchronize()
+            got = d_pcm[shift: shift + len(jobs) * stride].view(len(jobs), stride).cpu().numpy()
+            for k in range(len(jobs)):
+                ns = (120 << int(jobs["lm"][k])) * cc
+                assert np.array_equal(got[k, :ns], want[k, :ns]), (s["name"], stride, shift, k)
+        L.anm_celt_ctx_destroy(ctx)
+
+
+@pytest.mark.gpu
 def test_gpu_receive_chain_pcm_in_pcm_out():
     """The widened hot path end to end on the GPU: ToReceiver{AudioData{CELT packet}} messages -> modem frames -> modem PCM -> k_demod -> k_pb_deframe ->
     k_opus_parse -> the five CELT kernels: the AUDIO that comes out equals what the reference's opus_decode() returns for the packets that went in."""
