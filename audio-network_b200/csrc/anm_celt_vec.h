@@ -214,7 +214,12 @@ ANM_CE_FN unsigned cv_collapse_mask(const int *iy, int N, int B, int lane, int n
     const int N0 = (int)((uint32_t)N / (uint32_t)B);
     unsigned mask = 0;
     CV_SYNC();
-    for (int i = lane; i < N; i += nl) mask |= (unsigned)(iy[i] != 0) << (i / N0);
+    /* b = i / N0, kept up without dividing (here and below: an integer division is some thirty instructions, per element more than the work itself) */
+    int b = (int)((uint32_t)lane / (uint32_t)N0), r = lane - b * N0;
+    for (int i = lane; i < N; i += nl) {
+        mask |= (unsigned)(iy[i] != 0) << b;
+        for (r += nl; r >= N0; r -= N0) b++;
+    }
     return CV_OR(mask);
 }
 ANM_CE_FN void cv_renormalise(int16_t *X, int N, int16_t gain, int lane, int nl) {
@@ -231,11 +236,14 @@ ANM_CE_FN void cv_renormalise(int16_t *X, int N, int16_t gain, int lane, int nl)
 ANM_CE_FN void cv_haar1(int16_t *X, int N0, int stride, int lane, int nl) {
     N0 >>= 1;
     CV_SYNC();
+    /* element idx = j * stride + i of the upper halves: its pair sits at p = 2 * j * stride + i and p + stride */
+    int j = (int)((uint32_t)lane / (uint32_t)stride), i = lane - j * stride;
     for (int idx = lane; idx < stride * N0; idx += nl) {
-        const int i = idx % stride, j = idx / stride;
-        const int32_t t1 = CV_M16(23170, X[stride * 2 * j + i]), t2 = CV_M16(23170, X[stride * (2 * j + 1) + i]);
-        X[stride * 2 * j + i] = (int16_t)CV_PSHR32(t1 + t2, 15);
-        X[stride * (2 * j + 1) + i] = (int16_t)CV_PSHR32(t1 - t2, 15);
+        int16_t *p = X + 2 * j * stride + i;
+        const int32_t t1 = CV_M16(23170, p[0]), t2 = CV_M16(23170, p[stride]);
+        p[0] = (int16_t)CV_PSHR32(t1 + t2, 15);
+        p[stride] = (int16_t)CV_PSHR32(t1 - t2, 15);
+        for (i += nl; i >= stride; i -= stride) j++;
     }
     CV_SYNC();
 }
@@ -247,10 +255,11 @@ ANM_CE_FN int cv_ordery(int stride, int i) {
 ANM_CE_FN void cv_deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard, int lane, int nl) {
     const int N = N0 * stride;
     CV_SYNC();
+    int i = (int)((uint32_t)lane / (uint32_t)N0), j = lane - i * N0;
     for (int idx = lane; idx < N; idx += nl) {
-        const int i = idx / N0, j = idx % N0;
         const int o = hadamard ? cv_ordery(stride, i) : i;
         tmp[o * N0 + j] = X[j * stride + i];
+        for (j += nl; j >= N0; j -= N0) i++;
     }
     CV_SYNC();
     for (int i = lane; i < N; i += nl) X[i] = tmp[i];
@@ -259,10 +268,11 @@ ANM_CE_FN void cv_deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int st
 ANM_CE_FN void cv_interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard, int lane, int nl) {
     const int N = N0 * stride;
     CV_SYNC();
+    int i = (int)((uint32_t)lane / (uint32_t)N0), j = lane - i * N0;
     for (int idx = lane; idx < N; idx += nl) {
-        const int i = idx / N0, j = idx % N0;
         const int o = hadamard ? cv_ordery(stride, i) : i;
         tmp[j * stride + i] = X[o * N0 + j];
+        for (j += nl; j >= N0; j -= N0) i++;
     }
     CV_SYNC();
     for (int i = lane; i < N; i += nl) X[i] = tmp[i];

@@ -1,44 +1,61 @@
-#!/usr/bin/env python
-"""Executed warp-instructions per CUDA source line from an .ncu-rep (captured with --import-source on).
-Usage: python tools/ncu_lines.py prof.ncu-rep [min_share_pct]"""
+"""ncu_lines.py REPORT.ncu-rep LIB.so KERNEL_SUBSTRING [TOP]: the SASS page of an ncu report (--import-source on) joined with nvdisasm's line table of the
+same build, summed per source line: share of stall samples, share of warp instructions, lanes active, long-scoreboard and no-instruction share."""
+import collections
 import csv
 import io
+import os
+import re
 import subprocess
 import sys
+import tempfile
 
-def num(v):
+rep, lib, kern = sys.argv[1:4]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(src)))
+hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+h, data = rows[hdr], rows[hdr + 1:]
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
+ins = []
+for f in sorted(os.listdir(tmp)):
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+    if kern not in dis:
+        continue
+    on, cur = False, None
+    for l in dis.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+)", l)
+        if m:
+            on = kern in m.group(1)
+            continue
+        if not on:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
+        if m:
+            ins.append((m.group(2), cur))
+assert len(ins) == len(data), (len(ins), len(data))
+ci = {n: i for i, n in enumerate(h)}
+
+
+def f(r, k):
     try:
-        return int(v)
+        return float(r[ci[k]].replace(",", ""))
     except ValueError:
-        return 0
+        return 0.0
 
 
-rep = sys.argv[1]
-thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(txt)))
-h = None
-lines = []  # (file, line, src, inst, ops)
-cur_file = None
-for x in rows:
-    if x and x[0] == "File Path":
-        cur_file = x[1]
-    elif x and x[0] == "Line No":
-        h = x
-        ie = h.index("Instructions Executed")
-    elif h and len(x) == len(h):
-        if x[0] != "":
-            lines.append([cur_file, int(x[0]), x[1], num(x[ie]), {}])
-        elif lines:
-            op = x[3].split()
-            if op and op[0].startswith("@"):
-                op = op[1:]
-            if op:
-                k = op[0].split(".")[0]
-                lines[-1][4][k] = lines[-1][4].get(k, 0) + num(x[ie])
-tot = sum(l[3] for l in lines)
-print("total executed warp-instr: %d" % tot)
-for f, ln, src, n, ops in lines:
-    if n >= thr / 100.0 * tot:
-        top = sorted(ops.items(), key=lambda kv: -kv[1])[:5]
-        print("%5.1f%% %s:%d  %s\n        %s" % (100.0 * n / tot, f.split("/")[-1], ln, src.strip()[:100], {k: round(100.0 * v / tot, 2) for k, v in top}))
+keys = ["# Samples", "Instructions Executed", "Thread Instructions Executed", "stall_long_sb", "stall_no_inst"]
+agg, tot = collections.defaultdict(lambda: [0.0] * 5), [0.0] * 5
+for (txt, cur), r in zip(ins, data):
+    for i, k in enumerate(keys):
+        v = f(r, k)
+        agg[cur][i] += v
+        tot[i] += v
+print("samples %d  warp inst %.3g  lanes %.2f  long_sb %.0f%%  no_inst %.0f%%" % (tot[0], tot[1], tot[2] / tot[1], 100 * tot[3] / tot[0], 100 * tot[4] / tot[0]))
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    print("%-22s %5d  smp %5.1f%%  inst %5.1f%%  lanes %5.1f  long_sb %3.0f%%  no_inst %3.0f%%" %
+          (k[0], k[1], 100 * v[0] / tot[0], 100 * v[1] / tot[1], v[2] / max(v[1], 1), 100 * v[3] / max(v[0], 1), 100 * v[4] / max(v[0], 1)))
