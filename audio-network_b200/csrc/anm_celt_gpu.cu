@@ -87,12 +87,13 @@ __global__ void __launch_bounds__(128) k_celt_energies(const uint32_t *__restric
 /* stage 2, one thread per FRAME.  What a frame works on -- the folding source, the band being decoded, the pulse vector and the reordering scratch,
  * 5.1 KB -- sits in thread-local memory: its layout puts the same element of the 32 lanes of a warp side by side, and since the band and partition
  * walks of anm_celt_entropy.h keep the lanes in step, their accesses fall into the same lines.  A finished band is copied to the output once, where
- * working in the output in place wrote every coefficient half a dozen times through the write-through L1 (204,800 frames: 32.5 ms with the working
- * storage in a global slab, 30.7 ms thread-local without the band, 26.5 ms with it; register budget for 14 / 12 / 8 resident blocks of 64 threads:
- * 26.5 / 26.8 / 31.0 ms).  Bound by memory latency along the dependent chains of a frame, not by bandwidth: the more warps in flight the better.  A
- * warp-per-frame form with the working set in shared memory was 3 x slower (anm_celt_vec.h). */
+ * working in the output in place wrote every coefficient half a dozen times through the write-through L1 (204,800 frames, before the reordering loops
+ * lost their divisions: 32.5 ms with the working storage in a global slab, 30.7 ms thread-local without the band, 26.5 ms with it).  Register budget for
+ * 10 / 12 / 14 / 16 resident blocks of 64 threads (96 / 80 / 72 / 64 registers): entropy + spectrum 20.2 / 18.3 / 19.2 / 19.0 ms.  Bound by latency
+ * along the dependent chains of a frame and by instruction fetch (the warps of an SM are all somewhere else in 20,000 instructions), not by
+ * bandwidth.  A warp-per-frame form with the working set in shared memory was 3 x slower (anm_celt_vec.h). */
 #ifndef ANM_CELT_SPEC_MINB
-#define ANM_CELT_SPEC_MINB 14 /* resident blocks of 64 threads the register budget is set for */
+#define ANM_CELT_SPEC_MINB 12 /* resident blocks of 64 threads the register budget is set for */
 #endif
 __global__ void __launch_bounds__(64, ANM_CELT_SPEC_MINB) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
                                                       const uint8_t *__restrict__ bytes, uint32_t mask, const anm_celt_frame_t *__restrict__ recs,
