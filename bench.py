@@ -372,7 +372,7 @@ def decode_chain_leg(anm, torch, dev, recs, by, reps=20):
         ms = t_celt / (reps // 2)
         celt = {"k_celt_entropy_plus_energies_ms": round(ms, 4), "streams": int(len(chs)), "frames": int(len(jobs)), "Mframes_per_s": round(len(jobs) / (ms * 1e-3) / 1e6, 2),
                 "packet_bytes": int(jobs["len"].sum()), "frames_within_budget": int(((fr["flags"] & 1024) == 0).sum()),
-                "full_decode": {"kernels": "k_celt_entropy, k_celt_energies, k_celt_spectrum, k_celt_blocks, k_celt_overlap", "streams": ns_dec, "frames": nj_dec,
+                "full_decode": {"kernels": "k_celt_entropy, k_celt_energies, k_celt_spectrum, k_celt_blocks, k_celt_overlap, k_celt_deemphasis", "streams": ns_dec, "frames": nj_dec,
                                 "ms": round(t_dec, 3), "Mframes_per_s": round(nj_dec / (t_dec * 1e-3) / 1e6, 3), "audio_x_realtime": round(nj_dec * 0.02 / (t_dec * 1e-3), 1),
                                 "pcm_nonzero": pcm_nonzero,
                                 "note": "bounded sample of whole streams; PCM parity of these kernels is pinned on real encoder output in tests/test_celt_synth.py, "

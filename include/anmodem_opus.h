@@ -187,9 +187,11 @@ int anm_celt_spectrum_host(const anm_celt_job_t *jobs, const uint32_t *stream_be
                            anm_celt_stream_t *streams, anm_celt_frame_t *out, int16_t *x, uint32_t x_stride, uint8_t *collapse);
 /* All three stages: CELT frames -> PCM, sample for sample what the reference's celt_decode_with_ec() writes (fixed-point build; no packet-loss
  * concealment: frames of <= 1 byte produce no PCM and leave the stream's state untouched).  As anm_celt_spectrum_device, then k_celt_blocks (one warp
- * per frame: denormalisation and the inverse MDCT blocks of every output channel) and k_celt_overlap (one warp per stream and output channel: window
- * overlap-add, pitch post-filter, de-emphasis -- the per-stream recurrence).  Frames of one stream in one call: at most the caller's memory allows.  d_synth: one anm_celt_synth_t per stream; d_pcm: frame j's
- * (120 << lm) x out_channels interleaved int16 samples at d_pcm + j * pcm_stride (pcm_stride >= 1920 always fits). */
+ * per frame: denormalisation and the inverse MDCT blocks of every output channel), k_celt_overlap (one warp per stream and output channel: window
+ * overlap-add and pitch post-filter -- the per-stream recurrences that go over the lanes) and k_celt_deemphasis (one thread per stream and output
+ * channel: the one-pole recurrence to 16-bit PCM).  Frames of one stream in one call: at most the caller's memory allows.  d_synth: one
+ * anm_celt_synth_t per stream; d_pcm: frame j's (120 << lm) x out_channels interleaved int16 samples at d_pcm + j * pcm_stride (pcm_stride >= 1920
+ * always fits; rows that start on 16-byte boundaries -- d_pcm aligned, pcm_stride a multiple of 8 -- are written 16 bytes at a time). */
 int anm_celt_decode_device(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const uint32_t *d_stream_begin, uint32_t n_streams, uint32_t n_jobs,
                            const uint8_t *d_bytes, uint32_t bytes_mask, anm_celt_stream_t *d_streams, anm_celt_synth_t *d_synth, anm_celt_frame_t *d_out,
                            int16_t *d_pcm, uint32_t pcm_stride, void *stream);

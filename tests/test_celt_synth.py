@@ -181,7 +181,7 @@ def _jobs_from_gold(cc_of_stream):
 @pytest.mark.gpu
 @pytest.mark.parametrize("key", ["cc_native", "cc_mono", "cc_stereo"])
 def test_gpu_pcm_equals_the_reference_decoder_on_the_golden_frames(key):
-    """k_celt_entropy -> k_celt_energies -> k_celt_spectrum -> k_celt_blocks -> k_celt_overlap through the C ABI: 58 streams / 1,687 frames"""
+    """k_celt_entropy -> k_celt_energies -> k_celt_spectrum -> k_celt_blocks -> k_celt_overlap -> k_celt_deemphasis through the C ABI: 58 streams / 1,687 frames"""
     fr, sb = GOLD["frames"], GOLD["stream_begin"]
     native = np.array([fr["channels"][sb[s]: sb[s + 1]].max() for s in range(len(sb) - 1)])
     cc = {"cc_native": native, "cc_mono": np.ones_like(native), "cc_stereo": np.full_like(native, 2)}[key]
@@ -288,7 +288,7 @@ def test_gpu_device_call_with_pcm_rows_of_any_stride_and_alignment():
 @pytest.mark.gpu
 def test_gpu_receive_chain_pcm_in_pcm_out():
     """The widened hot path end to end on the GPU: ToReceiver{AudioData{CELT packet}} messages -> modem frames -> modem PCM -> k_demod -> k_pb_deframe ->
-    k_opus_parse -> the five CELT kernels: the AUDIO that comes out equals what the reference's opus_decode() returns for the packets that went in."""
+    k_opus_parse -> the six CELT kernels: the AUDIO that comes out equals what the reference's opus_decode() returns for the packets that went in."""
     s = [x for x in PACKETS["streams"] if x["name"] == "stereo_20ms"][0]
     L = anm.lib()
     L.anm_pb_encode_to_receiver_audio.restype = C.c_size_t

@@ -105,7 +105,7 @@ def main():
                       "entropy_ms": round(t_ent, 3), "entropy_plus_spectrum_ms": round(t_spec, 3), "full_decode_ms": round(t_dec, 3),
                       "Mframes_per_s_full": round(nfr / t_dec / 1e3, 3), "audio_seconds_per_second": round(audio_s / (t_dec * 1e-3), 1),
                       "algorithmic_GBps_full": round((pk_bytes + out_bytes) / (t_dec * 1e-3) / 1e9, 2), "pcm_digests_equal_reference": bool(ok), "cpu_baseline": cpu,
-                      "kernels": "k_celt_entropy, k_celt_energies, k_celt_spectrum, k_celt_blocks, k_celt_overlap"}))
+                      "kernels": "k_celt_entropy, k_celt_energies, k_celt_spectrum, k_celt_blocks, k_celt_overlap, k_celt_deemphasis"}))
 
 
 if __name__ == "__main__":

@@ -12,5 +12,5 @@ timeout 600 python tools/celt_bench.py --streams 4096 --cpu-baseline > gpurun_ou
 ANM_BENCH_CHUNKS=4 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-sustain > gpurun_out/r2_ncu_launch.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_celt_launches.csv python tools/celt_bench.py --streams 4096 --reps 1 > gpurun_out/r2_celt_ncu_launch.log 2>&1
 ANM_BENCH_CHUNKS=4 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_demod --launch-skip 1 -c 1 -f -o gpurun_out/prof_r2d python bench.py --steps 2 --warmup 1 --e2e-steps 0 --no-cpu-baseline --no-cfg4 --no-sustain > gpurun_out/r2_ncu_d.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:"k_celt_spectrum|k_celt_blocks|k_celt_overlap" --launch-skip 3 -c 3 -f -o gpurun_out/prof_r2_celt python tools/celt_bench.py --streams 1024 --reps 1 > gpurun_out/r2_ncu_celt.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:"k_celt_spectrum|k_celt_blocks|k_celt_overlap|k_celt_deemphasis" --launch-skip 2 -c 4 -f -o gpurun_out/prof_r2_celt python tools/celt_bench.py --streams 1024 --reps 1 > gpurun_out/r2_ncu_celt.log 2>&1
 echo done
