@@ -247,17 +247,20 @@ ANM_CE_FN void cv_haar1(int16_t *X, int N0, int stride, int lane, int nl) {
     }
     CV_SYNC();
 }
-ANM_CE_FN int cv_ordery(int stride, int i) {
-    const int8_t tab[30] = {1, 0, 3, 0, 2, 1, 7, 0, 4, 3, 6, 1, 5, 2, 15, 0, 8, 7, 12, 3, 11, 4, 14, 1, 9, 6, 13, 2, 10, 5};
-    return tab[stride - 2 + i];
+/* ordery_table (bands.c:580-585) for stride 2, 4, 8, 16, one entry per nibble, entry 0 lowest: {1,0} {3,0,2,1} {7,0,4,3,6,1,5,2}
+ * {15,0,8,7,12,3,11,4,14,1,9,6,13,2,10,5} (an array here is built on the stack on every call) */
+ANM_CE_FN uint64_t cv_ordery_row(int stride) {
+    return stride == 2 ? 0x01ull : stride == 4 ? 0x1203ull : stride == 8 ? 0x25163407ull : 0x5A2D691E4B3C780Full;
 }
+ANM_CE_FN int cv_ordery(uint64_t row, int i) { return (int)(row >> (4 * i)) & 15; }
 /* frequency order -> time order (tmp: N0 * stride entries of scratch) */
 ANM_CE_FN void cv_deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard, int lane, int nl) {
     const int N = N0 * stride;
     CV_SYNC();
     int i = (int)((uint32_t)lane / (uint32_t)N0), j = lane - i * N0;
+    const uint64_t row = cv_ordery_row(stride);
     for (int idx = lane; idx < N; idx += nl) {
-        const int o = hadamard ? cv_ordery(stride, i) : i;
+        const int o = hadamard ? cv_ordery(row, i) : i;
         tmp[o * N0 + j] = X[j * stride + i];
         for (j += nl; j >= N0; j -= N0) i++;
     }
@@ -269,8 +272,9 @@ ANM_CE_FN void cv_interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stri
     const int N = N0 * stride;
     CV_SYNC();
     int i = (int)((uint32_t)lane / (uint32_t)N0), j = lane - i * N0;
+    const uint64_t row = cv_ordery_row(stride);
     for (int idx = lane; idx < N; idx += nl) {
-        const int o = hadamard ? cv_ordery(stride, i) : i;
+        const int o = hadamard ? cv_ordery(row, i) : i;
         tmp[j * stride + i] = X[o * N0 + j];
         for (j += nl; j >= N0; j -= N0) i++;
     }

@@ -11,10 +11,13 @@ import tempfile
 
 rep, lib, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h, data = rows[hdr], rows[hdr + 1:]
+nxt = [i for i, r in enumerate(data) if r and r[0] == "Kernel Name"]
+if nxt:  # several launches of the kernel in the report: the first one
+    data = data[:nxt[0]]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
 ins = []
