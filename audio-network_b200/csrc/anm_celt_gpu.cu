@@ -128,10 +128,11 @@ __global__ void __launch_bounds__(64, ANM_CELT_SPEC_MINB) k_celt_spectrum(const 
     }
 }
 
-/* stage 3, frame-parallel part: one WARP per frame -- denormalisation and the raw inverse-MDCT blocks of every output channel; the butterflies of an
- * FFT stage, the rotations and the band loops go over the lanes, the coefficients sit in shared memory (anm_celt_synth.h) */
+/* stage 3, frame-parallel part: one WARP per (frame, output channel) -- denormalisation and the raw inverse-MDCT blocks of that channel; the butterflies
+ * of an FFT stage, the rotations and the band loops go over the lanes, the coefficients sit in shared memory (anm_celt_synth.h): 7.5 KB per warp, 28
+ * warps per SM (a warp per frame with both channels' 15 KB: 12 warps per SM) */
 constexpr uint32_t kBlkWarps = 4;
-constexpr uint32_t kBlkWarpBytes = 4u * 960u * 4u; /* freq [2][960] | raw [2][960], int32 */
+constexpr uint32_t kBlkWarpBytes = 2u * 960u * 4u; /* freq [960] | raw [960], int32 */
 __global__ void __launch_bounds__(kBlkWarps * 32) k_celt_blocks(const anm_celt_tables_t *__restrict__ t, const anm_celt_synth_tables_t *__restrict__ stb,
                                                                 const anm_celt_job_t *__restrict__ jobs, const uint32_t *__restrict__ stream_begin,
                                                                 uint32_t n_streams, uint32_t n_jobs, const anm_celt_frame_t *__restrict__ recs,
@@ -139,8 +140,10 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_celt_blocks(const anm_celt_t
     extern __shared__ __align__(16) unsigned char blk_smem[];
     const int lane = threadIdx.x & 31;
     const uint32_t w = threadIdx.x >> 5;
-    int32_t *fq = reinterpret_cast<int32_t *>(blk_smem + w * kBlkWarpBytes), *rw = fq + 2 * 960;
-    for (uint32_t j = blockIdx.x * kBlkWarps + w; j < n_jobs; j += gridDim.x * kBlkWarps) {
+    int32_t *fq = reinterpret_cast<int32_t *>(blk_smem + w * kBlkWarpBytes), *rw = fq + 960;
+    for (uint32_t it = blockIdx.x * kBlkWarps + w; it < 2u * n_jobs; it += gridDim.x * kBlkWarps) {
+        const uint32_t j = it >> 1;
+        const int c = (int)(it & 1u);
         const anm_celt_frame_t *fr = &recs[j];
         if (fr->flags & ANM_CELT_F_LOST) continue;
         /* the frame's stream: the last s with stream_begin[s] <= j */
@@ -152,10 +155,11 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_celt_blocks(const anm_celt_t
         }
         int CC = (int)synth[lo].out_channels;
         if (CC == 0) CC = jobs[stream_begin[lo]].channels;
-        cs_frame_blocks(t, stb, x + (size_t)j * 1920, fr->band_e, fr->channels, CC, fr->lm, fr->pad[0], (fr->flags & ANM_CELT_F_TRANSIENT) != 0,
-                        (fr->flags & ANM_CELT_F_SILENCE) != 0, fq, rw, lane, 32);
-        int32_t *ro = raw + (size_t)j * 1920;
-        const int n = CC * (120 << fr->lm);
+        if (c >= CC) continue;
+        const int n = 120 << fr->lm;
+        cs_channel_blocks(t, stb, x + (size_t)j * 1920, fr->band_e, fr->channels, CC, c, fr->lm, fr->pad[0], (fr->flags & ANM_CELT_F_TRANSIENT) != 0,
+                          (fr->flags & ANM_CELT_F_SILENCE) != 0, fq, rw, lane, 32);
+        int32_t *ro = raw + (size_t)j * 1920 + (size_t)c * n;
         for (int i = lane; i < n; i += 32) ro[i] = rw[i];
         __syncwarp();
     }
@@ -447,7 +451,7 @@ extern "C" int anm_celt_decode_device(anm_celt_ctx_t *c, const anm_celt_job_t *d
         return rc;
     cudaFuncSetAttribute((const void *)k_celt_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBlkWarps * kBlkWarpBytes)); /* per device */
     cudaFuncSetAttribute((const void *)k_celt_overlap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kOvlWarps * kOvlWarpBytes));
-    const uint32_t blk_blocks = (uint32_t)std::min<uint64_t>((n_jobs + kBlkWarps - 1u) / kBlkWarps, (uint64_t)sms * 3u);
+    const uint32_t blk_blocks = (uint32_t)std::min<uint64_t>((2ull * n_jobs + kBlkWarps - 1u) / kBlkWarps, (uint64_t)sms * 7u);
     k_celt_blocks<<<blk_blocks, kBlkWarps * 32, kBlkWarps * kBlkWarpBytes, s>>>(c->d_tables, c->d_synth_tables, d_jobs, d_stream_begin, n_streams, n_jobs, d_out, d_synth,
                                                                                  c->d_x, c->d_raw);
     k_celt_overlap<<<(2u * n_streams + kOvlWarps - 1u) / kOvlWarps, kOvlWarps * 32, kOvlWarps * kOvlWarpBytes, s>>>(c->d_synth_tables, d_jobs, d_stream_begin, n_streams,

@@ -288,29 +288,28 @@ ANM_CE_FN void cs_mirror(const anm_celt_synth_tables_t *st, int32_t *out, int la
 }
 
 /* ---------------------------------------------------------------- frame-parallel part: the raw blocks of every output channel */
-/* X: [C][N] normalised spectrum (stage 2), band_e: the frame's band energies [2][21]; raw: [CC][N] -- block b of channel c at raw + c * N + b * (N / B);
- * freq: N words of scratch (two N for the mono downmix of a stereo frame) */
-ANM_CE_FN void cs_frame_blocks(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *st, const int16_t *X, const int16_t *band_e, int C, int CC, int LM,
-                               int end, int transient, int silence, int32_t *freq, int32_t *raw, int lane, int nl) {
+/* The raw blocks of ONE output channel c of a frame.  X: [C][N] normalised spectrum (stage 2), band_e: the frame's band energies [2][21]; freq: N words of
+ * scratch; rawc: N words -- block b at rawc + b * (N / B) -- which also hold the second channel's coefficients on the way to the mono downmix of a
+ * stereo frame.  A mono frame feeds both channels of a stereo output (celt_synthesis, celt_decoder.c:434-489). */
+ANM_CE_FN void cs_channel_blocks(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *st, const int16_t *X, const int16_t *band_e, int C, int CC, int c, int LM,
+                                 int end, int transient, int silence, int32_t *freq, int32_t *rawc, int lane, int nl) {
     const int M = 1 << LM, N = 120 << LM;
     const int B = transient ? M : 1, NB = transient ? 120 : N, shift = transient ? 3 : 3 - LM;
-    if (CC == 2 && C == 1) {
+    if (CC == 1 && C == 2) {
         cs_denormalise(t, st, X, freq, band_e, end, M, silence, lane, nl);
-        for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + NB * b, lane, nl);
-        for (int i = lane; i < N; i += nl) raw[N + i] = raw[i];
-    } else if (CC == 1 && C == 2) {
-        int32_t *freq2 = freq + N;
-        cs_denormalise(t, st, X, freq, band_e, end, M, silence, lane, nl);
-        cs_denormalise(t, st, X + N, freq2, band_e + ANM_CE_NB, end, M, silence, lane, nl);
-        for (int i = lane; i < N; i += nl) freq[i] = (freq[i] >> 1) + (freq2[i] >> 1);
-        for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + NB * b, lane, nl);
+        cs_denormalise(t, st, X + N, rawc, band_e + ANM_CE_NB, end, M, silence, lane, nl);
+        for (int i = lane; i < N; i += nl) freq[i] = (freq[i] >> 1) + (rawc[i] >> 1);
     } else {
-        for (int c = 0; c < CC; c++) {
-            cs_denormalise(t, st, X + c * N, freq, band_e + c * ANM_CE_NB, end, M, silence, lane, nl);
-            for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, raw + c * N + NB * b, lane, nl);
-        }
+        const int sc = C == 1 ? 0 : c;
+        cs_denormalise(t, st, X + sc * N, freq, band_e + sc * ANM_CE_NB, end, M, silence, lane, nl);
     }
+    for (int b = 0; b < B; b++) cs_imdct_raw(st, freq + b, B, shift, rawc + NB * b, lane, nl);
     CS_SYNC();
+}
+/* all output channels of a frame (the host-side test harness; the kernel runs one warp per channel): raw: [CC][N] */
+ANM_CE_FN void cs_frame_blocks(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *st, const int16_t *X, const int16_t *band_e, int C, int CC, int LM,
+                               int end, int transient, int silence, int32_t *freq, int32_t *raw, int lane, int nl) {
+    for (int c = 0; c < CC; c++) cs_channel_blocks(t, st, X, band_e, C, CC, c, LM, end, transient, silence, freq, raw + c * (120 << LM), lane, nl);
 }
 
 /* ---------------------------------------------------------------- per-stream part */
