@@ -38,6 +38,8 @@ struct anm_celt_ctx {
     size_t hist_frames;
     ce_resume_t *d_resume; /* per frame: the range decoder in front of the band loop, where stage 2 picks the frame up */
     size_t resume_frames;
+    uint32_t *d_order;  /* [2 n + kSortKeys]: the frames grouped by kind (stage 2's thread -> frame map) | each frame's place in its group | group sizes */
+    size_t order_words;
     anm_celt_synth_tables_t *d_synth_tables; /* stage 3 */
     int16_t *d_x;       /* per frame: the normalised spectrum (anm_celt_decode_device keeps it to itself) */
     size_t x_frames;
@@ -84,6 +86,42 @@ __global__ void __launch_bounds__(128) k_celt_energies(const uint32_t *__restric
     streams[s] = st;
 }
 
+/* Which frames share a warp in stage 2.  The threads of a warp run together only where their frames do the same thing, and what a frame does is
+ * largely settled by a few of its header symbols: transient frames (eight short blocks, with the Haar / Hadamard reorderings around every band) and
+ * long ones, frame size, channel count, dual stereo, and roughly how many bits there are to spend.  So the frames are grouped by those (a counting sort
+ * over kSortKeys kinds, three small kernels; the place of a frame inside its group is whatever order the atomics happen to give -- it only decides
+ * which thread decodes the frame, not what comes out) and thread t of k_celt_spectrum takes frame order[t].  The expensive kinds come first. */
+constexpr uint32_t kSortKeys = 1024;
+__device__ __forceinline__ uint32_t celt_kind(const anm_celt_frame_t &fr, const anm_celt_job_t &job) {
+    if (fr.flags & ANM_CELT_F_LOST) return kSortKeys - 1u;
+    const uint32_t sz = 15u - min(15u, job.len / 96u);
+    return ((fr.flags & ANM_CELT_F_TRANSIENT) ? 0u : 1u) << 8 | (3u - (fr.lm & 3u)) << 6 | (fr.channels == 2 ? 0u : 1u) << 5 |
+           ((fr.flags & ANM_CELT_F_DUAL_STEREO) ? 0u : 1u) << 4 | sz;
+}
+__global__ void __launch_bounds__(256) k_celt_kind_count(const anm_celt_frame_t *__restrict__ recs, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
+                                                         uint32_t *place, uint32_t *count) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_jobs) place[j] = atomicAdd(&count[celt_kind(recs[j], jobs[j])], 1u);
+}
+__global__ void __launch_bounds__(kSortKeys) k_celt_kind_scan(uint32_t *count) { /* group sizes -> group starts, in place */
+    __shared__ uint32_t sh[kSortKeys];
+    const uint32_t t = threadIdx.x, own = count[t];
+    sh[t] = own;
+    __syncthreads();
+    for (uint32_t d = 1; d < kSortKeys; d <<= 1) {
+        const uint32_t v = t >= d ? sh[t - d] : 0u;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    count[t] = sh[t] - own;
+}
+__global__ void __launch_bounds__(256) k_celt_kind_place(const anm_celt_frame_t *__restrict__ recs, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
+                                                         const uint32_t *__restrict__ place, const uint32_t *__restrict__ start, uint32_t *order) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_jobs) order[start[celt_kind(recs[j], jobs[j])] + place[j]] = j;
+}
+
 /* stage 2, one thread per FRAME.  What a frame works on -- the folding source, the band being decoded, the pulse vector and the reordering scratch,
  * 5.1 KB -- sits in thread-local memory: its layout puts the same element of the 32 lanes of a warp side by side, and since the band and partition
  * walks of anm_celt_entropy.h keep the lanes in step, their accesses fall into the same lines.  A finished band is copied to the output once, where
@@ -97,8 +135,8 @@ __global__ void __launch_bounds__(128) k_celt_energies(const uint32_t *__restric
 #endif
 __global__ void __launch_bounds__(64, ANM_CELT_SPEC_MINB) k_celt_spectrum(const anm_celt_tables_t *__restrict__ t, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
                                                       const uint8_t *__restrict__ bytes, uint32_t mask, const anm_celt_frame_t *__restrict__ recs,
-                                                      const ce_hist_t *__restrict__ hist, const ce_resume_t *__restrict__ resume, int16_t *x, uint32_t x_stride,
-                                                      uint8_t *collapse) {
+                                                      const ce_hist_t *__restrict__ hist, const ce_resume_t *__restrict__ resume, const uint32_t *__restrict__ order,
+                                                      int16_t *x, uint32_t x_stride, uint8_t *collapse) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
     int16_t l_norm[CE_SPEC_NORM], l_tmp[CE_SPEC_TMP], l_band[CE_SPEC_BAND];
     int l_iy[CE_SPEC_IY];
@@ -110,7 +148,8 @@ __global__ void __launch_bounds__(64, ANM_CELT_SPEC_MINB) k_celt_spectrum(const 
     sp.lane = 0;
     sp.nl = 1;
     sp.spread = 0;
-    for (uint32_t j = tid; j < n_jobs; j += nthr) {
+    for (uint32_t k = tid; k < n_jobs; k += nthr) {
+        const uint32_t j = order[k];
         const anm_celt_job_t job = jobs[j];
         if (recs[j].flags & ANM_CELT_F_LOST) continue;
         uint8_t cm[2 * ANM_CE_NB];
@@ -319,6 +358,8 @@ extern "C" int anm_celt_ctx_create(int device, anm_celt_ctx_t **out) {
     c->hist_frames = 0;
     c->d_resume = nullptr;
     c->resume_frames = 0;
+    c->d_order = nullptr;
+    c->order_words = 0;
     c->d_synth_tables = nullptr;
     c->d_x = nullptr;
     c->x_frames = 0;
@@ -361,6 +402,7 @@ extern "C" void anm_celt_ctx_destroy(anm_celt_ctx_t *c) {
     cudaFree(c->d_scratch);
     cudaFree(c->d_hist);
     cudaFree(c->d_resume);
+    cudaFree(c->d_order);
     cudaFree(c->d_synth_tables);
     cudaFree(c->d_x);
     cudaFree(c->d_raw);
@@ -425,8 +467,15 @@ extern "C" int anm_celt_spectrum_device(anm_celt_ctx_t *c, const anm_celt_job_t 
     if ((rc = grow(&c->d_hist, &c->hist_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
     if ((rc = grow(&c->d_resume, &c->resume_frames, (size_t)n_jobs, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
     if ((rc = entropy_impl(c, d_jobs, d_stream_begin, n_streams, n_jobs, d_bytes, bytes_mask, d_streams, d_out, c->d_hist, c->d_resume, s)) != ANM_OK) return rc;
+    if ((rc = grow(&c->d_order, &c->order_words, 2u * (size_t)n_jobs + kSortKeys, s, "anm_celt_spectrum_device")) != ANM_OK) return rc;
+    uint32_t *order = c->d_order, *place = order + n_jobs, *count = place + n_jobs;
+    cudaMemsetAsync(count, 0, kSortKeys * sizeof(uint32_t), s);
+    k_celt_kind_count<<<(n_jobs + 255u) / 256u, 256, 0, s>>>(d_out, d_jobs, n_jobs, place, count);
+    k_celt_kind_scan<<<1, kSortKeys, 0, s>>>(count);
+    k_celt_kind_place<<<(n_jobs + 255u) / 256u, 256, 0, s>>>(d_out, d_jobs, n_jobs, place, count, order);
     /* one frame per thread: the hardware balances the very uneven frames block by block */
-    k_celt_spectrum<<<(n_jobs + 63u) / 64u, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, c->d_resume, d_x, x_stride, d_collapse);
+    k_celt_spectrum<<<(n_jobs + 63u) / 64u, 64, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, d_out, c->d_hist, c->d_resume, order, d_x, x_stride,
+                                                        d_collapse);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         anm_set_error("k_celt_spectrum launch failed: %s", cudaGetErrorString(e));
