@@ -12,10 +12,12 @@
  * reorderings, stereo merge, anti-collapse), seeded and informed by what the per-stream pass left (the noise seed is the previous frame's final range,
  * anti-collapse reads the stream's two log-energy histories).  The threads of a warp work on frames of their own, so what they do differs from band
  * to band; the band and partition walks are written so that the expensive steps sit at one place in the code each and the lanes meet there
- * (anm_celt_entropy.h: ce_partition, ce_band_channels) -- 7.9 of 32 lanes active per instruction against 3.3 for the straight transcription of the
- * reference's recursion.  A warp-per-frame form was measured 3 x slower (anm_celt_vec.h).  Stage 3 (anm_celt_decode_*) adds
- * k_celt_blocks (a warp per frame: denormalisation, the fixed-point FFT of the inverse MDCT in shared memory) and k_celt_overlap (a warp per stream and
- * output channel: overlap-add, pitch post-filter, de-emphasis with the output history in shared memory).
+ * (anm_celt_entropy.h: ce_partition, ce_band_channels), and the frames are grouped by kind first (k_celt_kind_*: transient or not, frame size,
+ * channels, dual stereo, packet bytes) so that frames which do the same thing share a warp -- 14.4 of 32 lanes active per instruction against 3.3
+ * for the straight transcription of the reference's recursion.  A warp-per-frame form was measured 3 x slower (anm_celt_vec.h).
+ * Stage 3 (anm_celt_decode_*) adds k_celt_blocks (a warp per frame and output channel: denormalisation, the fixed-point FFT of the inverse MDCT in
+ * shared memory), k_celt_overlap (a warp per stream and output channel: overlap-add and pitch post-filter with the output history in shared memory)
+ * and k_celt_deemphasis (a thread per stream and output channel: the one-pole recurrence to 16-bit PCM).
  *
  * Reference path replaced: playback.cpp:115-122 opus_decode() -> opus_decode_frame (opus_decoder.c:214-626, CELT-only branch)
  * -> celt_decode_with_ec (celt/celt_decoder.c:815-1180), without the concealment of lost frames.
