@@ -47,6 +47,26 @@ ANM_CE_FN int32_t cs_neg(int32_t a) { return (int32_t)(0u - (uint32_t)a); }
 ANM_CE_FN int32_t cs_sat(int32_t x) { return x > CS_SIG_SAT ? CS_SIG_SAT : x < -CS_SIG_SAT ? -CS_SIG_SAT : x; }
 
 /* ---------------------------------------------------------------- denormalise_bands (downsample = 1) */
+/* the gain of band i: g * 2^-shift (celt_exp2 of the band's log energy plus its mean, celt/bands.c:203-243) */
+ANM_CE_FN void cs_band_gain(const anm_celt_synth_tables_t *st, const int16_t *band_log_e, int i, int16_t *g_out, int *shift_out) {
+    int32_t lg32 = (int32_t)band_log_e[i] + (int32_t)((uint32_t)(int32_t)st->e_means[i] << 6);
+    const int16_t lg = (int16_t)(lg32 > 32767 ? 32767 : lg32 < -32768 ? -32768 : lg32); /* SATURATE16 */
+    int shift = 16 - (lg >> 10);
+    int16_t g;
+    if (shift > 31) {
+        shift = 0;
+        g = 0;
+    } else {
+        const int16_t frac = (int16_t)((uint16_t)(int16_t)(lg & 1023) << 4); /* celt_exp2_frac */
+        g = CV_A16(16383, CV_Q15(frac, CV_A16(22804, CV_Q15(frac, CV_A16(14819, CV_Q15(10204, frac))))));
+    }
+    if (shift <= -2) { /* a cap on extreme gains: only a corrupted stream gets here */
+        g = 16384;
+        shift = -2;
+    }
+    *g_out = g;
+    *shift_out = shift;
+}
 ANM_CE_FN void cs_denormalise(const anm_celt_tables_t *t, const anm_celt_synth_tables_t *st, const int16_t *X, int32_t *freq, const int16_t *band_log_e,
                               int end, int M, int silence, int lane, int nl) {
     const int N = M * 120;
@@ -56,24 +76,31 @@ ANM_CE_FN void cs_denormalise(const anm_celt_tables_t *t, const anm_celt_synth_t
         end = 0;
     }
     CS_SYNC();
+#ifdef __CUDA_ARCH__
+    if (nl == 32) {
+        /* a warp: lane i works out the gain of band i, then ONE pass over the coefficients with every load in flight at once -- band by band each
+         * band's few loads had to come back from memory before the next band's were issued (a third of k_celt_blocks' time) */
+        int16_t g = 0;
+        int shift = 0;
+        if (lane < end) cs_band_gain(st, band_log_e, lane, &g, &shift);
+        int b = 0, next = M * t->ebands[1];
+#pragma unroll 4
+        for (int j0 = 0; j0 < bound; j0 += 32) {
+            const int j = j0 + lane;
+            const bool act = j < bound;
+            const int16_t x = act ? X[j] : (int16_t)0;
+            while (act && j >= next) next = M * t->ebands[++b + 1];
+            const int gb = __shfl_sync(0xFFFFFFFFu, (int)g, b), sb = __shfl_sync(0xFFFFFFFFu, shift, b);
+            if (act) freq[j] = sb < 0 ? (int32_t)((uint32_t)CV_M16(x, gb) << -sb) : CV_M16(x, gb) >> sb;
+        }
+    } else
+#endif
     for (int i = 0; i < end; i++) {
         const int j0 = M * t->ebands[i], band_end = M * t->ebands[i + 1];
-        int32_t lg32 = (int32_t)band_log_e[i] + (int32_t)((uint32_t)(int32_t)st->e_means[i] << 6);
-        const int16_t lg = (int16_t)(lg32 > 32767 ? 32767 : lg32 < -32768 ? -32768 : lg32); /* SATURATE16 */
-        int shift = 16 - (lg >> 10);
         int16_t g;
-        if (shift > 31) {
-            shift = 0;
-            g = 0;
-        } else {
-            const int16_t frac = (int16_t)((uint16_t)(int16_t)(lg & 1023) << 4); /* celt_exp2_frac */
-            g = CV_A16(16383, CV_Q15(frac, CV_A16(22804, CV_Q15(frac, CV_A16(14819, CV_Q15(10204, frac))))));
-        }
+        int shift;
+        cs_band_gain(st, band_log_e, i, &g, &shift);
         if (shift < 0) {
-            if (shift <= -2) { /* a cap on extreme gains: only a corrupted stream gets here */
-                g = 16384;
-                shift = -2;
-            }
             for (int j = j0 + lane; j < band_end; j += nl) freq[j] = (int32_t)((uint32_t)CV_M16(X[j], g) << -shift);
         } else {
             for (int j = j0 + lane; j < band_end; j += nl) freq[j] = CV_M16(X[j], g) >> shift;

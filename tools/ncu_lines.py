@@ -51,8 +51,8 @@ def f(r, k):
         return 0.0
 
 
-keys = ["# Samples", "Instructions Executed", "Thread Instructions Executed", "stall_long_sb", "stall_no_inst"]
-agg, tot = collections.defaultdict(lambda: [0.0] * 5), [0.0] * 5
+keys = ["# Samples", "Instructions Executed", "Thread Instructions Executed", "stall_long_sb", "stall_no_inst", "L1 Wavefronts Shared", "L1 Wavefronts Shared Excessive"]
+agg, tot = collections.defaultdict(lambda: [0.0] * 7), [0.0] * 7
 for (txt, cur), r in zip(ins, data):
     for i, k in enumerate(keys):
         v = f(r, k)
@@ -60,5 +60,6 @@ for (txt, cur), r in zip(ins, data):
         tot[i] += v
 print("samples %d  warp inst %.3g  lanes %.2f  long_sb %.0f%%  no_inst %.0f%%" % (tot[0], tot[1], tot[2] / tot[1], 100 * tot[3] / tot[0], 100 * tot[4] / tot[0]))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    print("%-22s %5d  smp %5.1f%%  inst %5.1f%%  lanes %5.1f  long_sb %3.0f%%  no_inst %3.0f%%" %
-          (k[0], k[1], 100 * v[0] / tot[0], 100 * v[1] / tot[1], v[2] / max(v[1], 1), 100 * v[3] / max(v[0], 1), 100 * v[4] / max(v[0], 1)))
+    print("%-22s %5d  smp %5.1f%%  inst %5.1f%%  lanes %5.1f  long_sb %3.0f%%  no_inst %3.0f%%  smem wavefronts %5.1f%% (excess %5.1f%%)" %
+          (k[0], k[1], 100 * v[0] / tot[0], 100 * v[1] / tot[1], v[2] / max(v[1], 1), 100 * v[3] / max(v[0], 1), 100 * v[4] / max(v[0], 1),
+           100 * v[5] / max(tot[5], 1), 100 * v[6] / max(tot[5], 1)))
