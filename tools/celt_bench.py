@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--streams", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--name", default="gold_stereo_20ms")
+    ap.add_argument("--in-flight", type=int, default=0, help="also time the full decode with the streams split over K calls on K CUDA streams (K contexts)")
     ap.add_argument("--cpu-baseline", action="store_true", help="also time the REFERENCE decoder (oracle/_ref/libref_opus.so, one core) on the same stream")
     a = ap.parse_args()
     G = np.load(os.path.join(ROOT, "tests", "golden", "celt_entropy.npz"))
@@ -69,6 +70,38 @@ def main():
     t_ent = timed(lambda: L.anm_celt_entropy_device(*args, d_fr.data_ptr(), stream))
     t_spec = timed(lambda: L.anm_celt_spectrum_device(*args, d_fr.data_ptr(), d_x.data_ptr(), 1920, None, stream))
     t_dec = timed(lambda: L.anm_celt_decode_device(*args, d_sy.data_ptr(), d_fr.data_ptr(), d_pcm.data_ptr(), 1920, stream))
+    t_split = None
+    if a.in_flight > 1:
+        # the latency-bound kernels of one call (per-stream energies, de-emphasis: a thread per stream / channel) leave most of the GPU idle; with several
+        # calls in flight on streams of their own, one call's thin kernels run beside another's wide ones.  A context serves one call at a time: K contexts.
+        K = a.in_flight
+        cuts = [a.streams * k // K for k in range(K + 1)]
+        ctxs, strs, d_sbs = [], [], []
+        for k in range(K):
+            cx = ctypes.c_void_p()
+            assert L.anm_celt_ctx_create(0, ctypes.byref(cx)) == 0
+            ctxs.append(cx)
+            strs.append(torch.cuda.Stream())
+            d_sbs.append(torch.from_numpy(((np.arange(cuts[k + 1] - cuts[k] + 1)) * nf).astype(np.uint32).view(np.uint8).copy()).to(dev))
+        jsz, ssz, ysz, fsz = anm.CELT_JOB_DTYPE.itemsize, anm.CELT_STREAM_DTYPE.itemsize, anm.CELT_SYNTH_DTYPE.itemsize, anm.CELT_FRAME_DTYPE.itemsize
+        d_pcm.zero_()
+
+        def split_call():
+            cur = torch.cuda.current_stream()
+            for k in range(K):
+                s0, n_s = cuts[k], cuts[k + 1] - cuts[k]
+                j0, n_j = s0 * nf, n_s * nf
+                strs[k].wait_stream(cur)
+                rc = L.anm_celt_decode_device(ctxs[k], d_jobs.data_ptr() + j0 * jsz, d_sbs[k].data_ptr(), n_s, n_j, d_by.data_ptr(), 0xFFFFFFFF,
+                                              d_st.data_ptr() + s0 * ssz, d_sy.data_ptr() + s0 * ysz, d_fr.data_ptr() + j0 * fsz, d_pcm.data_ptr() + j0 * 1920 * 2, 1920,
+                                              strs[k].cuda_stream)
+                assert rc == 0
+            for k in range(K):
+                cur.wait_stream(strs[k])
+            return 0
+        t_split = timed(split_call)
+        for cx in ctxs:
+            L.anm_celt_ctx_destroy(cx)
     pcm = d_pcm.view(len(jobs), 1920)
     ok = True
     for rep in (0, a.streams // 2, a.streams - 1):
@@ -105,6 +138,7 @@ def main():
                       "entropy_ms": round(t_ent, 3), "entropy_plus_spectrum_ms": round(t_spec, 3), "full_decode_ms": round(t_dec, 3),
                       "Mframes_per_s_full": round(nfr / t_dec / 1e3, 3), "audio_seconds_per_second": round(audio_s / (t_dec * 1e-3), 1),
                       "algorithmic_GBps_full": round((pk_bytes + out_bytes) / (t_dec * 1e-3) / 1e9, 2), "pcm_digests_equal_reference": bool(ok), "cpu_baseline": cpu,
+                      "in_flight": None if t_split is None else {"calls": a.in_flight, "full_decode_ms": round(t_split, 3), "Mframes_per_s_full": round(nfr / t_split / 1e3, 3)},
                       "kernels": "k_celt_entropy, k_celt_energies, k_celt_spectrum, k_celt_blocks, k_celt_overlap, k_celt_deemphasis"}))
 
 
