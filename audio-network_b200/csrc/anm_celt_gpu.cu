@@ -74,18 +74,100 @@ __global__ void __launch_bounds__(128) k_celt_entropy(const anm_celt_tables_t *_
     out[j] = fr;
 }
 
-/* pass 2, one thread per STREAM: the band energies predict from frame to frame (celt/quant_bands.c:427-490) -- a short recurrence over the
- * stream's frames in order, about a hundred integer operations per frame */
+/* pass 2, one WARP per STREAM: the band energies predict from the previous frame of the same stream and, inside a frame, from the bands below
+ * (celt/quant_bands.c:427-490) -- a recurrence over the stream's frames in order.  Lane i holds band i of both channels; what runs up the bands
+ * inside a frame (prev) is a sum of terms that each depend on their own band's symbol only, so it is a warp prefix sum.  The same arithmetic as
+ * anm_celt_stream_step (anm_celt_entropy.h: the host-side harness runs that one; the GPU tests hold this kernel's output against the same golden
+ * vectors); a thread per stream took 42 dependent steps and as many scattered loads per frame (1.1 ms for 4,096 streams of 50 frames). */
 __global__ void __launch_bounds__(128) k_celt_energies(const uint32_t *__restrict__ stream_begin, uint32_t n_streams, const int16_t *__restrict__ scratch,
                                                        anm_celt_stream_t *streams, anm_celt_frame_t *out, ce_hist_t *hist) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
-    anm_celt_stream_t st = streams[s];
-    for (uint32_t j = stream_begin[s]; j < stream_begin[s + 1]; ++j) {
-        const int16_t *sc = scratch + (size_t)j * (4 * ANM_CE_NB);
-        anm_celt_stream_step(&out[j], sc, sc + 2 * ANM_CE_NB, &st, hist ? &hist[j] : nullptr);
+    constexpr unsigned kAll = 0xFFFFFFFFu;
+    constexpr int NB = ANM_CE_NB;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= n_streams) return; /* the whole warp */
+    anm_celt_stream_t *st = &streams[s];
+    const bool on = lane < NB;
+    const int i = on ? lane : 0;
+    uint32_t flags = st->flags, rng = st->rng;
+    int oe[2], l1[2], l2[2];
+    for (int c = 0; c < 2; ++c) {
+        oe[c] = st->old_e[c * NB + i];
+        l1[c] = st->log_e1[c * NB + i];
+        l2[c] = st->log_e2[c * NB + i];
     }
-    streams[s] = st;
+    for (uint32_t j = stream_begin[s]; j < stream_begin[s + 1]; ++j) {
+        const int16_t *qi = scratch + (size_t)j * (4 * NB), *eoff = qi + 2 * NB;
+        anm_celt_frame_t *fr = &out[j];
+        if (!(flags & 1u)) { /* a fresh decoder: both histories at -28 dB */
+            l1[0] = l1[1] = l2[0] = l2[1] = -28672;
+            flags |= 1u;
+        }
+        if (hist) {
+            if (on)
+                for (int c = 0; c < 2; ++c) {
+                    hist[j].log_e1[c * NB + i] = (int16_t)l1[c];
+                    hist[j].log_e2[c * NB + i] = (int16_t)l2[c];
+                }
+            if (lane == 0) hist[j].seed = rng;
+        }
+        const uint32_t ff = fr->flags;
+        const bool lost = (ff & ANM_CELT_F_LOST) != 0;
+        const int end = fr->pad[0];
+        if (!lost) {
+            const int C = fr->channels, LM = fr->lm, intra = (ff & ANM_CELT_F_INTRA) != 0;
+            const int coef = intra ? 0 : (LM == 0 ? 29440 : LM == 1 ? 26112 : LM == 2 ? 21248 : 16384);
+            const int beta = intra ? 4915 : (LM == 0 ? 30147 : LM == 1 ? 22282 : LM == 2 ? 12124 : 6554);
+            if (C == 1) oe[0] = oe[0] > oe[1] ? oe[0] : oe[1];
+            const bool act = on && i < end;
+            for (int c = 0; c < C; ++c) {
+                const int32_t q = act ? (int32_t)qi[i + c * NB] * 1024 : 0; /* SHL32(qi, DB_SHIFT) */
+                const int32_t term = q * 128 - (int32_t)beta * (int16_t)ce_pshr32(q, 8);
+                int32_t run = term; /* inclusive sum up the bands */
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int32_t v = __shfl_up_sync(kAll, run, d);
+                    if (lane >= d) run = (int32_t)((uint32_t)run + (uint32_t)v);
+                }
+                const int32_t prev = (int32_t)((uint32_t)run - (uint32_t)term);
+                if (act) {
+                    int e = oe[c];
+                    if (e < -9216) e = -9216; /* MAX16(-QCONST16(9, DB_SHIFT), .) */
+                    int32_t tmp = ce_pshr32((int32_t)coef * e, 8) + prev + q * 128;
+                    if (tmp < -3670016) tmp = -3670016; /* -QCONST32(28, DB_SHIFT + 7) */
+                    oe[c] = (int16_t)(ce_pshr32(tmp, 7) + eoff[i + c * NB]);
+                }
+            }
+            if (ff & ANM_CELT_F_SILENCE)
+                for (int c = 0; c < C; ++c) oe[c] = -28672; /* -QCONST16(28, DB_SHIFT) */
+            if (C == 1) oe[1] = oe[0];
+            if (i >= end) oe[0] = oe[1] = 0;
+        }
+        if (on) {
+            fr->band_e[i] = (int16_t)oe[0];
+            fr->band_e[NB + i] = (int16_t)oe[1];
+        }
+        if (lost) continue;
+        for (int c = 0; c < 2; ++c) {
+            if (!(ff & ANM_CELT_F_TRANSIENT)) {
+                l2[c] = l1[c];
+                l1[c] = oe[c];
+            } else {
+                l1[c] = l1[c] < oe[c] ? l1[c] : oe[c];
+            }
+            if (i >= end) l1[c] = l2[c] = -28672;
+        }
+        rng = fr->final_range;
+    }
+    if (on)
+        for (int c = 0; c < 2; ++c) {
+            st->old_e[c * NB + i] = (int16_t)oe[c];
+            st->log_e1[c * NB + i] = (int16_t)l1[c];
+            st->log_e2[c * NB + i] = (int16_t)l2[c];
+        }
+    if (lane == 0) {
+        st->rng = rng;
+        st->flags = flags;
+    }
 }
 
 /* Which frames share a warp in stage 2.  The threads of a warp run together only where their frames do the same thing, and what a frame does is
@@ -434,7 +516,7 @@ static int entropy_impl(anm_celt_ctx_t *c, const anm_celt_job_t *d_jobs, const u
     const int rcg = grow(&c->d_scratch, &c->scratch_frames, (size_t)n_jobs * 4 * ANM_CE_NB, s, "anm_celt_entropy_device");
     if (rcg != ANM_OK) return rcg;
     k_celt_entropy<<<(n_jobs + 127u) / 128u, 128, 0, s>>>(c->d_tables, d_jobs, n_jobs, d_bytes, bytes_mask, c->d_scratch, d_out, d_resume);
-    k_celt_energies<<<(n_streams + 127u) / 128u, 128, 0, s>>>(d_stream_begin, n_streams, c->d_scratch, d_streams, d_out, d_hist);
+    k_celt_energies<<<(n_streams + 3u) / 4u, 128, 0, s>>>(d_stream_begin, n_streams, c->d_scratch, d_streams, d_out, d_hist);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         anm_set_error("k_celt_entropy launch failed: %s", cudaGetErrorString(e));
