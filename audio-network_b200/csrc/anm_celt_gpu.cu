@@ -2,10 +2,10 @@
  * anm_celt_gpu.cu -- the batched CELT decoder on the GPU (include/anmodem_opus.h, anm_celt_entropy_* / _spectrum_* / _decode_*).
  * Stage 1, two passes.  k_celt_entropy, one thread per FRAME: the range decoder is sequential inside a frame, but no symbol of a
  * frame depends on any other frame, so every frame of every stream decodes at once (integer / byte work on a few hundred bytes of
- * packet, latency bound per thread: the batch of frames is what fills the machine).  k_celt_energies, one thread per STREAM: the band
- * energies predict from the previous frame of the same stream (celt/quant_bands.c:427-490) -- a recurrence of about a hundred integer
- * operations per frame over the coarse symbols and offsets pass 1 left in a scratch array (anm_celt_entropy.h holds the decode itself,
- * shared with the host-side test harness).
+ * packet, latency bound per thread: the batch of frames is what fills the machine).  k_celt_energies, one warp per STREAM: the band
+ * energies predict from the previous frame of the same stream (celt/quant_bands.c:427-490) -- a recurrence over the stream's frames in order
+ * on the coarse symbols and offsets pass 1 left in a scratch array, band i on lane i (anm_celt_entropy.h holds the decode itself, shared
+ * with the host-side test harness).
  *
  * Stage 2 (anm_celt_spectrum_*) adds k_celt_spectrum, one thread per frame again: the frame is picked up where pass 1 left its range decoder in
  * front of the band loop, and the bands are decoded with the spectrum arithmetic switched on (anm_celt_vec.h: PVQ vectors, rotations, folding,
