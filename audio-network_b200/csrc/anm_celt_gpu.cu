@@ -185,7 +185,15 @@ __device__ __forceinline__ uint32_t celt_kind(const anm_celt_frame_t &fr, const 
 __global__ void __launch_bounds__(256) k_celt_kind_count(const anm_celt_frame_t *__restrict__ recs, const anm_celt_job_t *__restrict__ jobs, uint32_t n_jobs,
                                                          uint32_t *place, uint32_t *count) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_jobs) place[j] = atomicAdd(&count[celt_kind(recs[j], jobs[j])], 1u);
+    if (j >= n_jobs) return;
+    /* a batch is a few kinds, so the lanes of a warp mostly want the same counter: one atomic per kind and warp, the lanes take consecutive places */
+    const uint32_t kind = celt_kind(recs[j], jobs[j]);
+    const unsigned lane = threadIdx.x & 31u, peers = __match_any_sync(__activemask(), kind);
+    const int leader = __ffs((int)peers) - 1;
+    uint32_t first = 0;
+    if ((int)lane == leader) first = atomicAdd(&count[kind], (uint32_t)__popc(peers));
+    first = __shfl_sync(peers, first, leader);
+    place[j] = first + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
 __global__ void __launch_bounds__(kSortKeys) k_celt_kind_scan(uint32_t *count) { /* group sizes -> group starts, in place */
     __shared__ uint32_t sh[kSortKeys];
